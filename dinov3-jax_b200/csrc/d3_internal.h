@@ -1,0 +1,52 @@
+// Internal declarations shared by the kernels behind the C ABI in include/dinov3_b200.h.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include "../../include/dinov3_b200.h"
+
+namespace d3 {
+
+// epilogue flag bits mirror D3_EP_* in the public header
+enum : int {
+  EP_BIAS = D3_EP_BIAS,
+  EP_GELU = D3_EP_GELU,
+  EP_STORE_PRE = D3_EP_STORE_PRE,
+  EP_MUL_DGELU = D3_EP_MUL_DGELU,
+  EP_GAMMA = D3_EP_GAMMA,
+  EP_RESID = D3_EP_RESID,
+  EP_OUT_F32 = D3_EP_OUT_F32,
+  EP_ACCUM = D3_EP_ACCUM,
+  EP_SLOW = 1 << 30,  // internal: force the bounds-checked scalar epilogue
+};
+
+struct GemmEpilogue {
+  const float* bias;             // [N] fp32
+  const float* gamma;            // [N] fp32 (LayerScale)
+  const float* resid;            // [M, ld_resid] fp32 residual stream (may alias out)
+  const __nv_bfloat16* aux_in;   // [M, ld_aux] bf16 pre-activation for GELU'
+  __nv_bfloat16* aux_out;        // [M, ld_aux] bf16 pre-activation stash
+  void* out;                     // [M, ld_out] bf16 or fp32
+  int ld_out, ld_aux, ld_resid;
+  int flags;
+  float alpha;
+};
+
+int set_error(int code, const char* msg);
+int sm_count();
+void count_launch(int n = 1);
+int encode_tensor_map_2d_bf16(CUtensorMap* map, const void* ptr, const cuuint64_t dims[2],
+                              const cuuint64_t strides[1], const cuuint32_t box[2], const cuuint32_t estr[2]);
+
+int gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, int M, int N, int K,
+              GemmEpilogue ep, int force_bn, cudaStream_t stream);
+
+#define D3_CHECK_LAUNCH()                                               \
+  do {                                                                  \
+    cudaError_t e__ = cudaPeekAtLastError();                            \
+    if (e__ != cudaSuccess) return d3::set_error(D3_ERR_CUDA, cudaGetErrorString(e__)); \
+    d3::count_launch();                                                 \
+  } while (0)
+
+}  // namespace d3

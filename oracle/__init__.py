@@ -1,0 +1,24 @@
+"""CPU oracle for the DINOv3 SSL training hot path — TEST INFRASTRUCTURE ONLY.
+
+This package is a plain-PyTorch (fp32 / fp64, CPU) restatement of the arithmetic of the reference
+Dhia-naouali/dinov3-jax @ 27e64762 for the path BASELINE.json names: student/teacher ViT forward, DINO / iBOT /
+KoLeo heads and losses, gradient, per-submodule clip, AdamW and teacher EMA.  Every function cites the reference
+file:line it follows (paths relative to the reference checkout, `dinov3_jax/...`).
+
+Who may import it: only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s `cpu_baseline` / `--impl reference`
+legs, and there only as the checker (or the timed CPU baseline) — never from the product path under
+`dinov3-jax_b200/`.  The product path has no CPU fallback and fails loudly without the CUDA library.
+
+PARITY STATUS: the reference ships no golden vectors, known-answer tests or numeric asserts and
+its third-party stack (jax 0.7.1 / flax 0.11.2 / optax 0.2.5) is not installable in the build container, so the
+reference cannot be executed end to end here.  The oracle is pinned as far as that allows:
+  * `data/masking.py`, `data/collate.py` (mask part), `train/cosine_lr_scheduler.py` are pure numpy/torch and ARE
+    imported from /root/reference by `tests/golden/make_golden.py`; the oracle's restatement is bit-exact against them;
+  * the loss / RoPE / head / attention / block / ViT / SSLMetaArch modules of the reference are executed
+    *unmodified* under a small numpy-backed shim of the jax / flax API (`oracle/jaxshim`, semantics of the third-party
+    ops restated per SURVEY.md Appendix F) and their outputs are committed as fixtures under `tests/golden/`;
+  * analytic micro-cases (uniform Sinkhorn, LN of constant rows, orthogonal KoLeo pairs ...) in `tests/`.
+What is therefore *not* pinned: the third-party op semantics themselves (flax gelu/LayerNorm/attention defaults,
+optax adamw) — "parity unpinned" for those, stated here and in DESIGN.md.
+"""
+from .arch import ARCHS, ModelCfg, tiny_cfg, cfg_for  # noqa: F401
