@@ -1,0 +1,474 @@
+// Multi-head self-attention forward / backward on tcgen05 tensor cores for the short ViT sequences of the DINOv3
+// crops (N = 197 / 37 / 257 / 50 tokens, head_dim = 64): replaces flax `nn.dot_product_attention(q, k, v)` at
+// dinov3_jax/layers/attention.py:116 (softmax((q / sqrt(64)) k^T) v, no mask, no dropout) and its jax.grad.
+//
+// Forward: one CTA per (q-tile of 128 rows, head, crop).  The whole key range of a crop fits one pass, so there is
+// no online softmax: S = Q K^T lands in tensor memory (<= 512 fp32 columns), each of the 128 threads owns one
+// query row (tcgen05.ld 32x32b), writes P = softmax(S) as a bf16 K-major SWIZZLE_128B tile into shared memory
+// (over the dead Q/K tiles), and a second UMMA computes O = P V with V consumed as an MN-major operand straight
+// from its TMA tile.  Operands come by TMA from the fused qkv buffer [T, 3D] (q | k | v thirds, heads contiguous).
+#include "ptx.cuh"
+#include "d3_internal.h"
+
+namespace d3 {
+
+constexpr float LOG2E = 1.4426950408889634f;
+
+struct AttnShape {
+  int N;         // tokens per crop
+  int Nkp;       // keys padded (multiple of 16 * nbox)
+  int nbox;      // TMA boxes per K / V tile
+  int box_rows;  // rows per box
+  int D;         // embed dim (row stride of o / do); qkv row stride = 3D
+  int H;
+  float scale;   // head_dim^-0.5
+};
+
+// swizzled (SWIZZLE_128B, K-major) address of element (row, col) in a [128 x 64] bf16 chunk; col multiple of 8
+__device__ __forceinline__ uint32_t sw128_offset(int row, int col) {
+  return (uint32_t)(row * 128 + ((((col >> 3) ^ (row & 7)) & 7) << 4));
+}
+
+template <int TMEM_COLS>
+__global__ void __launch_bounds__(128)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                __nv_bfloat16* __restrict__ O, float* __restrict__ LSE, const AttnShape sh) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // layout: [ region A: Q (16 KB) | K (Nkp*128 B)  -- later overwritten by P (ceil(Nkp/64) * 16 KB) ] [ V (Nkp*128 B) ]
+  const int kv_bytes = sh.Nkp * 128;
+  const int p_chunks = (sh.Nkp + 63) / 64;
+  const int regA = max(16384 + kv_bytes, p_chunks * 16384);
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + 16384;
+  uint8_t* sP = smem;
+  uint8_t* sV = smem + regA;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kv_bytes);
+  uint64_t* bar_load = bars;
+  uint64_t* bar_mma = bars + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, h = blockIdx.y, c = blockIdx.z;
+  const int q0 = qt * 128;
+  const int row_base = c * sh.N;  // first token row of this crop in [T, ...]
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+    mbar_init(bar_load, 1);
+    mbar_init(bar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar_load, 16384 + 2 * kv_bytes);
+    tma_load_2d(&tmQ, bar_load, sQ, h * 64, row_base + q0);
+    for (int b = 0; b < sh.nbox; ++b) {
+      tma_load_2d(&tmKV, bar_load, sK + b * sh.box_rows * 128, sh.D + h * 64, row_base + b * sh.box_rows);
+      tma_load_2d(&tmKV, bar_load, sV + b * sh.box_rows * 128, 2 * sh.D + h * 64, row_base + b * sh.box_rows);
+    }
+    mbar_wait(bar_load, 0);
+    tc_fence_after();
+    // S[128, Nkp] = Q K^T   (A = Q K-major, B = K K-major; UMMA N <= 256 per instruction)
+    const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK);
+    for (int n0 = 0; n0 < sh.Nkp; n0 += 256) {
+      const int nn = min(256, sh.Nkp - n0);
+      const uint32_t idesc = umma_idesc_bf16(128, nn, 0, 0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint64_t ad = umma_desc_sw128(qa + k * 32, 16, 1024);
+        const uint64_t bd = umma_desc_sw128(ka + n0 * 128 + k * 32, 16, 1024);
+        umma_bf16(tmem + n0, ad, bd, idesc, k > 0);
+      }
+    }
+    umma_commit(bar_mma);
+  }
+  __syncwarp();
+  mbar_wait(bar_mma, 0);
+  tc_fence_after();
+
+  // ---- softmax: thread r owns query row q0 + r (TMEM lane r)
+  const int r = threadIdx.x;
+  const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
+  const float cs = sh.scale * LOG2E;
+  float mx = -3.0e38f;
+  for (int c0 = 0; c0 < sh.Nkp; c0 += 16) {
+    uint32_t v[16];
+    tmem_ld16(t_row + c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (c0 + j < sh.N) mx = fmaxf(mx, __uint_as_float(v[j]));
+  }
+  const float mxs = mx * cs;
+  float sum = 0.f;
+  // all threads must have finished reading nothing from sQ/sK via the async proxy: the MMA that read them is
+  // complete (bar_mma), so region A may now be overwritten with P.
+  for (int c0 = 0; c0 < sh.Nkp; c0 += 16) {
+    uint32_t v[16];
+    tmem_ld16(t_row + c0, v);
+    tmem_ld_wait();
+    float p[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      p[j] = (c0 + j < sh.N) ? exp2f(__uint_as_float(v[j]) * cs - mxs) : 0.f;
+      sum += p[j];
+    }
+    uint8_t* chunk = sP + (c0 >> 6) * 16384;
+    const int cc = c0 & 63;
+    *reinterpret_cast<uint4*>(chunk + sw128_offset(r, cc)) =
+        make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
+    *reinterpret_cast<uint4*>(chunk + sw128_offset(r, cc + 8)) =
+        make_uint4(pack_bf16(p[8], p[9]), pack_bf16(p[10], p[11]), pack_bf16(p[12], p[13]), pack_bf16(p[14], p[15]));
+  }
+  fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    tc_fence_after();
+    // O[128, 64] = P[128, Nkp] V[Nkp, 64]  (A = P K-major, B = V MN-major: 16 keys per UMMA_K = 2 x 1024 B)
+    const uint32_t pa = smem_u32(sP), va = smem_u32(sV);
+    const uint32_t idesc = umma_idesc_bf16(128, 64, 0, 1);
+    const int ksteps = sh.Nkp / 16;
+    for (int k = 0; k < ksteps; ++k) {
+      const uint64_t ad = umma_desc_sw128(pa + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
+      const uint64_t bd = umma_desc_sw128(va + k * 2048, 8192, 1024);
+      umma_bf16(tmem, ad, bd, idesc, k > 0);   // O aliases the (fully consumed) S columns [0, 64)
+    }
+    umma_commit(bar_mma);
+  }
+  __syncwarp();
+  mbar_wait(bar_mma, 1);
+  tc_fence_after();
+
+  const int q = q0 + r;
+  const float inv = 1.f / sum;
+  uint32_t o[64];
+  tmem_ld32(t_row, o);
+  tmem_ld32(t_row + 32, o + 32);
+  tmem_ld_wait();
+  if (q < sh.N) {
+    __nv_bfloat16* dst = O + (size_t)(row_base + q) * sh.D + h * 64;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      reinterpret_cast<uint4*>(dst)[j] = make_uint4(
+          pack_bf16(__uint_as_float(o[8 * j]) * inv, __uint_as_float(o[8 * j + 1]) * inv),
+          pack_bf16(__uint_as_float(o[8 * j + 2]) * inv, __uint_as_float(o[8 * j + 3]) * inv),
+          pack_bf16(__uint_as_float(o[8 * j + 4]) * inv, __uint_as_float(o[8 * j + 5]) * inv),
+          pack_bf16(__uint_as_float(o[8 * j + 6]) * inv, __uint_as_float(o[8 * j + 7]) * inv));
+    }
+    if (LSE) LSE[((size_t)c * sh.H + h) * sh.N + q] = mx * sh.scale + logf(sum);   // natural-log LSE of scaled scores
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_free<TMEM_COLS>(tmem);
+}
+
+// Delta[c,h,q] = sum_d dO[q, h, d] * O[q, h, d]    (backward softmax term)
+__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ O, const __nv_bfloat16* __restrict__ dO,
+                                  float* __restrict__ delta, long T, int N, int D, int H) {
+  const long w = blockIdx.x * (long)(blockDim.x >> 5) + (threadIdx.x >> 5);   // one warp per (row, head)
+  const int lane = threadIdx.x & 31;
+  if (w >= T * H) return;
+  const long row = w / H;
+  const int h = (int)(w % H);
+  const uint32_t a = *reinterpret_cast<const uint32_t*>(O + row * D + h * 64 + lane * 2);
+  const uint32_t b = *reinterpret_cast<const uint32_t*>(dO + row * D + h * 64 + lane * 2);
+  const float2 fa = unpack_bf16(a), fb = unpack_bf16(b);
+  float s = fa.x * fb.x + fa.y * fb.y;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) delta[((row / N) * H + h) * N + (row % N)] = s;
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+// One CTA per (head, crop); N <= 256 (2 query tiles x 2 key tiles of 128).  For each key tile kt and query tile qt:
+//   S  = Q K^T, dP = dO V^T           (tensor memory, 128 + 128 columns)
+//   P  = exp(S*scale - lse), dS = P * (dP - Delta) * scale     -> bf16 tiles in shared memory
+//   dV[kt] += P^T dO,  dK[kt] += dS^T Q   (A = P / dS read MN-major, B = dO / Q read MN-major)
+//   dQ[qt] += dS K                        (A = dS K-major, B = K MN-major)
+// dQ accumulates in tensor memory across key tiles (2 x 64 columns), dK/dV across query tiles (64 + 64).
+__global__ void __launch_bounds__(128)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                const float* __restrict__ LSE, const float* __restrict__ Delta, __nv_bfloat16* __restrict__ dQKV,
+                const AttnShape sh) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                 // [2][128 x 64] 32 KB (both query tiles stay resident)
+  uint8_t* sDO = smem + 32768;        // [2][128 x 64] 32 KB
+  uint8_t* sK = smem + 65536;         // 16 KB (current key tile)
+  uint8_t* sV = smem + 81920;         // 16 KB
+  uint8_t* sP = smem + 98304;         // [2 chunks of 64 keys][128 q x 128 B] 32 KB
+  uint8_t* sDS = smem + 131072;       // 32 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 163840);
+  uint64_t* bar_q = bars;             // Q / dO tiles
+  uint64_t* bar_kv = bars + 1;
+  uint64_t* bar_mma = bars + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x, c = blockIdx.y;
+  const int row_base = c * sh.N;
+  const int nQ = (sh.N + 127) / 128, nK = nQ;
+  const int r = threadIdx.x;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmDO);
+    mbar_init(bar_q, 1);
+    mbar_init(bar_kv, 1);
+    mbar_init(bar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  // TMEM columns: S [0,128) | dP [128,256) | dK [256,320) | dV [320,384) | dQ[qt] [384 + 64 qt, ...)
+  const uint32_t tS = tmem, tDP = tmem + 128, tDK = tmem + 256, tDV = tmem + 320, tDQ = tmem + 384;
+  const uint32_t t_lane = (uint32_t)(warp * 32) << 16;
+
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar_q, nQ * 2 * 16384);
+    for (int qt = 0; qt < nQ; ++qt) {
+      tma_load_2d(&tmQKV, bar_q, sQ + qt * 16384, h * 64, row_base + qt * 128);
+      tma_load_2d(&tmDO, bar_q, sDO + qt * 16384, h * 64, row_base + qt * 128);
+    }
+  }
+  uint32_t mma_phase = 0, kv_phase = 0;
+  const float cs = sh.scale * LOG2E;
+
+  for (int kt = 0; kt < nK; ++kt) {
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(bar_kv, 2 * 16384);
+      tma_load_2d(&tmQKV, bar_kv, sK, sh.D + h * 64, row_base + kt * 128);
+      tma_load_2d(&tmQKV, bar_kv, sV, 2 * sh.D + h * 64, row_base + kt * 128);
+    }
+    for (int qt = 0; qt < nQ; ++qt) {
+      if (threadIdx.x == 0) {
+        if (kt == 0 && qt == 0) mbar_wait(bar_q, 0);
+        if (qt == 0) mbar_wait(bar_kv, kv_phase);
+        tc_fence_after();
+        const uint32_t qa = smem_u32(sQ + qt * 16384), doa = smem_u32(sDO + qt * 16384);
+        const uint32_t ka = smem_u32(sK), va = smem_u32(sV);
+        const uint32_t idesc = umma_idesc_bf16(128, 128, 0, 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tS, umma_desc_sw128(qa + k * 32, 16, 1024), umma_desc_sw128(ka + k * 32, 16, 1024), idesc, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tDP, umma_desc_sw128(doa + k * 32, 16, 1024), umma_desc_sw128(va + k * 32, 16, 1024), idesc, k > 0);
+        umma_commit(bar_mma);
+      }
+      __syncwarp();
+      mbar_wait(bar_mma, mma_phase);
+      mma_phase ^= 1;
+      tc_fence_after();
+
+      // ---- elementwise: thread r owns query row q = qt*128 + r
+      const int q = qt * 128 + r;
+      const bool q_ok = q < sh.N;
+      const size_t stat = ((size_t)c * sh.H + h) * sh.N + (q_ok ? q : 0);
+      const float lse2 = q_ok ? LSE[stat] * LOG2E : 0.f;
+      const float dl = q_ok ? Delta[stat] : 0.f;
+      for (int c0 = 0; c0 < 128; c0 += 16) {
+        uint32_t s[16], dp[16];
+        tmem_ld16(tS + t_lane + c0, s);
+        tmem_ld16(tDP + t_lane + c0, dp);
+        tmem_ld_wait();
+        float p[16], ds[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const bool ok = q_ok && (kt * 128 + c0 + j < sh.N);
+          p[j] = ok ? exp2f(__uint_as_float(s[j]) * cs - lse2) : 0.f;
+          ds[j] = ok ? p[j] * (__uint_as_float(dp[j]) - dl) * sh.scale : 0.f;
+        }
+        const int cc = c0 & 63;
+        uint8_t* pc = sP + (c0 >> 6) * 16384;
+        uint8_t* dc = sDS + (c0 >> 6) * 16384;
+        *reinterpret_cast<uint4*>(pc + sw128_offset(r, cc)) =
+            make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
+        *reinterpret_cast<uint4*>(pc + sw128_offset(r, cc + 8)) =
+            make_uint4(pack_bf16(p[8], p[9]), pack_bf16(p[10], p[11]), pack_bf16(p[12], p[13]), pack_bf16(p[14], p[15]));
+        *reinterpret_cast<uint4*>(dc + sw128_offset(r, cc)) =
+            make_uint4(pack_bf16(ds[0], ds[1]), pack_bf16(ds[2], ds[3]), pack_bf16(ds[4], ds[5]), pack_bf16(ds[6], ds[7]));
+        *reinterpret_cast<uint4*>(dc + sw128_offset(r, cc + 8)) = make_uint4(
+            pack_bf16(ds[8], ds[9]), pack_bf16(ds[10], ds[11]), pack_bf16(ds[12], ds[13]), pack_bf16(ds[14], ds[15]));
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        tc_fence_after();
+        const uint32_t pa = smem_u32(sP), dsa = smem_u32(sDS);
+        const uint32_t qa = smem_u32(sQ + qt * 16384), doa = smem_u32(sDO + qt * 16384), ka = smem_u32(sK);
+        // dV[128 keys, 64] += P^T dO : A = P as MN-major (M = keys: two 64-key groups 16 KB apart; K = 16 query rows
+        //                               = 2 x 1024 B), B = dO MN-major (N = d: one group)
+        const uint32_t id_tt = umma_idesc_bf16(128, 64, 1, 1);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_bf16(tDV, umma_desc_sw128(pa + k * 2048, 16384, 1024), umma_desc_sw128(doa + k * 2048, 8192, 1024), id_tt,
+                    (qt > 0 || k > 0));
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_bf16(tDK, umma_desc_sw128(dsa + k * 2048, 16384, 1024), umma_desc_sw128(qa + k * 2048, 8192, 1024), id_tt,
+                    (qt > 0 || k > 0));
+        // dQ[128 q, 64] += dS K : A = dS K-major (64-key chunks 16 KB apart), B = K MN-major
+        const uint32_t id_nt = umma_idesc_bf16(128, 64, 0, 1);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_bf16(tDQ + qt * 64, umma_desc_sw128(dsa + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                    umma_desc_sw128(ka + k * 2048, 8192, 1024), id_nt, (kt > 0 || k > 0));
+        umma_commit(bar_mma);
+      }
+      __syncwarp();
+      // the MMAs read sP / sDS / sK: wait before the next iteration overwrites them
+      mbar_wait(bar_mma, mma_phase);
+      mma_phase ^= 1;
+      tc_fence_after();
+    }
+    // ---- dK / dV of this key tile: thread r owns key row kt*128 + r
+    {
+      const int key = kt * 128 + r;
+      uint32_t a[64];
+      tmem_ld32(tDK + t_lane, a);
+      tmem_ld32(tDK + t_lane + 32, a + 32);
+      tmem_ld_wait();
+      if (key < sh.N) {
+        __nv_bfloat16* dst = dQKV + (size_t)(row_base + key) * (3 * sh.D) + sh.D + h * 64;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          reinterpret_cast<uint4*>(dst)[j] = make_uint4(
+              pack_bf16(__uint_as_float(a[8 * j]), __uint_as_float(a[8 * j + 1])),
+              pack_bf16(__uint_as_float(a[8 * j + 2]), __uint_as_float(a[8 * j + 3])),
+              pack_bf16(__uint_as_float(a[8 * j + 4]), __uint_as_float(a[8 * j + 5])),
+              pack_bf16(__uint_as_float(a[8 * j + 6]), __uint_as_float(a[8 * j + 7])));
+      }
+      tmem_ld32(tDV + t_lane, a);
+      tmem_ld32(tDV + t_lane + 32, a + 32);
+      tmem_ld_wait();
+      if (key < sh.N) {
+        __nv_bfloat16* dst = dQKV + (size_t)(row_base + key) * (3 * sh.D) + 2 * sh.D + h * 64;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          reinterpret_cast<uint4*>(dst)[j] = make_uint4(
+              pack_bf16(__uint_as_float(a[8 * j]), __uint_as_float(a[8 * j + 1])),
+              pack_bf16(__uint_as_float(a[8 * j + 2]), __uint_as_float(a[8 * j + 3])),
+              pack_bf16(__uint_as_float(a[8 * j + 4]), __uint_as_float(a[8 * j + 5])),
+              pack_bf16(__uint_as_float(a[8 * j + 6]), __uint_as_float(a[8 * j + 7])));
+      }
+    }
+    kv_phase ^= 1;
+    tc_fence_before();
+    __syncthreads();   // all TMEM reads of dK/dV done before the next key tile's MMAs overwrite them
+    tc_fence_after();
+  }
+  // ---- dQ
+  for (int qt = 0; qt < nQ; ++qt) {
+    const int q = qt * 128 + r;
+    uint32_t a[64];
+    tmem_ld32(tDQ + qt * 64 + t_lane, a);
+    tmem_ld32(tDQ + qt * 64 + t_lane + 32, a + 32);
+    tmem_ld_wait();
+    if (q < sh.N) {
+      __nv_bfloat16* dst = dQKV + (size_t)(row_base + q) * (3 * sh.D) + h * 64;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        reinterpret_cast<uint4*>(dst)[j] = make_uint4(
+            pack_bf16(__uint_as_float(a[8 * j]), __uint_as_float(a[8 * j + 1])),
+            pack_bf16(__uint_as_float(a[8 * j + 2]), __uint_as_float(a[8 * j + 3])),
+            pack_bf16(__uint_as_float(a[8 * j + 4]), __uint_as_float(a[8 * j + 5])),
+            pack_bf16(__uint_as_float(a[8 * j + 6]), __uint_as_float(a[8 * j + 7])));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_free<512>(tmem);
+}
+
+static int make_map(CUtensorMap* map, const void* ptr, long rows, int cols, int ld, int box_rows) {
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return encode_tensor_map_2d_bf16(map, ptr, dims, strides, box, estr);
+}
+
+static int attn_shape(AttnShape* s, int N, int D, int H) {
+  if (D != H * 64) return set_error(D3_ERR_ARG, "attention: head_dim must be 64");
+  s->N = N; s->D = D; s->H = H; s->scale = 0.125f;
+  s->nbox = (N + 255) / 256;
+  const int q = 16 * s->nbox;
+  s->Nkp = (N + q - 1) / q * q;
+  s->box_rows = s->Nkp / s->nbox;
+  if (s->Nkp > 448) return set_error(D3_ERR_ARG, "attention: N > 448 tokens per crop not supported by the single-pass kernel");
+  return D3_OK;
+}
+
+}  // namespace d3
+
+using namespace d3;
+
+extern "C" {
+
+int d3_attn_fwd(const void* qkv, void* o, float* lse, int n_crops, int N, int D, int H, void* stream) {
+  AttnShape s;
+  int rc = attn_shape(&s, N, D, H);
+  if (rc) return rc;
+  const long T = (long)n_crops * N;
+  CUtensorMap tq, tkv;
+  if ((rc = make_map(&tq, qkv, T, 3 * D, 3 * D, 128))) return rc;
+  if ((rc = make_map(&tkv, qkv, T, 3 * D, 3 * D, s.box_rows))) return rc;
+  const int kv_bytes = s.Nkp * 128;
+  const int p_chunks = (s.Nkp + 63) / 64;
+  const int regA = max(16384 + kv_bytes, p_chunks * 16384);
+  const int smem = regA + kv_bytes + 64 + 1024;
+  dim3 grid((N + 127) / 128, H, n_crops);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (s.Nkp <= 256) {
+    static bool cfg = false;
+    if (!cfg) { cudaFuncSetAttribute(attn_fwd_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); cfg = true; }
+    attn_fwd_kernel<256><<<grid, 128, smem, st>>>(tq, tkv, (__nv_bfloat16*)o, lse, s);
+  } else {
+    static bool cfg = false;
+    if (!cfg) { cudaFuncSetAttribute(attn_fwd_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); cfg = true; }
+    attn_fwd_kernel<512><<<grid, 128, smem, st>>>(tq, tkv, (__nv_bfloat16*)o, lse, s);
+  }
+  D3_CHECK_LAUNCH();
+  return D3_OK;
+}
+
+int d3_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, float* delta_scratch, void* dqkv,
+                int n_crops, int N, int D, int H, void* stream) {
+  AttnShape s;
+  int rc = attn_shape(&s, N, D, H);
+  if (rc) return rc;
+  if (N > 256) return set_error(D3_ERR_ARG, "d3_attn_bwd: N > 256 not supported yet");
+  const long T = (long)n_crops * N;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  {
+    const long warps = T * H;
+    attn_delta_kernel<<<(int)((warps + 7) / 8), 256, 0, st>>>((const __nv_bfloat16*)o, (const __nv_bfloat16*)d_o,
+                                                            delta_scratch, T, N, D, H);
+    D3_CHECK_LAUNCH();
+  }
+  CUtensorMap tqkv, tdo;
+  if ((rc = make_map(&tqkv, qkv, T, 3 * D, 3 * D, 128))) return rc;
+  if ((rc = make_map(&tdo, d_o, T, D, D, 128))) return rc;
+  static bool cfg = false;
+  if (!cfg) { cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); cfg = true; }
+  const int smem = 163840 + 64 + 1024;
+  dim3 grid(H, n_crops);
+  attn_bwd_kernel<<<grid, 128, smem, st>>>(tqkv, tdo, lse, delta_scratch, (__nv_bfloat16*)dqkv, s);
+  D3_CHECK_LAUNCH();
+  return D3_OK;
+}
+
+}  // extern "C"

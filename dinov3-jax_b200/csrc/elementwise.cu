@@ -1,0 +1,486 @@
+// HBM-bound kernels of the ViT forward/backward: im2col, token assembly, LayerNorm fwd/bwd, RoPE, row
+// gather/scatter, L2-normalise, LayerScale/GELU backward, column sums.  All use 128-bit loads where the layout
+// allows, warp-shuffle reductions, fp32 statistics.
+#include "ptx.cuh"
+#include "d3_internal.h"
+
+namespace d3 {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------ im2col
+// layers/patch_embed.py:38-51: conv with kernel == stride == p is a GEMM over flattened patches.
+// img bf16 [n, H, W, 3] -> out bf16 [n*Hp*Wp, p*p*3], k = (a*p + b)*3 + c  (kernel layout [p,p,3,D]).
+__global__ void im2col_kernel(const __nv_bfloat16* __restrict__ img, __nv_bfloat16* __restrict__ out, int n, int H,
+                              int W, int p) {
+  const int Hp = H / p, Wp = W / p;
+  const int rowlen = p * 3;              // contiguous run in the image per (patch row a)
+  const long total = (long)n * Hp * Wp * p;   // one work item = one contiguous run
+  for (long w = blockIdx.x * (long)blockDim.x / 32 + threadIdx.x / 32; w < total; w += (long)gridDim.x * blockDim.x / 32) {
+    const int a = (int)(w % p);
+    long r = w / p;                      // patch row index in out
+    const int j = (int)(r % Wp);
+    const int i = (int)((r / Wp) % Hp);
+    const long c = r / ((long)Wp * Hp);
+    const __nv_bfloat16* src = img + ((c * H + (long)i * p + a) * W + (long)j * p) * 3;
+    __nv_bfloat16* dst = out + r * (long)(p * rowlen) + (long)a * rowlen;
+    for (int e = threadIdx.x & 31; e < rowlen; e += 32) dst[e] = src[e];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ tokens
+// models/vision_transformer.py:173-203: where(mask, mask_token, x); prepend cls (+0*mask_token).
+// tok fp32 [n*P, D] -> X fp32 [n, 1+P, D]
+__global__ void assemble_tokens_kernel(const float* __restrict__ tok, const float* __restrict__ cls,
+                                       const float* __restrict__ mask_token, const uint8_t* __restrict__ masks,
+                                       float* __restrict__ X, int n, int P, int D) {
+  const long rows = (long)n * (P + 1);
+  const int D4 = D / 4;
+  for (long r = blockIdx.x; r < rows; r += gridDim.x) {
+    const long c = r / (P + 1);
+    const int t = (int)(r % (P + 1));
+    const float4* src;
+    if (t == 0) src = reinterpret_cast<const float4*>(cls);
+    else if (masks && masks[c * P + (t - 1)]) src = reinterpret_cast<const float4*>(mask_token);
+    else src = reinterpret_cast<const float4*>(tok + (c * P + (t - 1)) * (long)D);
+    float4* dst = reinterpret_cast<float4*>(X + r * (long)D);
+    for (int e = threadIdx.x; e < D4; e += blockDim.x) dst[e] = src[e];
+  }
+}
+// backward: dX fp32 [n,1+P,D] -> dTok bf16 [n*P, D] (0 where masked); dcls[D] += sum_c dX[c,0]; dmask[D] += masked rows
+__global__ void assemble_tokens_bwd_kernel(const float* __restrict__ dX, const uint8_t* __restrict__ masks,
+                                           __nv_bfloat16* __restrict__ dTok, float* __restrict__ dcls,
+                                           float* __restrict__ dmask, int n, int P, int D) {
+  // grid.x = column chunks of 128 floats (threads 128: one column each), grid.y = row slabs
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const long rows = (long)n * (P + 1);
+  const long slab = (rows + gridDim.y - 1) / gridDim.y;
+  const long r0 = blockIdx.y * slab, r1 = min(rows, r0 + slab);
+  if (col >= D) return;
+  float acc_cls = 0.f, acc_mask = 0.f;
+  for (long r = r0; r < r1; ++r) {
+    const long c = r / (P + 1);
+    const int t = (int)(r % (P + 1));
+    const float g = dX[r * (long)D + col];
+    if (t == 0) { acc_cls += g; continue; }
+    const bool m = masks && masks[c * P + (t - 1)];
+    if (m) acc_mask += g;
+    dTok[(c * P + (t - 1)) * (long)D + col] = __float2bfloat16(m ? 0.f : g);
+  }
+  atomicAdd(&dcls[col], acc_cls);
+  if (masks) atomicAdd(&dmask[col], acc_mask);
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm
+// models/vision_transformer.py:40 (flax nn.LayerNorm, eps 1e-6, biased variance E[x^2]-E[x]^2, fp32 stats).
+// One warp per row; x fp32 [T, D]; y bf16 or fp32.
+template <typename OutT>
+__global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                                     const float* __restrict__ bias, OutT* __restrict__ y, float* __restrict__ mean_out,
+                                     float* __restrict__ rstd_out, int T, int D, float eps) {
+  const int warps = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int D4 = D >> 2;
+  for (long row = (long)blockIdx.x * warps + (threadIdx.x >> 5); row < T; row += (long)gridDim.x * warps) {
+    const float4* xr = reinterpret_cast<const float4*>(x + row * (long)D);
+    float s = 0.f, s2 = 0.f;
+    for (int e = lane; e < D4; e += 32) {
+      float4 v = xr[e];
+      s += v.x + v.y + v.z + v.w;
+      s2 += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    s = warp_sum(s);
+    s2 = warp_sum(s2);
+    const float mean = s / D;
+    const float var = fmaxf(s2 / D - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    if (lane == 0 && mean_out) { mean_out[row] = mean; rstd_out[row] = rstd; }
+    for (int e = lane; e < D4; e += 32) {
+      float4 v = xr[e];
+      float4 g = reinterpret_cast<const float4*>(scale)[e];
+      float4 b = reinterpret_cast<const float4*>(bias)[e];
+      float o0 = (v.x - mean) * rstd * g.x + b.x, o1 = (v.y - mean) * rstd * g.y + b.y;
+      float o2 = (v.z - mean) * rstd * g.z + b.z, o3 = (v.w - mean) * rstd * g.w + b.w;
+      if constexpr (sizeof(OutT) == 2) {
+        reinterpret_cast<uint2*>(y + row * (long)D)[e] = make_uint2(pack_bf16(o0, o1), pack_bf16(o2, o3));
+      } else {
+        reinterpret_cast<float4*>(y + row * (long)D)[e] = make_float4(o0, o1, o2, o3);
+      }
+    }
+  }
+}
+
+// backward: dx = rstd * (g*scale - mean_D(g*scale) - xhat * mean_D(g*scale*xhat));   dx_out = dx (+ dx_add)
+// One warp per row (row pass); parameter gradients come from a second, column-major pass (coalesced, no atomics in
+// the inner loop): dscale[D] += sum_rows g*xhat ; dbias[D] += sum_rows g.
+template <typename InT>
+__global__ void layernorm_bwd_kernel(const InT* __restrict__ dy, const float* __restrict__ x,
+                                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                                     const float* __restrict__ scale, const float* __restrict__ dx_add,
+                                     float* __restrict__ dx, int T, int D) {
+  const int warps = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  for (long row = (long)blockIdx.x * warps + (threadIdx.x >> 5); row < T; row += (long)gridDim.x * warps) {
+    const float mu = mean[row], rs = rstd[row];
+    const float* xr = x + row * (long)D;
+    const InT* gr = dy + row * (long)D;
+    float a = 0.f, b = 0.f;
+    for (int e = lane; e < D; e += 32) {
+      float g;
+      if constexpr (sizeof(InT) == 2) g = __bfloat162float(gr[e]); else g = gr[e];
+      const float xh = (xr[e] - mu) * rs;
+      const float gs = g * scale[e];
+      a += gs;
+      b += gs * xh;
+    }
+    a = warp_sum(a) / D;
+    b = warp_sum(b) / D;
+    for (int e = lane; e < D; e += 32) {
+      float g;
+      if constexpr (sizeof(InT) == 2) g = __bfloat162float(gr[e]); else g = gr[e];
+      const float xh = (xr[e] - mu) * rs;
+      float v = rs * (g * scale[e] - a - xh * b);
+      if (dx_add) v += dx_add[row * (long)D + e];
+      dx[row * (long)D + e] = v;
+    }
+  }
+}
+template <typename InT>
+__global__ void layernorm_param_grad_kernel(const InT* __restrict__ dy, const float* __restrict__ x,
+                                            const float* __restrict__ mean, const float* __restrict__ rstd,
+                                            float* __restrict__ dscale, float* __restrict__ dbias, int T, int D) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const long slab = ((long)T + gridDim.y - 1) / gridDim.y;
+  const long r0 = blockIdx.y * slab, r1 = min((long)T, r0 + slab);
+  if (col >= D) return;
+  float as = 0.f, ab = 0.f;
+  for (long r = r0; r < r1; ++r) {
+    float g;
+    if constexpr (sizeof(InT) == 2) g = __bfloat162float(dy[r * D + col]); else g = dy[r * D + col];
+    as += g * (x[r * D + col] - mean[r]) * rstd[r];
+    ab += g;
+  }
+  atomicAdd(&dscale[col], as);
+  atomicAdd(&dbias[col], ab);
+}
+
+// ------------------------------------------------------------------------------------------------ RoPE
+// layers/attention.py:14-20,69-90 + layers/rope_position_encoding.py:117-123.  In place on the q and k thirds of
+// qkv bf16 [T, 3D]; token t of each crop (N tokens) is rotated iff t >= prefix; math in fp32.
+// sincos fp32 [P, hd] each.  inverse=1 applies the transpose rotation (backward).
+__global__ void rope_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restrict__ sin_t,
+                            const float* __restrict__ cos_t, long T, int Ntok, int prefix, int D, int hd, int inverse) {
+  const int half = hd / 2;
+  const int pairs_per_row = 2 * (D / hd) * half;   // q and k, all heads
+  const long total = T * (long)pairs_per_row;
+  for (long w = blockIdx.x * (long)blockDim.x + threadIdx.x; w < total; w += (long)gridDim.x * blockDim.x) {
+    const long row = w / pairs_per_row;
+    int r = (int)(w % pairs_per_row);
+    const int t = (int)(row % Ntok);
+    if (t < prefix) continue;
+    const int which = r / ((D / hd) * half);   // 0 = q, 1 = k
+    r -= which * (D / hd) * half;
+    const int head = r / half, i = r % half;
+    const int pidx = t - prefix;
+    const float s1 = sin_t[pidx * hd + i], c1 = cos_t[pidx * hd + i];
+    const float s2 = sin_t[pidx * hd + i + half], c2 = cos_t[pidx * hd + i + half];
+    __nv_bfloat16* base = qkv + row * (long)(3 * D) + which * D + head * hd;
+    const float x1 = __bfloat162float(base[i]), x2 = __bfloat162float(base[i + half]);
+    float y1, y2;
+    if (!inverse) {            // y = x*cos + rot_half(x)*sin, rot_half([x1,x2]) = [-x2, x1]
+      y1 = x1 * c1 - x2 * s1;
+      y2 = x2 * c2 + x1 * s2;
+    } else {                   // transpose: dx1 = dy1*c1 + dy2*s2 ; dx2 = dy2*c2 - dy1*s1
+      y1 = x1 * c1 + x2 * s2;
+      y2 = x2 * c2 - x1 * s1;
+    }
+    base[i] = __float2bfloat16(y1);
+    base[i + half] = __float2bfloat16(y2);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ gather / scatter
+// train/ssl_meta_arch.py:377,432: patch.reshape(-1, D)[mask_indices_list]; cls rows = token 0 of each crop.
+// mode 0: rows[i] = idx[i]/P*(P+1) + 1 + idx[i]%P (masked patch i -> token row); mode 1: rows[i] = i*(P+1) (cls)
+__global__ void token_rows_kernel(const long long* __restrict__ idx, int* __restrict__ rows, int count, int P, int mode) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  if (mode == 0) {
+    const long long m = idx[i];
+    rows[i] = (int)(m / P * (P + 1) + 1 + m % P);
+  } else {
+    rows[i] = i * (P + 1);
+  }
+}
+__global__ void gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ rows,
+                                   __nv_bfloat16* __restrict__ dst_bf16, float* __restrict__ dst_f32, int R, int D) {
+  for (int r = blockIdx.x; r < R; r += gridDim.x) {
+    const float* s = src + (long)rows[r] * D;
+    for (int e = threadIdx.x; e < D; e += blockDim.x) {
+      const float v = s[e];
+      if (dst_bf16) dst_bf16[(long)r * D + e] = __float2bfloat16(v);
+      if (dst_f32) dst_f32[(long)r * D + e] = v;
+    }
+  }
+}
+// dst[rows[r]] += src[r]  (rows unique within a call)
+template <typename InT>
+__global__ void scatter_add_rows_kernel(const InT* __restrict__ src, const int* __restrict__ rows,
+                                        float* __restrict__ dst, int R, int D) {
+  for (int r = blockIdx.x; r < R; r += gridDim.x) {
+    float* d = dst + (long)rows[r] * D;
+    for (int e = threadIdx.x; e < D; e += blockDim.x) {
+      float v;
+      if constexpr (sizeof(InT) == 2) v = __bfloat162float(src[(long)r * D + e]); else v = src[(long)r * D + e];
+      d[e] += v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ L2 normalise
+// layers/dino_head.py:80-82: x / (||x||_2 + 1e-12).  u fp32 [R, C] -> y bf16 [R, C]; one warp per row.
+__global__ void l2norm_fwd_kernel(const float* __restrict__ u, __nv_bfloat16* __restrict__ y, float* __restrict__ nrm,
+                                  int R, int C, float eps) {
+  const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
+  for (long row = (long)blockIdx.x * warps + (threadIdx.x >> 5); row < R; row += (long)gridDim.x * warps) {
+    const float* ur = u + row * C;
+    float s = 0.f;
+    for (int e = lane; e < C; e += 32) s += ur[e] * ur[e];
+    s = warp_sum(s);
+    const float n = sqrtf(s);
+    const float inv = 1.f / (n + eps);
+    if (lane == 0) nrm[row] = n;
+    for (int e = lane; e < C; e += 32) y[row * C + e] = __float2bfloat16(ur[e] * inv);
+  }
+}
+// du = g/(n+eps) - u * (u.g) / (n (n+eps)^2);  g bf16 [R,C] (dgrad of the prototype layer), du bf16 out
+__global__ void l2norm_bwd_kernel(const __nv_bfloat16* __restrict__ g, const float* __restrict__ u,
+                                  const float* __restrict__ nrm, __nv_bfloat16* __restrict__ du, int R, int C, float eps) {
+  const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
+  for (long row = (long)blockIdx.x * warps + (threadIdx.x >> 5); row < R; row += (long)gridDim.x * warps) {
+    const float* ur = u + row * C;
+    const __nv_bfloat16* gr = g + row * C;
+    float dot = 0.f;
+    for (int e = lane; e < C; e += 32) dot += ur[e] * __bfloat162float(gr[e]);
+    dot = warp_sum(dot);
+    const float n = nrm[row];
+    const float inv = 1.f / (n + eps);
+    const float coef = (n > 0.f) ? dot * inv * inv / n : 0.f;
+    for (int e = lane; e < C; e += 32)
+      du[row * C + e] = __float2bfloat16(__bfloat162float(gr[e]) * inv - ur[e] * coef);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ LayerScale / GELU bwd
+// block output x_out = x_in + gamma * act(u),  act = gelu_tanh (use_gelu) or identity   (layers/block.py:198-199)
+// given dX fp32 [T,D] and the bf16 stash u: du bf16 = dX*gamma*act'(u); dgamma += colsum(dX*act(u)); dbias += colsum(du)
+__global__ void ls_act_bwd_kernel(const float* __restrict__ dX, const __nv_bfloat16* __restrict__ u,
+                                  const float* __restrict__ gamma, __nv_bfloat16* __restrict__ du,
+                                  float* __restrict__ dgamma, float* __restrict__ dbias, int T, int D, int use_gelu) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const long slab = ((long)T + gridDim.y - 1) / gridDim.y;
+  const long r0 = blockIdx.y * slab, r1 = min((long)T, r0 + slab);
+  if (col >= D) return;
+  const float gm = gamma[col];
+  float ag = 0.f, ab = 0.f;
+  for (long r = r0; r < r1; ++r) {
+    const float g = dX[r * D + col];
+    const float uu = __bfloat162float(u[r * D + col]);
+    const float act = use_gelu ? gelu_tanh(uu) : uu;
+    const float dact = use_gelu ? gelu_tanh_grad(uu) : 1.f;
+    const float d = g * gm * dact;
+    ag += g * act;
+    ab += d;
+    du[r * D + col] = __float2bfloat16(d);
+  }
+  atomicAdd(&dgamma[col], ag);
+  atomicAdd(&dbias[col], ab);
+}
+
+// out[n] += sum_t x[t, n]   (bias gradients).  x bf16 [T, N]
+__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long T, int N, int ld) {
+  const int col = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  const long slab = (T + gridDim.y - 1) / gridDim.y;
+  const long r0 = blockIdx.y * slab, r1 = min(T, r0 + slab);
+  if (col >= N) return;
+  float a0 = 0.f, a1 = 0.f;
+  if (col + 1 < N) {
+    for (long r = r0; r < r1; ++r) {
+      float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(x + r * ld + col));
+      a0 += v.x; a1 += v.y;
+    }
+    atomicAdd(&out[col], a0);
+    atomicAdd(&out[col + 1], a1);
+  } else {
+    for (long r = r0; r < r1; ++r) a0 += __bfloat162float(x[r * ld + col]);
+    atomicAdd(&out[col], a0);
+  }
+}
+
+// dst bf16 <- src fp32 (compute copy of weight matrices)
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long n) {
+  const long i4 = (blockIdx.x * (long)blockDim.x + threadIdx.x) * 4;
+  if (i4 + 3 < n) {
+    float4 v = *reinterpret_cast<const float4*>(src + i4);
+    *reinterpret_cast<uint2*>(dst + i4) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  } else {
+    for (long i = i4; i < n; ++i) dst[i] = __float2bfloat16(src[i]);
+  }
+}
+
+}  // namespace d3
+
+using namespace d3;
+#define STREAM(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+int d3_im2col(const void* img, void* out, int n, int H, int W, int p, void* stream) {
+  if (!img || !out || H % p || W % p) return set_error(D3_ERR_ARG, "d3_im2col: bad args (H, W must divide by p)");
+  long runs = (long)n * (H / p) * (W / p) * p;
+  int blocks = (int)min((runs + 7) / 8, (long)sm_count() * 16);
+  im2col_kernel<<<blocks, 256, 0, STREAM(stream)>>>((const __nv_bfloat16*)img, (__nv_bfloat16*)out, n, H, W, p);
+  D3_CHECK_LAUNCH();
+  return D3_OK;
+}
+
+int d3_assemble_tokens(const float* tok, const float* cls, const float* mask_token, const unsigned char* masks,
+                       float* X, int n, int P, int D, void* stream) {
+  if (D % 4) return set_error(D3_ERR_ARG, "d3_assemble_tokens: D % 4");
+  long rows = (long)n * (P + 1);
+  assemble_tokens_kernel<<<(int)min(rows, (long)sm_count() * 16), 128, 0, STREAM(stream)>>>(tok, cls, mask_token, masks,
+                                                                                           X, n, P, D);
+  D3_CHECK_LAUNCH();
+  return D3_OK;
+}
+
+int d3_assemble_tokens_bwd(const float* dX, const unsigned char* masks, void* dTok, float* dcls, float* dmask, int n,
+                           int P, int D, void* stream) {
+  dim3 grid((D + 127) / 128, 64);
+  assemble_tokens_bwd_kernel<<<grid, 128, 0, STREAM(stream)>>>(dX, masks, (__nv_bfloat16*)dTok, dcls, dmask, n, P, D);
+  D3_CHECK_LAUNCH();
+  return D3_OK;
+}
+
+int d3_layernorm_fwd(const float* x, const float* scale, const float* bias, void* y, int y_is_f32, float* mean,
+                     float* rstd, int T, int D, float eps, void* stream) {
+  if (D % 4) return set_error(D3_ERR_ARG, "d3_layernorm_fwd: D % 4");
+  int blocks = min((T + 7) / 8, sm_count() * 8);
+  if (y_is_f32)
+    layernorm_fwd_kernel<float><<<blocks, 256, 0, STREAM(stream)>>>(x, scale, bias, (float*)y, mean, rstd, T, D, eps);
+  else
+    layernorm_fwd_kernel<__nv_bfloat16><<<blocks, 256, 0, STREAM(stream)>>>(x, scale, bias, (__nv_bfloat16*)y, mean,
+                                                                          rstd, T, D, eps);
+  D3_CHECK_LAUNCH();
+  return D3_OK;
+}
+
+int d3_layernorm_bwd(const void* dy, int dy_is_f32, const float* x, const float* mean, const float* rstd,
+                     const float* scale, const float* dx_add, float* dx, float* dscale, float* dbias, int T, int D,
+                     void* stream) {
+  if (T <= 0) return D3_OK;
+  int blocks = min((T + 7) / 8, sm_count() * 8);
+  dim3 pgrid((D + 127) / 128, min(128, max(1, T / 64)));
+  if (dy_is_f32) {
+    layernorm_bwd_kernel<float><<<blocks, 256, 0, STREAM(stream)>>>((const float*)dy, x, mean, rstd, scale, dx_add, dx, T, D);
+    if (dscale) layernorm_param_grad_kernel<float><<<pgrid, 128, 0, STREAM(stream)>>>((const float*)dy, x, mean, rstd, dscale, dbias, T, D);
+  } else {
+    layernorm_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, STREAM(stream)>>>((const __nv_bfloat16*)dy, x, mean, rstd,
+                                                                          scale, dx_add, dx, T, D);
+    if (dscale) layernorm_param_grad_kernel<__nv_bfloat16><<<pgrid, 128, 0, STREAM(stream)>>>((const __nv_bfloat16*)dy, x, mean, rstd, dscale, dbias, T, D);
+  }
+  D3_CHECK_LAUNCH();
+  if (dscale) count_launch();
+  return D3_OK;
+}
+
+int d3_rope(void* qkv, const float* sin_t, const float* cos_t, long long T, int Ntok, int prefix, int D, int head_dim,
+            int inverse, void* stream) {
+  if (head_dim % 2 || D % head_dim) return set_error(D3_ERR_ARG, "d3_rope: head_dim");
+  long total = T * (long)(2 * (D / head_dim) * (head_dim / 2));
+  int blocks = (int)min((total + 255) / 256, (long)sm_count() * 32);
+  rope_kernel<<<blocks, 256, 0, STREAM(stream)>>>((__nv_bfloat16*)qkv, sin_t, cos_t, T, Ntok, prefix, D, head_dim,
+                                                 inverse);
+  D3_CHECK_LAUNCH();
+  return D3_OK;
+}
+
+int d3_token_rows(const long long* idx, int* rows, int count, int P, int mode, void* stream) {
+  if (count <= 0) return D3_OK;
+  token_rows_kernel<<<(count + 255) / 256, 256, 0, STREAM(stream)>>>(idx, rows, count, P, mode);
+  D3_CHECK_LAUNCH();
+  return D3_OK;
+}
+
+int d3_gather_rows(const float* src, const int* rows, void* dst_bf16, float* dst_f32, int R, int D, void* stream) {
+  if (R <= 0) return D3_OK;
+  gather_rows_kernel<<<min(R, sm_count() * 16), 128, 0, STREAM(stream)>>>(src, rows, (__nv_bfloat16*)dst_bf16, dst_f32,
+                                                                          R, D);
+  D3_CHECK_LAUNCH();
+  return D3_OK;
+}
+
+int d3_scatter_add_rows(const void* src, int src_is_f32, const int* rows, float* dst, int R, int D, void* stream) {
+  if (R <= 0) return D3_OK;
+  if (src_is_f32)
+    scatter_add_rows_kernel<float><<<min(R, sm_count() * 16), 128, 0, STREAM(stream)>>>((const float*)src, rows, dst, R, D);
+  else
+    scatter_add_rows_kernel<__nv_bfloat16><<<min(R, sm_count() * 16), 128, 0, STREAM(stream)>>>(
+        (const __nv_bfloat16*)src, rows, dst, R, D);
+  D3_CHECK_LAUNCH();
+  return D3_OK;
+}
+
+int d3_l2norm_fwd(const float* u, void* y, float* nrm, int R, int C, float eps, void* stream) {
+  if (R <= 0) return D3_OK;
+  l2norm_fwd_kernel<<<min((R + 7) / 8, sm_count() * 8), 256, 0, STREAM(stream)>>>(u, (__nv_bfloat16*)y, nrm, R, C, eps);
+  D3_CHECK_LAUNCH();
+  return D3_OK;
+}
+
+int d3_l2norm_bwd(const void* g, const float* u, const float* nrm, void* du, int R, int C, float eps, void* stream) {
+  if (R <= 0) return D3_OK;
+  l2norm_bwd_kernel<<<min((R + 7) / 8, sm_count() * 8), 256, 0, STREAM(stream)>>>((const __nv_bfloat16*)g, u, nrm,
+                                                                                  (__nv_bfloat16*)du, R, C, eps);
+  D3_CHECK_LAUNCH();
+  return D3_OK;
+}
+
+int d3_ls_act_bwd(const float* dX, const void* u, const float* gamma, void* du, float* dgamma, float* dbias, int T,
+                  int D, int use_gelu, void* stream) {
+  dim3 grid((D + 127) / 128, min(256, max(1, T / 64)));
+  ls_act_bwd_kernel<<<grid, 128, 0, STREAM(stream)>>>(dX, (const __nv_bfloat16*)u, gamma, (__nv_bfloat16*)du, dgamma,
+                                                     dbias, T, D, use_gelu);
+  D3_CHECK_LAUNCH();
+  return D3_OK;
+}
+
+int d3_colsum_bf16(const void* x, float* out, long long T, int N, int ld, void* stream) {
+  if (T <= 0) return D3_OK;
+  if (ld % 2) return set_error(D3_ERR_ARG, "d3_colsum_bf16: ld % 2");
+  dim3 grid((N / 2 + 127) / 128 + ((N / 2) % 128 == 0 && N % 2 ? 1 : 0), (int)min(256LL, max(1LL, T / 64)));
+  if (((N + 1) / 2 + 127) / 128 > (int)grid.x) grid.x = ((N + 1) / 2 + 127) / 128;
+  colsum_bf16_kernel<<<grid, 128, 0, STREAM(stream)>>>((const __nv_bfloat16*)x, out, T, N, ld);
+  D3_CHECK_LAUNCH();
+  return D3_OK;
+}
+
+int d3_cast_f32_bf16(const float* src, void* dst, long long n, void* stream) {
+  if (n <= 0) return D3_OK;
+  if (((uintptr_t)src & 15) || ((uintptr_t)dst & 7)) return set_error(D3_ERR_ARG, "d3_cast_f32_bf16: alignment");
+  long th = (n + 3) / 4;
+  cast_f32_bf16_kernel<<<(int)((th + 255) / 256), 256, 0, STREAM(stream)>>>(src, (__nv_bfloat16*)dst, n);
+  D3_CHECK_LAUNCH();
+  return D3_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,278 @@
+// Loss-head kernels: Sinkhorn-Knopp teacher normalisation (as diagonal scalings of exp(logits/temp)),
+// fused cross-entropy forward+backward over the prototype dimension, KoLeo regulariser forward+backward.
+// References: dinov3_jax/loss/dino_clstoken_loss.py:35-89, loss/ibot_patch_loss.py:13-14,45-109,
+// loss/koleo_loss.py:16-35, train/ssl_meta_arch.py:463-525.
+#include <math_constants.h>
+#include "ptx.cuh"
+#include "d3_internal.h"
+
+namespace d3 {
+
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float wmax(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// block reductions over 256 threads (8 warps)
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  v = wsum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.f;
+  if (threadIdx.x < 32) t = wsum(t);
+  if (threadIdx.x == 0) sh[0] = t;
+  __syncthreads();
+  return sh[0];
+}
+__device__ __forceinline__ float block_max(float v, float* sh) {
+  v = wmax(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : -CUDART_INF_F;
+  if (threadIdx.x < 32) t = wmax(t);
+  if (threadIdx.x == 0) sh[0] = t;
+  __syncthreads();
+  return sh[0];
+}
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+  // ordered-int trick; *addr must be initialised to -inf
+  if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+// ------------------------------------------------------------------------------------------------ Sinkhorn-Knopp
+// Q = exp(L/temp)^T; Q/=sum; 3x { Q /= rowsum*K ; Q /= colsum*B } ; Q*=B      (dino_clstoken_loss.py:35-62)
+// is a sequence of diagonal scalings:  Q[b,k] = E[b,k] * r[k] * a[b],  E = exp((L - mx)/temp)  (any global shift mx
+// cancels in the first normalisation), with   r = 1/(K * E^T a)   and   a = 1/(B * E r)   alternating.
+// The row step's E^T a (K floats) is what the reference psums over "dp" (:53 / ibot :99).
+__global__ void absmax_kernel(const float* __restrict__ L, long n, float* __restrict__ out) {
+  __shared__ float sh[32];
+  float m = -CUDART_INF_F;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) m = fmaxf(m, L[i]);
+  m = block_max(m, sh);
+  if (threadIdx.x == 0) atomic_max_float(out, m);
+}
+// s[k] += sum_b E[b,k] * a[b]      (a == nullptr -> a = 1)
+__global__ void sk_colsum_kernel(const float* __restrict__ L, const float* __restrict__ mx, float inv_temp,
+                                 const float* __restrict__ a, float* __restrict__ s, int R, int K) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int slab = (R + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * slab, r1 = min(R, r0 + slab);
+  if (k >= K) return;
+  const float m = *mx;
+  float acc = 0.f;
+  for (int b = r0; b < r1; ++b) acc += __expf((L[(long)b * K + k] - m) * inv_temp) * (a ? a[b] : 1.f);
+  atomicAdd(&s[k], acc);
+}
+// a[b] = 1 / (Btot * sum_k E[b,k] * r[k]),  r[k] = 1/(K*s[k])
+__global__ void sk_rowsum_kernel(const float* __restrict__ L, const float* __restrict__ mx, float inv_temp,
+                                 const float* __restrict__ s, const float* __restrict__ btot, float* __restrict__ a,
+                                 int R, int K) {
+  __shared__ float sh[32];
+  const int b = blockIdx.x;
+  const float m = *mx;
+  float acc = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x)
+    acc += __expf((L[(long)b * K + k] - m) * inv_temp) / ((float)K * s[k]);
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) a[b] = 1.f / (*btot * acc);
+}
+// materialise teacher probabilities (tests / optional consumers): Q[b,k] = Btot * E * r[k] * a[b]
+__global__ void sk_probs_kernel(const float* __restrict__ L, const float* __restrict__ mx, float inv_temp,
+                                const float* __restrict__ s, const float* __restrict__ a,
+                                const float* __restrict__ btot, float* __restrict__ Q, int R, int K) {
+  const long n = (long)R * K;
+  const float m = *mx, bt = *btot;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / K), k = (int)(i % K);
+    Q[i] = bt * __expf((L[i] - m) * inv_temp) / ((float)K * s[k]) * a[b];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ cross-entropy
+// per student row i (logits S[i,:]):  loss_i = - sum_p sum_k Q_p[k] * log_softmax(S[i,:]/ts)[k]   over its teacher
+// rows p in {t0[i], t1[i]} (-1 = none), Q_p from the Sinkhorn scalings above.
+// metric[slot[i]] += wm[i] * loss_i ;  dS[i,k] = wg[i]/ts * (npairs * softmax[k] - sum_p Q_p[k])   (bf16)
+// (dino_clstoken_loss.py:66-89; ibot_patch_loss.py:13-14,55-67; weights per train/ssl_meta_arch.py:480-525)
+__global__ void __launch_bounds__(256)
+ce_fwd_bwd_kernel(const float* __restrict__ S, float inv_ts, const float* __restrict__ Lt,
+                  const float* __restrict__ mx, float inv_tt, const float* __restrict__ s_t,
+                  const float* __restrict__ a_t, const float* __restrict__ btot, const int* __restrict__ t0,
+                  const int* __restrict__ t1, const float* __restrict__ wm, const float* __restrict__ wg,
+                  const int* __restrict__ slot, float* __restrict__ metric, __nv_bfloat16* __restrict__ dS, int K) {
+  __shared__ float sh[32];
+  const int i = blockIdx.x;
+  const float* Si = S + (long)i * K;
+  // online max / sum-exp
+  float m = -CUDART_INF_F, z = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float v = Si[k] * inv_ts;
+    if (v > m) { z = z * __expf(m - v) + 1.f; m = v; }
+    else z += __expf(v - m);
+  }
+  const float gm = block_max(m, sh);
+  z = block_sum(z * __expf(m - gm), sh);
+  const float lse = gm + logf(z);
+  const int p0 = t0[i], p1 = t1[i];
+  const float np = (p0 >= 0 ? 1.f : 0.f) + (p1 >= 0 ? 1.f : 0.f);
+  const float mt = *mx, bt = *btot;
+  const float c0 = p0 >= 0 ? bt * a_t[p0] : 0.f;
+  const float c1 = p1 >= 0 ? bt * a_t[p1] : 0.f;
+  const float* L0 = Lt + (long)(p0 >= 0 ? p0 : 0) * K;
+  const float* L1 = Lt + (long)(p1 >= 0 ? p1 : 0) * K;
+  const float g = wg[i] * inv_ts;
+  float loss = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float lsm = Si[k] * inv_ts - lse;
+    const float rk = 1.f / ((float)K * s_t[k]);
+    float q = 0.f;
+    if (p0 >= 0) q += c0 * __expf((L0[k] - mt) * inv_tt) * rk;
+    if (p1 >= 0) q += c1 * __expf((L1[k] - mt) * inv_tt) * rk;
+    loss -= q * lsm;
+    dS[(long)i * K + k] = __float2bfloat16(g * (np * __expf(lsm) - q));
+  }
+  loss = block_sum(loss, sh);
+  if (threadIdx.x == 0) atomicAdd(&metric[slot[i]], wm[i] * loss);
+}
+
+// ------------------------------------------------------------------------------------------------ KoLeo
+// loss/koleo_loss.py:16-35:  xn = x/(||x||+eps); nn(i) = argmax_{j!=i} xn_i.xn_j; L = -mean_i log(||xn_i - xn_nn(i)|| + 2 eps)
+__global__ void koleo_norm_kernel(const float* __restrict__ x, float* __restrict__ xn, float* __restrict__ nrm, int D,
+                                  float eps) {
+  __shared__ float sh[32];
+  const int i = blockIdx.x;
+  float s = 0.f;
+  for (int e = threadIdx.x; e < D; e += blockDim.x) { const float v = x[(long)i * D + e]; s += v * v; }
+  s = block_sum(s, sh);
+  const float n = sqrtf(s);
+  if (threadIdx.x == 0) nrm[i] = n;
+  const float inv = 1.f / (n + eps);
+  for (int e = threadIdx.x; e < D; e += blockDim.x) xn[(long)i * D + e] = x[(long)i * D + e] * inv;
+}
+__global__ void koleo_nn_kernel(const float* __restrict__ xn, int* __restrict__ nn, float* __restrict__ coef,
+                                float* __restrict__ metric, int B, int D, float eps, float w_metric, float w_grad) {
+  __shared__ float sh[32];
+  __shared__ float best_v;
+  __shared__ int best_j;
+  const int i = blockIdx.x;
+  if (threadIdx.x == 0) { best_v = -CUDART_INF_F; best_j = 0; }
+  __syncthreads();
+  for (int j = 0; j < B; ++j) {
+    float d = 0.f;
+    for (int e = threadIdx.x; e < D; e += blockDim.x) d += xn[(long)i * D + e] * xn[(long)j * D + e];
+    d = block_sum(d, sh);
+    if (threadIdx.x == 0) {
+      if (j == i) d = -1.f;                       // dots.at[diag].set(-1)
+      if (d > best_v) { best_v = d; best_j = j; } // first maximum, like jnp.argmax
+    }
+    __syncthreads();
+  }
+  const int j = best_j;
+  float dd = 0.f;
+  for (int e = threadIdx.x; e < D; e += blockDim.x) {
+    const float t = xn[(long)i * D + e] - xn[(long)j * D + e];
+    dd += t * t;
+  }
+  dd = block_sum(dd, sh);
+  if (threadIdx.x == 0) {
+    const float dn = sqrtf(dd);
+    const float dist = dn + eps;                  // pairwise_distance(...) + eps
+    nn[i] = j;
+    atomicAdd(metric, -w_metric * logf(dist + eps) / B);
+    // d(-w/B * log(dist+eps))/d(delta) = -w/B / (dist+eps) * delta/||delta||
+    coef[i] = dn > 0.f ? -w_grad / B / (dist + eps) / dn : 0.f;
+  }
+}
+// dx_i += J_norm^T ( coef_i * delta_i - sum_{j: nn(j)=i} coef_j * delta_j ),  delta_j = xn_j - xn_nn(j)
+__global__ void koleo_bwd_kernel(const float* __restrict__ x, const float* __restrict__ xn,
+                                 const float* __restrict__ nrm, const int* __restrict__ nn,
+                                 const float* __restrict__ coef, float* __restrict__ dx, int B, int D, float eps) {
+  extern __shared__ float gsm[];  // [D] gradient w.r.t. xn_i
+  __shared__ float sh[32];
+  const int i = blockIdx.x;
+  const int ni = nn[i];
+  const float ci = coef[i];
+  for (int e = threadIdx.x; e < D; e += blockDim.x) gsm[e] = ci * (xn[(long)i * D + e] - xn[(long)ni * D + e]);
+  __syncthreads();
+  for (int j = 0; j < B; ++j) {
+    if (nn[j] != i) continue;
+    const float cj = coef[j];
+    for (int e = threadIdx.x; e < D; e += blockDim.x) gsm[e] -= cj * (xn[(long)j * D + e] - xn[(long)i * D + e]);
+  }
+  __syncthreads();
+  float dot = 0.f;
+  for (int e = threadIdx.x; e < D; e += blockDim.x) dot += x[(long)i * D + e] * gsm[e];
+  dot = block_sum(dot, sh);
+  const float n = nrm[i];
+  const float inv = 1.f / (n + eps);
+  const float c2 = n > 0.f ? dot * inv * inv / n : 0.f;
+  for (int e = threadIdx.x; e < D; e += blockDim.x) dx[(long)i * D + e] += gsm[e] * inv - x[(long)i * D + e] * c2;
+}
+
+}  // namespace d3
+
+using namespace d3;
+#define STREAM(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+int d3_absmax(const float* L, long long n, float* out /* pre-set to -inf */, void* stream) {
+  if (n <= 0) return D3_OK;
+  absmax_kernel<<<(int)min((n + 1023) / 1024, (long long)sm_count() * 8), 256, 0, STREAM(stream)>>>(L, n, out);
+  D3_CHECK_LAUNCH();
+  return D3_OK;
+}
+int d3_sinkhorn_colsum(const float* L, const float* mx, float temp, const float* a, float* s /* zeroed */, int R, int K,
+                       void* stream) {
+  if (R <= 0) return D3_OK;
+  dim3 grid((K + 255) / 256, max(1, min(R / 8, 64)));
+  sk_colsum_kernel<<<grid, 256, 0, STREAM(stream)>>>(L, mx, 1.f / temp, a, s, R, K);
+  D3_CHECK_LAUNCH();
+  return D3_OK;
+}
+int d3_sinkhorn_rowsum(const float* L, const float* mx, float temp, const float* s, const float* btot, float* a, int R,
+                       int K, void* stream) {
+  if (R <= 0) return D3_OK;
+  sk_rowsum_kernel<<<R, 256, 0, STREAM(stream)>>>(L, mx, 1.f / temp, s, btot, a, R, K);
+  D3_CHECK_LAUNCH();
+  return D3_OK;
+}
+int d3_sinkhorn_probs(const float* L, const float* mx, float temp, const float* s, const float* a, const float* btot,
+                      float* Q, int R, int K, void* stream) {
+  if (R <= 0) return D3_OK;
+  long n = (long)R * K;
+  sk_probs_kernel<<<(int)min((n + 255) / 256, (long)sm_count() * 16), 256, 0, STREAM(stream)>>>(L, mx, 1.f / temp, s, a,
+                                                                                             btot, Q, R, K);
+  D3_CHECK_LAUNCH();
+  return D3_OK;
+}
+int d3_ce_fwd_bwd(const float* S, float student_temp, const float* Lt, const float* mx, float teacher_temp,
+                  const float* s_t, const float* a_t, const float* btot, const int* t0, const int* t1, const float* wm,
+                  const float* wg, const int* slot, float* metric, void* dS, int Rs, int K, void* stream) {
+  if (Rs <= 0) return D3_OK;
+  ce_fwd_bwd_kernel<<<Rs, 256, 0, STREAM(stream)>>>(S, 1.f / student_temp, Lt, mx, 1.f / teacher_temp, s_t, a_t, btot, t0,
+                                                   t1, wm, wg, slot, metric, (__nv_bfloat16*)dS, K);
+  D3_CHECK_LAUNCH();
+  return D3_OK;
+}
+int d3_koleo_fwd_bwd(const float* x, float* xn_scratch, float* nrm_scratch, int* nn_scratch, float* coef_scratch,
+                     float* metric, float* dx, int B, int D, float eps, float w_metric, float w_grad, void* stream) {
+  if (B <= 1) return D3_OK;
+  koleo_norm_kernel<<<B, 256, 0, STREAM(stream)>>>(x, xn_scratch, nrm_scratch, D, eps);
+  koleo_nn_kernel<<<B, 256, 0, STREAM(stream)>>>(xn_scratch, nn_scratch, coef_scratch, metric, B, D, eps, w_metric,
+                                                w_grad);
+  koleo_bwd_kernel<<<B, 256, D * sizeof(float), STREAM(stream)>>>(x, xn_scratch, nrm_scratch, nn_scratch, coef_scratch,
+                                                                dx, B, D, eps);
+  D3_CHECK_LAUNCH();
+  count_launch(2);
+  return D3_OK;
+}
+
+}  // extern "C"

@@ -33,6 +33,39 @@ class GemmEpilogue(C.Structure):
     ]
 
 
+P, I, LL, F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
+# name -> argtypes, mirrors include/dinov3_b200.h (tests/test_abi.py checks every declared symbol is exported)
+SIGNATURES = {
+    "d3_init": [I],
+    "d3_gemm_bf16": [P, I, I, P, I, I, I, I, I, C.POINTER(GemmEpilogue), I, P],
+    "d3_im2col": [P, P, I, I, I, I, P],
+    "d3_assemble_tokens": [P, P, P, P, P, I, I, I, P],
+    "d3_assemble_tokens_bwd": [P, P, P, P, P, I, I, I, P],
+    "d3_layernorm_fwd": [P, P, P, P, I, P, P, I, I, F, P],
+    "d3_layernorm_bwd": [P, I, P, P, P, P, P, P, P, P, I, I, P],
+    "d3_rope": [P, P, P, LL, I, I, I, I, I, P],
+    "d3_attn_fwd": [P, P, P, I, I, I, I, P],
+    "d3_attn_bwd": [P, P, P, P, P, P, I, I, I, I, P],
+    "d3_token_rows": [P, P, I, I, I, P],
+    "d3_gather_rows": [P, P, P, P, I, I, P],
+    "d3_scatter_add_rows": [P, I, P, P, I, I, P],
+    "d3_l2norm_fwd": [P, P, P, I, I, F, P],
+    "d3_l2norm_bwd": [P, P, P, P, I, I, F, P],
+    "d3_ls_act_bwd": [P, P, P, P, P, P, I, I, I, P],
+    "d3_colsum_bf16": [P, P, LL, I, I, P],
+    "d3_cast_f32_bf16": [P, P, LL, P],
+    "d3_absmax": [P, LL, P, P],
+    "d3_sinkhorn_colsum": [P, P, F, P, P, I, I, P],
+    "d3_sinkhorn_rowsum": [P, P, F, P, P, P, I, I, P],
+    "d3_sinkhorn_probs": [P, P, F, P, P, P, P, I, I, P],
+    "d3_ce_fwd_bwd": [P, F, P, P, F, P, P, P, P, P, P, P, P, P, P, I, I, P],
+    "d3_koleo_fwd_bwd": [P, P, P, P, P, P, P, I, I, F, F, F, P],
+    "d3_sumsq": [P, LL, P, P],
+    "d3_adamw_ema": [P, P, P, P, P, P, P, LL, P, I, LL, P, F, F, F, F, F, F, F, I, F, P],
+}
+NO_ARG_SYMBOLS = ["d3_last_error", "d3_abi_version", "d3_launch_count", "d3_reset_launch_count"]
+
+
 def lib() -> C.CDLL:
     """Load the shared library (no GPU needed for loading / symbol checks)."""
     global _LIB
@@ -45,6 +78,10 @@ def lib() -> C.CDLL:
         _LIB = C.CDLL(path)
         _LIB.d3_last_error.restype = C.c_char_p
         _LIB.d3_launch_count.restype = C.c_longlong
+        for name, args in SIGNATURES.items():
+            fn = getattr(_LIB, name)
+            fn.argtypes = args
+            fn.restype = C.c_int
     return _LIB
 
 

@@ -64,3 +64,165 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, a_mn: bool = Fa
     N.check(l.d3_gemm_bf16(N.ptr(A), _ld(A), int(a_mn), N.ptr(B), _ld(B), int(b_mn), M, Nn, K, C.byref(ep),
                            int(tile_n), N.stream_ptr()), "d3_gemm_bf16")
     return out
+
+
+# --------------------------------------------------------------------------------------------------------------------
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def im2col(img: torch.Tensor, out: torch.Tensor, patch: int) -> torch.Tensor:
+    n, H, W, c = img.shape
+    assert c == 3 and img.dtype == bf16 and img.is_contiguous() and out.dtype == bf16 and out.is_contiguous()
+    N.check(N.init().d3_im2col(_p(img), _p(out), n, H, W, patch, _s()), "d3_im2col")
+    return out
+
+
+def assemble_tokens(tok, cls, mask_token, masks_u8, X, n, P, D):
+    assert tok.dtype == f32 and X.dtype == f32 and (masks_u8 is None or masks_u8.dtype == torch.uint8)
+    N.check(N.init().d3_assemble_tokens(_p(tok), _p(cls), _p(mask_token), _p(masks_u8), _p(X), n, P, D, _s()),
+            "d3_assemble_tokens")
+    return X
+
+
+def assemble_tokens_bwd(dX, masks_u8, dTok, dcls, dmask, n, P, D):
+    assert dX.dtype == f32 and dTok.dtype == bf16 and dcls.dtype == f32
+    N.check(N.init().d3_assemble_tokens_bwd(_p(dX), _p(masks_u8), _p(dTok), _p(dcls), _p(dmask), n, P, D, _s()),
+            "d3_assemble_tokens_bwd")
+
+
+def layernorm_fwd(x, scale, bias, y, mean=None, rstd=None, eps=1e-6):
+    T, D = x.shape
+    assert x.dtype == f32 and x.is_contiguous() and y.shape == x.shape and y.is_contiguous()
+    N.check(N.init().d3_layernorm_fwd(_p(x), _p(scale), _p(bias), _p(y), int(y.dtype == f32), _p(mean), _p(rstd), T, D,
+                                      eps, _s()), "d3_layernorm_fwd")
+    return y
+
+
+def layernorm_bwd(dy, x, mean, rstd, scale, dx, dx_add=None, dscale=None, dbias=None):
+    T, D = x.shape
+    assert dy.shape == x.shape and dx.dtype == f32 and dy.is_contiguous()
+    N.check(N.init().d3_layernorm_bwd(_p(dy), int(dy.dtype == f32), _p(x), _p(mean), _p(rstd), _p(scale), _p(dx_add),
+                                      _p(dx), _p(dscale), _p(dbias), T, D, _s()), "d3_layernorm_bwd")
+    return dx
+
+
+def rope(qkv, sin_t, cos_t, tokens_per_crop, prefix, D, head_dim, inverse=False):
+    T = qkv.shape[0]
+    assert qkv.dtype == bf16 and qkv.shape[1] == 3 * D and qkv.is_contiguous() and sin_t.dtype == f32
+    N.check(N.init().d3_rope(_p(qkv), _p(sin_t), _p(cos_t), T, tokens_per_crop, prefix, D, head_dim, int(inverse),
+                             _s()), "d3_rope")
+    return qkv
+
+
+def attn_fwd(qkv, o, lse, n_crops, Ntok, D, H):
+    assert qkv.dtype == bf16 and o.dtype == bf16 and qkv.is_contiguous() and o.is_contiguous()
+    N.check(N.init().d3_attn_fwd(_p(qkv), _p(o), _p(lse), n_crops, Ntok, D, H, _s()), "d3_attn_fwd")
+    return o
+
+
+def attn_bwd(qkv, o, do, lse, delta, dqkv, n_crops, Ntok, D, H):
+    assert all(t.dtype == bf16 and t.is_contiguous() for t in (qkv, o, do, dqkv))
+    N.check(N.init().d3_attn_bwd(_p(qkv), _p(o), _p(do), _p(lse), _p(delta), _p(dqkv), n_crops, Ntok, D, H, _s()),
+            "d3_attn_bwd")
+    return dqkv
+
+
+def token_rows(mask_indices, rows, count, P, mode):
+    assert rows.dtype == torch.int32 and (mask_indices is None or mask_indices.dtype == torch.int64)
+    N.check(N.init().d3_token_rows(_p(mask_indices), _p(rows), count, P, mode, _s()), "d3_token_rows")
+    return rows
+
+
+def gather_rows(src, rows, R, D, dst_bf16=None, dst_f32=None):
+    assert src.dtype == f32 and rows.dtype == torch.int32
+    N.check(N.init().d3_gather_rows(_p(src), _p(rows), _p(dst_bf16), _p(dst_f32), R, D, _s()), "d3_gather_rows")
+
+
+def scatter_add_rows(src, rows, dst, R, D):
+    assert dst.dtype == f32
+    N.check(N.init().d3_scatter_add_rows(_p(src), int(src.dtype == f32), _p(rows), _p(dst), R, D, _s()),
+            "d3_scatter_add_rows")
+
+
+def l2norm_fwd(u, y, nrm, eps=1e-12):
+    R, Cc = u.shape
+    assert u.dtype == f32 and y.dtype == bf16
+    N.check(N.init().d3_l2norm_fwd(_p(u), _p(y), _p(nrm), R, Cc, eps, _s()), "d3_l2norm_fwd")
+    return y
+
+
+def l2norm_bwd(g, u, nrm, du, eps=1e-12):
+    R, Cc = u.shape
+    assert g.dtype == bf16 and du.dtype == bf16
+    N.check(N.init().d3_l2norm_bwd(_p(g), _p(u), _p(nrm), _p(du), R, Cc, eps, _s()), "d3_l2norm_bwd")
+    return du
+
+
+def ls_act_bwd(dX, u, gamma, du, dgamma, dbias, use_gelu: bool):
+    T, D = dX.shape
+    assert dX.dtype == f32 and u.dtype == bf16 and du.dtype == bf16
+    N.check(N.init().d3_ls_act_bwd(_p(dX), _p(u), _p(gamma), _p(du), _p(dgamma), _p(dbias), T, D, int(use_gelu), _s()),
+            "d3_ls_act_bwd")
+
+
+def colsum_bf16(x, out):
+    T, Nn = x.shape
+    assert x.dtype == bf16 and out.dtype == f32
+    N.check(N.init().d3_colsum_bf16(_p(x), _p(out), T, Nn, x.stride(0), _s()), "d3_colsum_bf16")
+
+
+def cast_f32_bf16(src, dst):
+    assert src.dtype == f32 and dst.dtype == bf16 and src.numel() == dst.numel()
+    N.check(N.init().d3_cast_f32_bf16(_p(src), _p(dst), src.numel(), _s()), "d3_cast_f32_bf16")
+
+
+def absmax(L, out):
+    N.check(N.init().d3_absmax(_p(L), L.numel(), _p(out), _s()), "d3_absmax")
+
+
+def sinkhorn_colsum(L, mx, temp, a, s):
+    R, K = L.shape
+    N.check(N.init().d3_sinkhorn_colsum(_p(L), _p(mx), temp, _p(a), _p(s), R, K, _s()), "d3_sinkhorn_colsum")
+
+
+def sinkhorn_rowsum(L, mx, temp, s, btot, a):
+    R, K = L.shape
+    N.check(N.init().d3_sinkhorn_rowsum(_p(L), _p(mx), temp, _p(s), _p(btot), _p(a), R, K, _s()), "d3_sinkhorn_rowsum")
+
+
+def sinkhorn_probs(L, mx, temp, s, a, btot, Q):
+    R, K = L.shape
+    N.check(N.init().d3_sinkhorn_probs(_p(L), _p(mx), temp, _p(s), _p(a), _p(btot), _p(Q), R, K, _s()),
+            "d3_sinkhorn_probs")
+
+
+def ce_fwd_bwd(S, student_temp, Lt, mx, teacher_temp, s_t, a_t, btot, t0, t1, wm, wg, slot, metric, dS):
+    Rs, K = S.shape
+    assert S.dtype == f32 and Lt.dtype == f32 and dS.dtype == bf16 and t0.dtype == torch.int32
+    N.check(N.init().d3_ce_fwd_bwd(_p(S), student_temp, _p(Lt), _p(mx), teacher_temp, _p(s_t), _p(a_t), _p(btot),
+                                   _p(t0), _p(t1), _p(wm), _p(wg), _p(slot), _p(metric), _p(dS), Rs, K, _s()),
+            "d3_ce_fwd_bwd")
+
+
+def koleo_fwd_bwd(x, xn, nrm, nn, coef, metric, dx, w_metric, w_grad, eps=1e-8):
+    B, D = x.shape
+    assert x.dtype == f32 and nn.dtype == torch.int32
+    N.check(N.init().d3_koleo_fwd_bwd(_p(x), _p(xn), _p(nrm), _p(nn), _p(coef), _p(metric), _p(dx), B, D, eps,
+                                      w_metric, w_grad, _s()), "d3_koleo_fwd_bwd")
+
+
+def sumsq(g, out):
+    N.check(N.init().d3_sumsq(_p(g), g.numel(), _p(out), _s()), "d3_sumsq")
+
+
+def adamw_ema(p, g, m, v, teacher, p_bf16, t_bf16, n_bf16, segs, nseg, sumsq_t, max_norm, lr, last_layer_lr, wd, step,
+              momentum, b1=0.9, b2=0.999, eps=1e-8):
+    n = p.numel()
+    N.check(N.init().d3_adamw_ema(_p(p), _p(g), _p(m), _p(v), _p(teacher), _p(p_bf16), _p(t_bf16), n_bf16, _p(segs),
+                                  nseg, n, _p(sumsq_t), max_norm, lr, last_layer_lr, wd, b1, b2, eps, step, momentum,
+                                  _s()), "d3_adamw_ema")

@@ -64,6 +64,90 @@ typedef struct {
 int d3_gemm_bf16(const void* A, int lda, int a_major, const void* B, int ldb, int b_major, int M, int N, int K,
                  const d3_gemm_epilogue* ep, int tile_n /*0 = auto; 64/128/256*/, void* stream);
 
+/* ---- patch embedding / token assembly ---------------------------------------------------------------------------
+ * layers/patch_embed.py:38-51: the stride==kernel conv is im2col + GEMM (d3_gemm_bf16 with the kernel viewed as
+ * [p*p*3, D]); models/vision_transformer.py:173-203: where(mask, mask_token, x), prepend cls.                        */
+int d3_im2col(const void* img_bf16 /*[n,H,W,3]*/, void* out_bf16 /*[n*Hp*Wp, p*p*3]*/, int n, int H, int W, int p,
+              void* stream);
+int d3_assemble_tokens(const float* tok /*[n*P,D]*/, const float* cls /*[D]*/, const float* mask_token /*[D]*/,
+                       const unsigned char* masks /*[n*P] or NULL*/, float* X /*[n,1+P,D]*/, int n, int P, int D,
+                       void* stream);
+int d3_assemble_tokens_bwd(const float* dX, const unsigned char* masks, void* dTok_bf16 /*[n*P,D]*/,
+                           float* dcls /*[D] +=*/, float* dmask_token /*[D] +=*/, int n, int P, int D, void* stream);
+
+/* ---- LayerNorm (models/vision_transformer.py:40: eps 1e-6, biased variance E[x^2]-E[x]^2, fp32 statistics) ------- */
+int d3_layernorm_fwd(const float* x /*[T,D]*/, const float* scale, const float* bias, void* y, int y_is_f32,
+                     float* mean /*[T] or NULL*/, float* rstd, int T, int D, float eps, void* stream);
+int d3_layernorm_bwd(const void* dy, int dy_is_f32, const float* x, const float* mean, const float* rstd,
+                     const float* scale, const float* dx_add /*residual-stream gradient or NULL*/, float* dx,
+                     float* dscale /*[D] += or NULL*/, float* dbias /*[D] +=*/, int T, int D, void* stream);
+
+/* ---- RoPE (layers/attention.py:14-20,69-90; tables from layers/rope_position_encoding.py:117-123) -----------------
+ * in place on the q and k thirds of qkv bf16 [T,3D]; tokens t < prefix of every crop are left untouched.             */
+int d3_rope(void* qkv_bf16, const float* sin_t /*[P,hd]*/, const float* cos_t, long long T, int tokens_per_crop,
+            int prefix, int D, int head_dim, int inverse, void* stream);
+
+/* ---- attention (layers/attention.py:116 nn.dot_product_attention; head_dim 64, N <= 448 fwd / 256 bwd) ------------ */
+int d3_attn_fwd(const void* qkv_bf16 /*[n*N,3D] post-RoPE*/, void* o_bf16 /*[n*N,D]*/, float* lse /*[n,H,N] or NULL*/,
+                int n_crops, int N, int D, int H, void* stream);
+int d3_attn_bwd(const void* qkv_bf16, const void* o_bf16, const void* do_bf16, const float* lse,
+                float* delta_scratch /*[n,H,N]*/, void* dqkv_bf16 /*[n*N,3D] (pre-inverse-RoPE)*/, int n_crops, int N,
+                int D, int H, void* stream);
+
+/* ---- row gather / scatter (train/ssl_meta_arch.py:377,432 patch.reshape(-1,D)[mask_indices_list]; cls = token 0) --- */
+int d3_token_rows(const long long* mask_indices /*int64 [count] (mode 0)*/, int* rows /*int32 [count]*/, int count,
+                  int P, int mode /*0: masked patch -> token row, 1: cls row of crop i*/, void* stream);
+int d3_gather_rows(const float* src /*[*,D]*/, const int* rows, void* dst_bf16 /*or NULL*/, float* dst_f32 /*or NULL*/,
+                   int R, int D, void* stream);
+int d3_scatter_add_rows(const void* src, int src_is_f32, const int* rows, float* dst /*+=*/, int R, int D, void* stream);
+
+/* ---- DINO head pieces (layers/dino_head.py:78-85) ----------------------------------------------------------------- */
+int d3_l2norm_fwd(const float* u /*[R,C]*/, void* y_bf16, float* nrm /*[R]*/, int R, int C, float eps, void* stream);
+int d3_l2norm_bwd(const void* g_bf16, const float* u, const float* nrm, void* du_bf16, int R, int C, float eps,
+                  void* stream);
+
+/* ---- backward helpers ----------------------------------------------------------------------------------------------
+ * d3_ls_act_bwd: x_out = x_in + gamma * act(u) (layers/block.py:198-199): du = dX*gamma*act'(u) (bf16),
+ * dgamma += colsum(dX*act(u)), dbias += colsum(du).  d3_colsum_bf16: bias gradients.                                 */
+int d3_ls_act_bwd(const float* dX /*[T,D]*/, const void* u_bf16, const float* gamma, void* du_bf16, float* dgamma,
+                  float* dbias, int T, int D, int use_gelu, void* stream);
+int d3_colsum_bf16(const void* x_bf16 /*[T,N], row stride ld*/, float* out /*[N] +=*/, long long T, int N, int ld,
+                   void* stream);
+int d3_cast_f32_bf16(const float* src, void* dst_bf16, long long n, void* stream);
+
+/* ---- Sinkhorn-Knopp (loss/dino_clstoken_loss.py:35-62, loss/ibot_patch_loss.py:77-109) ----------------------------
+ * Q[b,k] = Btot * exp((L[b,k]-mx)/temp) * r[k] * a[b],  r = 1/(K * E^T a),  a = 1/(Btot * E r); the caller alternates
+ * colsum (-> all-reduce over ranks of s[K]) and rowsum three times; mx = global max (all-reduce MAX over ranks).     */
+int d3_absmax(const float* L, long long n, float* out /*pre-set to -inf*/, void* stream);
+int d3_sinkhorn_colsum(const float* L /*[R,K]*/, const float* mx, float temp, const float* a /*[R] or NULL (=1)*/,
+                       float* s /*[K] zeroed, +=*/, int R, int K, void* stream);
+int d3_sinkhorn_rowsum(const float* L, const float* mx, float temp, const float* s, const float* btot /*device*/,
+                       float* a /*[R]*/, int R, int K, void* stream);
+int d3_sinkhorn_probs(const float* L, const float* mx, float temp, const float* s, const float* a, const float* btot,
+                      float* Q /*[R,K]*/, int R, int K, void* stream);
+
+/* ---- cross-entropy over prototypes, forward + backward fused (loss/dino_clstoken_loss.py:66-89,
+ * loss/ibot_patch_loss.py:13-14,55-67; weights train/ssl_meta_arch.py:480-525) ---------------------------------------
+ * per student row i with teacher rows t0[i], t1[i] (-1 = none): metric[slot[i]] += wm[i] * CE_i;
+ * dS[i,:] = wg[i]/student_temp * (npairs*softmax(S_i/student_temp) - sum_p Q_p)  (bf16).                             */
+int d3_ce_fwd_bwd(const float* S /*[Rs,K]*/, float student_temp, const float* Lt /*[Rt,K] teacher logits*/,
+                  const float* mx, float teacher_temp, const float* s_t /*[K]*/, const float* a_t /*[Rt]*/,
+                  const float* btot, const int* t0, const int* t1, const float* wm, const float* wg, const int* slot,
+                  float* metric, void* dS_bf16, int Rs, int K, void* stream);
+
+/* ---- KoLeo (loss/koleo_loss.py:16-35), forward + backward: metric += w_metric * loss; dx += w_grad * dloss/dx ------ */
+int d3_koleo_fwd_bwd(const float* x /*[B,D]*/, float* xn_scratch /*[B,D]*/, float* nrm_scratch /*[B]*/,
+                     int* nn_scratch /*[B]*/, float* coef_scratch /*[B]*/, float* metric, float* dx /*[B,D] +=*/, int B,
+                     int D, float eps, float w_metric, float w_grad, void* stream);
+
+/* ---- optimiser (train/train.py:516-541 clip, :95-106,562-563 optax.adamw; train/ssl_meta_arch.py:650-652 EMA) -------
+ * flat fp32 buffers; segs = array of {int64 start; float lr_mult, wd_mult; int is_last_layer, pad} sorted by start.  */
+int d3_sumsq(const float* g, long long n, float* out /*+=*/, void* stream);
+int d3_adamw_ema(float* p, const float* g, float* m, float* v, float* teacher, void* p_bf16, void* t_bf16,
+                 long long n_bf16, const void* segs, int nseg, long long n, const float* sumsq /*device, clip*/,
+                 float max_norm, float lr, float last_layer_lr, float wd, float b1, float b2, float eps, int step,
+                 float momentum, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
