@@ -1,0 +1,466 @@
+"""B200 step executor for the DINOv3 SSL hot path (replaces the jitted `train_step` of the reference,
+dinov3_jax/train/train.py:491-565, and `SSLMetaArch.__call__`, train/ssl_meta_arch.py:289-363).
+
+There is no autograd and no PyTorch math here: the forward and the hand-derived backward are explicit sequences of
+C-ABI kernel launches (`..ops`) on pre-allocated device buffers; torch only owns the memory and the stream.
+Student tokens of the global and the local crops live in ONE row-concatenated stream [T_g + T_l, D] so every
+token-wise op (LayerNorm, the four GEMMs of a block and their wgrads) is a single launch; only RoPE / attention see
+the crop structure.  Activations needed by the backward are stashed per block (bf16 except the fp32 residual stream).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from .. import ops
+from .config import EngineConfig
+from .params import ParamStore
+
+f32, bf16 = torch.float32, torch.bfloat16
+
+
+def rope_tables(Hp: int, Wp: int, head_dim: int, base: float, device):
+    """sin / cos [Hp*Wp, head_dim] fp32 — layers/rope_position_encoding.py:36-40,64-73,117-123 (normalize 'separate').
+    Host-side table construction (a few KB, once per crop size); the rotation itself is d3_rope."""
+    dt = torch.float64
+    periods = base ** (2.0 * torch.arange(head_dim // 4, dtype=dt) / (head_dim // 2))
+    ch = torch.arange(0.5, Hp, dtype=dt) / Hp
+    cw = torch.arange(0.5, Wp, dtype=dt) / Wp
+    coords = torch.stack(torch.meshgrid(ch, cw, indexing="ij"), dim=-1).reshape(-1, 2)
+    coords = 2.0 * coords - 1.0
+    ang = 2 * math.pi * coords[:, :, None] / periods[None, None, :]
+    ang = ang.reshape(ang.shape[0], -1)
+    ang = torch.cat([ang, ang], dim=-1)
+    # the reference computes the tables in fp32; fp64 -> fp32 rounding differs by < 1 ulp
+    return (torch.sin(ang).to(f32).to(device).contiguous(), torch.cos(ang).to(f32).to(device).contiguous())
+
+
+class CropSet:
+    """Static geometry of one crop resolution inside a token stream."""
+
+    def __init__(self, cfg: EngineConfig, n_crops: int, size: int, row0: int, device):
+        self.n = n_crops
+        self.size = size
+        self.Hp = size // cfg.patch
+        self.P = self.Hp * self.Hp
+        self.N = self.P + 1
+        self.T = n_crops * self.N
+        self.row0 = row0
+        self.sin, self.cos = rope_tables(self.Hp, self.Hp, cfg.head_dim, cfg.rope_base, device)
+        self.patches = torch.empty(n_crops * self.P, cfg.patch * cfg.patch * 3, dtype=bf16, device=device)
+        self.tok = torch.empty(n_crops * self.P, cfg.embed_dim, dtype=f32, device=device)
+        self.lse = None
+
+
+class Stream:
+    """Activation buffers of one network pass over a list of crop sets (teacher: global only; student: global+local)."""
+
+    def __init__(self, cfg: EngineConfig, sets, device, stash: bool):
+        D, Hd, L = cfg.embed_dim, cfg.hidden, cfg.depth
+        self.sets = sets
+        self.T = sum(s.T for s in sets)
+        T = self.T
+        self.stash = stash
+        nb = L if stash else 1
+        e = lambda *shape, dt=bf16: torch.empty(*shape, dtype=dt, device=device)
+        self.X = [e(T, D, dt=f32) for _ in range(L + 1)] if stash else [e(T, D, dt=f32), e(T, D, dt=f32)]
+        self.Xmid = [e(T, D, dt=f32) for _ in range(nb)]
+        self.Y = [e(T, D) for _ in range(nb)]
+        self.QKV = [e(T, 3 * D) for _ in range(nb)]
+        self.O = [e(T, D) for _ in range(nb)]
+        self.Z = [e(T, D) for _ in range(nb)]
+        self.Hh = [e(T, Hd) for _ in range(nb)]
+        self.Xn = e(T, D, dt=f32)
+        self.LSE = [[e(s.n, cfg.heads, s.N, dt=f32) for s in sets] for _ in range(nb)]
+        if stash:
+            self.Pst = [e(T, D) for _ in range(L)]
+            self.U1 = [e(T, Hd) for _ in range(L)]
+            self.U2 = [e(T, D) for _ in range(L)]
+            self.stats = [[e(T, dt=f32) for _ in range(4)] for _ in range(L)]   # mean1, rstd1, mean2, rstd2
+            self.fstats = [e(T, dt=f32), e(T, dt=f32)]
+
+    def x_in(self, i):
+        return self.X[i] if self.stash else self.X[i % 2]
+
+    def x_out(self, i):
+        return self.X[i + 1] if self.stash else self.X[(i + 1) % 2]
+
+    def b(self, lst, i):
+        return lst[i] if self.stash else lst[0]
+
+
+class HeadBufs:
+    def __init__(self, cfg: EngineConfig, R: int, device, stash: bool):
+        D, Hh, Bn, K = cfg.embed_dim, cfg.head_hidden, cfg.head_bottleneck, cfg.n_prototypes
+        e = lambda *shape, dt=bf16: torch.empty(*shape, dtype=dt, device=device)
+        self.R = R
+        self.A0 = e(R, D)
+        self.H1, self.H2 = e(R, Hh), e(R, Hh)
+        self.U3 = e(R, Bn, dt=f32)
+        self.nrm = e(R, dt=f32)
+        self.Yn = e(R, Bn)
+        self.logits = e(R, K, dt=f32)
+        if stash:
+            self.Ua, self.Ub = e(R, Hh), e(R, Hh)
+            self.dS = e(R, K)
+            self.dYn, self.dU3 = e(R, Bn), e(R, Bn)
+            self.dUb, self.dUa = e(R, Hh), e(R, Hh)
+            self.dA0 = e(R, D, dt=f32)
+
+
+class SinkhornBufs:
+    def __init__(self, R: int, K: int, device):
+        self.mx = torch.empty(1, dtype=f32, device=device)
+        self.s = torch.empty(K, dtype=f32, device=device)
+        self.a = torch.empty(R, dtype=f32, device=device)
+        self.btot = torch.empty(1, dtype=f32, device=device)
+
+
+class Engine:
+    """One rank's training engine: parameters, buffers and the step.
+
+    `B` = images per rank.  The number of masked tokens M varies per batch; buffers are sized for `max_masked`
+    (default: the collate upper bound, data/collate.py:47-61) and the live M comes from `mask_indices_list`.
+    """
+
+    def __init__(self, cfg: EngineConfig, B: int, device="cuda", max_masked: int | None = None, comm=None):
+        assert cfg.head_dim == 64, "kernels are specialised for head_dim 64 (every BASELINE arch)"
+        self.cfg, self.B, self.device = cfg, B, torch.device(device)
+        self.comm = comm  # distributed context (None = single GPU)
+        self.world = 1 if comm is None else comm.world
+        dev = self.device
+        self.params = ParamStore(cfg, dev)
+        ng, nl = cfg.n_global * B, cfg.n_local * B
+        # teacher stream: global crops only; student stream: global then local rows
+        self.t_sets = [CropSet(cfg, ng, cfg.global_size, 0, dev)]
+        self.s_sets = [CropSet(cfg, ng, cfg.global_size, 0, dev)]
+        self.s_sets.append(CropSet(cfg, nl, cfg.local_size, self.s_sets[0].T, dev))
+        self.teacher = Stream(cfg, self.t_sets, dev, stash=False)
+        self.student = Stream(cfg, self.s_sets, dev, stash=True)
+        P = self.s_sets[0].P
+        if max_masked is None:
+            n_masked_crops = int(ng * cfg.mask_probability)
+            max_masked = sum(int(P * (cfg.mask_ratio[0] + (cfg.mask_ratio[1] - cfg.mask_ratio[0]) * (i + 1) /
+                                      max(n_masked_crops, 1))) for i in range(n_masked_crops)) + 8
+        self.max_masked = max(int(max_masked), 1)
+        K, D = cfg.n_prototypes, cfg.embed_dim
+        self.Rc = ng + nl                         # student dino-head rows: concat(g_cls, l_cls)
+        self.h_s_dino = HeadBufs(cfg, self.Rc, dev, stash=True)
+        self.h_s_ibot = HeadBufs(cfg, self.max_masked, dev, stash=True)
+        self.h_t_dino = HeadBufs(cfg, ng, dev, stash=False)
+        self.h_t_ibot = HeadBufs(cfg, self.max_masked, dev, stash=False)
+        self.sk_dino = SinkhornBufs(ng, K, dev)
+        self.sk_ibot = SinkhornBufs(self.max_masked, K, dev)
+        i32 = torch.int32
+        self.rows_masked_t = torch.empty(self.max_masked, dtype=i32, device=dev)
+        self.rows_cls_t = torch.empty(ng, dtype=i32, device=dev)
+        self.rows_cls_s = torch.empty(self.Rc, dtype=i32, device=dev)
+        self.cls_f32 = torch.empty(self.Rc, D, dtype=f32, device=dev)     # student cls rows (fp32) for KoLeo
+        self.dcls = torch.empty(self.Rc, D, dtype=f32, device=dev)
+        self.koleo_xn = torch.empty(B, D, dtype=f32, device=dev)
+        self.koleo_nrm = torch.empty(B, dtype=f32, device=dev)
+        self.koleo_nn = torch.empty(B, dtype=i32, device=dev)
+        self.koleo_coef = torch.empty(B, dtype=f32, device=dev)
+        self.metrics = torch.zeros(8, dtype=f32, device=dev)   # 0 dino_local 1 dino_global 2 koleo 3 ibot
+        # backward scratch over the student stream
+        T, Hd = self.student.T, cfg.hidden
+        e = lambda *shape, dt=bf16: torch.empty(*shape, dtype=dt, device=dev)
+        self.dX = [e(T, D, dt=f32), e(T, D, dt=f32)]
+        self.dXmid = e(T, D, dt=f32)
+        self.dU2, self.dP, self.dZ, self.dY, self.dO = e(T, D), e(T, D), e(T, D), e(T, D), e(T, D)
+        self.dU1 = e(T, Hd)
+        self.dQKV = e(T, 3 * D)
+        self.delta = [e(s.n, cfg.heads, s.N, dt=f32) for s in self.s_sets]
+        self.dTok = [e(s.n * s.P, D) for s in self.s_sets]
+        self._build_ce_tables()
+        self._build_rows()
+        self.step_count = 0
+        self.masks_u8 = torch.zeros(ng, P, dtype=torch.uint8, device=dev)
+        self.mask_idx = torch.zeros(self.max_masked, dtype=torch.int64, device=dev)
+        self.M = 0
+
+    # ------------------------------------------------------------------------------------------------ static tables
+    def _build_rows(self):
+        sg, sl = self.s_sets
+        ops.token_rows(None, self.rows_cls_t, self.t_sets[0].n, self.t_sets[0].P, 1)
+        # student cls rows: global crops then local crops (local rows offset by the global part)
+        rows_g = torch.arange(sg.n, dtype=torch.int32) * sg.N
+        rows_l = torch.arange(sl.n, dtype=torch.int32) * sl.N + sl.row0
+        self.rows_cls_s.copy_(torch.cat([rows_g, rows_l]))
+
+    def _build_ce_tables(self):
+        """Per-student-row teacher pairing and weights (loss/dino_clstoken_loss.py:66-89; train/ssl_meta_arch.py:480-525)."""
+        cfg, B = self.cfg, self.B
+        ng, nl = cfg.n_global, cfg.n_local
+        g_terms, l_terms = ng * (ng - 1), ng * nl
+        g_scale, l_scale = g_terms / (g_terms + l_terms), l_terms / (g_terms + l_terms)
+        R = self.Rc
+        t0 = torch.full((R,), -1, dtype=torch.int32)
+        t1 = torch.full((R,), -1, dtype=torch.int32)
+        wm, wg = torch.zeros(R), torch.zeros(R)
+        slot = torch.zeros(R, dtype=torch.int32)
+        assert ng == 2, "pair tables are written for two global crops (n_global_crops = 2, ssl_meta_arch.py:296)"
+        for i in range(R):
+            s, b = divmod(i, B)
+            if s < ng:      # global student crop s pairs with the OTHER teacher crop (ignore_diagonal)
+                t0[i] = (1 - s) * B + b
+                norm = B * ng * ng - B * min(ng, ng)
+                wm[i] = 1.0 / norm
+                wg[i] = cfg.dino_loss_weight * g_scale / norm
+                slot[i] = 1
+            else:           # local student crop pairs with both teacher crops
+                t0[i], t1[i] = b, B + b
+                norm = B * nl * ng
+                wm[i] = 1.0 / norm
+                wg[i] = cfg.dino_loss_weight * l_scale / norm
+                slot[i] = 0
+        dev = self.device
+        self.ce_dino = tuple(x.to(dev) for x in (t0, t1, wm, wg, slot))
+        Mx = self.max_masked
+        n_rows = ng * B    # masks.shape[0] (loss/ibot_patch_loss.py:67)
+        self.ce_ibot = (torch.arange(Mx, dtype=torch.int32, device=dev), torch.full((Mx,), -1, dtype=torch.int32, device=dev),
+                        torch.full((Mx,), 1.0 / n_rows, device=dev), torch.full((Mx,), cfg.ibot_loss_weight / n_rows, device=dev),
+                        torch.full((Mx,), 3, dtype=torch.int32, device=dev))
+
+    # ------------------------------------------------------------------------------------------------ forward pieces
+    def _embed(self, st: Stream, images, masks_list, teacher: bool):
+        cfg, bb = self.cfg, self.params.mods["backbone"]
+        X0 = st.x_in(0)
+        Wpe = bb.w("patch_embed/proj/kernel", teacher)
+        for cs, img, masks in zip(st.sets, images, masks_list):
+            ops.im2col(img, cs.patches, cfg.patch)
+            ops.gemm(cs.patches, Wpe, cs.tok, b_mn=True, bias=bb.vec("patch_embed/proj/bias", teacher))
+            ops.assemble_tokens(cs.tok, bb.vec("cls_token", teacher), bb.vec("mask_token", teacher), masks,
+                                X0[cs.row0: cs.row0 + cs.T], cs.n, cs.P, cfg.embed_dim)
+
+    def _block_fwd(self, st: Stream, i: int, teacher: bool):
+        cfg, bb = self.cfg, self.params.mods["backbone"]
+        D, H = cfg.embed_dim, cfg.heads
+        p = f"blocks_{i}/"
+        v = lambda n: bb.vec(p + n, teacher)
+        w = lambda n: bb.w(p + n, teacher)
+        X, Xmid, Xo = st.x_in(i), st.b(st.Xmid, i), st.x_out(i)
+        Y, QKV, O, Z, Hh = st.b(st.Y, i), st.b(st.QKV, i), st.b(st.O, i), st.b(st.Z, i), st.b(st.Hh, i)
+        stats = st.stats[i] if st.stash else [None] * 4
+        ops.layernorm_fwd(X, v("norm1/scale"), v("norm1/bias"), Y, stats[0], stats[1], cfg.ln_eps)
+        ops.gemm(Y, w("attn/qkv/kernel"), QKV, b_mn=True, bias=v("attn/qkv/bias"))
+        lses = st.b(st.LSE, i)
+        for cs, lse in zip(st.sets, lses):
+            q = QKV[cs.row0: cs.row0 + cs.T]
+            ops.rope(q, cs.sin, cs.cos, cs.N, 1, D, cfg.head_dim)
+            ops.attn_fwd(q, O[cs.row0: cs.row0 + cs.T], lse if st.stash else None, cs.n, cs.N, D, H)
+        ops.gemm(O, w("attn/proj/kernel"), Xmid, b_mn=True, bias=v("attn/proj/bias"),
+                 store_pre=st.Pst[i] if st.stash else None, gamma=v("ls1/gamma"), resid=X)
+        ops.layernorm_fwd(Xmid, v("norm2/scale"), v("norm2/bias"), Z, stats[2], stats[3], cfg.ln_eps)
+        ops.gemm(Z, w("mlp/Dense_0/kernel"), Hh, b_mn=True, bias=v("mlp/Dense_0/bias"), gelu=True,
+                 store_pre=st.U1[i] if st.stash else None)
+        ops.gemm(Hh, w("mlp/Dense_1/kernel"), Xo, b_mn=True, bias=v("mlp/Dense_1/bias"), gelu=cfg.mlp_second_act,
+                 store_pre=st.U2[i] if st.stash else None, gamma=v("ls2/gamma"), resid=Xmid)
+
+    def _backbone_fwd(self, st: Stream, images, masks_list, teacher: bool):
+        cfg, bb = self.cfg, self.params.mods["backbone"]
+        self._embed(st, images, masks_list, teacher)
+        for i in range(cfg.depth):
+            self._block_fwd(st, i, teacher)
+        XL = st.x_in(cfg.depth)
+        fs = st.fstats if st.stash else [None, None]
+        ops.layernorm_fwd(XL, bb.vec("norm/scale", teacher), bb.vec("norm/bias", teacher), st.Xn, fs[0], fs[1], cfg.ln_eps)
+
+    def _head_fwd(self, hb: HeadBufs, module: str, R: int, teacher: bool, stash: bool):
+        hd = self.params.mods[module]
+        w = lambda n: hd.w(n, teacher)
+        v = lambda n: hd.vec(n, teacher)
+        r = lambda t: t[:R]
+        if R == 0:
+            return
+        ops.gemm(r(hb.A0), w("mlp/layers_0/kernel"), r(hb.H1), b_mn=True, bias=v("mlp/layers_0/bias"), gelu=True,
+                 store_pre=r(hb.Ua) if stash else None)
+        ops.gemm(r(hb.H1), w("mlp/layers_2/kernel"), r(hb.H2), b_mn=True, bias=v("mlp/layers_2/bias"), gelu=True,
+                 store_pre=r(hb.Ub) if stash else None)
+        ops.gemm(r(hb.H2), w("mlp/layers_4/kernel"), r(hb.U3), b_mn=True, bias=v("mlp/layers_4/bias"))
+        ops.l2norm_fwd(r(hb.U3), r(hb.Yn), r(hb.nrm), 1e-12)
+        ops.gemm(r(hb.Yn), w("last_layer/kernel"), r(hb.logits), b_mn=True)
+
+    def _sinkhorn(self, sk: SinkhornBufs, logits, R: int, temp: float, btot_local: float, n_iter: int = 3):
+        """loss/dino_clstoken_loss.py:35-62 as alternating diagonal scalings (see csrc/losses.cu)."""
+        L = logits[:R]
+        sk.mx.fill_(float("-inf"))
+        sk.btot.fill_(float(btot_local))
+        ops.absmax(L, sk.mx)
+        if self.comm is not None:
+            self.comm.all_reduce_max(sk.mx)
+            self.comm.all_reduce_sum(sk.btot)
+        a = None
+        for _ in range(n_iter):
+            sk.s.zero_()
+            ops.sinkhorn_colsum(L, sk.mx, temp, a, sk.s)
+            if self.comm is not None:
+                self.comm.all_reduce_sum(sk.s)          # psum of the row sums (:53 / ibot :99)
+            ops.sinkhorn_rowsum(L, sk.mx, temp, sk.s, sk.btot, sk.a[:R])
+            a = sk.a[:R]
+
+    # ------------------------------------------------------------------------------------------------ backward pieces
+    def _head_bwd(self, hb: HeadBufs, module: str, R: int):
+        hd = self.params.mods[module]
+        w, gw, gv = (lambda n: hd.w(n)), hd.gw, hd.gv
+        r = lambda t: t[:R]
+        if R == 0:
+            return
+        # prototype layer: logits = Yn Wl
+        ops.gemm(r(hb.dS), w("last_layer/kernel"), r(hb.dYn))                                   # dYn = dS Wl^T
+        ops.gemm(r(hb.Yn), r(hb.dS), gw("last_layer/kernel"), a_mn=True, b_mn=True)              # dWl = Yn^T dS
+        ops.l2norm_bwd(r(hb.dYn), r(hb.U3), r(hb.nrm), r(hb.dU3), 1e-12)
+        ops.colsum_bf16(r(hb.dU3), gv("mlp/layers_4/bias"))
+        ops.gemm(r(hb.H2), r(hb.dU3), gw("mlp/layers_4/kernel"), a_mn=True, b_mn=True)
+        ops.gemm(r(hb.dU3), w("mlp/layers_4/kernel"), r(hb.dUb), dgelu_of=r(hb.Ub))
+        ops.colsum_bf16(r(hb.dUb), gv("mlp/layers_2/bias"))
+        ops.gemm(r(hb.H1), r(hb.dUb), gw("mlp/layers_2/kernel"), a_mn=True, b_mn=True)
+        ops.gemm(r(hb.dUb), w("mlp/layers_2/kernel"), r(hb.dUa), dgelu_of=r(hb.Ua))
+        ops.colsum_bf16(r(hb.dUa), gv("mlp/layers_0/bias"))
+        ops.gemm(r(hb.A0), r(hb.dUa), gw("mlp/layers_0/kernel"), a_mn=True, b_mn=True)
+        ops.gemm(r(hb.dUa), w("mlp/layers_0/kernel"), r(hb.dA0))                                 # fp32 [R, D]
+
+    def _block_bwd(self, i: int, dX, dXprev):
+        cfg, bb, st = self.cfg, self.params.mods["backbone"], self.student
+        D, H = cfg.embed_dim, cfg.heads
+        p = f"blocks_{i}/"
+        v, w, gw, gv = (lambda n: bb.vec(p + n)), (lambda n: bb.w(p + n)), (lambda n: bb.gw(p + n)), (lambda n: bb.gv(p + n))
+        m1, r1, m2, r2 = st.stats[i]
+        # ---- MLP branch: x_out = x_mid + g2 * act(u2), u2 = h W2 + b2, h = gelu(u1), u1 = z W1 + b1
+        ops.ls_act_bwd(dX, st.U2[i], v("ls2/gamma"), self.dU2, gv("ls2/gamma"), gv("mlp/Dense_1/bias"), cfg.mlp_second_act)
+        ops.gemm(self.dU2, w("mlp/Dense_1/kernel"), self.dU1, dgelu_of=st.U1[i])                 # dU1 = (dU2 W2^T) * gelu'(u1)
+        ops.gemm(st.Hh[i], self.dU2, gw("mlp/Dense_1/kernel"), a_mn=True, b_mn=True)            # dW2 = h^T dU2
+        ops.colsum_bf16(self.dU1, gv("mlp/Dense_0/bias"))
+        ops.gemm(self.dU1, w("mlp/Dense_0/kernel"), self.dZ)                                    # dZ = dU1 W1^T
+        ops.gemm(st.Z[i], self.dU1, gw("mlp/Dense_0/kernel"), a_mn=True, b_mn=True)             # dW1 = z^T dU1
+        ops.layernorm_bwd(self.dZ, st.Xmid[i], m2, r2, v("norm2/scale"), self.dXmid, dx_add=dX,
+                          dscale=gv("norm2/scale"), dbias=gv("norm2/bias"))
+        # ---- attention branch: x_mid = x_in + g1 * (o Wp + bp)
+        ops.ls_act_bwd(self.dXmid, st.Pst[i], v("ls1/gamma"), self.dP, gv("ls1/gamma"), gv("attn/proj/bias"), False)
+        ops.gemm(self.dP, w("attn/proj/kernel"), self.dO)                                       # dO = dP Wp^T
+        ops.gemm(st.O[i], self.dP, gw("attn/proj/kernel"), a_mn=True, b_mn=True)                # dWp = o^T dP
+        for cs, lse, delta in zip(st.sets, st.LSE[i], self.delta):
+            sl = slice(cs.row0, cs.row0 + cs.T)
+            ops.attn_bwd(st.QKV[i][sl], st.O[i][sl], self.dO[sl], lse, delta, self.dQKV[sl], cs.n, cs.N, D, H)
+            ops.rope(self.dQKV[sl], cs.sin, cs.cos, cs.N, 1, D, cfg.head_dim, inverse=True)
+        ops.colsum_bf16(self.dQKV, gv("attn/qkv/bias"))
+        ops.gemm(self.dQKV, w("attn/qkv/kernel"), self.dY)                                      # dY = dQKV Wqkv^T
+        ops.gemm(st.Y[i], self.dQKV, gw("attn/qkv/kernel"), a_mn=True, b_mn=True)               # dWqkv = y^T dQKV
+        ops.layernorm_bwd(self.dY, st.X[i], m1, r1, v("norm1/scale"), dXprev, dx_add=self.dXmid,
+                          dscale=gv("norm1/scale"), dbias=gv("norm1/bias"))
+
+    # ------------------------------------------------------------------------------------------------ the step
+    def set_batch(self, batch: dict):
+        """Accepts the reference's collate dict (data/collate.py:72-93): crop-major NHWC bf16 crops, bool masks
+        [2B, P], int64 mask_indices_list [M].  Device tensors are used as they are; host tensors are copied
+        (pinned + non_blocking when possible)."""
+        dev = self.device
+        to = lambda t, dt=None: t.to(device=dev, dtype=dt, non_blocking=True)
+        self.g_img = to(batch["collated_global_crops"], bf16).contiguous()
+        self.l_img = to(batch["collated_local_crops"], bf16).contiguous()
+        masks = batch["collated_masks"]
+        self.masks_u8.copy_(masks.to(torch.uint8) if masks.dtype != torch.uint8 else masks, non_blocking=True)
+        idx = batch["mask_indices_list"]
+        self.M = int(idx.shape[0])
+        assert self.M <= self.max_masked, f"M={self.M} exceeds max_masked={self.max_masked}"
+        self.mask_idx[: self.M].copy_(idx, non_blocking=True)
+        ops.token_rows(self.mask_idx, self.rows_masked_t, self.M, self.s_sets[0].P, 0)
+
+    def forward_backward(self, teacher_temp: float):
+        cfg, B, M = self.cfg, self.B, self.M
+        D, K = cfg.embed_dim, cfg.n_prototypes
+        ng = cfg.n_global * B
+        self.metrics.zero_()
+        for st in self.params.mods.values():
+            st.zero_vector_grads()
+        # ---- teacher (train/ssl_meta_arch.py:366-402)
+        T_ = self.teacher
+        self._backbone_fwd(T_, [self.g_img], [None], teacher=True)
+        ops.gather_rows(T_.Xn, self.rows_cls_t, ng, D, dst_bf16=self.h_t_dino.A0)
+        ops.gather_rows(T_.Xn, self.rows_masked_t, M, D, dst_bf16=self.h_t_ibot.A0)
+        self._head_fwd(self.h_t_dino, "dino_head", ng, teacher=True, stash=False)
+        self._head_fwd(self.h_t_ibot, "ibot_head", M, teacher=True, stash=False)
+        self._sinkhorn(self.sk_dino, self.h_t_dino.logits, ng, teacher_temp, btot_local=ng)
+        self._sinkhorn(self.sk_ibot, self.h_t_ibot.logits, M, teacher_temp, btot_local=M)
+        # ---- student (train/ssl_meta_arch.py:406-460)
+        S_ = self.student
+        self._backbone_fwd(S_, [self.g_img, self.l_img], [self.masks_u8, None], teacher=False)
+        ops.gather_rows(S_.Xn, self.rows_cls_s, self.Rc, D, dst_bf16=self.h_s_dino.A0, dst_f32=self.cls_f32)
+        ops.gather_rows(S_.Xn, self.rows_masked_t, M, D, dst_bf16=self.h_s_ibot.A0)
+        self._head_fwd(self.h_s_dino, "dino_head", self.Rc, teacher=False, stash=True)
+        self._head_fwd(self.h_s_ibot, "ibot_head", M, teacher=False, stash=True)
+        # ---- losses + d(logits) (train/ssl_meta_arch.py:463-525)
+        t0, t1, wm, wg, slot = self.ce_dino
+        ops.ce_fwd_bwd(self.h_s_dino.logits, cfg.student_temp, self.h_t_dino.logits, self.sk_dino.mx, teacher_temp,
+                       self.sk_dino.s, self.sk_dino.a, self.sk_dino.btot, t0, t1, wm, wg, slot, self.metrics,
+                       self.h_s_dino.dS)
+        if M:
+            t0, t1, wm, wg, slot = self.ce_ibot
+            ops.ce_fwd_bwd(self.h_s_ibot.logits[:M], cfg.student_temp, self.h_t_ibot.logits[:M], self.sk_ibot.mx,
+                           teacher_temp, self.sk_ibot.s, self.sk_ibot.a, self.sk_ibot.btot, t0, t1, wm, wg, slot,
+                           self.metrics, self.h_s_ibot.dS[:M])
+        # ---- backward: heads
+        self._head_bwd(self.h_s_dino, "dino_head", self.Rc)
+        self._head_bwd(self.h_s_ibot, "ibot_head", M)
+        # KoLeo on the pre-head global cls tokens, per crop (train/ssl_meta_arch.py:513): loss weight
+        # koleo_loss_weight * n_global * (1/n_global) per crop; metric = mean over crops
+        for c in range(cfg.n_global):
+            ops.koleo_fwd_bwd(self.cls_f32[c * B:(c + 1) * B], self.koleo_xn, self.koleo_nrm, self.koleo_nn,
+                              self.koleo_coef, self.metrics[2:3], self.h_s_dino.dA0[c * B:(c + 1) * B],
+                              1.0 / cfg.n_global, cfg.koleo_loss_weight)
+        # ---- backward: final norm (dXn is zero except cls rows and masked-patch rows)
+        dXn = self.dX[0]
+        dXn.zero_()
+        ops.scatter_add_rows(self.h_s_dino.dA0, self.rows_cls_s, dXn, self.Rc, D)
+        ops.scatter_add_rows(self.h_s_ibot.dA0, self.rows_masked_t, dXn, M, D)
+        bb = self.params.mods["backbone"]
+        dXL = self.dX[1]
+        ops.layernorm_bwd(dXn, S_.X[cfg.depth], S_.fstats[0], S_.fstats[1], bb.vec("norm/scale"), dXL,
+                          dscale=bb.gv("norm/scale"), dbias=bb.gv("norm/bias"))
+        cur, nxt = 1, 0
+        for i in reversed(range(cfg.depth)):
+            self._block_bwd(i, self.dX[cur], self.dX[nxt])
+            cur, nxt = nxt, cur
+        # ---- backward: token assembly + patch embedding
+        dX0 = self.dX[cur]
+        first = True
+        for cs, masks, dTok in zip(S_.sets, [self.masks_u8, None], self.dTok):
+            ops.assemble_tokens_bwd(dX0[cs.row0: cs.row0 + cs.T], masks, dTok, bb.gv("cls_token"),
+                                    bb.gv("mask_token"), cs.n, cs.P, D)
+            ops.colsum_bf16(dTok, bb.gv("patch_embed/proj/bias"))
+            ops.gemm(cs.patches, dTok, bb.gw("patch_embed/proj/kernel"), a_mn=True, b_mn=True, accum=not first)
+            first = False
+
+    def optimizer_step(self, lr: float, wd: float, last_layer_lr: float, momentum: float):
+        """Per-module clip (train/train.py:516-541) + AdamW (:95-106) + teacher EMA (ssl_meta_arch.py:650-652)."""
+        cfg = self.cfg
+        self.step_count += 1
+        for st in self.params.mods.values():
+            ops.sumsq(st.grad, st.sumsq)
+            ops.adamw_ema(st.master, st.grad, st.m, st.v, st.t_master, st.bf16, st.t_bf16, st.n_mat, st.segs,
+                          len(st.seg_names), st.sumsq, float(cfg.clip_grad or 0.0), lr, last_layer_lr, wd,
+                          self.step_count, momentum, cfg.adamw_beta1, cfg.adamw_beta2)
+
+    def train_step(self, batch: dict | None, *, teacher_temp: float, lr: float, wd: float, last_layer_lr: float,
+                   momentum: float):
+        if batch is not None:
+            self.set_batch(batch)
+        self.forward_backward(teacher_temp)
+        self.optimizer_step(lr, wd, last_layer_lr, momentum)
+
+    # ------------------------------------------------------------------------------------------------ results
+    def read_metrics(self) -> dict:
+        """Device -> host read of the step's metrics (one small sync; callers do it every print_freq, not every step)."""
+        cfg = self.cfg
+        m = self.metrics.cpu().tolist()
+        ng, nl = cfg.n_global, cfg.n_local
+        g_terms, l_terms = ng * (ng - 1), ng * nl
+        g_scale, l_scale = g_terms / (g_terms + l_terms), l_terms / (g_terms + l_terms)
+        loss = (cfg.dino_loss_weight * l_scale * m[0] + cfg.dino_loss_weight * g_scale * m[1]
+                + cfg.koleo_loss_weight * ng * m[2] + cfg.ibot_loss_weight * m[3])
+        out = {"dino_local_crops_loss": m[0], "dino_local_loss_weight": 1.0, "dino_global_crops_loss": m[1],
+               "koleo_loss": m[2], "ibot_loss": m[3], "local_batch_size": float(self.B), "total_loss": loss}
+        for name, st in self.params.mods.items():
+            out[f"student_{name}_grad_norm"] = math.sqrt(max(st.sumsq.item(), 0.0))
+        return out

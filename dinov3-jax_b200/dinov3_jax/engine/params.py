@@ -1,0 +1,199 @@
+"""Flat parameter / gradient / optimiser-state storage for the B200 engine.
+
+One `ModuleStore` per top-level module of the reference's parameter tree (`backbone`, `dino_head`, `ibot_head`;
+train/ssl_meta_arch.py:62-64,86-87,130-131), holding the student (fp32 master, bf16 compute copy, fp32 gradient, Adam
+m / v) and the teacher (fp32 EMA master, bf16 compute copy) as flat device buffers.  Tensors keep the reference's
+names and layouts (Dense kernels [in, out], conv kernel [p, p, 3, D]); matrices (GEMM operands)
+come first in the flat buffer, vectors (biases, LayerNorm affine, LayerScale gamma, cls / mask tokens) after, so that
+  * the bf16 compute copy covers exactly the leading matrix region,
+  * only the small vector region of the gradient buffer needs zeroing each step (vector grads accumulate atomically,
+    matrix grads are overwritten by the wgrad GEMMs),
+  * clip-norm, AdamW and EMA run as one launch per module (train/train.py:516-541 clips per top-level module).
+FSDP units (models/vision_transformer.py:93,137; train/ssl_meta_arch.py:77-78,122-123) are sub-ranges of these buffers.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import ops
+from .config import EngineConfig
+
+ALIGN = 64  # elements; keeps every tensor 128-byte (bf16) / 256-byte (fp32) aligned for TMA and float4 access
+
+SEG_DTYPE = np.dtype([("start", "<i8"), ("lr_mult", "<f4"), ("wd_mult", "<f4"), ("is_last", "<i4"), ("pad", "<i4")])
+
+
+def backbone_spec(cfg: EngineConfig):
+    """(name, shape, kind) in creation order — models/vision_transformer.py:86-171."""
+    D, p, Hd = cfg.embed_dim, cfg.patch, cfg.hidden
+    spec = [("patch_embed/proj/kernel", (p, p, 3, D), "mat"), ("patch_embed/proj/bias", (D,), "vec"),
+            ("cls_token", (1, 1, D), "vec"), ("mask_token", (1, D), "vec")]
+    for i in range(cfg.depth):
+        b = f"blocks_{i}/"
+        spec += [(b + "norm1/scale", (D,), "vec"), (b + "norm1/bias", (D,), "vec"),
+                 (b + "attn/qkv/kernel", (D, 3 * D), "mat"), (b + "attn/qkv/bias", (3 * D,), "vec"),
+                 (b + "attn/proj/kernel", (D, D), "mat"), (b + "attn/proj/bias", (D,), "vec"),
+                 (b + "ls1/gamma", (D,), "vec"),
+                 (b + "norm2/scale", (D,), "vec"), (b + "norm2/bias", (D,), "vec"),
+                 (b + "mlp/Dense_0/kernel", (D, Hd), "mat"), (b + "mlp/Dense_0/bias", (Hd,), "vec"),
+                 (b + "mlp/Dense_1/kernel", (Hd, D), "mat"), (b + "mlp/Dense_1/bias", (D,), "vec"),
+                 (b + "ls2/gamma", (D,), "vec")]
+    spec += [("norm/scale", (D,), "vec"), ("norm/bias", (D,), "vec")]
+    return spec
+
+
+def head_spec(cfg: EngineConfig):
+    """layers/dino_head.py:15-43,65-74."""
+    D, Hh, Bn, K = cfg.embed_dim, cfg.head_hidden, cfg.head_bottleneck, cfg.n_prototypes
+    return [("mlp/layers_0/kernel", (D, Hh), "mat"), ("mlp/layers_0/bias", (Hh,), "vec"),
+            ("mlp/layers_2/kernel", (Hh, Hh), "mat"), ("mlp/layers_2/bias", (Hh,), "vec"),
+            ("mlp/layers_4/kernel", (Hh, Bn), "mat"), ("mlp/layers_4/bias", (Bn,), "vec"),
+            ("last_layer/kernel", (Bn, K), "mat")]
+
+
+def lr_wd_multipliers(module: str, name: str, cfg: EngineConfig):
+    """Per-tensor (lr_mult, wd_mult, is_last_layer): train/param_groups.py:56-96 and :104-134."""
+    is_backbone = module == "backbone"
+    n_layers = cfg.depth if is_backbone else 0
+    layer_id = n_layers + 1
+    if is_backbone:
+        if any(t in name for t in ("pos_embed", "patch_embed", "mask_token", "cls_token", "storage_tokens")):
+            layer_id = 0
+        elif "blocks_" in name:
+            layer_id = int(name.split("blocks_")[1].split("/")[0]) + 1
+    lr_mult = cfg.layerwise_decay ** (n_layers + 1 - layer_id)
+    wd_mult = 1.0
+    if "dino_head" in name:
+        wd_mult = cfg.dino_head_wd_multiplier
+    is_last = "last_layer" in name
+    if name.endswith("bias") or "norm" in name or "gamma" in name:
+        wd_mult = 0.0
+    if "patch_embed" in name:
+        lr_mult *= cfg.patch_embed_lr_mult
+    return lr_mult, wd_mult, is_last
+
+
+def _round_up(x: int, a: int) -> int:
+    return (x + a - 1) // a * a
+
+
+class ModuleStore:
+    def __init__(self, module: str, spec, cfg: EngineConfig, device, trainable: bool = True):
+        self.module = module
+        self.spec = spec
+        self.cfg = cfg
+        self.offsets = {}
+        self.shapes = {}
+        self.kinds = {}
+        off = 0
+        for kind in ("mat", "vec"):
+            for name, shape, k in spec:
+                if k != kind:
+                    continue
+                self.offsets[name] = off
+                self.shapes[name] = tuple(shape)
+                self.kinds[name] = k
+                off += _round_up(int(np.prod(shape)), ALIGN)
+            if kind == "mat":
+                self.n_mat = off
+        self.n = off
+        f32, bf16 = torch.float32, torch.bfloat16
+        self.master = torch.zeros(self.n, dtype=f32, device=device)
+        self.bf16 = torch.zeros(self.n_mat, dtype=bf16, device=device)
+        self.t_master = torch.zeros(self.n, dtype=f32, device=device)
+        self.t_bf16 = torch.zeros(self.n_mat, dtype=bf16, device=device)
+        self.trainable = trainable
+        if trainable:
+            self.grad = torch.zeros(self.n, dtype=f32, device=device)
+            self.m = torch.zeros(self.n, dtype=f32, device=device)
+            self.v = torch.zeros(self.n, dtype=f32, device=device)
+            self.sumsq = torch.zeros(1, dtype=f32, device=device)
+        # optimiser segment table (sorted by start)
+        names = sorted(self.offsets, key=lambda k: self.offsets[k])
+        segs = np.zeros(len(names), dtype=SEG_DTYPE)
+        for i, nm in enumerate(names):
+            lr_m, wd_m, last = lr_wd_multipliers(module, nm, cfg)
+            segs[i] = (self.offsets[nm], lr_m, wd_m, int(last), 0)
+        self.seg_names = names
+        self.segs_host = segs
+        self.segs = torch.from_numpy(segs.view(np.uint8).copy()).to(device)
+
+    # ---- views -------------------------------------------------------------------------------------------------
+    def _view(self, flat, name, as2d=False):
+        o, shp = self.offsets[name], self.shapes[name]
+        n = int(np.prod(shp))
+        v = flat[o:o + n]
+        if as2d:
+            return v.view(-1, shp[-1])
+        return v.view(shp)
+
+    def w(self, name, teacher=False):
+        """bf16 compute copy of a matrix, as [in, out] (conv kernel flattened to [p*p*3, D])."""
+        return self._view(self.t_bf16 if teacher else self.bf16, name, as2d=True)
+
+    def vec(self, name, teacher=False):
+        """fp32 vector (flattened)."""
+        return self._view(self.t_master if teacher else self.master, name).reshape(-1)
+
+    def gw(self, name):
+        return self._view(self.grad, name, as2d=True)
+
+    def gv(self, name):
+        return self._view(self.grad, name).reshape(-1)
+
+    # ---- host <-> device ---------------------------------------------------------------------------------------
+    def load(self, tensors: dict, teacher: bool):
+        flat = self.t_master if teacher else self.master
+        for name in self.offsets:
+            t = tensors[name]
+            self._view(flat, name).copy_(t.to(device=flat.device, dtype=torch.float32).reshape(self.shapes[name]))
+        self.refresh_bf16(teacher)
+
+    def refresh_bf16(self, teacher: bool):
+        if self.n_mat:
+            ops.cast_f32_bf16((self.t_master if teacher else self.master)[: self.n_mat],
+                              self.t_bf16 if teacher else self.bf16)
+
+    def export(self, teacher: bool, what: str = "param") -> dict:
+        flat = {"param": self.t_master if teacher else self.master, "grad": getattr(self, "grad", None),
+                "m": getattr(self, "m", None), "v": getattr(self, "v", None)}[what]
+        return {name: self._view(flat, name).detach().clone() for name in self.offsets}
+
+    def zero_vector_grads(self):
+        self.grad[self.n_mat:].zero_()
+        self.sumsq.zero_()
+
+
+class ParamStore:
+    """Student + teacher parameters of the three top-level modules."""
+
+    MODULES = ("backbone", "dino_head", "ibot_head")
+
+    def __init__(self, cfg: EngineConfig, device):
+        self.cfg = cfg
+        self.mods = {
+            "backbone": ModuleStore("backbone", backbone_spec(cfg), cfg, device),
+            "dino_head": ModuleStore("dino_head", head_spec(cfg), cfg, device),
+            "ibot_head": ModuleStore("ibot_head", head_spec(cfg), cfg, device),
+        }
+
+    def load_reference_tree(self, params: dict):
+        """params: flat dict 'student_backbone/blocks_0/attn/qkv/kernel' -> tensor (reference names/layouts)."""
+        for m, st in self.mods.items():
+            for who, teacher in (("student", False), ("teacher", True)):
+                pre = f"{who}_{m}/"
+                st.load({k[len(pre):]: v for k, v in params.items() if k.startswith(pre)}, teacher)
+
+    def export_reference_tree(self, what: str = "param") -> dict:
+        out = {}
+        for m, st in self.mods.items():
+            for k, v in st.export(False, what).items():
+                out[f"student_{m}/{k}"] = v
+            if what == "param":
+                for k, v in st.export(True, what).items():
+                    out[f"teacher_{m}/{k}"] = v
+        return out
+
+    def n_params(self) -> int:
+        return sum(int(np.prod(s)) for st in self.mods.values() for s in st.shapes.values())
