@@ -1,0 +1,264 @@
+#!/usr/bin/env python
+"""bench.py — DINOv3 SSL training step on B200: global-crops/sec, ViT-L/16, 224^2, 2 global + 8 local crops, bf16.
+
+Contract (driver): `python bench.py --gpus N --steps K --warmup W` (torchrun launches N ranks for N > 1) prints ONE
+JSON line on rank 0.  `--impl reference` times the CPU restatement of the reference step (oracle/, "port") on the
+host cores instead (the reference's JAX stack is not installable here).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "dinov3-jax_b200"))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+ARCH_FLOPS = {}  # filled by block_flops()
+
+
+def f_img(D, L, Ng, Nl, n_local=8):
+    """Algorithmic attention+MLP FLOPs per image: teacher fwd on 2 global crops + 3x student."""
+    f_blk = lambda N: 24 * N * D * D + 4 * N * N * D
+    return L * (2 * f_blk(Ng) + 3 * (2 * f_blk(Ng) + n_local * f_blk(Nl)))
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured"
+    return 1590.0, 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for t, line in self.rows:
+            if t < t0 or t > t1 + 0.2:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def log(msg):
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
+def hyper(it):
+    # ssl_default_config.yaml:124-128,142-146 at iteration `it` of the default schedule (values only matter for parity)
+    return dict(teacher_temp=0.04, lr=1e-4, wd=0.04, last_layer_lr=0.0, momentum=0.996)
+
+
+def cpu_reference_rate(arch, threads, sample_B, steps=1, warmup=0):
+    """Times oracle.step.train_step (CPU restatement of the reference step) on `sample_B` images per step."""
+    from oracle import cfg_for
+    from oracle.batch import synthetic_batch
+    from oracle.model import init_params
+    from oracle.step import init_opt_state, train_step
+    torch.set_num_threads(threads)
+    cfg = cfg_for(arch)
+    P = init_params(cfg, 0)
+    st = init_opt_state(P)
+    batch = synthetic_batch(cfg, sample_B, 0)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.time()
+        P, st, loss, m, _ = train_step(P, st, batch, cfg, **hyper(i))
+        times.append(time.time() - t0)
+    dt = sum(times[warmup:]) / steps
+    return 2 * sample_B / dt, dt, float(loss)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--arch", default="vit_large")
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU (ssl_default_config.yaml:75)")
+    ap.add_argument("--prototypes", type=int, default=65536)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-batch", type=int, default=2)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = os.cpu_count() or 1
+
+    from dinov3_jax.engine.config import ARCHS
+    D, L, H = ARCHS[args.arch]
+    Ng, Nl = (224 // 16) ** 2 + 1, (96 // 16) ** 2 + 1
+    flops_per_gcrop = f_img(D, L, Ng, Nl) / 2
+    cfg_desc = {"workload": f"{args.arch}/16 student+teacher, 2x224^2 + 8x96^2 crops, {args.batch} img/GPU, "
+                            f"K={args.prototypes} prototypes, DINO+iBOT+KoLeo, clip+AdamW+EMA (BASELINE configs[3] per-GPU shape)",
+                "global_batch": args.batch * world, "parallelism": f"fsdp{world}" if world > 1 else "single",
+                "l2": "inputs+activations per step >> 126 MB L2 (no flush needed)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        w = max(args.warmup, 0)
+        val, dt, _ = cpu_reference_rate(args.arch, cores, args.cpu_sample_batch, steps=max(args.steps, 1), warmup=min(w, 1))
+        print(json.dumps({
+            "impl": "reference", "metric": "global_crops_per_sec", "value": val, "unit": "global-crops/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": cfg_desc,
+            "cpu_baseline": {"value": val, "unit": "global-crops/s", "cores": cores, "kind": "port",
+                             "sample": f"torch-CPU fp32 restatement of the reference train_step (oracle/), {args.arch}, "
+                                       f"{args.cpu_sample_batch} images/step; JAX stack not installable offline"},
+            "e2e": {"value": val, "unit": "global-crops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 engine has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    comm = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        from dinov3_jax.fsdp.runtime import Comm
+        comm = Comm(dist.group.WORLD)
+    from dinov3_jax import _native, ops
+    from dinov3_jax.engine import Engine, config_for
+    from dinov3_jax.engine.synth import synthetic_batch, init_reference_like
+    _native.init(local_rank)
+    cfg = config_for(args.arch, n_prototypes=args.prototypes)
+    B = args.batch
+    log(f"building synthetic batch B={B}")
+    batch = synthetic_batch(cfg, B, seed=rank, pin=True)
+    M = int(batch["mask_indices_list"].shape[0])
+    eng = Engine(cfg, B, device=f"cuda:{local_rank}", max_masked=M, comm=comm)
+    log(f"engine allocated ({torch.cuda.memory_allocated() / 2**30:.1f} GiB); initialising {eng.params.n_params() / 1e6:.1f} M student params")
+    init_reference_like(eng, seed=0)
+    log("params loaded")
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def step_device(i):
+        eng.train_step(None, **hyper(i))
+
+    def step_e2e(i):
+        eng.train_step(batch, **hyper(i))     # pinned host -> device copies inside
+        return eng.read_metrics()["total_loss"]  # device -> host read of the loss
+
+    # ---- warm-up (device-resident inputs)
+    eng.set_batch(batch)
+    for i in range(max(args.warmup, 3)):
+        tw = time.time()
+        step_device(i)
+        torch.cuda.synchronize()
+        log(f"warm-up step {i}: {time.time() - tw:.3f} s")
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    _native.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    for i in range(args.steps):
+        step_device(i)
+    e1.record()
+    barrier()
+    t1 = time.time()
+    launches = _native.launch_count()
+    ms = e0.elapsed_time(e1) / args.steps
+    log(f"timed region: {ms:.2f} ms/step")
+    clocks = sampler.stop(t0, t1) if sampler else None
+    # ---- end-to-end: host buffers, H2D inside, loss read back every step
+    for i in range(2):
+        step_e2e(i)
+    barrier()
+    e0.record()
+    loss = 0.0
+    for i in range(args.steps):
+        loss = step_e2e(i)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1) / args.steps
+    log(f"e2e: {ms_e2e:.2f} ms/step")
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device="cuda")
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms, ms_e2e = t.tolist()
+    h2d = sum(batch[k].numel() * batch[k].element_size() for k in ("collated_global_crops", "collated_local_crops", "collated_masks", "mask_indices_list"))
+    # ---- roofline leg: one instrumented step, CUDA events around every tensor-core GEMM launch
+    ops.PROFILE = []
+    step_device(0)
+    torch.cuda.synchronize()
+    prof, ops.PROFILE = ops.PROFILE, None
+    g_flops = sum(p[1] for p in prof)
+    g_ms = sum(p[2].elapsed_time(p[3]) for p in prof)
+    burst, sustained, hbm, how = peaks()
+    gemm_tf = g_flops / (g_ms * 1e-3) / 1e12 if g_ms else 0.0
+    value = 2 * B * world / (ms * 1e-3)
+    e2e_value = 2 * B * world / (ms_e2e * 1e-3)
+    step_tf = value * flops_per_gcrop / world / 1e12
+    out = {
+        "metric": "global_crops_per_sec", "value": value, "unit": "global-crops/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic", "config": cfg_desc, "clocks": clocks, "gpu_launches": int(launches),
+        "e2e": {"value": e2e_value, "unit": "global-crops/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 32,
+                "ms_per_step": ms_e2e, "loss": loss},
+        "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tc_kernel (all tcgen05 GEMM launches of one step)",
+                     "achieved": gemm_tf, "peak": sustained, "unit": "TFLOP/s", "frac": gemm_tf / sustained,
+                     "traffic": None, "peak_source": f"bf16_tflops_sustained ({how})", "launches": len(prof),
+                     "share_of_step": g_ms / ms if ms else None},
+        "step_roofline": {"achieved": step_tf, "peak": sustained, "unit": "TFLOP/s", "frac": step_tf / sustained,
+                          "note": "attention+MLP algorithmic FLOPs (BASELINE.md §3) / step time / GPU"},
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            log("cpu baseline (oracle port) ...")
+            v, dt, _ = cpu_reference_rate(args.arch, cores, args.cpu_sample_batch)
+            log(f"cpu baseline: {dt:.1f} s/step")
+            out["cpu_baseline"] = {"value": v, "unit": "global-crops/s", "cores": cores, "kind": "port",
+                                   "sample": f"oracle train_step (torch-CPU fp32 restatement), {args.arch}, "
+                                             f"{args.cpu_sample_batch} images, 1 step of {dt:.1f} s"}
+        print(json.dumps(out))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -14,6 +14,9 @@ from . import _native as N
 bf16 = torch.bfloat16
 f32 = torch.float32
 
+# optional per-launch timing hook (bench.py roofline leg): a list that receives (kind, flops, start_evt, end_evt)
+PROFILE: list | None = None
+
 
 def _ld(t: torch.Tensor) -> int:
     assert t.dim() == 2 and t.stride(1) == 1, "expect 2-D row-major (unit inner stride)"
@@ -61,8 +64,14 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, a_mn: bool = Fa
         flags |= N.EP_ACCUM
     ep.flags = flags
     ep.alpha = float(alpha)
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     N.check(l.d3_gemm_bf16(N.ptr(A), _ld(A), int(a_mn), N.ptr(B), _ld(B), int(b_mn), M, Nn, K, C.byref(ep),
                            int(tile_n), N.stream_ptr()), "d3_gemm_bf16")
+    if PROFILE is not None:
+        e1.record()
+        PROFILE.append(("gemm", 2.0 * M * Nn * K, e0, e1, (M, Nn, K, int(a_mn), int(b_mn))))
     return out
 
 

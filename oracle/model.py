@@ -244,7 +244,8 @@ def backbone_forward(P: dict, x_list, masks_list, cfg: ModelCfg, emu: Emu = Emu(
             cls = P["cls_token"] + 0 * P["mask_token"]
         t = torch.cat([cls.expand(t.shape[0], -1, -1), t], dim=1)   # :197-201 (no storage tokens by default)
         toks.append(t)
-        ropes.append(rope_sincos(Hp, Wp, cfg.head_dim, cfg.rope_base, t.dtype))
+        sc = rope_sincos(Hp, Wp, cfg.head_dim, cfg.rope_base, t.dtype)
+        ropes.append((sc[0].to(t.device), sc[1].to(t.device)))
     for i in range(cfg.depth):
         toks = [block_forward(P, f"blocks_{i}/", t, s, c, cfg, emu) for t, (s, c) in zip(toks, ropes)]
     outs = []
