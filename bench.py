@@ -92,6 +92,7 @@ def cpu_reference_rate(arch, threads, sample_B, steps=1, warmup=0):
     from oracle.batch import synthetic_batch
     from oracle.model import init_params
     from oracle.step import init_opt_state, train_step
+    threads = max(1, min(threads, 32))   # beyond ~32 threads the fp32 restatement stops scaling (many small ops)
     torch.set_num_threads(threads)
     cfg = cfg_for(arch)
     P = init_params(cfg, 0)
@@ -103,7 +104,7 @@ def cpu_reference_rate(arch, threads, sample_B, steps=1, warmup=0):
         P, st, loss, m, _ = train_step(P, st, batch, cfg, **hyper(i))
         times.append(time.time() - t0)
     dt = sum(times[warmup:]) / steps
-    return 2 * sample_B / dt, dt, float(loss)
+    return 2 * sample_B / dt, dt, float(loss), threads
 
 
 def main():
@@ -116,7 +117,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="images per GPU (ssl_default_config.yaml:75)")
     ap.add_argument("--prototypes", type=int, default=65536)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-batch", type=int, default=2)
+    ap.add_argument("--cpu-sample-batch", type=int, default=1)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -136,7 +137,8 @@ def main():
         if rank != 0:
             return
         w = max(args.warmup, 0)
-        val, dt, _ = cpu_reference_rate(args.arch, cores, args.cpu_sample_batch, steps=max(args.steps, 1), warmup=min(w, 1))
+        val, dt, _, used = cpu_reference_rate(args.arch, cores, args.cpu_sample_batch, steps=max(min(args.steps, 3), 1), warmup=min(w, 1))
+        cores = used
         print(json.dumps({
             "impl": "reference", "metric": "global_crops_per_sec", "value": val, "unit": "global-crops/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
@@ -250,7 +252,7 @@ def main():
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             log("cpu baseline (oracle port) ...")
-            v, dt, _ = cpu_reference_rate(args.arch, cores, args.cpu_sample_batch)
+            v, dt, _, cores = cpu_reference_rate(args.arch, cores, args.cpu_sample_batch)
             log(f"cpu baseline: {dt:.1f} s/step")
             out["cpu_baseline"] = {"value": v, "unit": "global-crops/s", "cores": cores, "kind": "port",
                                    "sample": f"oracle train_step (torch-CPU fp32 restatement), {args.arch}, "

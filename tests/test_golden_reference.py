@@ -1,0 +1,103 @@
+"""Pins the oracle (and the product's host-side mirrors) against golden vectors produced by EXECUTING reference files
+(tests/golden/make_golden.py): masks / collate / schedules directly, losses / RoPE / param groups under the numpy
+stand-in for jax+flax.  Nothing here reads /root/reference."""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+G = np.load(os.path.join(GOLDEN, "reference_vectors.npz"))
+T = lambda a: torch.from_numpy(np.asarray(a))
+
+
+@pytest.mark.parametrize("impl", ["oracle", "product"])
+@pytest.mark.parametrize("tag,n,grid,size", [("b8", 16, 14, 224), ("tiny", 8, 4, 64)])
+def test_masks_bit_exact(impl, tag, n, grid, size):
+    if impl == "oracle":
+        from oracle.batch import MaskGen as Gen, collate_masks
+    else:
+        from dinov3_jax.data.masking import MaskingGenerator as Gen
+        from dinov3_jax.data.collate import collate_masks
+    random.seed(7); np.random.seed(7)
+    gen = Gen(input_size=(grid, grid), max_num_patches=0.5 * size // 16 * size // 16)
+    d = collate_masks(n, grid * grid, (0.1, 0.5), 0.5, gen)
+    assert np.array_equal(d["collated_masks"].numpy(), G[f"masks_{tag}"])
+    assert np.array_equal(d["mask_indices_list"].numpy(), G[f"mask_indices_{tag}"])
+    assert np.array_equal(d["masks_weight"].numpy(), G[f"masks_weight_{tag}"])
+    assert d["upperbound"] == int(G[f"upperbound_{tag}"])
+    assert int(d["n_masked_patches"]) == len(G[f"mask_indices_{tag}"])
+
+
+@pytest.mark.parametrize("impl", ["oracle", "product"])
+def test_schedules_bit_exact(impl):
+    if impl == "oracle":
+        from oracle.step import cosine_schedule
+    else:
+        from dinov3_jax.train.cosine_lr_scheduler import CosineScheduler
+        cosine_schedule = lambda *a, **k: CosineScheduler(*a, **k).gen()
+    assert np.array_equal(cosine_schedule(1e-3, 1e-6, 500, warmup_iters=50, start_warmup_value=0), G["sched_lr"])
+    assert np.array_equal(cosine_schedule(0.04, 0.4, 500), G["sched_wd"])
+    assert np.array_equal(cosine_schedule(0.07, 0.07, 120, warmup_iters=120, start_warmup_value=0.04), G["sched_temp"])
+    assert np.array_equal(cosine_schedule(1.0, 0.0, 60, warmup_iters=10, freeze_iters=5), G["sched_freeze"])
+
+
+def test_sinkhorn_and_dino_loss_match_reference_code():
+    from oracle.losses import dino_loss, sinkhorn_knopp
+    B, K = 5, 48
+    Q = sinkhorn_knopp(T(G["dino_t_logits"]), 0.05, B_total=2 * B)
+    assert torch.allclose(Q, T(G["dino_probs"]), rtol=1e-10, atol=1e-14)
+    Qr = T(G["dino_probs"]).reshape(2, B, K)
+    assert abs(dino_loss(T(G["dino_s_local"]), Qr, 0.1, False).item() - float(G["dino_loss_local"])) < 1e-12
+    assert abs(dino_loss(T(G["dino_s_global"]), Qr, 0.1, True).item() - float(G["dino_loss_global"])) < 1e-12
+
+
+def test_ibot_matches_reference_code():
+    from oracle.losses import ibot_loss_masked, sinkhorn_knopp
+    M = G["ibot_t_logits"].shape[0]
+    Q = sinkhorn_knopp(T(G["ibot_t_logits"]), 0.05, B_total=float(M))
+    assert torch.allclose(Q, T(G["ibot_probs"]), rtol=1e-10, atol=1e-14)
+    assert abs(ibot_loss_masked(T(G["ibot_s"]), T(G["ibot_probs"]), 0.1, n_mask_rows=10).item() - float(G["ibot_loss"])) < 1e-12
+
+
+def test_koleo_matches_reference_code():
+    from oracle.losses import koleo_loss
+    assert abs(koleo_loss(T(G["koleo_x"])).item() - float(G["koleo_loss"])) < 1e-12
+
+
+@pytest.mark.parametrize("H,W", [(14, 14), (6, 6), (3, 5)])
+def test_rope_tables_match_reference_code(H, W):
+    from oracle.model import rope_sincos
+    sin, cos = rope_sincos(H, W, 64, 100.0, torch.float64)
+    assert torch.allclose(sin, T(G[f"rope_sin_{H}x{W}"]), atol=1e-13) and torch.allclose(cos, T(G[f"rope_cos_{H}x{W}"]), atol=1e-13)
+    from dinov3_jax.engine.core import rope_tables      # the product's table builder (host side, fp32 output)
+    if H == W:
+        s32, c32 = rope_tables(H, W, 64, 100.0, "cpu")
+        assert torch.allclose(s32.double(), T(G[f"rope_sin_{H}x{W}"]), atol=1e-6)
+        assert torch.allclose(c32.double(), T(G[f"rope_cos_{H}x{W}"]), atol=1e-6)
+
+
+def test_rope_apply_matches_reference_code():
+    from oracle.model import rope_apply, rope_sincos
+    sin, cos = rope_sincos(3, 3, 64, 100.0, torch.float64)
+    assert torch.allclose(rope_apply(T(G["rope_x"]), sin, cos), T(G["rope_y"]), atol=1e-13)
+
+
+@pytest.mark.parametrize("impl", ["oracle", "product"])
+def test_param_group_multipliers_match_reference_code(impl):
+    names = [str(n) for n in G["pg_names"]]
+    vals = G["pg_values"]
+    if impl == "oracle":
+        from oracle.step import param_multipliers
+        got = param_multipliers(names, depth=4)
+        rows = [got[n] for n in names]
+    else:
+        from dinov3_jax.engine.config import EngineConfig
+        from dinov3_jax.engine.params import lr_wd_multipliers
+        cfg = EngineConfig(depth=4)
+        rows = [lr_wd_multipliers(n.split("/", 1)[0][len("student_"):], n.split("/", 1)[1], cfg) for n in names]
+    for n, (lr, wd, last), want in zip(names, rows, vals):
+        assert abs(lr - want[0]) < 1e-12 and wd == want[1] and float(last) == want[2], n

@@ -1,0 +1,283 @@
+"""-m gpu: every CUDA kernel behind the C ABI against plain PyTorch fp32 on the same inputs (tolerances are the
+bf16 storage rounding of the kernel's output; integer / indexing work is checked bit-exactly)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+BF16_TOL = 6e-3      # norm-wise relative error of a bf16-stored result (2^-9 per element)
+
+
+def rel(a, b):
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-30)).item()
+
+
+@pytest.fixture(autouse=True)
+def _seed(native):
+    torch.manual_seed(0)
+
+
+# --------------------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("shape", [(128, 64, 64), (384, 320, 192), (296, 200, 136), (1000, 1152, 384), (4096, 1024, 1024)])
+@pytest.mark.parametrize("bn", [0, 64, 128, 256])
+def test_gemm_matches_fp32_matmul(a_mn, b_mn, shape, bn):
+    from dinov3_jax import ops
+    M, N, K = shape
+    A = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+    B = torch.randn(K, N, device="cuda").to(torch.bfloat16)
+    ref = A.float() @ B.float()
+    out = torch.full((M, N), float("nan"), device="cuda")
+    ops.gemm(A.t().contiguous() if a_mn else A, B if b_mn else B.t().contiguous(), out, a_mn=bool(a_mn), b_mn=bool(b_mn), tile_n=bn)
+    assert rel(out, ref) < 1e-5      # fp32 accumulation of exact bf16 products
+
+
+def test_gemm_epilogues():
+    from dinov3_jax import ops
+    M, N, K = 500, 384, 256
+    A = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+    B = (torch.randn(K, N, device="cuda") * 0.1).to(torch.bfloat16)
+    bias, gamma, resid = torch.randn(N, device="cuda"), torch.randn(N, device="cuda"), torch.randn(M, N, device="cuda")
+    acc = A.float() @ B.float()
+    u = acc + bias
+    out = torch.empty(M, N, device="cuda"); pre = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(A, B, out, b_mn=True, bias=bias, gelu=True, store_pre=pre, gamma=gamma, resid=resid)
+    assert rel(out, resid + gamma * torch.nn.functional.gelu(u, approximate="tanh")) < 1e-5
+    assert rel(pre, u) < BF16_TOL
+    ub = torch.randn(M, N, device="cuda").to(torch.bfloat16)
+    uf = ub.float().requires_grad_(True)
+    torch.nn.functional.gelu(uf, approximate="tanh").sum().backward()
+    out2 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(A, B, out2, b_mn=True, dgelu_of=ub)
+    assert rel(out2, acc * uf.grad) < BF16_TOL
+    out3 = torch.ones(M, N, device="cuda")
+    ops.gemm(A, B, out3, b_mn=True, accum=True, alpha=0.5)
+    assert rel(out3, 1 + 0.5 * acc) < 1e-5
+
+
+def test_gemm_rejects_bad_arguments():
+    from dinov3_jax import ops, _native
+    A = torch.randn(64, 60, device="cuda").to(torch.bfloat16)     # ld = 60 is not a multiple of 8
+    B = torch.randn(64, 60, device="cuda").to(torch.bfloat16)
+    with pytest.raises(_native.NativeError):
+        ops.gemm(A, B, torch.empty(64, 64, device="cuda"))
+
+
+# --------------------------------------------------------------------------------------------------- attention
+def attn_ref(qkv, n, N, D, H):
+    q, k, v = qkv.float().reshape(n, N, 3, H, 64).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-1, -2)) * 0.125
+    o = (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(n * N, D)
+    return o, torch.logsumexp(s, -1)
+
+
+@pytest.mark.parametrize("n,N,H", [(3, 197, 2), (5, 37, 2), (2, 128, 1), (2, 257, 1), (4, 50, 3), (1, 1, 1), (2, 17, 6)])
+def test_attention_forward(n, N, H):
+    from dinov3_jax import ops
+    D = 64 * H
+    qkv = torch.randn(n * N, 3 * D, device="cuda").to(torch.bfloat16)
+    o = torch.full((n * N, D), float("nan"), device="cuda", dtype=torch.bfloat16)
+    lse = torch.zeros(n, H, N, device="cuda")
+    ops.attn_fwd(qkv, o, lse, n, N, D, H)
+    ro, rl = attn_ref(qkv, n, N, D, H)
+    assert rel(o, ro) < BF16_TOL and rel(lse, rl) < 1e-5
+
+
+@pytest.mark.parametrize("n,N,H", [(2, 128, 1), (3, 197, 2), (5, 37, 2), (4, 50, 3), (2, 256, 1), (2, 17, 6)])
+def test_attention_backward(n, N, H):
+    from dinov3_jax import ops
+    D = 64 * H
+    qkv = torch.randn(n * N, 3 * D, device="cuda").to(torch.bfloat16)
+    do = torch.randn(n * N, D, device="cuda").to(torch.bfloat16)
+    x = qkv.float().requires_grad_(True)
+    attn_ref(x, n, N, D, H)[0].backward(do.float())
+    o = torch.empty(n * N, D, device="cuda", dtype=torch.bfloat16); lse = torch.zeros(n, H, N, device="cuda")
+    ops.attn_fwd(qkv, o, lse, n, N, D, H)
+    dqkv = torch.full((n * N, 3 * D), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.attn_bwd(qkv, o, do, lse, torch.zeros(n, H, N, device="cuda"), dqkv, n, N, D, H)
+    for j in range(3):
+        assert rel(dqkv[:, j * D:(j + 1) * D], x.grad[:, j * D:(j + 1) * D]) < 1e-2
+
+
+# --------------------------------------------------------------------------------------------------- integer / layout work
+def test_im2col_and_tokens_bit_exact():
+    from dinov3_jax import ops
+    n, Hh, p, D = 3, 64, 16, 128
+    img = torch.randn(n, Hh, Hh, 3, device="cuda").to(torch.bfloat16)
+    P = (Hh // p) ** 2
+    out = torch.empty(n * P, p * p * 3, device="cuda", dtype=torch.bfloat16)
+    ops.im2col(img, out, p)
+    ref = img.reshape(n, Hh // p, p, Hh // p, p, 3).permute(0, 1, 3, 2, 4, 5).reshape(out.shape)
+    assert torch.equal(out, ref)
+    tok, cls, mt = torch.randn(n * P, D, device="cuda"), torch.randn(D, device="cuda"), torch.randn(D, device="cuda")
+    masks = torch.rand(n, P, device="cuda") < 0.3
+    X = torch.empty(n, P + 1, D, device="cuda")
+    ops.assemble_tokens(tok, cls, mt, masks.to(torch.uint8), X, n, P, D)
+    assert torch.equal(X, torch.cat([cls.expand(n, 1, D), torch.where(masks[..., None], mt, tok.reshape(n, P, D))], 1))
+    X2 = torch.empty(n, P + 1, D, device="cuda")
+    ops.assemble_tokens(tok, cls, mt, None, X2, n, P, D)
+    assert torch.equal(X2[:, 1:], tok.reshape(n, P, D))
+    dX = torch.randn(n, P + 1, D, device="cuda"); dTok = torch.empty(n * P, D, device="cuda", dtype=torch.bfloat16)
+    dcls, dm = torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda")
+    ops.assemble_tokens_bwd(dX, masks.to(torch.uint8), dTok, dcls, dm, n, P, D)
+    assert torch.equal(dTok, torch.where(masks[..., None], torch.zeros_like(dX[:, 1:]), dX[:, 1:]).reshape(n * P, D).to(torch.bfloat16))
+    assert rel(dcls, dX[:, 0].sum(0)) < 1e-5 and rel(dm, (dX[:, 1:] * masks[..., None]).sum((0, 1))) < 1e-5
+
+
+def test_token_rows_gather_scatter_bit_exact():
+    from dinov3_jax import ops
+    P, n, D = 16, 4, 128
+    src = torch.randn(n * (P + 1), D, device="cuda")
+    midx = torch.tensor([0, 3, 17, 18, 40, 63], device="cuda", dtype=torch.int64)
+    rows = torch.empty(6, dtype=torch.int32, device="cuda")
+    ops.token_rows(midx, rows, 6, P, 0)
+    want = (midx // P * (P + 1) + 1 + midx % P)
+    assert torch.equal(rows.long(), want)
+    crow = torch.empty(n, dtype=torch.int32, device="cuda")
+    ops.token_rows(None, crow, n, P, 1)
+    assert torch.equal(crow.long(), torch.arange(n, device="cuda") * (P + 1))
+    gb, gf = torch.empty(6, D, device="cuda", dtype=torch.bfloat16), torch.empty(6, D, device="cuda")
+    ops.gather_rows(src, rows, 6, D, gb, gf)
+    assert torch.equal(gf, src[want]) and torch.equal(gb, src[want].to(torch.bfloat16))
+    dst = torch.zeros_like(src)
+    ops.scatter_add_rows(gf, rows, dst, 6, D)
+    ref = torch.zeros_like(src); ref[want] += gf
+    assert torch.equal(dst, ref)
+    ops.gather_rows(src, rows, 0, D, gb, gf)      # empty gather is a no-op
+
+
+# --------------------------------------------------------------------------------------------------- normalisation / rope
+@pytest.mark.parametrize("T,D", [(1000, 384), (333, 1024), (7, 128)])
+def test_layernorm_forward_backward(T, D):
+    from dinov3_jax import ops
+    from oracle.model import layer_norm
+    x = torch.randn(T, D, device="cuda") * 2 + 0.5
+    sc, bi = torch.randn(D, device="cuda"), torch.randn(D, device="cuda")
+    y, yf = torch.empty(T, D, device="cuda", dtype=torch.bfloat16), torch.empty(T, D, device="cuda")
+    mean, rstd = torch.empty(T, device="cuda"), torch.empty(T, device="cuda")
+    ops.layernorm_fwd(x, sc, bi, y, mean, rstd); ops.layernorm_fwd(x, sc, bi, yf)
+    xr, scr, bir = x.clone().requires_grad_(True), sc.clone().requires_grad_(True), bi.clone().requires_grad_(True)
+    ref = layer_norm(xr, scr, bir, 1e-6)
+    assert rel(y, ref) < BF16_TOL and rel(yf, ref) < 1e-5
+    dy, add = torch.randn(T, D, device="cuda"), torch.randn(T, D, device="cuda")
+    ref.backward(dy)
+    dx, ds, db = torch.empty(T, D, device="cuda"), torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda")
+    ops.layernorm_bwd(dy, x, mean, rstd, sc, dx, dx_add=add, dscale=ds, dbias=db)
+    assert rel(dx, xr.grad + add) < 1e-4 and rel(ds, scr.grad) < 1e-4 and rel(db, bir.grad) < 1e-4
+
+
+def test_rope_forward_and_adjoint():
+    from dinov3_jax import ops
+    from oracle.model import rope_apply, rope_sincos
+    n, Hp, H = 3, 6, 2
+    N, D = Hp * Hp + 1, 64 * H
+    sin, cos = [t.cuda().contiguous() for t in rope_sincos(Hp, Hp, 64, 100.0, torch.float32)]
+    qkv = torch.randn(n * N, 3 * D, device="cuda").to(torch.bfloat16)
+    ref = qkv.float().reshape(n, N, 3, H, 64).clone()
+    for w in (0, 1):
+        ref[:, 1:, w] = rope_apply(ref[:, 1:, w].transpose(1, 2), sin, cos).transpose(1, 2)
+    q2 = qkv.clone()
+    ops.rope(q2, sin, cos, N, 1, D, 64)
+    assert rel(q2, ref.reshape(n * N, 3 * D)) < BF16_TOL
+    assert torch.equal(q2.reshape(n, N, 3 * D)[:, 0], qkv.reshape(n, N, 3 * D)[:, 0])       # cls token untouched
+    assert torch.equal(q2[:, 2 * D:], qkv[:, 2 * D:])                                     # v untouched
+    g = torch.randn(n * N, 3 * D, device="cuda").to(torch.bfloat16); gi = g.clone()
+    ops.rope(gi, sin, cos, N, 1, D, 64, inverse=True)
+    lhs, rhs = (ref.reshape(n * N, 3 * D) * g.float()).sum().item(), (qkv.float() * gi.float()).sum().item()
+    assert abs(lhs - rhs) < 2e-2 * abs(lhs) + 0.5
+
+
+def test_l2norm_and_layerscale_backward():
+    from dinov3_jax import ops
+    R, C = 300, 256
+    u = torch.randn(R, C, device="cuda"); y = torch.empty(R, C, device="cuda", dtype=torch.bfloat16); nr = torch.empty(R, device="cuda")
+    ops.l2norm_fwd(u, y, nr)
+    ur = u.clone().requires_grad_(True); yr = ur / (ur.norm(dim=-1, keepdim=True) + 1e-12)
+    assert rel(y, yr) < BF16_TOL
+    g = torch.randn(R, C, device="cuda").to(torch.bfloat16); yr.backward(g.float())
+    du = torch.empty(R, C, device="cuda", dtype=torch.bfloat16); ops.l2norm_bwd(g, u, nr, du)
+    assert rel(du, ur.grad) < BF16_TOL
+    T, D = 777, 384
+    dX = torch.randn(T, D, device="cuda"); ub = torch.randn(T, D, device="cuda").to(torch.bfloat16); gam = torch.randn(D, device="cuda")
+    for use_gelu in (True, False):
+        uu, gg = ub.float().requires_grad_(True), gam.clone().requires_grad_(True)
+        act = torch.nn.functional.gelu(uu, approximate="tanh") if use_gelu else uu
+        (gg * act * dX).sum().backward()
+        du = torch.empty(T, D, device="cuda", dtype=torch.bfloat16); dg, db = torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda")
+        ops.ls_act_bwd(dX, ub, gam, du, dg, db, use_gelu)
+        assert rel(du, uu.grad) < BF16_TOL and rel(dg, gg.grad) < 1e-4 and rel(db, uu.grad.sum(0)) < 1e-4
+    xb = torch.randn(1001, 1152, device="cuda").to(torch.bfloat16); cs = torch.zeros(1152, device="cuda")
+    ops.colsum_bf16(xb, cs)
+    assert rel(cs, xb.float().sum(0)) < 1e-5
+
+
+# --------------------------------------------------------------------------------------------------- losses
+def test_sinkhorn_ce_koleo_match_oracle():
+    from dinov3_jax import ops
+    from oracle.losses import dino_loss, ibot_loss_masked, koleo_loss, sinkhorn_knopp
+    R, K, temp = 24, 4096, 0.05
+    L = torch.randn(R, K, device="cuda") * 0.3
+    mx = torch.full((1,), float("-inf"), device="cuda"); ops.absmax(L, mx)
+    assert mx.item() == L.max().item()
+    btot = torch.tensor([float(R)], device="cuda")
+    a, s, av = None, torch.zeros(K, device="cuda"), torch.empty(R, device="cuda")
+    for _ in range(3):
+        s.zero_(); ops.sinkhorn_colsum(L, mx, temp, a, s); ops.sinkhorn_rowsum(L, mx, temp, s, btot, av); a = av
+    Q = torch.empty(R, K, device="cuda"); ops.sinkhorn_probs(L, mx, temp, s, a, btot, Q)
+    Qr = sinkhorn_knopp(L.double(), temp, R)
+    assert rel(Q, Qr) < 1e-4
+    B = R // 2
+    S = torch.randn(10 * B, K, device="cuda") * 0.5
+    Sr = S.double().requires_grad_(True)
+    Ll = dino_loss(Sr[2 * B:].reshape(8, B, K), Qr.reshape(2, B, K), 0.1, False)
+    Lg = dino_loss(Sr[:2 * B].reshape(2, B, K), Qr.reshape(2, B, K), 0.1, True)
+    (16 / 18 * Ll + 2 / 18 * Lg).backward()
+    t0 = torch.empty(10 * B, dtype=torch.int32); t1 = torch.full((10 * B,), -1, dtype=torch.int32)
+    wm, wg, slot = torch.empty(10 * B), torch.empty(10 * B), torch.empty(10 * B, dtype=torch.int32)
+    for i in range(10 * B):
+        sidx, b = divmod(i, B)
+        if sidx < 2:
+            t0[i] = (1 - sidx) * B + b; wm[i] = 1 / (2 * B); wg[i] = 2 / 18 / (2 * B); slot[i] = 1
+        else:
+            t0[i] = b; t1[i] = B + b; wm[i] = 1 / (16 * B); wg[i] = 16 / 18 / (16 * B); slot[i] = 0
+    metric = torch.zeros(4, device="cuda"); dS = torch.empty(10 * B, K, device="cuda", dtype=torch.bfloat16)
+    ops.ce_fwd_bwd(S, 0.1, L, mx, temp, s, a, btot, t0.cuda(), t1.cuda(), wm.cuda(), wg.cuda(), slot.cuda(), metric, dS)
+    assert abs(metric[0].item() - Ll.item()) < 1e-4 * abs(Ll.item()) and abs(metric[1].item() - Lg.item()) < 1e-4 * abs(Lg.item())
+    assert rel(dS, Sr.grad) < BF16_TOL
+    Bk, D = 64, 384
+    x = torch.randn(Bk, D, device="cuda")
+    xr = x.double().requires_grad_(True); lk = koleo_loss(xr); (0.1 * lk).backward()
+    xn, nr = torch.empty(Bk, D, device="cuda"), torch.empty(Bk, device="cuda")
+    nn, cf = torch.empty(Bk, dtype=torch.int32, device="cuda"), torch.empty(Bk, device="cuda")
+    met, dx = torch.zeros(1, device="cuda"), torch.zeros(Bk, D, device="cuda")
+    ops.koleo_fwd_bwd(x, xn, nr, nn, cf, met, dx, 1.0, 0.1)
+    assert abs(met.item() - lk.item()) < 1e-5 and rel(dx, xr.grad) < 1e-4
+
+
+def test_adamw_ema_clip_matches_optax_formula():
+    from dinov3_jax import ops
+    n = 4096 * 3 + 64
+    p, g = torch.randn(n, device="cuda"), torch.randn(n, device="cuda") * 0.01
+    m, v, t = torch.randn(n, device="cuda") * 1e-3, torch.rand(n, device="cuda") * 1e-4, torch.randn(n, device="cuda")
+    ss = torch.zeros(1, device="cuda"); ops.sumsq(g, ss)
+    assert rel(ss, (g.double() ** 2).sum().reshape(1)) < 1e-5
+    segs_np = np.zeros(3, dtype=[("start", "<i8"), ("lr", "<f4"), ("wd", "<f4"), ("last", "<i4"), ("pad", "<i4")])
+    segs_np["start"] = [0, 4096, 8256]; segs_np["lr"] = [1.0, 0.5, 0.2]; segs_np["wd"] = [1.0, 0.0, 1.0]; segs_np["last"] = [0, 0, 1]
+    segs = torch.from_numpy(segs_np.view(np.uint8)).cuda()
+    lr, llr, wd, mom, step, maxn = 1e-3, 5e-4, 0.04, 0.99, 3, 0.5
+    P0, M0, V0, T0 = p.double(), m.double(), v.double(), t.double()
+    G = g.double() * min(1.0, maxn / (math.sqrt(ss.item()) + 1e-6))
+    idx = torch.arange(n, device="cuda")
+    lrm = torch.where(idx < 4096, 1.0, torch.where(idx < 8256, 0.5, 0.2)).double()
+    wdm = torch.where(idx < 4096, 1.0, torch.where(idx < 8256, 0.0, 1.0)).double()
+    base = torch.where(idx < 8256, lr, llr).double()
+    M1 = 0.9 * M0 + 0.1 * G; V1 = 0.999 * V0 + 0.001 * G * G
+    upd = (M1 / (1 - 0.9 ** step)) / ((V1 / (1 - 0.999 ** step)).sqrt() + 1e-8) + wd * wdm * P0
+    P1 = P0 - base * lrm * upd; T1 = T0 * mom + P1 * (1 - mom)
+    pb, tb = torch.zeros(8192, device="cuda", dtype=torch.bfloat16), torch.zeros(8192, device="cuda", dtype=torch.bfloat16)
+    ops.adamw_ema(p, g, m, v, t, pb, tb, 8192, segs, 3, ss, maxn, lr, llr, wd, step, mom)
+    assert rel(p, P1) < 1e-6 and rel(m, M1) < 1e-6 and rel(v, V1) < 1e-6 and rel(t, T1) < 1e-6
+    assert torch.equal(pb, p[:8192].to(torch.bfloat16)) and torch.equal(tb, t[:8192].to(torch.bfloat16))

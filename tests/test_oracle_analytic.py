@@ -1,0 +1,105 @@
+"""Analytic pins of the oracle: closed-form micro-cases and fp32-vs-fp64 self-consistency."""
+import math
+
+import torch
+
+from oracle import tiny_cfg
+from oracle.batch import synthetic_batch
+from oracle.losses import dino_loss, ibot_loss_masked, koleo_loss, sinkhorn_knopp
+from oracle.model import gelu, init_params, layer_norm, rope_apply, rope_sincos
+from oracle.step import cosine_schedule, param_multipliers, ssl_forward
+
+
+def test_sinkhorn_constant_logits_gives_uniform():
+    Q = sinkhorn_knopp(torch.zeros(6, 32, dtype=torch.float64), 0.05, B_total=6)
+    assert torch.allclose(Q, torch.full_like(Q, 1 / 32), atol=1e-12)
+
+
+def test_sinkhorn_columns_sum_to_one_and_rows_balanced():
+    torch.manual_seed(0)
+    Q = sinkhorn_knopp(torch.randn(16, 64, dtype=torch.float64) * 0.02, 0.07, B_total=16)
+    assert torch.allclose(Q.sum(-1), torch.ones(16, dtype=torch.float64), atol=1e-10)   # per sample
+    # with mild logits, three iterations leave the prototype mass close to B/K each
+    assert (Q.sum(0) - 16 / 64).abs().max() < 0.01
+
+
+def test_layernorm_constant_row_is_bias():
+    x = torch.full((3, 8), 2.5)
+    y = layer_norm(x, torch.ones(8) * 3, torch.arange(8.0), 1e-6)
+    assert torch.allclose(y, torch.arange(8.0).expand(3, 8), atol=1e-3)
+
+
+def test_gelu_is_tanh_form():
+    u = torch.tensor([-2.0, -0.5, 0.0, 0.7, 3.0], dtype=torch.float64)
+    ref = 0.5 * u * (1 + torch.tanh(math.sqrt(2 / math.pi) * (u + 0.044715 * u ** 3)))
+    assert torch.allclose(gelu(u), ref, atol=1e-12)
+
+
+def test_dino_loss_uniform_student_is_log_k():
+    K, B = 16, 3
+    t = torch.softmax(torch.randn(2, B, K, dtype=torch.float64), -1)
+    s = torch.zeros(8, B, K, dtype=torch.float64)
+    assert abs(dino_loss(s, t, 0.1, False).item() - math.log(K)) < 1e-12
+    sg = torch.zeros(2, B, K, dtype=torch.float64)
+    assert abs(dino_loss(sg, t, 0.1, True).item() - math.log(K)) < 1e-12
+
+
+def test_ibot_loss_divides_by_number_of_mask_rows():
+    K, M = 8, 5
+    t = torch.full((M, K), 1 / K, dtype=torch.float64)
+    s = torch.zeros(M, K, dtype=torch.float64)
+    assert abs(ibot_loss_masked(s, t, 0.1, n_mask_rows=4).item() - M * math.log(K) / 4) < 1e-12
+
+
+def test_koleo_orthogonal_pairs():
+    x = torch.eye(4, dtype=torch.float64) * 3.0          # normalised rows are orthonormal: all distances sqrt(2)
+    assert abs(koleo_loss(x).item() + math.log(math.sqrt(2) + 2e-8)) < 1e-6
+
+
+def test_rope_is_a_rotation_and_prefix_free():
+    sin, cos = rope_sincos(3, 3, 64, 100.0, torch.float64)
+    assert sin.shape == (9, 64)
+    x = torch.randn(9, 64, dtype=torch.float64)
+    y = rope_apply(x, sin, cos)
+    assert torch.allclose(y.norm(dim=-1), x.norm(dim=-1), atol=1e-10)
+    # angle of the first frequency at the first patch: 2*pi*coord/period with coord = 2*(0.5/3)-1, period = 1
+    assert abs(math.sin(2 * math.pi * (2 * 0.5 / 3 - 1)) - sin[0, 0].item()) < 1e-12
+
+
+def test_cosine_schedule_shape_and_ends():
+    s = cosine_schedule(1.0, 0.1, 100, warmup_iters=10, start_warmup_value=0.0)
+    assert len(s) == 100 and s[0] == 0.0 and abs(s[9] - 1.0) < 1e-12 and abs(s[10] - 1.0) < 1e-12
+    assert s[-1] > 0.1 and s[-1] < 0.11
+
+
+def test_param_multipliers_follow_layerwise_decay():
+    names = ["student_backbone/patch_embed/proj/kernel", "student_backbone/blocks_0/attn/qkv/kernel",
+             "student_backbone/blocks_11/mlp/Dense_1/bias", "student_backbone/norm/scale", "student_backbone/cls_token",
+             "student_dino_head/last_layer/kernel", "student_ibot_head/mlp/layers_0/bias"]
+    m = param_multipliers(names, depth=12)
+    assert abs(m[names[0]][0] - 0.2 * 0.9 ** 13) < 1e-12 and m[names[0]][1] == 1.0
+    assert abs(m[names[1]][0] - 0.9 ** 12) < 1e-12
+    assert abs(m[names[2]][0] - 0.9) < 1e-12 and m[names[2]][1] == 0.0
+    assert m[names[3]] == (1.0, 0.0, False)
+    assert abs(m[names[4]][0] - 0.9 ** 13) < 1e-12 and m[names[4]][1] == 1.0
+    assert m[names[5]] == (1.0, 1.0, True)
+    assert m[names[6]] == (1.0, 0.0, False)
+
+
+def test_fp32_and_fp64_oracle_agree():
+    cfg = tiny_cfg()
+    P = init_params(cfg, 0, perturb=0.05)
+    b = synthetic_batch(cfg, 2, 0)
+    l32, _ = ssl_forward(P, b, 0.05, cfg)
+    l64, _ = ssl_forward({k: v.double() for k, v in P.items()}, b, 0.05, cfg, dtype=torch.float64)
+    assert abs(l32.item() - l64.item()) / abs(l64.item()) < 1e-5
+
+
+def test_second_gelu_flag_changes_result():
+    cfg = tiny_cfg()
+    P = init_params(cfg, 0, perturb=0.05)
+    b = synthetic_batch(cfg, 2, 0)
+    import dataclasses
+    a, _ = ssl_forward(P, b, 0.05, dataclasses.replace(cfg, layerscale=1.0), )
+    c, _ = ssl_forward(P, b, 0.05, dataclasses.replace(cfg, layerscale=1.0, mlp_second_act=False))
+    assert abs(a.item() - c.item()) > 1e-6
