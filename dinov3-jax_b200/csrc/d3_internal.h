@@ -18,7 +18,12 @@ enum : int {
   EP_RESID = D3_EP_RESID,
   EP_OUT_F32 = D3_EP_OUT_F32,
   EP_ACCUM = D3_EP_ACCUM,
-  EP_SLOW = 1 << 30,  // internal: force the bounds-checked scalar epilogue
+  EP_SLOW = 1 << 30,      // internal: force the bounds-checked scalar epilogue
+  EP_ATOMIC = 1 << 29,    // internal: split-K partial sums, fp32 atomic reduction into out
+  EP_DEBUG_NOSTORE = 1 << 27,  // internal (D3_GEMM_DEBUG=1): skip epilogue global traffic
+  EP_M_FASTEST = 1 << 26,      // internal (D3_GEMM_DEBUG=2): M-fastest tile order
+  EP_TMA_EPI = 1 << 25,        // internal: epilogue tiles move through swizzled smem staging + TMA store / load
+  EP_FAST_ACT = 1 << 28,  // internal: hardware tanh in GELU / GELU' (bf16-rounded outputs)
 };
 
 struct GemmEpilogue {
@@ -38,9 +43,12 @@ int sm_count();
 void count_launch(int n = 1);
 int encode_tensor_map_2d_bf16(CUtensorMap* map, const void* ptr, const cuuint64_t dims[2],
                               const cuuint64_t strides[1], const cuuint32_t box[2], const cuuint32_t estr[2]);
+// generic 2-D map: elt_bytes 2 (bf16) or 4 (fp32); swizzle_bytes 0 / 64 / 128
+int encode_tensor_map_2d(CUtensorMap* map, const void* ptr, int elt_bytes, cuuint64_t cols, cuuint64_t rows,
+                         cuuint64_t row_stride_bytes, cuuint32_t box_cols, cuuint32_t box_rows, int swizzle_bytes);
 
 int gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, int M, int N, int K,
-              GemmEpilogue ep, int force_bn, cudaStream_t stream);
+              GemmEpilogue ep, int tile_n, int split_k, cudaStream_t stream);
 
 #define D3_CHECK_LAUNCH()                                               \
   do {                                                                  \

@@ -2,16 +2,23 @@
 // operand staging).  One kernel family covers every dense contraction on the DINOv3 training path:
 //   forward  Y = X W        (A K-major, B MN-major: reference kernels are stored [in,out])
 //   dgrad    dX = dY W^T    (A K-major, B K-major)
-//   wgrad    dW = X^T dY    (A MN-major, B MN-major, fp32 output, optional accumulate)
+//   wgrad    dW = X^T dY    (A MN-major, B MN-major, fp32 output, split-K with fp32 reductions)
 // replacing nn.Dense / nn.Conv(stride=kernel) call sites of the reference:
 //   dinov3_jax/layers/attention.py:63-65,94,101   dinov3_jax/layers/ffn_layers.py:36-47
 //   dinov3_jax/layers/patch_embed.py:38-51        dinov3_jax/layers/dino_head.py:20-43,65-85
 // The epilogue fuses bias, tanh-GELU, GELU', LayerScale (gamma) and the residual add
 // (dinov3_jax/layers/block.py:198-199, dinov3_jax/layers/layer_scale.py:17-21).
 //
-// Roles (256 threads): warp0 = TMA producer, warp1 = MMA issuer (one elected lane), warp2 = TMEM allocator,
-// warps4-7 = epilogue (TMEM -> registers -> global).  Two accumulator stages in TMEM (2 x BN columns) let the
-// epilogue of tile i overlap the main loop of tile i+1.
+// Two kernels:
+//   gemm2sm_kernel — CTA pairs (cluster 2x1, tcgen05 cta_group::2): a 256x256 output tile per pair, each CTA stages
+//                    its 128 A rows and half (128) of the B columns, halving L2->SM operand traffic per FLOP
+//                    (a 1-CTA 128x256 tile needs 96 B/clk/SM of operands: above what L2 can feed 148 SMs).
+//   gemm1sm_kernel — single-CTA 128 x {64,128,256} tiles for small / ragged problems.
+// Roles: warp0 = TMA producer, warp1 = MMA issuer (one elected lane), warp2 = TMEM allocator, warps4-11 = epilogue
+// (TMEM -> registers -> global; two warps per TMEM lane quarter, each taking half of the tile's columns).
+// Two accumulator stages in TMEM let the epilogue of tile i overlap the main loop of tile i+1.
+#include <cstdlib>
+#include <cstring>
 #include "ptx.cuh"
 #include "d3_internal.h"
 
@@ -19,45 +26,327 @@ namespace d3 {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
+constexpr int EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 128 + 32 * EPI_WARPS;
+
+// ---------------------------------------------------------------------------------------------------------------
+// epilogue for one row x 32 consecutive columns held in registers
+__device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, size_t ro, int nc, int N, float (&v)[32],
+                                               bool full) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] *= ep.alpha;
+  if (ep.flags & EP_ATOMIC) {   // split-K partial: fp32 reduction into a zero-initialised output
+    float* o = reinterpret_cast<float*>(ep.out) + ro * ep.ld_out + nc;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) atomicAdd(reinterpret_cast<float4*>(o + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (nc + j < N) atomicAdd(o + j, v[j]);
+    }
+    return;
+  }
+  const bool fast_act = (ep.flags & EP_FAST_ACT) != 0;
+  if (ep.flags & EP_DEBUG_NOSTORE) {   // diagnostic: keep the math, drop the global traffic
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc += (ep.flags & EP_GELU) ? gelu_tanh_fast(v[j]) : v[j];
+    if (acc == 1.2345e38f) reinterpret_cast<float*>(ep.out)[0] = acc;
+    return;
+  }
+  if (full) {
+    if (ep.flags & EP_BIAS) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 b = *reinterpret_cast<const float4*>(ep.bias + nc + j);
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      }
+    }
+    if (ep.flags & EP_STORE_PRE) {
+      uint4* dst = reinterpret_cast<uint4*>(ep.aux_out + ro * ep.ld_aux + nc);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        dst[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                            pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+    }
+    if (ep.flags & EP_GELU) {
+      if (fast_act) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_fast(v[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
+      }
+    }
+    if (ep.flags & EP_MUL_DGELU) {
+      const uint4* src = reinterpret_cast<const uint4*>(ep.aux_in + ro * ep.ld_aux + nc);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 u = src[j];
+        float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), cc = unpack_bf16(u.z), d = unpack_bf16(u.w);
+        if (fast_act) {
+          v[8 * j] *= gelu_tanh_grad_fast(a.x); v[8 * j + 1] *= gelu_tanh_grad_fast(a.y);
+          v[8 * j + 2] *= gelu_tanh_grad_fast(b.x); v[8 * j + 3] *= gelu_tanh_grad_fast(b.y);
+          v[8 * j + 4] *= gelu_tanh_grad_fast(cc.x); v[8 * j + 5] *= gelu_tanh_grad_fast(cc.y);
+          v[8 * j + 6] *= gelu_tanh_grad_fast(d.x); v[8 * j + 7] *= gelu_tanh_grad_fast(d.y);
+        } else {
+          v[8 * j] *= gelu_tanh_grad(a.x); v[8 * j + 1] *= gelu_tanh_grad(a.y);
+          v[8 * j + 2] *= gelu_tanh_grad(b.x); v[8 * j + 3] *= gelu_tanh_grad(b.y);
+          v[8 * j + 4] *= gelu_tanh_grad(cc.x); v[8 * j + 5] *= gelu_tanh_grad(cc.y);
+          v[8 * j + 6] *= gelu_tanh_grad(d.x); v[8 * j + 7] *= gelu_tanh_grad(d.y);
+        }
+      }
+    }
+    if (ep.flags & EP_GAMMA) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 g = *reinterpret_cast<const float4*>(ep.gamma + nc + j);
+        v[j] *= g.x; v[j + 1] *= g.y; v[j + 2] *= g.z; v[j + 3] *= g.w;
+      }
+    }
+    if (ep.flags & EP_RESID) {
+      const float4* rs = reinterpret_cast<const float4*>(ep.resid + ro * ep.ld_resid + nc);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 x = rs[j];
+        v[4 * j] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
+      }
+    }
+    if (ep.flags & EP_OUT_F32) {
+      float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + ro * ep.ld_out + nc);
+      if (ep.flags & EP_ACCUM) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 x = dst[j];
+          v[4 * j] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + ro * ep.ld_out + nc);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        dst[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                            pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+    }
+  } else {
+    // ragged / unaligned edge: scalar path with bounds checks
+#pragma unroll 1
+    for (int j = 0; j < 32; ++j) {
+      const int n = nc + j;
+      if (n >= N) break;
+      float x = v[j];
+      if (ep.flags & EP_BIAS) x += ep.bias[n];
+      if (ep.flags & EP_STORE_PRE) ep.aux_out[ro * ep.ld_aux + n] = __float2bfloat16(x);
+      if (ep.flags & EP_GELU) x = fast_act ? gelu_tanh_fast(x) : gelu_tanh(x);
+      if (ep.flags & EP_MUL_DGELU) {
+        const float u = __bfloat162float(ep.aux_in[ro * ep.ld_aux + n]);
+        x *= fast_act ? gelu_tanh_grad_fast(u) : gelu_tanh_grad(u);
+      }
+      if (ep.flags & EP_GAMMA) x *= ep.gamma[n];
+      if (ep.flags & EP_RESID) x += ep.resid[ro * ep.ld_resid + n];
+      if (ep.flags & EP_OUT_F32) {
+        float* o = reinterpret_cast<float*>(ep.out) + ro * ep.ld_out + n;
+        if (ep.flags & EP_ACCUM) x += *o;
+        *o = x;
+      } else {
+        reinterpret_cast<__nv_bfloat16*>(ep.out)[ro * ep.ld_out + n] = __float2bfloat16(x);
+      }
+    }
+  }
+}
+
+// drain one accumulator stage: this warp owns TMEM lanes [32q, 32q+32) and the column half `half` of the tile
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, uint32_t t_addr, int row, int n0, int M, int N,
+                                              int half) {
+  const bool row_ok = row < M;
+  const bool fast = (ep.flags & EP_SLOW) == 0;
+  constexpr int CHUNKS = BN / 32 / 2 > 0 ? BN / 32 / 2 : 1;
+  const int c_begin = (BN >= 64) ? half * CHUNKS : 0;
+  if (BN < 64 && half == 1) return;
+#pragma unroll 1
+  for (int c = c_begin; c < c_begin + CHUNKS; ++c) {
+    const int nc = n0 + c * 32;
+    if (nc >= N) break;  // warp-uniform
+    uint32_t r[32];
+    tmem_ld32(t_addr + c * 32, r);
+    tmem_ld_wait();
+    if (!row_ok) continue;
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    epilogue_chunk(ep, (size_t)row, nc, N, v, fast && (nc + 32 <= N));
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// TMA epilogue (CTA-pair kernel): every [32 rows x 32 cols] unit of a warp moves through swizzled shared-memory
+// staging: residual / GELU' operands arrive by TMA load, results leave by TMA store, so global traffic is in full
+// 128-byte lines regardless of the row-per-thread TMEM layout.  sOut: 4 KB (fp32: 128-B rows, SWIZZLE_128B; bf16:
+// 64-B rows, SWIZZLE_64B), sAux: 2 KB bf16 (SWIZZLE_64B).
+__device__ __forceinline__ uint32_t stg128(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
+__device__ __forceinline__ uint32_t stg64(int row, int chunk) { return (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4)); }
 
 template <int BN>
-struct GemmCfg {
+__device__ __forceinline__ void epilogue_tile_tma(const GemmEpilogue& ep, const CUtensorMap* tmOut,
+                                                  const CUtensorMap* tmAux, const CUtensorMap* tmRes, uint32_t t_addr,
+                                                  int row0, int n0, int M, int N, int half, uint8_t* sOut, uint8_t* sAux,
+                                                  uint64_t* ld_bar, uint32_t& ld_phase) {
+  const int lane = threadIdx.x & 31;
+  const bool out_f32 = (ep.flags & EP_OUT_F32) != 0;
+  const bool has_res = (ep.flags & EP_RESID) != 0;
+  const bool has_auxin = (ep.flags & EP_MUL_DGELU) != 0;
+  const bool store_pre = (ep.flags & EP_STORE_PRE) != 0;
+  const bool fast_act = (ep.flags & EP_FAST_ACT) != 0;
+  constexpr int CHUNKS = BN / 64;
+  if (row0 >= M) return;   // warp-uniform: this warp's 32 rows are all padding
+#pragma unroll 1
+  for (int c = half * CHUNKS; c < (half + 1) * CHUNKS; ++c) {
+    const int nc = n0 + c * 32;
+    if (nc >= N) break;
+    if (lane == 0) tma_store_wait_read();      // staging buffers free again
+    __syncwarp();
+    if ((has_res || has_auxin) && lane == 0) {
+      mbar_expect_tx(ld_bar, (has_res ? 4096u : 0u) + (has_auxin ? 2048u : 0u));
+      if (has_res) tma_load_2d_cta(tmRes, ld_bar, sOut, nc, row0);
+      if (has_auxin) tma_load_2d_cta(tmAux, ld_bar, sAux, nc, row0);
+    }
+    uint32_t r[32];
+    tmem_ld32(t_addr + c * 32, r);
+    tmem_ld_wait();
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * ep.alpha;
+    if (ep.flags & EP_BIAS) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 b = *reinterpret_cast<const float4*>(ep.bias + nc + j);
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      }
+    }
+    if (store_pre) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(sAux + stg64(lane, j)) =
+            make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                       pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+    }
+    if (ep.flags & EP_GELU) {
+      if (fast_act) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_fast(v[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
+      }
+    }
+    if (has_res || has_auxin) {
+      mbar_wait(ld_bar, ld_phase);
+      ld_phase ^= 1;
+    }
+    if (has_auxin) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 u = *reinterpret_cast<const uint4*>(sAux + stg64(lane, j));
+        const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), cc = unpack_bf16(u.z), d = unpack_bf16(u.w);
+        v[8 * j] *= gelu_tanh_grad_fast(a.x); v[8 * j + 1] *= gelu_tanh_grad_fast(a.y);
+        v[8 * j + 2] *= gelu_tanh_grad_fast(b.x); v[8 * j + 3] *= gelu_tanh_grad_fast(b.y);
+        v[8 * j + 4] *= gelu_tanh_grad_fast(cc.x); v[8 * j + 5] *= gelu_tanh_grad_fast(cc.y);
+        v[8 * j + 6] *= gelu_tanh_grad_fast(d.x); v[8 * j + 7] *= gelu_tanh_grad_fast(d.y);
+      }
+    }
+    if (ep.flags & EP_GAMMA) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 g = *reinterpret_cast<const float4*>(ep.gamma + nc + j);
+        v[j] *= g.x; v[j + 1] *= g.y; v[j + 2] *= g.z; v[j + 3] *= g.w;
+      }
+    }
+    if (has_res) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 x = *reinterpret_cast<const float4*>(sOut + stg128(lane, j));
+        v[4 * j] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
+      }
+    }
+    if (out_f32) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(sOut + stg128(lane, j)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(sOut + stg64(lane, j)) =
+            make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                       pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(tmOut, sOut, nc, row0);
+      if (store_pre) tma_store_2d(tmAux, sAux, nc, row0);
+      tma_store_commit();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+template <int BN>
+struct Cfg1 {
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 };
 
+// work item = (tile, split): k-blocks [kb0, kb1)
+struct WorkRange { int m0, n0, kb0, kb1; };
+// Tiles are rasterised N-fastest: the CTAs resident at any moment cover a few M row-panels times all N tiles, so the
+// large activation operand streams from HBM once while the (small) weight operand stays L2-resident.
+__device__ __forceinline__ WorkRange work_item(int w, int num_m, int num_n, int num_k, int splits, int tile_m,
+                                               int tile_n, int m_fastest) {
+  const int tile = w / splits, sp = w % splits;
+  const int per = (num_k + splits - 1) / splits;
+  WorkRange r;
+  if (m_fastest) {
+    r.m0 = (tile % num_m) * tile_m;
+    r.n0 = (tile / num_m) * tile_n;
+  } else {
+    r.n0 = (tile % num_n) * tile_n;
+    r.m0 = (tile / num_n) * tile_m;
+  }
+  r.kb0 = sp * per;
+  r.kb1 = min(num_k, r.kb0 + per);
+  return r;
+}
+
 template <int BN, int A_MN, int B_MN>
-__global__ void __launch_bounds__(256, 1)
-gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const GemmEpilogue ep, int M, int N, int K) {
-  using Cfg = GemmCfg<BN>;
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm1sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const GemmEpilogue ep, int M, int N, int K, int splits) {
+  using Cfg = Cfg1<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
-  uint64_t* full_bar = bars;                       // [STAGES]
-  uint64_t* empty_bar = bars + Cfg::STAGES;        // [STAGES]
-  uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;    // [2]
-  uint64_t* tempty_bar = bars + 2 * Cfg::STAGES + 2;  // [2]
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::STAGES;
+  uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;
+  uint64_t* tempty_bar = bars + 2 * Cfg::STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int s = 0; s < Cfg::STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
-    }
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], EPI_WARPS); }
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
@@ -68,55 +357,53 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int num_m = (M + BM - 1) / BM;
   const int num_n = (N + BN - 1) / BN;
-  const int num_tiles = num_m * num_n;
   const int num_k = (K + BK - 1) / BK;
+  const int num_work = num_m * num_n * splits;
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile % num_m) * BM;
-        const int n0 = (tile / num_m) * BN;
-        for (int kb = 0; kb < num_k; ++kb) {
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const WorkRange wr = work_item(w, num_m, num_n, num_k, splits, BM, BN, ep.flags & EP_M_FASTEST);
+        for (int kb = wr.kb0; kb < wr.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           if (A_MN) {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) tma_load_2d(&tmA, &full_bar[stage], sa + j * 8192, m0 + j * 64, kb * BK);
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(&tmA, &full_bar[stage], sa + j * 8192, wr.m0 + j * 64, kb * BK);
           } else {
-            tma_load_2d(&tmA, &full_bar[stage], sa, kb * BK, m0);
+            tma_load_2d(&tmA, &full_bar[stage], sa, kb * BK, wr.m0);
           }
           if (B_MN) {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) tma_load_2d(&tmB, &full_bar[stage], sb + j * 8192, n0 + j * 64, kb * BK);
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(&tmB, &full_bar[stage], sb + j * 8192, wr.n0 + j * 64, kb * BK);
           } else {
-            tma_load_2d(&tmB, &full_bar[stage], sb, kb * BK, n0);
+            tma_load_2d(&tmB, &full_bar[stage], sb, kb * BK, wr.n0);
           }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
-      // per-UMMA_K (16 elements) advance of the descriptor start address, in 16-byte units
       constexpr uint32_t a_adv = A_MN ? (2 * 1024 >> 4) : (32 >> 4);
       constexpr uint32_t b_adv = B_MN ? (2 * 1024 >> 4) : (32 >> 4);
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++local) {
+        const WorkRange wr = work_item(w, num_m, num_n, num_k, splits, BM, BN, ep.flags & EP_M_FASTEST);
         const int acc = local & 1;
         const uint32_t acc_phase = (local >> 1) & 1;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_k; ++kb) {
+        for (int kb = wr.kb0; kb < wr.kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -124,140 +411,192 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint64_t adesc = A_MN ? umma_desc_sw128(sa, 8192, 1024) : umma_desc_sw128(sa, 16, 1024);
           const uint64_t bdesc = B_MN ? umma_desc_sw128(sb, 8192, 1024) : umma_desc_sw128(sb, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
+          for (int k = 0; k < BK / 16; ++k)
             umma_bf16(d_tmem, adesc + (uint64_t)(k * a_adv), bdesc + (uint64_t)(k * b_adv), idesc,
-                      (kb > 0 || k > 0) ? 1u : 0u);
-          }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+                      (kb > wr.kb0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        umma_commit(&tfull_bar[acc]);
       }
     }
+    __syncwarp();
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue
-    const int q = warp - 4;  // TMEM lane quarter == warp % 4
+    const int q = warp & 3;            // TMEM lane quarter == warp % 4
+    const int half = (warp - 4) >> 2;  // column half of the tile
     int local = 0;
-    const bool fast = (ep.flags & EP_SLOW) == 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++local) {
+      const WorkRange wr = work_item(w, num_m, num_n, num_k, splits, BM, BN, ep.flags & EP_M_FASTEST);
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
-      const int m0 = (tile % num_m) * BM;
-      const int n0 = (tile / num_m) * BN;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int row = m0 + q * 32 + lane;
-      const bool row_ok = row < M;
-      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int nc = n0 + c * 32;
-        if (nc >= N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld32(t_addr + c * 32, r);
-        tmem_ld_wait();
-        if (!row_ok) continue;
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * ep.alpha;
-        const bool full = fast && (nc + 32 <= N);
-        const size_t ro = (size_t)row;
-        if (full) {
-          if (ep.flags & EP_BIAS) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 b = *reinterpret_cast<const float4*>(ep.bias + nc + j);
-              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-            }
-          }
-          if (ep.flags & EP_STORE_PRE) {
-            uint4* dst = reinterpret_cast<uint4*>(ep.aux_out + ro * ep.ld_aux + nc);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              dst[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                  pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-          }
-          if (ep.flags & EP_GELU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
-          }
-          if (ep.flags & EP_MUL_DGELU) {
-            const uint4* src = reinterpret_cast<const uint4*>(ep.aux_in + ro * ep.ld_aux + nc);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 u = src[j];
-              float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), cc = unpack_bf16(u.z), d = unpack_bf16(u.w);
-              v[8 * j] *= gelu_tanh_grad(a.x); v[8 * j + 1] *= gelu_tanh_grad(a.y);
-              v[8 * j + 2] *= gelu_tanh_grad(b.x); v[8 * j + 3] *= gelu_tanh_grad(b.y);
-              v[8 * j + 4] *= gelu_tanh_grad(cc.x); v[8 * j + 5] *= gelu_tanh_grad(cc.y);
-              v[8 * j + 6] *= gelu_tanh_grad(d.x); v[8 * j + 7] *= gelu_tanh_grad(d.y);
-            }
-          }
-          if (ep.flags & EP_GAMMA) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 g = *reinterpret_cast<const float4*>(ep.gamma + nc + j);
-              v[j] *= g.x; v[j + 1] *= g.y; v[j + 2] *= g.z; v[j + 3] *= g.w;
-            }
-          }
-          if (ep.flags & EP_RESID) {
-            const float4* rs = reinterpret_cast<const float4*>(ep.resid + ro * ep.ld_resid + nc);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 x = rs[j];
-              v[4 * j] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
-            }
-          }
-          if (ep.flags & EP_OUT_F32) {
-            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + ro * ep.ld_out + nc);
-            if (ep.flags & EP_ACCUM) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float4 x = dst[j];
-                v[4 * j] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
-            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + ro * ep.ld_out + nc);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              dst[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                  pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-          }
-        } else {
-          // ragged / unaligned edge: scalar path with bounds checks
-#pragma unroll 1
-          for (int j = 0; j < 32; ++j) {
-            const int n = nc + j;
-            if (n >= N) break;
-            float x = v[j];
-            if (ep.flags & EP_BIAS) x += ep.bias[n];
-            if (ep.flags & EP_STORE_PRE) ep.aux_out[ro * ep.ld_aux + n] = __float2bfloat16(x);
-            if (ep.flags & EP_GELU) x = gelu_tanh(x);
-            if (ep.flags & EP_MUL_DGELU) x *= gelu_tanh_grad(__bfloat162float(ep.aux_in[ro * ep.ld_aux + n]));
-            if (ep.flags & EP_GAMMA) x *= ep.gamma[n];
-            if (ep.flags & EP_RESID) x += ep.resid[ro * ep.ld_resid + n];
-            if (ep.flags & EP_OUT_F32) {
-              float* o = reinterpret_cast<float*>(ep.out) + ro * ep.ld_out + n;
-              if (ep.flags & EP_ACCUM) x += *o;
-              *o = x;
-            } else {
-              reinterpret_cast<__nv_bfloat16*>(ep.out)[ro * ep.ld_out + n] = __float2bfloat16(x);
-            }
-          }
-        }
-      }
+      if (wr.kb1 > wr.kb0)
+        epilogue_tile<BN>(ep, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN, wr.m0 + q * 32 + lane, wr.n0, M, N, half);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
   }
-
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_free<Cfg::TMEM_COLS>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-pair kernel: 256 x 256 tile per cluster; per CTA and stage: A 128x64 (16 KB) + B 128x64 (16 KB)
+struct Cfg2 {
+  static constexpr int BN = 256;
+  static constexpr int STAGES = 5;
+  static constexpr int A_BYTES = 128 * BK * 2;
+  static constexpr int B_BYTES = 128 * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int STG_WARP = 4096 + 2048;                 // per epilogue warp: out tile + aux tile
+  static constexpr int STG_BYTES = EPI_WARPS * STG_WARP;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024 + 256;
+};
+
+template <int A_MN, int B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAux,
+               const __grid_constant__ CUtensorMap tmRes, const GemmEpilogue ep, int M, int N, int K, int splits) {
+  using Cfg = Cfg2;
+  constexpr int BN = Cfg::BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* staging = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::STG_BYTES);
+  uint64_t* full_bar = bars;                          // used in the leader CTA: 2 producer arrivals + 4 TMA transactions
+  uint64_t* empty_bar = bars + Cfg::STAGES;           // per CTA, signalled by the leader's multicast commit
+  uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;       // per CTA, multicast commit
+  uint64_t* tempty_bar = bars + 2 * Cfg::STAGES + 2;  // leader: 2 x EPI_WARPS arrivals
+  uint64_t* ld_bar = bars + 2 * Cfg::STAGES + 4;      // [EPI_WARPS] epilogue TMA loads (residual / GELU' operand)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4 + EPI_WARPS);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 2 * EPI_WARPS); }
+    for (int s = 0; s < EPI_WARPS; ++s) mbar_init(&ld_bar[s], 1);
+    if (ep.flags & EP_TMA_EPI) { tma_prefetch_desc(&tmOut); tma_prefetch_desc(&tmAux); tma_prefetch_desc(&tmRes); }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc_2sm<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_m = (M + 255) / 256;
+  const int num_n = (N + BN - 1) / BN;
+  const int num_k = (K + BK - 1) / BK;
+  const int num_work = num_m * num_n * splits;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = cluster_id; w < num_work; w += num_clusters) {
+        const WorkRange wr = work_item(w, num_m, num_n, num_k, splits, 256, BN, ep.flags & EP_M_FASTEST);
+        const int m0 = wr.m0 + rank * 128;     // this CTA's 128 A rows
+        const int n0 = wr.n0 + rank * 128;     // this CTA's half of the B tile
+        for (int kb = wr.kb0; kb < wr.kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+          else mbar_arrive_cluster(&full_bar[stage], 0);
+          if (A_MN) {
+            tma_load_2d_2sm(&tmA, &full_bar[stage], sa, m0, kb * BK);
+            tma_load_2d_2sm(&tmA, &full_bar[stage], sa + 8192, m0 + 64, kb * BK);
+          } else {
+            tma_load_2d_2sm(&tmA, &full_bar[stage], sa, kb * BK, m0);
+          }
+          if (B_MN) {
+            tma_load_2d_2sm(&tmB, &full_bar[stage], sb, n0, kb * BK);
+            tma_load_2d_2sm(&tmB, &full_bar[stage], sb + 8192, n0 + 64, kb * BK);
+          } else {
+            tma_load_2d_2sm(&tmB, &full_bar[stage], sb, kb * BK, n0);
+          }
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, BN, A_MN, B_MN);
+      constexpr uint32_t a_adv = A_MN ? (2 * 1024 >> 4) : (32 >> 4);
+      constexpr uint32_t b_adv = B_MN ? (2 * 1024 >> 4) : (32 >> 4);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int w = cluster_id; w < num_work; w += num_clusters, ++local) {
+        const WorkRange wr = work_item(w, num_m, num_n, num_k, splits, 256, BN, ep.flags & EP_M_FASTEST);
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = wr.kb0; kb < wr.kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          const uint64_t adesc = A_MN ? umma_desc_sw128(sa, 8192, 1024) : umma_desc_sw128(sa, 16, 1024);
+          const uint64_t bdesc = B_MN ? umma_desc_sw128(sb, 8192, 1024) : umma_desc_sw128(sb, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16_2sm(d_tmem, adesc + (uint64_t)(k * a_adv), bdesc + (uint64_t)(k * b_adv), idesc,
+                          (kb > wr.kb0 || k > 0) ? 1u : 0u);
+          umma_commit_2sm(&empty_bar[stage]);   // frees the slot in both CTAs
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(&tfull_bar[acc]);       // accumulator complete in both CTAs
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    uint8_t* sOut = staging + (warp - 4) * Cfg::STG_WARP;
+    uint8_t* sAux = sOut + 4096;
+    uint32_t ld_phase = 0;
+    const bool tma_epi = (ep.flags & EP_TMA_EPI) != 0;
+    int local = 0;
+    for (int w = cluster_id; w < num_work; w += num_clusters, ++local) {
+      const WorkRange wr = work_item(w, num_m, num_n, num_k, splits, 256, BN, ep.flags & EP_M_FASTEST);
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      if (wr.kb1 > wr.kb0) {
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+        if (tma_epi)
+          epilogue_tile_tma<BN>(ep, &tmOut, &tmAux, &tmRes, t_addr, wr.m0 + rank * 128 + q * 32, wr.n0, M, N, half, sOut,
+                                sAux, &ld_bar[warp - 4], ld_phase);
+        else
+          epilogue_tile<BN>(ep, t_addr, wr.m0 + rank * 128 + q * 32 + lane, wr.n0, M, N, half);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);   // the leader's MMA thread waits for both CTAs
+    }
+    if (tma_epi && lane == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  cluster_sync_all();   // peer smem / barriers stay valid until both CTAs are done
+  if (warp == 2) tmem_free_2sm<Cfg::TMEM_COLS>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -275,20 +614,46 @@ static int make_operand_map(CUtensorMap* map, const void* ptr, int mn, int k, in
   return encode_tensor_map_2d_bf16(map, ptr, dims, strides, box, estr);
 }
 
-template <int BN, int A_MN, int B_MN>
-static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int K,
-                      cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
-  auto kern = gemm_bf16_tc_kernel<BN, A_MN, B_MN>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+template <typename KernT>
+static int configure_once(KernT kern, int smem, bool* done) {
+  if (!*done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return set_error(D3_ERR_CUDA, cudaGetErrorString(e));
-    configured = true;
+    *done = true;
   }
-  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-  const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(ta, tb, ep, M, N, K);
+  return D3_OK;
+}
+
+template <int BN, int A_MN, int B_MN>
+static int launch1(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int K,
+                   int splits, cudaStream_t stream) {
+  using Cfg = Cfg1<BN>;
+  auto kern = gemm1sm_kernel<BN, A_MN, B_MN>;
+  static bool configured = false;
+  int rc = configure_once(kern, Cfg::SMEM_BYTES, &configured);
+  if (rc) return rc;
+  const int work = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * splits;
+  const int grid = work < sm_count() ? work : sm_count();
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, ep, M, N, K, splits);
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) return set_error(D3_ERR_CUDA, cudaGetErrorString(e));
+  count_launch();
+  return D3_OK;
+}
+
+struct EpiMaps { CUtensorMap out, aux, res; };
+
+template <int A_MN, int B_MN>
+static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, const GemmEpilogue& ep, int M, int N,
+                   int K, int splits, cudaStream_t stream) {
+  auto kern = gemm2sm_kernel<A_MN, B_MN>;
+  static bool configured = false;
+  int rc = configure_once(kern, Cfg2::SMEM_BYTES, &configured);
+  if (rc) return rc;
+  const int work = ((M + 255) / 256) * ((N + 255) / 256) * splits;
+  const int max_clusters = sm_count() / 2;
+  const int clusters = work < max_clusters ? work : max_clusters;
+  kern<<<2 * clusters, GEMM_THREADS, Cfg2::SMEM_BYTES, stream>>>(ta, tb, em.out, em.aux, em.res, ep, M, N, K, splits);
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) return set_error(D3_ERR_CUDA, cudaGetErrorString(e));
   count_launch();
@@ -296,32 +661,74 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEp
 }
 
 template <int BN>
-static int launch_major(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep,
-                        int M, int N, int K, cudaStream_t s) {
-  if (!a_mn && !b_mn) return launch_cfg<BN, 0, 0>(ta, tb, ep, M, N, K, s);
-  if (!a_mn && b_mn) return launch_cfg<BN, 0, 1>(ta, tb, ep, M, N, K, s);
-  if (a_mn && !b_mn) return launch_cfg<BN, 1, 0>(ta, tb, ep, M, N, K, s);
-  return launch_cfg<BN, 1, 1>(ta, tb, ep, M, N, K, s);
+static int dispatch1(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M,
+                     int N, int K, int splits, cudaStream_t s) {
+  if (!a_mn && !b_mn) return launch1<BN, 0, 0>(ta, tb, ep, M, N, K, splits, s);
+  if (!a_mn && b_mn) return launch1<BN, 0, 1>(ta, tb, ep, M, N, K, splits, s);
+  if (a_mn && !b_mn) return launch1<BN, 1, 0>(ta, tb, ep, M, N, K, splits, s);
+  return launch1<BN, 1, 1>(ta, tb, ep, M, N, K, splits, s);
+}
+static int dispatch2(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em,
+                     const GemmEpilogue& ep, int M, int N, int K, int splits, cudaStream_t s) {
+  if (!a_mn && !b_mn) return launch2<0, 0>(ta, tb, em, ep, M, N, K, splits, s);
+  if (!a_mn && b_mn) return launch2<0, 1>(ta, tb, em, ep, M, N, K, splits, s);
+  if (a_mn && !b_mn) return launch2<1, 0>(ta, tb, em, ep, M, N, K, splits, s);
+  return launch2<1, 1>(ta, tb, em, ep, M, N, K, splits, s);
 }
 
+// tile_n: 0 = auto; 64/128/256 force the single-CTA kernel with that tile; 512 forces the CTA-pair kernel.
+// split_k: 0 = auto (only when the epilogue is a plain fp32 accumulate-able output), >= 1 forced.
 int gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, int M, int N, int K,
-              GemmEpilogue ep, int force_bn, cudaStream_t stream) {
+              GemmEpilogue ep, int tile_n, int split_k, cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return set_error(D3_ERR_ARG, "gemm: empty problem");
   if ((lda % 8) || (ldb % 8) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15))
     return set_error(D3_ERR_ARG, "gemm: operands must be 16-byte aligned with ld % 8 == 0");
-  // tile-N choice: minimise (waves x tile cost)
-  int bn = force_bn;
-  if (bn == 0) {
-    const int cand[3] = {256, 128, 64};
-    long best = -1;
-    for (int i = 0; i < 3; ++i) {
-      long tiles = (long)((M + BM - 1) / BM) * ((N + cand[i] - 1) / cand[i]);
-      long waves = (tiles + sm_count() - 1) / sm_count();
-      long cost = waves * (cand[i] + 24);
-      if (best < 0 || cost < best) { best = cost; bn = cand[i]; }
+  const int sms = sm_count();
+  const int num_k = (K + BK - 1) / BK;
+  // ---- kernel / tile choice
+  bool use2 = false;
+  int bn = tile_n;
+  if (tile_n == 512) {
+    use2 = true;
+  } else if (tile_n == 0) {
+    const long tiles2 = (long)((M + 255) / 256) * ((N + 255) / 256);
+    const double eff2 = (double)M * N / ((double)tiles2 * 256 * 256);        // padding efficiency of 256x256 tiles
+    if (tiles2 >= 8 && eff2 >= 0.70) {
+      use2 = true;
+    } else {
+      const int cand[3] = {256, 128, 64};
+      long best = -1;
+      for (int i = 0; i < 3; ++i) {
+        long tiles = (long)((M + BM - 1) / BM) * ((N + cand[i] - 1) / cand[i]);
+        long waves = (tiles + sms - 1) / sms;
+        long cost = waves * (cand[i] + 24);
+        if (best < 0 || cost < best) { best = cost; bn = cand[i]; }
+      }
     }
   }
-  // fast (vectorised) epilogue needs 16-byte aligned rows everywhere
+  // ---- split-K: only for plain fp32 outputs (weight gradients); partial sums are reduced with fp32 atomics into
+  //      an output the caller has zeroed (or wants accumulated into: EP_ACCUM semantics)
+  const bool plain_f32 = (ep.flags & EP_OUT_F32) && !(ep.flags & (EP_BIAS | EP_GELU | EP_STORE_PRE | EP_MUL_DGELU |
+                                                                  EP_GAMMA | EP_RESID));
+  int splits = 1;
+  if (split_k >= 1) {
+    splits = split_k;
+  } else if (plain_f32 && (ep.flags & EP_ACCUM)) {
+    const long units = use2 ? (long)((M + 255) / 256) * ((N + 255) / 256) : (long)((M + BM - 1) / BM) * ((N + bn - 1) / bn);
+    const long slots = use2 ? sms / 2 : sms;
+    if (units * 2 <= slots && num_k >= 16) {
+      splits = (int)(slots / units);
+      if (splits > num_k / 4) splits = num_k / 4;
+      if (splits < 1) splits = 1;
+    }
+  }
+  if (splits > 1) {
+    if (!plain_f32) return set_error(D3_ERR_ARG, "gemm: split-K needs a plain fp32 output");
+    if (!(ep.flags & EP_ACCUM)) return set_error(D3_ERR_ARG, "gemm: split-K accumulates into out (set ACCUM, zero it first)");
+    if (splits > num_k) splits = num_k;
+    ep.flags |= EP_ATOMIC;
+  }
+  // ---- epilogue fast-path eligibility
   const int out_elt = (ep.flags & EP_OUT_F32) ? 4 : 2;
   bool aligned = ((uintptr_t)ep.out % 16 == 0) && ((ep.ld_out * out_elt) % 16 == 0);
   if (ep.flags & EP_BIAS) aligned = aligned && ((uintptr_t)ep.bias % 16 == 0);
@@ -330,16 +737,52 @@ int gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn
   if (ep.flags & EP_STORE_PRE) aligned = aligned && ((uintptr_t)ep.aux_out % 16 == 0) && (ep.ld_aux % 8 == 0);
   if (ep.flags & EP_MUL_DGELU) aligned = aligned && ((uintptr_t)ep.aux_in % 16 == 0) && (ep.ld_aux % 8 == 0);
   if (!aligned) ep.flags |= EP_SLOW;
+  ep.flags |= EP_FAST_ACT;   // hardware tanh (rel. error 2^-11, below the bf16 rounding of the GEMM operands feeding it)
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("D3_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
+    if (dbg & 1) ep.flags |= EP_DEBUG_NOSTORE;
+    if (dbg & 2) ep.flags |= EP_M_FASTEST;
+  }
 
   CUtensorMap ta, tb;
-  int rc = make_operand_map(&ta, A, M, K, lda, a_mn, BM);
+  int rc = make_operand_map(&ta, A, M, K, lda, a_mn, 128);
   if (rc) return rc;
-  rc = make_operand_map(&tb, B, N, K, ldb, b_mn, bn);
+  rc = make_operand_map(&tb, B, N, K, ldb, b_mn, use2 ? 128 : bn);
   if (rc) return rc;
+  if (use2) {
+    EpiMaps em;
+    memset(&em, 0, sizeof(em));
+    static int no_tma = -1;
+    if (no_tma < 0) { const char* e = getenv("D3_GEMM_NO_TMA_EPI"); no_tma = e ? atoi(e) : 0; }
+    const bool tma_ok = aligned && !no_tma && (N % 32 == 0) && !(ep.flags & (EP_ATOMIC | EP_ACCUM | EP_DEBUG_NOSTORE));
+    if (tma_ok) {
+      const int oe = (ep.flags & EP_OUT_F32) ? 4 : 2;
+      rc = encode_tensor_map_2d(&em.out, ep.out, oe, N, M, (cuuint64_t)ep.ld_out * oe, 32, 32, oe == 4 ? 128 : 64);
+      if (rc) return rc;
+      if (ep.flags & (EP_STORE_PRE | EP_MUL_DGELU)) {
+        const void* ap = (ep.flags & EP_STORE_PRE) ? (const void*)ep.aux_out : (const void*)ep.aux_in;
+        rc = encode_tensor_map_2d(&em.aux, ap, 2, N, M, (cuuint64_t)ep.ld_aux * 2, 32, 32, 64);
+        if (rc) return rc;
+      } else {
+        em.aux = em.out;
+      }
+      if (ep.flags & EP_RESID) {
+        rc = encode_tensor_map_2d(&em.res, ep.resid, 4, N, M, (cuuint64_t)ep.ld_resid * 4, 32, 32, 128);
+        if (rc) return rc;
+      } else {
+        em.res = em.out;
+      }
+      ep.flags |= EP_TMA_EPI;
+    } else {
+      em.out = ta; em.aux = ta; em.res = ta;   // valid descriptors, never dereferenced
+    }
+    return dispatch2(a_mn, b_mn, ta, tb, em, ep, M, N, K, splits, stream);
+  }
   switch (bn) {
-    case 256: return launch_major<256>(a_mn, b_mn, ta, tb, ep, M, N, K, stream);
-    case 128: return launch_major<128>(a_mn, b_mn, ta, tb, ep, M, N, K, stream);
-    case 64: return launch_major<64>(a_mn, b_mn, ta, tb, ep, M, N, K, stream);
+    case 256: return dispatch1<256>(a_mn, b_mn, ta, tb, ep, M, N, K, splits, stream);
+    case 128: return dispatch1<128>(a_mn, b_mn, ta, tb, ep, M, N, K, splits, stream);
+    case 64: return dispatch1<64>(a_mn, b_mn, ta, tb, ep, M, N, K, splits, stream);
   }
   return set_error(D3_ERR_ARG, "gemm: bad tile N");
 }

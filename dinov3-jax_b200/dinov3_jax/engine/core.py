@@ -309,16 +309,16 @@ class Engine:
             return
         # prototype layer: logits = Yn Wl
         ops.gemm(r(hb.dS), w("last_layer/kernel"), r(hb.dYn))                                   # dYn = dS Wl^T
-        ops.gemm(r(hb.Yn), r(hb.dS), gw("last_layer/kernel"), a_mn=True, b_mn=True)              # dWl = Yn^T dS
+        ops.gemm(r(hb.Yn), r(hb.dS), gw("last_layer/kernel"), a_mn=True, b_mn=True, accum=True)              # dWl = Yn^T dS
         ops.l2norm_bwd(r(hb.dYn), r(hb.U3), r(hb.nrm), r(hb.dU3), 1e-12)
         ops.colsum_bf16(r(hb.dU3), gv("mlp/layers_4/bias"))
-        ops.gemm(r(hb.H2), r(hb.dU3), gw("mlp/layers_4/kernel"), a_mn=True, b_mn=True)
+        ops.gemm(r(hb.H2), r(hb.dU3), gw("mlp/layers_4/kernel"), a_mn=True, b_mn=True, accum=True)
         ops.gemm(r(hb.dU3), w("mlp/layers_4/kernel"), r(hb.dUb), dgelu_of=r(hb.Ub))
         ops.colsum_bf16(r(hb.dUb), gv("mlp/layers_2/bias"))
-        ops.gemm(r(hb.H1), r(hb.dUb), gw("mlp/layers_2/kernel"), a_mn=True, b_mn=True)
+        ops.gemm(r(hb.H1), r(hb.dUb), gw("mlp/layers_2/kernel"), a_mn=True, b_mn=True, accum=True)
         ops.gemm(r(hb.dUb), w("mlp/layers_2/kernel"), r(hb.dUa), dgelu_of=r(hb.Ua))
         ops.colsum_bf16(r(hb.dUa), gv("mlp/layers_0/bias"))
-        ops.gemm(r(hb.A0), r(hb.dUa), gw("mlp/layers_0/kernel"), a_mn=True, b_mn=True)
+        ops.gemm(r(hb.A0), r(hb.dUa), gw("mlp/layers_0/kernel"), a_mn=True, b_mn=True, accum=True)
         ops.gemm(r(hb.dUa), w("mlp/layers_0/kernel"), r(hb.dA0))                                 # fp32 [R, D]
 
     def _block_bwd(self, i: int, dX, dXprev):
@@ -330,23 +330,23 @@ class Engine:
         # ---- MLP branch: x_out = x_mid + g2 * act(u2), u2 = h W2 + b2, h = gelu(u1), u1 = z W1 + b1
         ops.ls_act_bwd(dX, st.U2[i], v("ls2/gamma"), self.dU2, gv("ls2/gamma"), gv("mlp/Dense_1/bias"), cfg.mlp_second_act)
         ops.gemm(self.dU2, w("mlp/Dense_1/kernel"), self.dU1, dgelu_of=st.U1[i])                 # dU1 = (dU2 W2^T) * gelu'(u1)
-        ops.gemm(st.Hh[i], self.dU2, gw("mlp/Dense_1/kernel"), a_mn=True, b_mn=True)            # dW2 = h^T dU2
+        ops.gemm(st.Hh[i], self.dU2, gw("mlp/Dense_1/kernel"), a_mn=True, b_mn=True, accum=True)            # dW2 = h^T dU2
         ops.colsum_bf16(self.dU1, gv("mlp/Dense_0/bias"))
         ops.gemm(self.dU1, w("mlp/Dense_0/kernel"), self.dZ)                                    # dZ = dU1 W1^T
-        ops.gemm(st.Z[i], self.dU1, gw("mlp/Dense_0/kernel"), a_mn=True, b_mn=True)             # dW1 = z^T dU1
+        ops.gemm(st.Z[i], self.dU1, gw("mlp/Dense_0/kernel"), a_mn=True, b_mn=True, accum=True)             # dW1 = z^T dU1
         ops.layernorm_bwd(self.dZ, st.Xmid[i], m2, r2, v("norm2/scale"), self.dXmid, dx_add=dX,
                           dscale=gv("norm2/scale"), dbias=gv("norm2/bias"))
         # ---- attention branch: x_mid = x_in + g1 * (o Wp + bp)
         ops.ls_act_bwd(self.dXmid, st.Pst[i], v("ls1/gamma"), self.dP, gv("ls1/gamma"), gv("attn/proj/bias"), False)
         ops.gemm(self.dP, w("attn/proj/kernel"), self.dO)                                       # dO = dP Wp^T
-        ops.gemm(st.O[i], self.dP, gw("attn/proj/kernel"), a_mn=True, b_mn=True)                # dWp = o^T dP
+        ops.gemm(st.O[i], self.dP, gw("attn/proj/kernel"), a_mn=True, b_mn=True, accum=True)                # dWp = o^T dP
         for cs, lse, delta in zip(st.sets, st.LSE[i], self.delta):
             sl = slice(cs.row0, cs.row0 + cs.T)
             ops.attn_bwd(st.QKV[i][sl], st.O[i][sl], self.dO[sl], lse, delta, self.dQKV[sl], cs.n, cs.N, D, H)
             ops.rope(self.dQKV[sl], cs.sin, cs.cos, cs.N, 1, D, cfg.head_dim, inverse=True)
         ops.colsum_bf16(self.dQKV, gv("attn/qkv/bias"))
         ops.gemm(self.dQKV, w("attn/qkv/kernel"), self.dY)                                      # dY = dQKV Wqkv^T
-        ops.gemm(st.Y[i], self.dQKV, gw("attn/qkv/kernel"), a_mn=True, b_mn=True)               # dWqkv = y^T dQKV
+        ops.gemm(st.Y[i], self.dQKV, gw("attn/qkv/kernel"), a_mn=True, b_mn=True, accum=True)               # dWqkv = y^T dQKV
         ops.layernorm_bwd(self.dY, st.X[i], m1, r1, v("norm1/scale"), dXprev, dx_add=self.dXmid,
                           dscale=gv("norm1/scale"), dbias=gv("norm1/bias"))
 
@@ -373,7 +373,7 @@ class Engine:
         ng = cfg.n_global * B
         self.metrics.zero_()
         for st in self.params.mods.values():
-            st.zero_vector_grads()
+            st.zero_grads()
         # ---- teacher (train/ssl_meta_arch.py:366-402)
         T_ = self.teacher
         self._backbone_fwd(T_, [self.g_img], [None], teacher=True)
@@ -429,7 +429,7 @@ class Engine:
             ops.assemble_tokens_bwd(dX0[cs.row0: cs.row0 + cs.T], masks, dTok, bb.gv("cls_token"),
                                     bb.gv("mask_token"), cs.n, cs.P, D)
             ops.colsum_bf16(dTok, bb.gv("patch_embed/proj/bias"))
-            ops.gemm(cs.patches, dTok, bb.gw("patch_embed/proj/kernel"), a_mn=True, b_mn=True, accum=not first)
+            ops.gemm(cs.patches, dTok, bb.gw("patch_embed/proj/kernel"), a_mn=True, b_mn=True, accum=True)
             first = False
 
     def optimizer_step(self, lr: float, wd: float, last_layer_lr: float, momentum: float):

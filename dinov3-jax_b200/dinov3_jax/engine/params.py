@@ -6,8 +6,8 @@ m / v) and the teacher (fp32 EMA master, bf16 compute copy) as flat device buffe
 names and layouts (Dense kernels [in, out], conv kernel [p, p, 3, D]); matrices (GEMM operands)
 come first in the flat buffer, vectors (biases, LayerNorm affine, LayerScale gamma, cls / mask tokens) after, so that
   * the bf16 compute copy covers exactly the leading matrix region,
-  * only the small vector region of the gradient buffer needs zeroing each step (vector grads accumulate atomically,
-    matrix grads are overwritten by the wgrad GEMMs),
+  * vector grads accumulate atomically and matrix grads are (split-K) accumulations of the wgrad GEMMs into the
+    zeroed gradient buffer,
   * clip-norm, AdamW and EMA run as one launch per module (train/train.py:516-541 clips per top-level module).
 FSDP units (models/vision_transformer.py:93,137; train/ssl_meta_arch.py:77-78,122-123) are sub-ranges of these buffers.
 """
@@ -160,8 +160,10 @@ class ModuleStore:
                 "m": getattr(self, "m", None), "v": getattr(self, "v", None)}[what]
         return {name: self._view(flat, name).detach().clone() for name in self.offsets}
 
-    def zero_vector_grads(self):
-        self.grad[self.n_mat:].zero_()
+    def zero_grads(self):
+        """Vector gradients accumulate atomically and weight gradients are split-K reductions (fp32 atomics), so the
+        whole gradient buffer starts each step at zero."""
+        self.grad.zero_()
         self.sumsq.zero_()
 
 

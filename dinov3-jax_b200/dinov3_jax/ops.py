@@ -26,7 +26,8 @@ def _ld(t: torch.Tensor) -> int:
 def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False,
          bias: torch.Tensor | None = None, gelu: bool = False, store_pre: torch.Tensor | None = None,
          dgelu_of: torch.Tensor | None = None, gamma: torch.Tensor | None = None,
-         resid: torch.Tensor | None = None, accum: bool = False, alpha: float = 1.0, tile_n: int = 0) -> torch.Tensor:
+         resid: torch.Tensor | None = None, accum: bool = False, alpha: float = 1.0, tile_n: int = 0,
+         split_k: int = 0) -> torch.Tensor:
     """out[M,N] = epilogue(alpha * A.B) on the tcgen05 tensor cores (d3_gemm_bf16).
 
     A is [M,K] (a_mn=False) or stored transposed [K,M] (a_mn=True); B is [N,K] (b_mn=False) or [K,N] (b_mn=True).
@@ -68,7 +69,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, a_mn: bool = Fa
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     N.check(l.d3_gemm_bf16(N.ptr(A), _ld(A), int(a_mn), N.ptr(B), _ld(B), int(b_mn), M, Nn, K, C.byref(ep),
-                           int(tile_n), N.stream_ptr()), "d3_gemm_bf16")
+                           int(tile_n), int(split_k), N.stream_ptr()), "d3_gemm_bf16")
     if PROFILE is not None:
         e1.record()
         PROFILE.append(("gemm", 2.0 * M * Nn * K, e0, e1, (M, Nn, K, int(a_mn), int(b_mn))))

@@ -61,8 +61,11 @@ typedef struct {
   int flags;
   float alpha;
 } d3_gemm_epilogue;
+/* tile_n : 0 = auto; 64 / 128 / 256 = single-CTA kernel with that tile width; 512 = CTA-pair (cta_group::2) 256x256 kernel.
+ * split_k: 0 = auto (used only for plain fp32 outputs with D3_EP_ACCUM, i.e. weight gradients: partial sums are reduced
+ *          with fp32 atomics into `out`, which the caller zeroes or wants accumulated into); >= 1 = forced.            */
 int d3_gemm_bf16(const void* A, int lda, int a_major, const void* B, int ldb, int b_major, int M, int N, int K,
-                 const d3_gemm_epilogue* ep, int tile_n /*0 = auto; 64/128/256*/, void* stream);
+                 const d3_gemm_epilogue* ep, int tile_n, int split_k, void* stream);
 
 /* ---- patch embedding / token assembly ---------------------------------------------------------------------------
  * layers/patch_embed.py:38-51: the stride==kernel conv is im2col + GEMM (d3_gemm_bf16 with the kernel viewed as
