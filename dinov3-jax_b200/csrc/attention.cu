@@ -22,6 +22,9 @@ struct AttnShape {
   int D;         // embed dim (row stride of o / do); qkv row stride = 3D
   int H;
   float scale;   // head_dim^-0.5
+  const float* sin_t;  // backward only: RoPE tables [P, 64] (nullptr = gradients stay in the rotated frame)
+  const float* cos_t;
+  int prefix;          // tokens before the first patch token (cls + storage tokens)
 };
 
 // swizzled (SWIZZLE_128B, K-major) address of element (row, col) in a [128 x 64] bf16 chunk; col multiple of 8
@@ -30,7 +33,7 @@ __device__ __forceinline__ uint32_t sw128_offset(int row, int col) {
 }
 
 template <int TMEM_COLS>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                 __nv_bfloat16* __restrict__ O, float* __restrict__ LSE, const AttnShape sh) {
   extern __shared__ uint8_t smem_raw[];
@@ -47,8 +50,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* bar_load = bars;
   uint64_t* bar_mma = bars + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  float* red = reinterpret_cast<float*>(bars + 4);   // [2][128] cross-warp row reductions
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // 256 threads: two threads per query row (r = tid & 127), each owning one half of the key columns / output columns
+  const int warp = threadIdx.x >> 5;
+  const int r = threadIdx.x & 127;
+  const int ch = threadIdx.x >> 7;
   const int qt = blockIdx.x, h = blockIdx.y, c = blockIdx.z;
   const int q0 = qt * 128;
   const int row_base = c * sh.N;  // first token row of this crop in [T, ...]
@@ -93,12 +100,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   mbar_wait(bar_mma, 0);
   tc_fence_after();
 
-  // ---- softmax: thread r owns query row q0 + r (TMEM lane r)
-  const int r = threadIdx.x;
-  const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
+  // ---- softmax over this thread's half of the key columns
+  const uint32_t t_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  const int csplit = ((sh.Nkp / 16 + 1) / 2) * 16;
+  const int cbeg = ch ? csplit : 0, cend = ch ? sh.Nkp : csplit;
   const float cs = sh.scale * LOG2E;
   float mx = -3.0e38f;
-  for (int c0 = 0; c0 < sh.Nkp; c0 += 16) {
+  for (int c0 = cbeg; c0 < cend; c0 += 16) {
     uint32_t v[16];
     tmem_ld16(t_row + c0, v);
     tmem_ld_wait();
@@ -106,11 +114,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int j = 0; j < 16; ++j)
       if (c0 + j < sh.N) mx = fmaxf(mx, __uint_as_float(v[j]));
   }
+  red[ch * 128 + r] = mx;
+  __syncthreads();
+  mx = fmaxf(red[r], red[128 + r]);
+  __syncthreads();
   const float mxs = mx * cs;
   float sum = 0.f;
-  // all threads must have finished reading nothing from sQ/sK via the async proxy: the MMA that read them is
-  // complete (bar_mma), so region A may now be overwritten with P.
-  for (int c0 = 0; c0 < sh.Nkp; c0 += 16) {
+  // the MMA that read sQ / sK has completed (bar_mma), so region A may now be overwritten with P
+  for (int c0 = cbeg; c0 < cend; c0 += 16) {
     uint32_t v[16];
     tmem_ld16(t_row + c0, v);
     tmem_ld_wait();
@@ -127,9 +138,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     *reinterpret_cast<uint4*>(chunk + sw128_offset(r, cc + 8)) =
         make_uint4(pack_bf16(p[8], p[9]), pack_bf16(p[10], p[11]), pack_bf16(p[12], p[13]), pack_bf16(p[14], p[15]));
   }
+  red[ch * 128 + r] = sum;
   fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
   tc_fence_before();
   __syncthreads();
+  sum = red[r] + red[128 + r];
   if (threadIdx.x == 0) {
     tc_fence_after();
     // O[128, 64] = P[128, Nkp] V[Nkp, 64]  (A = P K-major, B = V MN-major: 16 keys per UMMA_K = 2 x 1024 B)
@@ -149,21 +162,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   const int q = q0 + r;
   const float inv = 1.f / sum;
-  uint32_t o[64];
-  tmem_ld32(t_row, o);
-  tmem_ld32(t_row + 32, o + 32);
+  uint32_t o[32];
+  tmem_ld32(t_row + ch * 32, o);
   tmem_ld_wait();
   if (q < sh.N) {
-    __nv_bfloat16* dst = O + (size_t)(row_base + q) * sh.D + h * 64;
+    __nv_bfloat16* dst = O + (size_t)(row_base + q) * sh.D + h * 64 + ch * 32;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < 4; ++j) {
       reinterpret_cast<uint4*>(dst)[j] = make_uint4(
           pack_bf16(__uint_as_float(o[8 * j]) * inv, __uint_as_float(o[8 * j + 1]) * inv),
           pack_bf16(__uint_as_float(o[8 * j + 2]) * inv, __uint_as_float(o[8 * j + 3]) * inv),
           pack_bf16(__uint_as_float(o[8 * j + 4]) * inv, __uint_as_float(o[8 * j + 5]) * inv),
           pack_bf16(__uint_as_float(o[8 * j + 6]) * inv, __uint_as_float(o[8 * j + 7]) * inv));
     }
-    if (LSE) LSE[((size_t)c * sh.H + h) * sh.N + q] = mx * sh.scale + logf(sum);   // natural-log LSE of scaled scores
+    if (LSE && ch == 0) LSE[((size_t)c * sh.H + h) * sh.N + q] = mx * sh.scale + logf(sum);   // natural-log LSE
   }
   tc_fence_before();
   __syncthreads();
@@ -194,7 +206,39 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ O, const __n
 //   dV[kt] += P^T dO,  dK[kt] += dS^T Q   (A = P / dS read MN-major, B = dO / Q read MN-major)
 //   dQ[qt] += dS K                        (A = dS K-major, B = K MN-major)
 // dQ accumulates in tensor memory across key tiles (2 x 64 columns), dK/dV across query tiles (64 + 64).
-__global__ void __launch_bounds__(128)
+// inverse RoPE on a gradient row held in registers (a[0..31] = first half, a[32..63] = second half of the head):
+// transpose of y = x*cos + rot_half(x)*sin  (dinov3_jax/layers/attention.py:14-20)
+__device__ __forceinline__ void rope_inverse_row(float (&a)[64], const float* __restrict__ sin_row,
+                                                 const float* __restrict__ cos_row) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float4 s4 = *reinterpret_cast<const float4*>(sin_row + j);
+    const float4 c4 = *reinterpret_cast<const float4*>(cos_row + j);
+    const float sn[4] = {s4.x, s4.y, s4.z, s4.w}, cs[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float lo = a[j + e], hi = a[j + e + 32];
+      a[j + e] = lo * cs[e] + hi * sn[e];
+      a[j + e + 32] = hi * cs[e] - lo * sn[e];
+    }
+  }
+}
+__device__ __forceinline__ void store_row64_bf16(__nv_bfloat16* dst, const float (&a)[64]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    reinterpret_cast<uint4*>(dst)[j] = make_uint4(pack_bf16(a[8 * j], a[8 * j + 1]), pack_bf16(a[8 * j + 2], a[8 * j + 3]),
+                                                  pack_bf16(a[8 * j + 4], a[8 * j + 5]), pack_bf16(a[8 * j + 6], a[8 * j + 7]));
+}
+__device__ __forceinline__ void load_row64(uint32_t taddr, float (&a)[64]) {
+  uint32_t u[64];
+  tmem_ld32(taddr, u);
+  tmem_ld32(taddr + 32, u + 32);
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 64; ++j) a[j] = __uint_as_float(u[j]);
+}
+
+__global__ void __launch_bounds__(256)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                 const float* __restrict__ LSE, const float* __restrict__ Delta, __nv_bfloat16* __restrict__ dQKV,
                 const AttnShape sh) {
@@ -212,11 +256,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   uint64_t* bar_mma = bars + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // 256 threads: two per row (r = tid & 127); ch = tid >> 7 picks the key-column half in the elementwise phase,
+  // dK (ch 0) vs dV (ch 1) in the key-tile output phase, and the query tile in the dQ output phase
+  const int warp = threadIdx.x >> 5;
+  const int r = threadIdx.x & 127;
+  const int ch = threadIdx.x >> 7;
   const int h = blockIdx.x, c = blockIdx.y;
   const int row_base = c * sh.N;
   const int nQ = (sh.N + 127) / 128, nK = nQ;
-  const int r = threadIdx.x;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQKV);
@@ -233,7 +280,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const uint32_t tmem = *tmem_slot;
   // TMEM columns: S [0,128) | dP [128,256) | dK [256,320) | dV [320,384) | dQ[qt] [384 + 64 qt, ...)
   const uint32_t tS = tmem, tDP = tmem + 128, tDK = tmem + 256, tDV = tmem + 320, tDQ = tmem + 384;
-  const uint32_t t_lane = (uint32_t)(warp * 32) << 16;
+  const uint32_t t_lane = (uint32_t)((warp & 3) * 32) << 16;
 
   if (threadIdx.x == 0) {
     mbar_expect_tx(bar_q, nQ * 2 * 16384);
@@ -272,13 +319,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       mma_phase ^= 1;
       tc_fence_after();
 
-      // ---- elementwise: thread r owns query row q = qt*128 + r
+      // ---- elementwise: this thread owns query row q = qt*128 + r and key columns [64 ch, 64 ch + 64)
       const int q = qt * 128 + r;
       const bool q_ok = q < sh.N;
       const size_t stat = ((size_t)c * sh.H + h) * sh.N + (q_ok ? q : 0);
       const float lse2 = q_ok ? LSE[stat] * LOG2E : 0.f;
       const float dl = q_ok ? Delta[stat] : 0.f;
-      for (int c0 = 0; c0 < 128; c0 += 16) {
+      uint8_t* pc = sP + ch * 16384;
+      uint8_t* dc = sDS + ch * 16384;
+#pragma unroll 1
+      for (int cc = 0; cc < 64; cc += 16) {
+        const int c0 = ch * 64 + cc;
         uint32_t s[16], dp[16];
         tmem_ld16(tS + t_lane + c0, s);
         tmem_ld16(tDP + t_lane + c0, dp);
@@ -290,9 +341,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           p[j] = ok ? exp2f(__uint_as_float(s[j]) * cs - lse2) : 0.f;
           ds[j] = ok ? p[j] * (__uint_as_float(dp[j]) - dl) * sh.scale : 0.f;
         }
-        const int cc = c0 & 63;
-        uint8_t* pc = sP + (c0 >> 6) * 16384;
-        uint8_t* dc = sDS + (c0 >> 6) * 16384;
         *reinterpret_cast<uint4*>(pc + sw128_offset(r, cc)) =
             make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
         *reinterpret_cast<uint4*>(pc + sw128_offset(r, cc + 8)) =
@@ -334,35 +382,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       mma_phase ^= 1;
       tc_fence_after();
     }
-    // ---- dK / dV of this key tile: thread r owns key row kt*128 + r
+    // ---- dK (ch 0) / dV (ch 1) of this key tile: thread owns key row kt*128 + r
     {
       const int key = kt * 128 + r;
-      uint32_t a[64];
-      tmem_ld32(tDK + t_lane, a);
-      tmem_ld32(tDK + t_lane + 32, a + 32);
-      tmem_ld_wait();
+      float a[64];
+      load_row64((ch ? tDV : tDK) + t_lane, a);
       if (key < sh.N) {
-        __nv_bfloat16* dst = dQKV + (size_t)(row_base + key) * (3 * sh.D) + sh.D + h * 64;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          reinterpret_cast<uint4*>(dst)[j] = make_uint4(
-              pack_bf16(__uint_as_float(a[8 * j]), __uint_as_float(a[8 * j + 1])),
-              pack_bf16(__uint_as_float(a[8 * j + 2]), __uint_as_float(a[8 * j + 3])),
-              pack_bf16(__uint_as_float(a[8 * j + 4]), __uint_as_float(a[8 * j + 5])),
-              pack_bf16(__uint_as_float(a[8 * j + 6]), __uint_as_float(a[8 * j + 7])));
-      }
-      tmem_ld32(tDV + t_lane, a);
-      tmem_ld32(tDV + t_lane + 32, a + 32);
-      tmem_ld_wait();
-      if (key < sh.N) {
-        __nv_bfloat16* dst = dQKV + (size_t)(row_base + key) * (3 * sh.D) + 2 * sh.D + h * 64;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          reinterpret_cast<uint4*>(dst)[j] = make_uint4(
-              pack_bf16(__uint_as_float(a[8 * j]), __uint_as_float(a[8 * j + 1])),
-              pack_bf16(__uint_as_float(a[8 * j + 2]), __uint_as_float(a[8 * j + 3])),
-              pack_bf16(__uint_as_float(a[8 * j + 4]), __uint_as_float(a[8 * j + 5])),
-              pack_bf16(__uint_as_float(a[8 * j + 6]), __uint_as_float(a[8 * j + 7])));
+        if (!ch && sh.sin_t && key >= sh.prefix)
+          rope_inverse_row(a, sh.sin_t + (size_t)(key - sh.prefix) * 64, sh.cos_t + (size_t)(key - sh.prefix) * 64);
+        store_row64_bf16(dQKV + (size_t)(row_base + key) * (3 * sh.D) + (ch ? 2 : 1) * sh.D + h * 64, a);
       }
     }
     kv_phase ^= 1;
@@ -370,22 +398,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     __syncthreads();   // all TMEM reads of dK/dV done before the next key tile's MMAs overwrite them
     tc_fence_after();
   }
-  // ---- dQ
-  for (int qt = 0; qt < nQ; ++qt) {
+  // ---- dQ: query tile qt is written by the threads with ch == (qt & 1)
+  for (int qt = ch; qt < nQ; qt += 2) {
     const int q = qt * 128 + r;
-    uint32_t a[64];
-    tmem_ld32(tDQ + qt * 64 + t_lane, a);
-    tmem_ld32(tDQ + qt * 64 + t_lane + 32, a + 32);
-    tmem_ld_wait();
+    float a[64];
+    load_row64(tDQ + qt * 64 + t_lane, a);
     if (q < sh.N) {
-      __nv_bfloat16* dst = dQKV + (size_t)(row_base + q) * (3 * sh.D) + h * 64;
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        reinterpret_cast<uint4*>(dst)[j] = make_uint4(
-            pack_bf16(__uint_as_float(a[8 * j]), __uint_as_float(a[8 * j + 1])),
-            pack_bf16(__uint_as_float(a[8 * j + 2]), __uint_as_float(a[8 * j + 3])),
-            pack_bf16(__uint_as_float(a[8 * j + 4]), __uint_as_float(a[8 * j + 5])),
-            pack_bf16(__uint_as_float(a[8 * j + 6]), __uint_as_float(a[8 * j + 7])));
+      if (sh.sin_t && q >= sh.prefix)
+        rope_inverse_row(a, sh.sin_t + (size_t)(q - sh.prefix) * 64, sh.cos_t + (size_t)(q - sh.prefix) * 64);
+      store_row64_bf16(dQKV + (size_t)(row_base + q) * (3 * sh.D) + h * 64, a);
     }
   }
   tc_fence_before();
@@ -404,6 +425,7 @@ static int make_map(CUtensorMap* map, const void* ptr, long rows, int cols, int 
 static int attn_shape(AttnShape* s, int N, int D, int H) {
   if (D != H * 64) return set_error(D3_ERR_ARG, "attention: head_dim must be 64");
   s->N = N; s->D = D; s->H = H; s->scale = 0.125f;
+  s->sin_t = nullptr; s->cos_t = nullptr; s->prefix = 0;
   s->nbox = (N + 255) / 256;
   const int q = 16 * s->nbox;
   s->Nkp = (N + q - 1) / q * q;
@@ -429,28 +451,31 @@ int d3_attn_fwd(const void* qkv, void* o, float* lse, int n_crops, int N, int D,
   const int kv_bytes = s.Nkp * 128;
   const int p_chunks = (s.Nkp + 63) / 64;
   const int regA = max(16384 + kv_bytes, p_chunks * 16384);
-  const int smem = regA + kv_bytes + 64 + 1024;
+  const int smem = regA + kv_bytes + 64 + 1024 + 1024;
   dim3 grid((N + 127) / 128, H, n_crops);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (s.Nkp <= 256) {
     static bool cfg = false;
     if (!cfg) { cudaFuncSetAttribute(attn_fwd_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); cfg = true; }
-    attn_fwd_kernel<256><<<grid, 128, smem, st>>>(tq, tkv, (__nv_bfloat16*)o, lse, s);
+    attn_fwd_kernel<256><<<grid, 256, smem, st>>>(tq, tkv, (__nv_bfloat16*)o, lse, s);
   } else {
     static bool cfg = false;
     if (!cfg) { cudaFuncSetAttribute(attn_fwd_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); cfg = true; }
-    attn_fwd_kernel<512><<<grid, 128, smem, st>>>(tq, tkv, (__nv_bfloat16*)o, lse, s);
+    attn_fwd_kernel<512><<<grid, 256, smem, st>>>(tq, tkv, (__nv_bfloat16*)o, lse, s);
   }
   D3_CHECK_LAUNCH();
   return D3_OK;
 }
 
 int d3_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, float* delta_scratch, void* dqkv,
-                int n_crops, int N, int D, int H, void* stream) {
+                int n_crops, int N, int D, int H, const float* rope_sin, const float* rope_cos, int rope_prefix,
+                void* stream) {
   AttnShape s;
   int rc = attn_shape(&s, N, D, H);
   if (rc) return rc;
   if (N > 256) return set_error(D3_ERR_ARG, "d3_attn_bwd: N > 256 not supported yet");
+  if ((rope_sin == nullptr) != (rope_cos == nullptr)) return set_error(D3_ERR_ARG, "d3_attn_bwd: sin/cos tables");
+  s.sin_t = rope_sin; s.cos_t = rope_cos; s.prefix = rope_prefix;
   const long T = (long)n_crops * N;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   {
@@ -466,7 +491,7 @@ int d3_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* ls
   if (!cfg) { cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); cfg = true; }
   const int smem = 163840 + 64 + 1024;
   dim3 grid(H, n_crops);
-  attn_bwd_kernel<<<grid, 128, smem, st>>>(tqkv, tdo, lse, delta_scratch, (__nv_bfloat16*)dqkv, s);
+  attn_bwd_kernel<<<grid, 256, smem, st>>>(tqkv, tdo, lse, delta_scratch, (__nv_bfloat16*)dqkv, s);
   D3_CHECK_LAUNCH();
   return D3_OK;
 }

@@ -173,38 +173,135 @@ __global__ void layernorm_param_grad_kernel(const InT* __restrict__ dy, const fl
   atomicAdd(&dbias[col], ab);
 }
 
+// Fused row + parameter-gradient backward for D = 128 * VPL: each lane keeps its 4*VPL columns of x / dy in registers
+// between the two row passes (one HBM read each), accumulates dscale / dbias partials in registers over all rows of
+// the warp, reduces them across the CTA's warps in shared memory and issues one global atomic per column per CTA.
+template <int VPL, typename InT>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_fused_kernel(const InT* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+                           const float* __restrict__ rstd, const float* __restrict__ scale,
+                           const float* __restrict__ dx_add, float* __restrict__ dx, float* __restrict__ dscale,
+                           float* __restrict__ dbias, int T) {
+  constexpr int D = VPL * 128;
+  __shared__ float part[2 * D];
+  for (int e = threadIdx.x; e < 2 * D; e += blockDim.x) part[e] = 0.f;
+  __syncthreads();
+  const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
+  float ads[VPL][4], adb[VPL][4];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { ads[k][j] = 0.f; adb[k][j] = 0.f; }
+  for (long row = (long)blockIdx.x * warps + (threadIdx.x >> 5); row < T; row += (long)gridDim.x * warps) {
+    const float mu = mean[row], rs = rstd[row];
+    float xh[VPL][4], gs[VPL][4];
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int e = (k * 32 + lane) * 4;
+      const float4 xv = *reinterpret_cast<const float4*>(x + row * (long)D + e);
+      float g[4];
+      if constexpr (sizeof(InT) == 2) {
+        const uint2 u = *reinterpret_cast<const uint2*>(dy + row * (long)D + e);
+        const float2 g0 = unpack_bf16(u.x), g1 = unpack_bf16(u.y);
+        g[0] = g0.x; g[1] = g0.y; g[2] = g1.x; g[3] = g1.y;
+      } else {
+        const float4 gv = *reinterpret_cast<const float4*>(dy + row * (long)D + e);
+        g[0] = gv.x; g[1] = gv.y; g[2] = gv.z; g[3] = gv.w;
+      }
+      const float4 sc = *reinterpret_cast<const float4*>(scale + e);
+      const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, scs[4] = {sc.x, sc.y, sc.z, sc.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        xh[k][j] = (xs[j] - mu) * rs;
+        gs[k][j] = g[j] * scs[j];
+        a += gs[k][j];
+        b += gs[k][j] * xh[k][j];
+        ads[k][j] += g[j] * xh[k][j];
+        adb[k][j] += g[j];
+      }
+    }
+    a = warp_sum(a) * (1.f / D);
+    b = warp_sum(b) * (1.f / D);
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int e = (k * 32 + lane) * 4;
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = rs * (gs[k][j] - a - xh[k][j] * b);
+      if (dx_add) {
+        const float4 r4 = *reinterpret_cast<const float4*>(dx_add + row * (long)D + e);
+        o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
+      }
+      *reinterpret_cast<float4*>(dx + row * (long)D + e) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+  if (dscale) {
+#pragma unroll
+    for (int k = 0; k < VPL; ++k)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int e = (k * 32 + lane) * 4 + j;
+        atomicAdd(&part[e], ads[k][j]);
+        atomicAdd(&part[D + e], adb[k][j]);
+      }
+    __syncthreads();
+    for (int e = threadIdx.x; e < D; e += blockDim.x) {
+      atomicAdd(&dscale[e], part[e]);
+      atomicAdd(&dbias[e], part[D + e]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ RoPE
 // layers/attention.py:14-20,69-90 + layers/rope_position_encoding.py:117-123.  In place on the q and k thirds of
 // qkv bf16 [T, 3D]; token t of each crop (N tokens) is rotated iff t >= prefix; math in fp32.
 // sincos fp32 [P, hd] each.  inverse=1 applies the transpose rotation (backward).
 __global__ void rope_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restrict__ sin_t,
                             const float* __restrict__ cos_t, long T, int Ntok, int prefix, int D, int hd, int inverse) {
+  // one thread = 8 rotation pairs: elements [i0, i0+8) and [i0+half, i0+half+8) of one head of q or k (16-byte accesses;
+  // the 4 threads of a head touch one full 128-byte line).  The tables repeat their first half (angles are tiled x2).
   const int half = hd / 2;
-  const int pairs_per_row = 2 * (D / hd) * half;   // q and k, all heads
-  const long total = T * (long)pairs_per_row;
+  const int groups = half / 8;
+  const int H = D / hd;
+  const int items_per_row = 2 * H * groups;
+  const long total = T * (long)items_per_row;
   for (long w = blockIdx.x * (long)blockDim.x + threadIdx.x; w < total; w += (long)gridDim.x * blockDim.x) {
-    const long row = w / pairs_per_row;
-    int r = (int)(w % pairs_per_row);
+    const long row = w / items_per_row;
+    int r = (int)(w % items_per_row);
     const int t = (int)(row % Ntok);
     if (t < prefix) continue;
-    const int which = r / ((D / hd) * half);   // 0 = q, 1 = k
-    r -= which * (D / hd) * half;
-    const int head = r / half, i = r % half;
-    const int pidx = t - prefix;
-    const float s1 = sin_t[pidx * hd + i], c1 = cos_t[pidx * hd + i];
-    const float s2 = sin_t[pidx * hd + i + half], c2 = cos_t[pidx * hd + i + half];
-    __nv_bfloat16* base = qkv + row * (long)(3 * D) + which * D + head * hd;
-    const float x1 = __bfloat162float(base[i]), x2 = __bfloat162float(base[i + half]);
-    float y1, y2;
-    if (!inverse) {            // y = x*cos + rot_half(x)*sin, rot_half([x1,x2]) = [-x2, x1]
-      y1 = x1 * c1 - x2 * s1;
-      y2 = x2 * c2 + x1 * s2;
-    } else {                   // transpose: dx1 = dy1*c1 + dy2*s2 ; dx2 = dy2*c2 - dy1*s1
-      y1 = x1 * c1 + x2 * s2;
-      y2 = x2 * c2 - x1 * s1;
+    const int which = r / (H * groups);
+    r -= which * H * groups;
+    const int head = r / groups, i0 = (r % groups) * 8;
+    const float* sp = sin_t + (long)(t - prefix) * hd + i0;
+    const float* cp = cos_t + (long)(t - prefix) * hd + i0;
+    float sn[8], cs[8];
+    *reinterpret_cast<float4*>(sn) = *reinterpret_cast<const float4*>(sp);
+    *reinterpret_cast<float4*>(sn + 4) = *reinterpret_cast<const float4*>(sp + 4);
+    *reinterpret_cast<float4*>(cs) = *reinterpret_cast<const float4*>(cp);
+    *reinterpret_cast<float4*>(cs + 4) = *reinterpret_cast<const float4*>(cp + 4);
+    __nv_bfloat16* base = qkv + row * (long)(3 * D) + which * D + head * hd + i0;
+    const uint4 lo = *reinterpret_cast<const uint4*>(base);
+    const uint4 hi = *reinterpret_cast<const uint4*>(base + half);
+    const uint32_t lw[4] = {lo.x, lo.y, lo.z, lo.w}, hw[4] = {hi.x, hi.y, hi.z, hi.w};
+    uint32_t ol[4], oh[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 a = unpack_bf16(lw[j]), b = unpack_bf16(hw[j]);
+      float y1a, y1b, y2a, y2b;
+      if (!inverse) {   // y = x*cos + rot_half(x)*sin, rot_half([x1,x2]) = [-x2, x1]
+        y1a = a.x * cs[2 * j] - b.x * sn[2 * j];          y2a = b.x * cs[2 * j] + a.x * sn[2 * j];
+        y1b = a.y * cs[2 * j + 1] - b.y * sn[2 * j + 1];  y2b = b.y * cs[2 * j + 1] + a.y * sn[2 * j + 1];
+      } else {          // transpose rotation (backward)
+        y1a = a.x * cs[2 * j] + b.x * sn[2 * j];          y2a = b.x * cs[2 * j] - a.x * sn[2 * j];
+        y1b = a.y * cs[2 * j + 1] + b.y * sn[2 * j + 1];  y2b = b.y * cs[2 * j + 1] - a.y * sn[2 * j + 1];
+      }
+      ol[j] = pack_bf16(y1a, y1b);
+      oh[j] = pack_bf16(y2a, y2b);
     }
-    base[i] = __float2bfloat16(y1);
-    base[i + half] = __float2bfloat16(y2);
+    *reinterpret_cast<uint4*>(base) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+    *reinterpret_cast<uint4*>(base + half) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
   }
 }
 
@@ -342,6 +439,20 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat1
 using namespace d3;
 #define STREAM(s) reinterpret_cast<cudaStream_t>(s)
 
+template <int VPL>
+static void launch_ln_bwd_fused(const void* dy, int dy_is_f32, const float* x, const float* mean, const float* rstd,
+                                const float* scale, const float* dx_add, float* dx, float* dscale, float* dbias, int T,
+                                cudaStream_t st) {
+  const int blocks = min((T + 7) / 8, sm_count() * 2);
+  if (dy_is_f32)
+    layernorm_bwd_fused_kernel<VPL, float><<<blocks, 256, 0, st>>>((const float*)dy, x, mean, rstd, scale, dx_add, dx,
+                                                                  dscale, dbias, T);
+  else
+    layernorm_bwd_fused_kernel<VPL, __nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)dy, x, mean, rstd, scale,
+                                                                          dx_add, dx, dscale, dbias, T);
+}
+
+
 extern "C" {
 
 int d3_im2col(const void* img, void* out, int n, int H, int W, int p, void* stream) {
@@ -388,15 +499,27 @@ int d3_layernorm_bwd(const void* dy, int dy_is_f32, const float* x, const float*
                      const float* scale, const float* dx_add, float* dx, float* dscale, float* dbias, int T, int D,
                      void* stream) {
   if (T <= 0) return D3_OK;
+  cudaStream_t st = STREAM(stream);
+  const bool vec_ok = (D % 128 == 0) && (((uintptr_t)dy | (uintptr_t)x | (uintptr_t)dx | (uintptr_t)scale | (uintptr_t)dx_add) % 16 == 0);
+  if (vec_ok && (D == 128 || D == 256 || D == 384 || D == 768 || D == 1024)) {
+    switch (D / 128) {
+      case 1: launch_ln_bwd_fused<1>(dy, dy_is_f32, x, mean, rstd, scale, dx_add, dx, dscale, dbias, T, st); break;
+      case 2: launch_ln_bwd_fused<2>(dy, dy_is_f32, x, mean, rstd, scale, dx_add, dx, dscale, dbias, T, st); break;
+      case 3: launch_ln_bwd_fused<3>(dy, dy_is_f32, x, mean, rstd, scale, dx_add, dx, dscale, dbias, T, st); break;
+      case 6: launch_ln_bwd_fused<6>(dy, dy_is_f32, x, mean, rstd, scale, dx_add, dx, dscale, dbias, T, st); break;
+      default: launch_ln_bwd_fused<8>(dy, dy_is_f32, x, mean, rstd, scale, dx_add, dx, dscale, dbias, T, st); break;
+    }
+    D3_CHECK_LAUNCH();
+    return D3_OK;
+  }
   int blocks = min((T + 7) / 8, sm_count() * 8);
   dim3 pgrid((D + 127) / 128, min(128, max(1, T / 64)));
   if (dy_is_f32) {
-    layernorm_bwd_kernel<float><<<blocks, 256, 0, STREAM(stream)>>>((const float*)dy, x, mean, rstd, scale, dx_add, dx, T, D);
-    if (dscale) layernorm_param_grad_kernel<float><<<pgrid, 128, 0, STREAM(stream)>>>((const float*)dy, x, mean, rstd, dscale, dbias, T, D);
+    layernorm_bwd_kernel<float><<<blocks, 256, 0, st>>>((const float*)dy, x, mean, rstd, scale, dx_add, dx, T, D);
+    if (dscale) layernorm_param_grad_kernel<float><<<pgrid, 128, 0, st>>>((const float*)dy, x, mean, rstd, dscale, dbias, T, D);
   } else {
-    layernorm_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, STREAM(stream)>>>((const __nv_bfloat16*)dy, x, mean, rstd,
-                                                                          scale, dx_add, dx, T, D);
-    if (dscale) layernorm_param_grad_kernel<__nv_bfloat16><<<pgrid, 128, 0, STREAM(stream)>>>((const __nv_bfloat16*)dy, x, mean, rstd, dscale, dbias, T, D);
+    layernorm_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)dy, x, mean, rstd, scale, dx_add, dx, T, D);
+    if (dscale) layernorm_param_grad_kernel<__nv_bfloat16><<<pgrid, 128, 0, st>>>((const __nv_bfloat16*)dy, x, mean, rstd, dscale, dbias, T, D);
   }
   D3_CHECK_LAUNCH();
   if (dscale) count_launch();
@@ -405,8 +528,8 @@ int d3_layernorm_bwd(const void* dy, int dy_is_f32, const float* x, const float*
 
 int d3_rope(void* qkv, const float* sin_t, const float* cos_t, long long T, int Ntok, int prefix, int D, int head_dim,
             int inverse, void* stream) {
-  if (head_dim % 2 || D % head_dim) return set_error(D3_ERR_ARG, "d3_rope: head_dim");
-  long total = T * (long)(2 * (D / head_dim) * (head_dim / 2));
+  if (head_dim % 16 || D % head_dim) return set_error(D3_ERR_ARG, "d3_rope: head_dim must be a multiple of 16");
+  long total = T * (long)(2 * (D / head_dim) * (head_dim / 16));
   int blocks = (int)min((total + 255) / 256, (long)sm_count() * 32);
   rope_kernel<<<blocks, 256, 0, STREAM(stream)>>>((__nv_bfloat16*)qkv, sin_t, cos_t, T, Ntok, prefix, D, head_dim,
                                                  inverse);

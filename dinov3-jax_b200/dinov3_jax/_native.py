@@ -45,7 +45,7 @@ SIGNATURES = {
     "d3_layernorm_bwd": [P, I, P, P, P, P, P, P, P, P, I, I, P],
     "d3_rope": [P, P, P, LL, I, I, I, I, I, P],
     "d3_attn_fwd": [P, P, P, I, I, I, I, P],
-    "d3_attn_bwd": [P, P, P, P, P, P, I, I, I, I, P],
+    "d3_attn_bwd": [P, P, P, P, P, P, I, I, I, I, P, P, I, P],
     "d3_token_rows": [P, P, I, I, I, P],
     "d3_gather_rows": [P, P, P, P, I, I, P],
     "d3_scatter_add_rows": [P, I, P, P, I, I, P],

@@ -342,8 +342,9 @@ class Engine:
         ops.gemm(st.O[i], self.dP, gw("attn/proj/kernel"), a_mn=True, b_mn=True, accum=True)                # dWp = o^T dP
         for cs, lse, delta in zip(st.sets, st.LSE[i], self.delta):
             sl = slice(cs.row0, cs.row0 + cs.T)
-            ops.attn_bwd(st.QKV[i][sl], st.O[i][sl], self.dO[sl], lse, delta, self.dQKV[sl], cs.n, cs.N, D, H)
-            ops.rope(self.dQKV[sl], cs.sin, cs.cos, cs.N, 1, D, cfg.head_dim, inverse=True)
+            # gradient w.r.t. the pre-RoPE projection: the inverse rotation is fused into the kernel's store stage
+            ops.attn_bwd(st.QKV[i][sl], st.O[i][sl], self.dO[sl], lse, delta, self.dQKV[sl], cs.n, cs.N, D, H,
+                         rope_sin=cs.sin, rope_cos=cs.cos, rope_prefix=1)
         ops.colsum_bf16(self.dQKV, gv("attn/qkv/bias"))
         ops.gemm(self.dQKV, w("attn/qkv/kernel"), self.dY)                                      # dY = dQKV Wqkv^T
         ops.gemm(st.Y[i], self.dQKV, gw("attn/qkv/kernel"), a_mn=True, b_mn=True, accum=True)               # dWqkv = y^T dQKV

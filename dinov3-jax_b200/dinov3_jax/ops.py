@@ -135,10 +135,10 @@ def attn_fwd(qkv, o, lse, n_crops, Ntok, D, H):
     return o
 
 
-def attn_bwd(qkv, o, do, lse, delta, dqkv, n_crops, Ntok, D, H):
+def attn_bwd(qkv, o, do, lse, delta, dqkv, n_crops, Ntok, D, H, rope_sin=None, rope_cos=None, rope_prefix=0):
     assert all(t.dtype == bf16 and t.is_contiguous() for t in (qkv, o, do, dqkv))
-    N.check(N.init().d3_attn_bwd(_p(qkv), _p(o), _p(do), _p(lse), _p(delta), _p(dqkv), n_crops, Ntok, D, H, _s()),
-            "d3_attn_bwd")
+    N.check(N.init().d3_attn_bwd(_p(qkv), _p(o), _p(do), _p(lse), _p(delta), _p(dqkv), n_crops, Ntok, D, H,
+                                 _p(rope_sin), _p(rope_cos), rope_prefix, _s()), "d3_attn_bwd")
     return dqkv
 
 

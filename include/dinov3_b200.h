@@ -93,9 +93,12 @@ int d3_rope(void* qkv_bf16, const float* sin_t /*[P,hd]*/, const float* cos_t, l
 /* ---- attention (layers/attention.py:116 nn.dot_product_attention; head_dim 64, N <= 448 fwd / 256 bwd) ------------ */
 int d3_attn_fwd(const void* qkv_bf16 /*[n*N,3D] post-RoPE*/, void* o_bf16 /*[n*N,D]*/, float* lse /*[n,H,N] or NULL*/,
                 int n_crops, int N, int D, int H, void* stream);
+/* rope_sin / rope_cos ([P,64] fp32, or NULL): when given, the inverse rotation (transpose of layers/attention.py:19-20)
+ * is applied to dq / dk of tokens >= rope_prefix before they are stored, i.e. dqkv is the gradient w.r.t. the
+ * pre-RoPE qkv projection output.                                                                                  */
 int d3_attn_bwd(const void* qkv_bf16, const void* o_bf16, const void* do_bf16, const float* lse,
-                float* delta_scratch /*[n,H,N]*/, void* dqkv_bf16 /*[n*N,3D] (pre-inverse-RoPE)*/, int n_crops, int N,
-                int D, int H, void* stream);
+                float* delta_scratch /*[n,H,N]*/, void* dqkv_bf16 /*[n*N,3D]*/, int n_crops, int N, int D, int H,
+                const float* rope_sin, const float* rope_cos, int rope_prefix, void* stream);
 
 /* ---- row gather / scatter (train/ssl_meta_arch.py:377,432 patch.reshape(-1,D)[mask_indices_list]; cls = token 0) --- */
 int d3_token_rows(const long long* mask_indices /*int64 [count] (mode 0)*/, int* rows /*int32 [count]*/, int count,

@@ -139,6 +139,26 @@ def test_attention_backward(n, N, H):
         assert rel(dqkv[:, j * D:(j + 1) * D], x.grad[:, j * D:(j + 1) * D]) < 1e-2
 
 
+def test_attention_backward_fused_inverse_rope():
+    """dqkv with rope tables == separate inverse-RoPE of the plain backward (tokens < prefix untouched, v untouched)."""
+    from dinov3_jax import ops
+    from oracle.model import rope_sincos
+    n, Hp, H = 3, 6, 2
+    N, D = Hp * Hp + 1, 64 * H
+    sin, cos = [t.cuda().contiguous() for t in rope_sincos(Hp, Hp, 64, 100.0, torch.float32)]
+    qkv = torch.randn(n * N, 3 * D, device="cuda").to(torch.bfloat16)
+    do = torch.randn(n * N, D, device="cuda").to(torch.bfloat16)
+    o = torch.empty(n * N, D, device="cuda", dtype=torch.bfloat16); lse = torch.zeros(n, H, N, device="cuda")
+    ops.attn_fwd(qkv, o, lse, n, N, D, H)
+    d1 = torch.empty(n * N, 3 * D, device="cuda", dtype=torch.bfloat16); d2 = torch.empty_like(d1)
+    delta = torch.zeros(n, H, N, device="cuda")
+    ops.attn_bwd(qkv, o, do, lse, delta, d1, n, N, D, H)
+    ops.rope(d1, sin, cos, N, 1, D, 64, inverse=True)
+    ops.attn_bwd(qkv, o, do, lse, delta, d2, n, N, D, H, rope_sin=sin, rope_cos=cos, rope_prefix=1)
+    assert rel(d2, d1) < BF16_TOL          # d1 is rounded to bf16 twice, d2 once
+    assert torch.equal(d2[:, 2 * D:], d1[:, 2 * D:])
+
+
 # --------------------------------------------------------------------------------------------------- integer / layout work
 def test_im2col_and_tokens_bit_exact():
     from dinov3_jax import ops
@@ -187,7 +207,7 @@ def test_token_rows_gather_scatter_bit_exact():
 
 
 # --------------------------------------------------------------------------------------------------- normalisation / rope
-@pytest.mark.parametrize("T,D", [(1000, 384), (333, 1024), (7, 128)])
+@pytest.mark.parametrize("T,D", [(1000, 384), (333, 1024), (7, 128), (2051, 768), (100, 256), (300, 1536), (64, 192)])
 def test_layernorm_forward_backward(T, D):
     from dinov3_jax import ops
     from oracle.model import layer_norm
