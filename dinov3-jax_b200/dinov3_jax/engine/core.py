@@ -127,10 +127,14 @@ class Engine:
     def __init__(self, cfg: EngineConfig, B: int, device="cuda", max_masked: int | None = None, comm=None):
         assert cfg.head_dim == 64, "kernels are specialised for head_dim 64 (every BASELINE arch)"
         self.cfg, self.B, self.device = cfg, B, torch.device(device)
-        self.comm = comm  # distributed context (None = single GPU)
+        self.comm = comm  # fsdp.runtime.Comm (None = single GPU)
         self.world = 1 if comm is None else comm.world
+        self.rank = 0 if comm is None else comm.rank
         dev = self.device
-        self.params = ParamStore(cfg, dev)
+        self.params = ParamStore(cfg, dev, self.world, self.rank)
+        from ..fsdp.runtime import FsdpRuntime
+        self.fsdp = FsdpRuntime(comm, self.params.mods, dev)
+        self.params.runtime = self.fsdp
         ng, nl = cfg.n_global * B, cfg.n_local * B
         # teacher stream: global crops only; student stream: global then local rows
         self.t_sets = [CropSet(cfg, ng, cfg.global_size, 0, dev)]
@@ -226,6 +230,7 @@ class Engine:
     # ------------------------------------------------------------------------------------------------ forward pieces
     def _embed(self, st: Stream, images, masks_list, teacher: bool):
         cfg, bb = self.cfg, self.params.mods["backbone"]
+        self.fsdp.acquire("backbone", "embed", teacher)
         X0 = st.x_in(0)
         Wpe = bb.w("patch_embed/proj/kernel", teacher)
         for cs, img, masks in zip(st.sets, images, masks_list):
@@ -237,6 +242,7 @@ class Engine:
     def _block_fwd(self, st: Stream, i: int, teacher: bool):
         cfg, bb = self.cfg, self.params.mods["backbone"]
         D, H = cfg.embed_dim, cfg.heads
+        self.fsdp.acquire("backbone", f"blocks_{i}", teacher)
         p = f"blocks_{i}/"
         v = lambda n: bb.vec(p + n, teacher)
         w = lambda n: bb.w(p + n, teacher)
@@ -264,6 +270,7 @@ class Engine:
         for i in range(cfg.depth):
             self._block_fwd(st, i, teacher)
         XL = st.x_in(cfg.depth)
+        self.fsdp.acquire("backbone", "norm", teacher)
         fs = st.fstats if st.stash else [None, None]
         ops.layernorm_fwd(XL, bb.vec("norm/scale", teacher), bb.vec("norm/bias", teacher), st.Xn, fs[0], fs[1], cfg.ln_eps)
 
@@ -272,6 +279,7 @@ class Engine:
         w = lambda n: hd.w(n, teacher)
         v = lambda n: hd.vec(n, teacher)
         r = lambda t: t[:R]
+        self.fsdp.acquire(module, "head", teacher)
         if R == 0:
             return
         ops.gemm(r(hb.A0), w("mlp/layers_0/kernel"), r(hb.H1), b_mn=True, bias=v("mlp/layers_0/bias"), gelu=True,
@@ -306,6 +314,7 @@ class Engine:
         w, gw, gv = (lambda n: hd.w(n)), hd.gw, hd.gv
         r = lambda t: t[:R]
         if R == 0:
+            self.fsdp.grads_ready(module, "head")
             return
         # prototype layer: logits = Yn Wl
         ops.gemm(r(hb.dS), w("last_layer/kernel"), r(hb.dYn))                                   # dYn = dS Wl^T
@@ -320,6 +329,7 @@ class Engine:
         ops.colsum_bf16(r(hb.dUa), gv("mlp/layers_0/bias"))
         ops.gemm(r(hb.A0), r(hb.dUa), gw("mlp/layers_0/kernel"), a_mn=True, b_mn=True, accum=True)
         ops.gemm(r(hb.dUa), w("mlp/layers_0/kernel"), r(hb.dA0))                                 # fp32 [R, D]
+        self.fsdp.grads_ready(module, "head")
 
     def _block_bwd(self, i: int, dX, dXprev):
         cfg, bb, st = self.cfg, self.params.mods["backbone"], self.student
@@ -350,6 +360,18 @@ class Engine:
         ops.gemm(st.Y[i], self.dQKV, gw("attn/qkv/kernel"), a_mn=True, b_mn=True, accum=True)               # dWqkv = y^T dQKV
         ops.layernorm_bwd(self.dY, st.X[i], m1, r1, v("norm1/scale"), dXprev, dx_add=self.dXmid,
                           dscale=gv("norm1/scale"), dbias=gv("norm1/bias"))
+        self.fsdp.grads_ready("backbone", f"blocks_{i}")
+
+    def _gather_schedule(self):
+        """(module, unit, teacher) in the order the step uses them: teacher pass, then student pass (student parameters
+        stay gathered for the backward: SHARD_GRAD_OP, ssl_default_config.yaml:19)."""
+        items = []
+        for teacher in (True, False):
+            bb = self.params.mods["backbone"].layout
+            items += [("backbone", u, teacher) for u in bb.units]
+            for m in (("dino_head", "ibot_head") if teacher else ("dino_head", "ibot_head")):
+                items += [(m, u, teacher) for u in self.params.mods[m].layout.units]
+        return items
 
     # ------------------------------------------------------------------------------------------------ the step
     def set_batch(self, batch: dict):
@@ -375,6 +397,7 @@ class Engine:
         self.metrics.zero_()
         for st in self.params.mods.values():
             st.zero_grads()
+        self.fsdp.prefetch(self._gather_schedule())
         # ---- teacher (train/ssl_meta_arch.py:366-402)
         T_ = self.teacher
         self._backbone_fwd(T_, [self.g_img], [None], teacher=True)
@@ -419,6 +442,7 @@ class Engine:
         dXL = self.dX[1]
         ops.layernorm_bwd(dXn, S_.X[cfg.depth], S_.fstats[0], S_.fstats[1], bb.vec("norm/scale"), dXL,
                           dscale=bb.gv("norm/scale"), dbias=bb.gv("norm/bias"))
+        self.fsdp.grads_ready("backbone", "norm")
         cur, nxt = 1, 0
         for i in reversed(range(cfg.depth)):
             self._block_bwd(i, self.dX[cur], self.dX[nxt])
@@ -432,16 +456,22 @@ class Engine:
             ops.colsum_bf16(dTok, bb.gv("patch_embed/proj/bias"))
             ops.gemm(cs.patches, dTok, bb.gw("patch_embed/proj/kernel"), a_mn=True, b_mn=True, accum=True)
             first = False
+        self.fsdp.grads_ready("backbone", "embed")
 
     def optimizer_step(self, lr: float, wd: float, last_layer_lr: float, momentum: float):
         """Per-module clip (train/train.py:516-541) + AdamW (:95-106) + teacher EMA (ssl_meta_arch.py:650-652)."""
         cfg = self.cfg
         self.step_count += 1
+        self.fsdp.finish_grads()
         for st in self.params.mods.values():
-            ops.sumsq(st.grad, st.sumsq)
-            ops.adamw_ema(st.master, st.grad, st.m, st.v, st.t_master, st.bf16, st.t_bf16, st.n_mat, st.segs,
-                          len(st.seg_names), st.sumsq, float(cfg.clip_grad or 0.0), lr, last_layer_lr, wd,
-                          self.step_count, momentum, cfg.adamw_beta1, cfg.adamw_beta2)
+            ops.sumsq(st.grad_shard, st.sumsq)
+        if self.comm is not None:       # global gradient norm per module (SURVEY A4): sum of the shards' squares
+            for st in self.params.mods.values():
+                self.comm.all_reduce_sum(st.sumsq)
+        for st in self.params.mods.values():
+            ops.adamw_ema(st.master, st.grad_shard, st.m, st.v, st.t_master, st.bf16_shard, st.t_bf16_shard,
+                          st.layout.n_mat_shard, st.segs, st.nseg, st.sumsq, float(cfg.clip_grad or 0.0), lr,
+                          last_layer_lr, wd, self.step_count, momentum, cfg.adamw_beta1, cfg.adamw_beta2)
 
     def train_step(self, batch: dict | None, *, teacher_temp: float, lr: float, wd: float, last_layer_lr: float,
                    momentum: float):
@@ -454,7 +484,12 @@ class Engine:
     def read_metrics(self) -> dict:
         """Device -> host read of the step's metrics (one small sync; callers do it every print_freq, not every step)."""
         cfg = self.cfg
-        m = self.metrics.cpu().tolist()
+        if self.comm is not None:       # pmean of the loss terms over "dp" (train/ssl_meta_arch.py:361, train/train.py:554-557)
+            mt = self.metrics.clone()
+            self.comm.all_reduce_mean(mt)
+            m = mt.cpu().tolist()
+        else:
+            m = self.metrics.cpu().tolist()
         ng, nl = cfg.n_global, cfg.n_local
         g_terms, l_terms = ng * (ng - 1), ng * nl
         g_scale, l_scale = g_terms / (g_terms + l_terms), l_terms / (g_terms + l_terms)

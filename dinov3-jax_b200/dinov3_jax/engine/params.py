@@ -79,13 +79,19 @@ def _round_up(x: int, a: int) -> int:
 
 
 class ModuleStore:
-    def __init__(self, module: str, spec, cfg: EngineConfig, device, trainable: bool = True):
-        self.module = module
-        self.spec = spec
-        self.cfg = cfg
-        self.offsets = {}
-        self.shapes = {}
-        self.kinds = {}
+    """Flat buffers of one top-level module on one rank.
+
+    world == 1: every buffer is full size; `vecs` aliases the vector region of the fp32 master.
+    world  > 1: persistent state (fp32 master, Adam m / v, teacher master, bf16 shard copies, gradient shard) holds the
+    rank's 1/world slice of every FSDP unit (fsdp/layout.py); `bf16` / `vecs` / `t_bf16` / `t_vecs` are the full
+    compute buffers the all-gathers fill, `grad` the full gradient buffer the reduce-scatters drain.
+    """
+
+    def __init__(self, module: str, spec, cfg: EngineConfig, device, world: int = 1, rank: int = 0):
+        from ..fsdp.layout import ShardLayout
+        self.module, self.spec, self.cfg = module, spec, cfg
+        self.world, self.rank = world, rank
+        self.offsets, self.shapes, self.kinds, padded = {}, {}, {}, {}
         off = 0
         for kind in ("mat", "vec"):
             for name, shape, k in spec:
@@ -94,34 +100,43 @@ class ModuleStore:
                 self.offsets[name] = off
                 self.shapes[name] = tuple(shape)
                 self.kinds[name] = k
-                off += _round_up(int(np.prod(shape)), ALIGN)
+                padded[name] = _round_up(int(np.prod(shape)), ALIGN)
+                off += padded[name]
             if kind == "mat":
                 self.n_mat = off
         self.n = off
+        names_in_order = [name for name, _, _ in spec]
+        self.layout = L = ShardLayout(module, names_in_order, self.offsets, padded, self.kinds, self.n_mat, self.n, world)
         f32, bf16 = torch.float32, torch.bfloat16
-        self.master = torch.zeros(self.n, dtype=f32, device=device)
-        self.bf16 = torch.zeros(self.n_mat, dtype=bf16, device=device)
-        self.t_master = torch.zeros(self.n, dtype=f32, device=device)
-        self.t_bf16 = torch.zeros(self.n_mat, dtype=bf16, device=device)
-        self.trainable = trainable
-        if trainable:
-            self.grad = torch.zeros(self.n, dtype=f32, device=device)
-            self.m = torch.zeros(self.n, dtype=f32, device=device)
-            self.v = torch.zeros(self.n, dtype=f32, device=device)
-            self.sumsq = torch.zeros(1, dtype=f32, device=device)
-        # optimiser segment table (sorted by start)
-        names = sorted(self.offsets, key=lambda k: self.offsets[k])
-        segs = np.zeros(len(names), dtype=SEG_DTYPE)
-        for i, nm in enumerate(names):
-            lr_m, wd_m, last = lr_wd_multipliers(module, nm, cfg)
-            segs[i] = (self.offsets[nm], lr_m, wd_m, int(last), 0)
-        self.seg_names = names
+        z = lambda n, dt: torch.zeros(n, dtype=dt, device=device)
+        ns, nms = L.n_shard, L.n_mat_shard
+        self.master, self.t_master = z(ns, f32), z(ns, f32)
+        self.m, self.v = z(ns, f32), z(ns, f32)
+        self.grad = z(self.n, f32)
+        self.sumsq = z(1, f32)
+        self.bf16, self.t_bf16 = z(self.n_mat, bf16), z(self.n_mat, bf16)
+        if world == 1:
+            self.grad_shard = self.grad
+            self.bf16_shard, self.t_bf16_shard = self.bf16, self.t_bf16
+            self.vecs, self.t_vecs = self.master[self.n_mat:], self.t_master[self.n_mat:]
+        else:
+            self.grad_shard = z(ns, f32)
+            self.bf16_shard, self.t_bf16_shard = z(nms, bf16), z(nms, bf16)
+            self.vecs, self.t_vecs = z(self.n - self.n_mat, f32), z(self.n - self.n_mat, f32)
+        # optimiser segment table of this rank's shard (sorted by start)
+        mult = {nm: lr_wd_multipliers(module, nm, cfg) for nm in self.offsets}
+        seg_list = L.shard_segments(rank, mult)
+        segs = np.zeros(len(seg_list), dtype=SEG_DTYPE)
+        for i, (st_, lr_m, wd_m, last) in enumerate(seg_list):
+            segs[i] = (st_, lr_m, wd_m, int(last), 0)
         self.segs_host = segs
+        self.nseg = len(seg_list)
         self.segs = torch.from_numpy(segs.view(np.uint8).copy()).to(device)
+        self._shard_index = None
 
-    # ---- views -------------------------------------------------------------------------------------------------
-    def _view(self, flat, name, as2d=False):
-        o, shp = self.offsets[name], self.shapes[name]
+    # ---- views (full compute buffers) ---------------------------------------------------------------------------
+    def _view(self, flat, name, as2d=False, base=0):
+        o, shp = self.offsets[name] - base, self.shapes[name]
         n = int(np.prod(shp))
         v = flat[o:o + n]
         if as2d:
@@ -133,8 +148,8 @@ class ModuleStore:
         return self._view(self.t_bf16 if teacher else self.bf16, name, as2d=True)
 
     def vec(self, name, teacher=False):
-        """fp32 vector (flattened)."""
-        return self._view(self.t_master if teacher else self.master, name).reshape(-1)
+        """fp32 vector (flattened) from the full vector buffer."""
+        return self._view(self.t_vecs if teacher else self.vecs, name, base=self.n_mat).reshape(-1)
 
     def gw(self, name):
         return self._view(self.grad, name, as2d=True)
@@ -143,22 +158,36 @@ class ModuleStore:
         return self._view(self.grad, name).reshape(-1)
 
     # ---- host <-> device ---------------------------------------------------------------------------------------
+    def shard_index(self):
+        if self._shard_index is None:
+            self._shard_index = torch.from_numpy(self.layout.full_to_shard_index(self.rank)).to(self.master.device)
+        return self._shard_index
+
     def load(self, tensors: dict, teacher: bool):
-        flat = self.t_master if teacher else self.master
+        """tensors: name -> full tensor (reference layout).  Fills this rank's fp32 shard and the compute copies."""
+        dev = self.master.device
+        full = torch.zeros(self.n, dtype=torch.float32, device=dev)
         for name in self.offsets:
-            t = tensors[name]
-            self._view(flat, name).copy_(t.to(device=flat.device, dtype=torch.float32).reshape(self.shapes[name]))
-        self.refresh_bf16(teacher)
+            self._view(full, name).copy_(tensors[name].to(device=dev, dtype=torch.float32).reshape(self.shapes[name]))
+        master = self.t_master if teacher else self.master
+        if self.world == 1:
+            master.copy_(full)
+        else:
+            master.copy_(full[self.shard_index()])
+            (self.t_vecs if teacher else self.vecs).copy_(full[self.n_mat:])
+        self.refresh_bf16(teacher, full=full)
 
-    def refresh_bf16(self, teacher: bool):
-        if self.n_mat:
-            ops.cast_f32_bf16((self.t_master if teacher else self.master)[: self.n_mat],
-                              self.t_bf16 if teacher else self.bf16)
+    def refresh_bf16(self, teacher: bool, full=None):
+        if not self.n_mat:
+            return
+        master = self.t_master if teacher else self.master
+        nms = self.layout.n_mat_shard
+        ops.cast_f32_bf16(master[:nms], (self.t_bf16_shard if teacher else self.bf16_shard))
+        if self.world > 1 and full is not None:
+            ops.cast_f32_bf16(full[: self.n_mat].contiguous(), self.t_bf16 if teacher else self.bf16)
 
-    def export(self, teacher: bool, what: str = "param") -> dict:
-        flat = {"param": self.t_master if teacher else self.master, "grad": getattr(self, "grad", None),
-                "m": getattr(self, "m", None), "v": getattr(self, "v", None)}[what]
-        return {name: self._view(flat, name).detach().clone() for name in self.offsets}
+    def export_full(self, flat_full: torch.Tensor) -> dict:
+        return {name: self._view(flat_full, name).detach().clone() for name in self.offsets}
 
     def zero_grads(self):
         """Vector gradients accumulate atomically and weight gradients are split-K reductions (fp32 atomics), so the
@@ -172,13 +201,14 @@ class ParamStore:
 
     MODULES = ("backbone", "dino_head", "ibot_head")
 
-    def __init__(self, cfg: EngineConfig, device):
+    def __init__(self, cfg: EngineConfig, device, world: int = 1, rank: int = 0):
         self.cfg = cfg
         self.mods = {
-            "backbone": ModuleStore("backbone", backbone_spec(cfg), cfg, device),
-            "dino_head": ModuleStore("dino_head", head_spec(cfg), cfg, device),
-            "ibot_head": ModuleStore("ibot_head", head_spec(cfg), cfg, device),
+            "backbone": ModuleStore("backbone", backbone_spec(cfg), cfg, device, world, rank),
+            "dino_head": ModuleStore("dino_head", head_spec(cfg), cfg, device, world, rank),
+            "ibot_head": ModuleStore("ibot_head", head_spec(cfg), cfg, device, world, rank),
         }
+        self.runtime = None     # set by the engine (fsdp.runtime.FsdpRuntime)
 
     def load_reference_tree(self, params: dict):
         """params: flat dict 'student_backbone/blocks_0/attn/qkv/kernel' -> tensor (reference names/layouts)."""
@@ -188,13 +218,18 @@ class ParamStore:
                 st.load({k[len(pre):]: v for k, v in params.items() if k.startswith(pre)}, teacher)
 
     def export_reference_tree(self, what: str = "param") -> dict:
+        """Full (un-sharded) tensors with the reference's names; under FSDP this all-gathers the shards."""
         out = {}
         for m, st in self.mods.items():
-            for k, v in st.export(False, what).items():
-                out[f"student_{m}/{k}"] = v
-            if what == "param":
-                for k, v in st.export(True, what).items():
-                    out[f"teacher_{m}/{k}"] = v
+            for who, teacher in (("student", False), ("teacher", True)):
+                if teacher and what != "param":
+                    continue
+                if self.runtime is not None:
+                    full = self.runtime.gather_full(m, what, teacher)
+                else:
+                    full = {"param": st.t_master if teacher else st.master, "grad": st.grad_shard, "m": st.m, "v": st.v}[what]
+                for k, v in st.export_full(full).items():
+                    out[f"{who}_{m}/{k}"] = v
         return out
 
     def n_params(self) -> int:

@@ -1,0 +1,148 @@
+"""FSDP runtime: NCCL all-gather of each unit's parameters before use and reduce-scatter (mean) of its gradients after
+its backward, issued on a side stream so they overlap the neighbouring unit's compute.
+
+Replaces `gather_params` / `fwd_gather_bwd_pmean_scatter` / `sync_grads` of the reference (dinov3_jax/fsdp/utils.py:
+56-110), which lower to per-leaf jax.lax.all_gather / psum_scatter / pmean inside the jitted step.  torch.distributed
+(backend "nccl"; "gloo" in the CPU tests) is the plumbing; payloads are the flat per-unit ranges of fsdp/layout.py.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+class Comm:
+    """Thin wrapper over a process group ("dp" axis of the reference's 1-D mesh, train/train.py:322-325)."""
+
+    def __init__(self, group=None):
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.backend = dist.get_backend(self.group)
+
+    def all_reduce_sum(self, t):
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    def all_reduce_max(self, t):
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+
+    def all_reduce_mean(self, t):
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        t.div_(self.world)
+
+    def all_gather(self, out, inp, async_op=False):
+        """out = concat over ranks of inp (tiled all-gather, fsdp/utils.py:66)."""
+        return dist.all_gather_into_tensor(out, inp, group=self.group, async_op=async_op)
+
+    def reduce_scatter_mean(self, out, inp, async_op=False):
+        """out = this rank's slice of mean over ranks of inp (psum_scatter / axis_size, fsdp/utils.py:61-64)."""
+        if self.backend == "nccl":
+            return dist.reduce_scatter_tensor(out, inp, op=dist.ReduceOp.AVG, group=self.group, async_op=async_op)
+        # gloo has no reduce_scatter: all-reduce a copy and keep our slice (CPU tests only)
+        tmp = inp.clone()
+        dist.all_reduce(tmp, op=dist.ReduceOp.SUM, group=self.group)
+        n = out.numel()
+        out.copy_(tmp[self.rank * n:(self.rank + 1) * n] / self.world)
+        return None
+
+
+class FsdpRuntime:
+    """Schedules the collectives of one rank.  `stores`: dict module -> ModuleStore (engine/params.py)."""
+
+    def __init__(self, comm: Comm | None, stores: dict, device):
+        self.comm = comm
+        self.stores = stores
+        self.world = 1 if comm is None else comm.world
+        self.cuda = torch.device(device).type == "cuda"
+        self.side = torch.cuda.Stream(device=device) if (self.cuda and self.world > 1) else None
+        self._pending = {}       # (module, unit, teacher) -> [works]
+        self._grad_works = []
+
+    # ------------------------------------------------------------------------------------------ parameter gathers
+    def _issue_gather(self, module: str, unit, teacher: bool):
+        st = self.stores[module]
+        L = st.layout
+        works = []
+        ma, mb = unit.mat
+        if mb > ma:
+            sa, sb = L.shard_range(unit, "mat")
+            src = (st.t_bf16_shard if teacher else st.bf16_shard)[sa:sb]
+            dst = (st.t_bf16 if teacher else st.bf16)[ma:mb]
+            works.append(self.comm.all_gather(dst, src, async_op=True))
+        va, vb = unit.vec
+        if vb > va:
+            sa, sb = L.shard_range(unit, "vec")
+            src = (st.t_master if teacher else st.master)[sa:sb]
+            dst = (st.t_vecs if teacher else st.vecs)[va - L.n_mat: vb - L.n_mat]
+            works.append(self.comm.all_gather(dst, src, async_op=True))
+        self._pending[(module, unit.name, teacher)] = works
+
+    def prefetch(self, items):
+        """items: iterable of (module, unit, teacher) in use order.  All gathers are queued on the side stream at once:
+        NCCL executes them back to back while the compute stream works through earlier units."""
+        if self.world == 1:
+            return
+        if self.side is not None:
+            self.side.wait_stream(torch.cuda.current_stream())   # parameters come from the previous optimizer step
+            with torch.cuda.stream(self.side):
+                for module, unit, teacher in items:
+                    self._issue_gather(module, unit, teacher)
+        else:
+            for module, unit, teacher in items:
+                self._issue_gather(module, unit, teacher)
+
+    def acquire(self, module: str, unit_name: str, teacher: bool):
+        """Make the compute stream wait for this unit's gathered parameters."""
+        if self.world == 1:
+            return
+        for w in self._pending.pop((module, unit_name, teacher), []):
+            if w is not None:
+                w.wait()
+
+    # ------------------------------------------------------------------------------------------ gradient reduction
+    def grads_ready(self, module: str, unit_name: str):
+        """Called right after the kernels of this unit's backward were enqueued: reduce-scatter (mean) its gradient
+        ranges into the rank's gradient shard, on the side stream."""
+        if self.world == 1:
+            return
+        st = self.stores[module]
+        L = st.layout
+        unit = next(u for u in L.units if u.name == unit_name)
+
+        def issue():
+            for region in ("mat", "vec"):
+                a, b = getattr(unit, region)
+                if b > a:
+                    sa, sb = L.shard_range(unit, region)
+                    w = self.comm.reduce_scatter_mean(st.grad_shard[sa:sb], st.grad[a:b], async_op=True)
+                    if w is not None:
+                        self._grad_works.append(w)
+        if self.side is not None:
+            self.side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.side):
+                issue()
+        else:
+            issue()
+
+    def finish_grads(self):
+        for w in self._grad_works:
+            w.wait()
+        self._grad_works = []
+
+    # ------------------------------------------------------------------------------------------ utilities
+    def gather_full(self, module: str, what: str, teacher: bool = False) -> torch.Tensor:
+        """Full fp32 flat buffer of a module assembled from all ranks' shards (export / checkpoint / tests)."""
+        st = self.stores[module]
+        L = st.layout
+        src = {"param": st.t_master if teacher else st.master, "grad": getattr(st, "grad_shard", None),
+               "m": getattr(st, "m", None), "v": getattr(st, "v", None)}[what]
+        if self.world == 1:
+            return src
+        full = torch.empty(L.n, dtype=src.dtype, device=src.device)
+        for u in L.units:
+            for region in ("mat", "vec"):
+                a, b = getattr(u, region)
+                if b > a:
+                    sa, sb = L.shard_range(u, region)
+                    self.comm.all_gather(full[a:b], src[sa:sb].contiguous())
+        return full

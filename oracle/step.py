@@ -73,6 +73,74 @@ def ssl_forward(params: dict, batch: dict, teacher_temp: float, cfg: ModelCfg, e
     return loss, metrics
 
 
+
+def ssl_forward_multi(params: dict, batches: list, teacher_temp: float, cfg: ModelCfg, emu: Emu = Emu(False),
+                      dtype=torch.float32):
+    """The same step on a 1-D "dp" mesh of len(batches) devices, each holding its own images and rank-local mask
+    indices (intended semantics): Sinkhorn row sums / totals are psum'ed over ranks
+    (loss/dino_clstoken_loss.py:46,53; loss/ibot_patch_loss.py:84,91,99), i.e. the normalisation runs over the
+    concatenation of all ranks' teacher rows; every other term is rank-local (KoLeo included, loss/koleo_loss.py:16-35)
+    and the scalar loss is the mean over ranks (train/ssl_meta_arch.py:361).  Returns (loss, [metrics per rank])."""
+    world = len(batches)
+    n_g, K = cfg.n_global, cfg.n_prototypes
+    t_cls_l, t_patch_l = [], []
+    with torch.no_grad():
+        for b in batches:
+            g = b["collated_global_crops"].to(dtype)
+            t_out = backbone_forward(sub(params, "teacher_backbone"), [g], [None], cfg, emu)[0]
+            t_buf = t_out["x_norm_patchtokens"].reshape(-1, cfg.embed_dim)[b["mask_indices_list"]]
+            t_patch_l.append(head_forward(sub(params, "teacher_ibot_head"), t_buf, emu))
+            t_cls_l.append(head_forward(sub(params, "teacher_dino_head"), t_out["x_norm_clstoken"], emu))
+        cls_all = sinkhorn_knopp(torch.cat(t_cls_l), teacher_temp, B_total=sum(t.shape[0] for t in t_cls_l))
+        patch_all = sinkhorn_knopp(torch.cat(t_patch_l), teacher_temp, B_total=float(sum(t.shape[0] for t in t_patch_l)))
+    total, mets = 0.0, []
+    c0 = p0 = 0
+    for r, b in enumerate(batches):
+        nc, npatch = t_cls_l[r].shape[0], t_patch_l[r].shape[0]
+        B = nc // n_g
+        cls_centered = cls_all[c0:c0 + nc].reshape(n_g, B, K)
+        patch_centered = patch_all[p0:p0 + npatch]
+        c0 += nc; p0 += npatch
+        loss, m = _student_losses(params, b, cls_centered, patch_centered, cfg, emu, dtype)
+        total = total + loss / world
+        mets.append(m)
+    return total, mets
+
+
+def _student_losses(params, batch, cls_centered, patch_centered, cfg, emu, dtype):
+    n_g, n_l, K = cfg.n_global, cfg.n_local, cfg.n_prototypes
+    g = batch["collated_global_crops"].to(dtype)
+    l = batch["collated_local_crops"].to(dtype)
+    masks, idx = batch["collated_masks"], batch["mask_indices_list"]
+    B = l.shape[0] // n_l
+    s_g, s_l = backbone_forward(sub(params, "student_backbone"), [g, l], [masks, None], cfg, emu)
+    g_cls, g_patch, l_cls = s_g["x_norm_clstoken"], s_g["x_norm_patchtokens"], s_l["x_norm_clstoken"]
+    s_patch_logits = head_forward(sub(params, "student_ibot_head"), g_patch.reshape(-1, g_patch.shape[-1])[idx], emu)
+    buf = head_forward(sub(params, "student_dino_head"), torch.cat([g_cls, l_cls], dim=0), emu)
+    s_g_logits, s_l_logits = buf[: g_cls.shape[0]].reshape(n_g, B, K), buf[g_cls.shape[0]:].reshape(n_l, B, K)
+    g_terms, l_terms = n_g * (n_g - 1), n_g * n_l
+    g_scale, l_scale = g_terms / (g_terms + l_terms), l_terms / (g_terms + l_terms)
+    L_local = dino_loss(s_l_logits, cls_centered, cfg.student_temp, ignore_diagonal=False)
+    L_global = dino_loss(s_g_logits, cls_centered, cfg.student_temp, ignore_diagonal=True)
+    L_koleo = sum(koleo_loss(x) for x in g_cls.reshape(n_g, B, -1)) / n_g
+    L_ibot = ibot_loss_masked(s_patch_logits, patch_centered, cfg.student_temp, n_mask_rows=masks.shape[0])
+    loss = (cfg.dino_loss_weight * l_scale * L_local + cfg.dino_loss_weight * g_scale * L_global
+            + cfg.koleo_loss_weight * n_g * L_koleo + cfg.ibot_loss_weight * L_ibot)
+    return loss, {"dino_local_crops_loss": L_local.detach(), "dino_global_crops_loss": L_global.detach(),
+                  "koleo_loss": L_koleo.detach(), "ibot_loss": L_ibot.detach()}
+
+
+def grads_multi(params: dict, batches: list, teacher_temp: float, cfg: ModelCfg, dtype=torch.float32):
+    """Loss and student gradients of the multi-rank step (what reduce-scatter(mean) must reproduce on every shard)."""
+    student = {k: v.detach().to(dtype).requires_grad_(True) for k, v in params.items() if k.startswith("student_")}
+    full = {k: v.detach().to(dtype) for k, v in params.items()}
+    full.update(student)
+    loss, mets = ssl_forward_multi(full, batches, teacher_temp, cfg, dtype=dtype)
+    keys = list(student)
+    gl = torch.autograd.grad(loss, [student[k] for k in keys], allow_unused=True)
+    return loss.detach(), mets, {k: (g if g is not None else torch.zeros_like(student[k])) for k, g in zip(keys, gl)}
+
+
 # ---------------------------------------------------------------------------------------------------- optimiser
 def param_multipliers(names, depth: int, layerwise_decay: float = 0.9, patch_embed_lr_mult: float = 0.2,
                       dino_head_wd_multiplier: float = 1.0) -> dict:

@@ -1,0 +1,126 @@
+"""Host-side FSDP logic on CPU: shard layout invariants, per-rank optimiser segment tables, and the all-gather /
+reduce-scatter(mean) plumbing over a world_size-2 gloo group (no CUDA kernels are called here)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from dinov3_jax.engine.config import EngineConfig
+from dinov3_jax.engine.params import ALIGN, backbone_spec, head_spec, lr_wd_multipliers
+from dinov3_jax.fsdp.layout import ShardLayout
+
+
+def build_layout(module, spec, world):
+    offsets, padded, kinds = {}, {}, {}
+    off = 0
+    n_mat = 0
+    for kind in ("mat", "vec"):
+        for name, shape, k in spec:
+            if k != kind:
+                continue
+            offsets[name] = off
+            kinds[name] = k
+            padded[name] = (int(np.prod(shape)) + ALIGN - 1) // ALIGN * ALIGN
+            off += padded[name]
+        if kind == "mat":
+            n_mat = off
+    return ShardLayout(module, [n for n, _, _ in spec], offsets, padded, kinds, n_mat, off, world), offsets, padded
+
+
+CFG = EngineConfig(embed_dim=128, depth=3, heads=2, n_prototypes=512, head_hidden=256, head_bottleneck=64)
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+@pytest.mark.parametrize("module", ["backbone", "dino_head"])
+def test_shards_partition_the_flat_buffer(world, module):
+    spec = backbone_spec(CFG) if module == "backbone" else head_spec(CFG)
+    L, offsets, padded = build_layout(module, spec, world)
+    seen = np.zeros(L.n, dtype=np.int32)
+    for r in range(world):
+        idx = L.full_to_shard_index(r)
+        assert len(idx) == L.n_shard
+        seen[idx] += 1
+    assert (seen == 1).all()                       # every element owned by exactly one rank
+    assert L.n_shard * world == L.n
+    names = [u.name for u in L.units]
+    if module == "backbone":
+        assert names == ["embed", "blocks_0", "blocks_1", "blocks_2", "norm"]   # FSDP units (vision_transformer.py:93,137)
+    else:
+        assert names == ["head"]
+
+
+@pytest.mark.parametrize("world", [1, 2, 8])
+def test_segment_tables_cover_each_tensor_once_with_its_multipliers(world):
+    spec = backbone_spec(CFG)
+    L, offsets, padded = build_layout("backbone", spec, world)
+    mult = {n: lr_wd_multipliers("backbone", n, CFG) for n in offsets}
+    covered = np.zeros(L.n, dtype=np.int32)
+    for r in range(world):
+        segs = L.shard_segments(r, mult)
+        idx = L.full_to_shard_index(r)
+        starts = [s[0] for s in segs] + [L.n_shard]
+        assert starts == sorted(starts) and starts[0] == 0
+        for (st, lr, wd, last), en in zip(segs, starts[1:]):
+            full = idx[st:en]
+            # all elements of a segment belong to one tensor whose multipliers match
+            owner = [n for n in offsets if offsets[n] <= full[0] < offsets[n] + padded[n]]
+            assert len(owner) == 1 and full[-1] < offsets[owner[0]] + padded[owner[0]]
+            assert (lr, wd, last) == mult[owner[0]]
+            covered[full] += 1
+    assert (covered == 1).all()
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from dinov3_jax.fsdp.runtime import Comm
+        comm = Comm()
+        spec = head_spec(CFG)
+        L, offsets, padded = build_layout("dino_head", spec, world)
+        torch.manual_seed(0)
+        full = torch.randn(L.n)                                  # identical on all ranks
+        shard = full[torch.from_numpy(L.full_to_shard_index(rank))]
+        # all-gather of every unit range reproduces the full buffer
+        out = torch.zeros(L.n)
+        for u in L.units:
+            for region in ("mat", "vec"):
+                a, b = getattr(u, region)
+                if b > a:
+                    sa, sb = L.shard_range(u, region)
+                    comm.all_gather(out[a:b], shard[sa:sb].contiguous())
+        ok_gather = torch.equal(out, full)
+        # reduce-scatter(mean) of rank-dependent gradients lands the mean slice in the shard layout
+        g = full * (rank + 1)
+        gs = torch.zeros(L.n_shard)
+        for u in L.units:
+            for region in ("mat", "vec"):
+                a, b = getattr(u, region)
+                if b > a:
+                    sa, sb = L.shard_range(u, region)
+                    comm.reduce_scatter_mean(gs[sa:sb], g[a:b].contiguous())
+        want = (full * (sum(range(1, world + 1)) / world))[torch.from_numpy(L.full_to_shard_index(rank))]
+        ok_rs = torch.allclose(gs, want, atol=1e-6)
+        t = torch.tensor([float(rank + 1)]); comm.all_reduce_sum(t)
+        m = torch.tensor([float(rank)]); comm.all_reduce_max(m)
+        ret[rank] = (ok_gather, ok_rs, t.item(), m.item())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_gather_and_reduce_scatter():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    for r in range(world):
+        ok_gather, ok_rs, s, m = ret[r]
+        assert ok_gather and ok_rs and s == 3.0 and m == 1.0
