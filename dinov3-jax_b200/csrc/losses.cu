@@ -122,21 +122,26 @@ ce_fwd_bwd_kernel(const float* __restrict__ S, float inv_ts, const float* __rest
   const float lse = gm + logf(z);
   const int p0 = t0[i], p1 = t1[i];
   const float np = (p0 >= 0 ? 1.f : 0.f) + (p1 >= 0 ? 1.f : 0.f);
-  const float mt = *mx, bt = *btot;
-  const float c0 = p0 >= 0 ? bt * a_t[p0] : 0.f;
-  const float c1 = p1 >= 0 ? bt * a_t[p1] : 0.f;
+  const float mt = s_t ? *mx : 0.f, bt = s_t ? *btot : 1.f;
+  const float c0 = (s_t && p0 >= 0) ? bt * a_t[p0] : 0.f;
+  const float c1 = (s_t && p1 >= 0) ? bt * a_t[p1] : 0.f;
   const float* L0 = Lt + (long)(p0 >= 0 ? p0 : 0) * K;
   const float* L1 = Lt + (long)(p1 >= 0 ? p1 : 0) * K;
   const float g = wg[i] * inv_ts;
   float loss = 0.f;
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
     const float lsm = Si[k] * inv_ts - lse;
-    const float rk = 1.f / ((float)K * s_t[k]);
     float q = 0.f;
-    if (p0 >= 0) q += c0 * __expf((L0[k] - mt) * inv_tt) * rk;
-    if (p1 >= 0) q += c1 * __expf((L1[k] - mt) * inv_tt) * rk;
+    if (s_t) {
+      const float rk = 1.f / ((float)K * s_t[k]);
+      if (p0 >= 0) q += c0 * __expf((L0[k] - mt) * inv_tt) * rk;
+      if (p1 >= 0) q += c1 * __expf((L1[k] - mt) * inv_tt) * rk;
+    } else {          // teacher rows are already probabilities
+      if (p0 >= 0) q += L0[k];
+      if (p1 >= 0) q += L1[k];
+    }
     loss -= q * lsm;
-    dS[(long)i * K + k] = __float2bfloat16(g * (np * __expf(lsm) - q));
+    if (dS) dS[(long)i * K + k] = __float2bfloat16(g * (np * __expf(lsm) - q));
   }
   loss = block_sum(loss, sh);
   if (threadIdx.x == 0) atomicAdd(&metric[slot[i]], wm[i] * loss);

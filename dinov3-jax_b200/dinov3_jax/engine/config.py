@@ -72,3 +72,35 @@ def from_oracle_cfg(c) -> EngineConfig:
     """Build from any object with the same field names (tests pass oracle.arch.ModelCfg)."""
     names = EngineConfig.__dataclass_fields__.keys()
     return EngineConfig(**{k: getattr(c, k) for k in names if hasattr(c, k)})
+
+
+def config_from_reference_cfg(cfg) -> EngineConfig:
+    """Map the reference's YAML keys (configs/ssl_default_config.yaml) onto the engine configuration; unsupported
+    options the reference asserts on (train/ssl_meta_arch.py:47-51) or that this engine does not implement raise."""
+    if cfg.train.centering != "sinkhorn_knopp":
+        raise NotImplementedError("train.centering must be sinkhorn_knopp (asserted by the reference, ssl_meta_arch.py:49)")
+    if not cfg.ibot.separate_head:
+        raise NotImplementedError("ibot.separate_head must be true (ssl_meta_arch.py:48)")
+    if cfg.crops.local_crops_number <= 0:
+        raise ValueError("crops.local_crops_number must be > 0 (ssl_meta_arch.py:47)")
+    if cfg.student.ffn_layer != "mlp" or cfg.student.norm_layer != "layernorm" or cfg.student.n_storage_tokens != 0:
+        raise NotImplementedError("only ffn_layer=mlp, norm_layer=layernorm, n_storage_tokens=0 are on the B200 path (SURVEY 8f)")
+    if cfg.gram.use_loss or cfg.dino.koleo_loss_distributed or cfg.dino.reweight_dino_local_loss:
+        raise NotImplementedError("gram loss / distributed KoLeo / local-loss reweighting are not on the B200 path yet")
+    arch = cfg.student.arch
+    if arch not in ARCHS:
+        raise ValueError(f"unknown student.arch {arch!r}")
+    if (cfg.dino.head_n_prototypes, cfg.dino.head_hidden_dim, cfg.dino.head_bottleneck_dim) != \
+            (cfg.ibot.head_n_prototypes, cfg.ibot.head_hidden_dim, cfg.ibot.head_bottleneck_dim):
+        raise NotImplementedError("dino and ibot heads must share their dimensions")
+    return config_for(
+        arch, patch=cfg.student.patch_size, ffn_ratio=cfg.student.ffn_ratio, global_size=cfg.crops.global_crops_size,
+        local_size=cfg.crops.local_crops_size, n_local=cfg.crops.local_crops_number,
+        n_prototypes=cfg.dino.head_n_prototypes, head_hidden=cfg.dino.head_hidden_dim,
+        head_bottleneck=cfg.dino.head_bottleneck_dim, layerscale=cfg.student.layerscale,
+        rope_base=cfg.student.pos_embed_rope_base, dino_loss_weight=cfg.dino.loss_weight,
+        koleo_loss_weight=cfg.dino.koleo_loss_weight, ibot_loss_weight=cfg.ibot.loss_weight,
+        clip_grad=cfg.optim.clip_grad, layerwise_decay=cfg.optim.layerwise_decay,
+        patch_embed_lr_mult=cfg.optim.patch_embed_lr_mult, dino_head_wd_multiplier=cfg.optim.dino_head_wd_multiplier,
+        adamw_beta1=cfg.optim.adamw_beta1, adamw_beta2=cfg.optim.adamw_beta2,
+        mask_probability=cfg.ibot.mask_sample_probability, mask_ratio=tuple(cfg.ibot.mask_ratio_min_max))

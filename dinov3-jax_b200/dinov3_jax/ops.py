@@ -213,7 +213,7 @@ def sinkhorn_probs(L, mx, temp, s, a, btot, Q):
 
 def ce_fwd_bwd(S, student_temp, Lt, mx, teacher_temp, s_t, a_t, btot, t0, t1, wm, wg, slot, metric, dS):
     Rs, K = S.shape
-    assert S.dtype == f32 and Lt.dtype == f32 and dS.dtype == bf16 and t0.dtype == torch.int32
+    assert S.dtype == f32 and Lt.dtype == f32 and (dS is None or dS.dtype == bf16) and t0.dtype == torch.int32
     N.check(N.init().d3_ce_fwd_bwd(_p(S), student_temp, _p(Lt), _p(mx), teacher_temp, _p(s_t), _p(a_t), _p(btot),
                                    _p(t0), _p(t1), _p(wm), _p(wg), _p(slot), _p(metric), _p(dS), Rs, K, _s()),
             "d3_ce_fwd_bwd")

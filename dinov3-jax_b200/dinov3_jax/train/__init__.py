@@ -1,0 +1,1 @@
+from .ssl_meta_arch import SSLMetaArch  # noqa: F401

@@ -1,0 +1,61 @@
+"""`SSLMetaArch` with the reference's constructor and helper names (dinov3_jax/train/ssl_meta_arch.py:32-660).
+
+The reference class is a Flax module whose `__call__` is traced by jax.jit; here it is a plain object that owns the
+configuration and builds the B200 step executor.  The top-level parameter keys (`student_backbone`, `student_dino_head`,
+`student_ibot_head`, `teacher_*`; :62-64,86-87,130-131) and the batch-dict contract are unchanged.
+"""
+from __future__ import annotations
+
+from ..engine import Engine, config_from_reference_cfg
+from ..engine.params import lr_wd_multipliers
+
+
+class SSLMetaArch:
+    PARAM_MODULES = ("backbone", "dino_head", "ibot_head")
+
+    def __init__(self, config):
+        self.config = config
+        self.engine_config = config_from_reference_cfg(config)       # raises on options the reference asserts on (:47-51)
+        self.n_local_crops = config.crops.local_crops_number
+        self.embed_dim = self.engine_config.embed_dim
+        self.dino_out_dim = config.dino.head_n_prototypes
+        self.dino_loss_weight = config.dino.loss_weight
+        self.dino_koleo_loss_weight = config.dino.koleo_loss_weight
+        self.ibot_loss_weight = config.ibot.loss_weight
+        self.engine = None
+
+    # -- B200 engine -------------------------------------------------------------------------------------------------
+    def build_engine(self, device="cuda", comm=None, max_masked=None) -> Engine:
+        self.engine = Engine(self.engine_config, self.config.train.batch_size_per_gpu, device=device,
+                             max_masked=max_masked, comm=comm)
+        return self.engine
+
+    def __call__(self, data, *, teacher_temp=0, iteration=0, deterministic=True, init_phase=False):
+        """Forward + backward of one batch (the reference returns (loss, metrics) and lets jax.grad differentiate it,
+        :289-363; here the gradients are left in the engine's gradient buffers)."""
+        if self.engine is None:
+            self.build_engine()
+        self.engine.set_batch(data)
+        self.engine.forward_backward(float(teacher_temp))
+        m = self.engine.read_metrics()
+        return m["total_loss"], m
+
+    def update_ema(self):
+        """The reference returns fn(ema, params, mom) (:644-660); the B200 EMA is fused into the optimizer kernel
+        (Engine.optimizer_step), so this returns a callable that documents that and is a no-op."""
+        def fn(ema_params=None, params=None, mom=None):
+            return ema_params
+        return fn
+
+    def get_params_groups(self, params=None):
+        """name -> (lr_multiplier, wd_multiplier, is_last_layer) for every student tensor (:577-598 / param_groups.py)."""
+        from ..engine.params import backbone_spec, head_spec
+        out = {}
+        for module, spec in (("backbone", backbone_spec(self.engine_config)), ("dino_head", head_spec(self.engine_config)),
+                             ("ibot_head", head_spec(self.engine_config))):
+            for name, _, _ in spec:
+                out[f"student_{module}/{name}"] = lr_wd_multipliers(module, name, self.engine_config)
+        return out
+
+    def prepare_for_distributed_training(self, params=None):
+        return params

@@ -135,7 +135,8 @@ int d3_sinkhorn_probs(const float* L, const float* mx, float temp, const float* 
 /* ---- cross-entropy over prototypes, forward + backward fused (loss/dino_clstoken_loss.py:66-89,
  * loss/ibot_patch_loss.py:13-14,55-67; weights train/ssl_meta_arch.py:480-525) ---------------------------------------
  * per student row i with teacher rows t0[i], t1[i] (-1 = none): metric[slot[i]] += wm[i] * CE_i;
- * dS[i,:] = wg[i]/student_temp * (npairs*softmax(S_i/student_temp) - sum_p Q_p)  (bf16).                             */
+ * dS[i,:] = wg[i]/student_temp * (npairs*softmax(S_i/student_temp) - sum_p Q_p)  (bf16; NULL = forward only).
+ * s_t == NULL: the rows of Lt are already teacher probabilities (mx / a_t / btot ignored).                         */
 int d3_ce_fwd_bwd(const float* S /*[Rs,K]*/, float student_temp, const float* Lt /*[Rt,K] teacher logits*/,
                   const float* mx, float teacher_temp, const float* s_t /*[K]*/, const float* a_t /*[Rt]*/,
                   const float* btot, const int* t0, const int* t1, const float* wm, const float* wg, const int* slot,

@@ -1,0 +1,39 @@
+"""Host-side mirrors of the reference's config / schedule surface (CPU)."""
+import math
+
+import pytest
+
+from dinov3_jax.configs import DinoV3SetupArgs, setup_config
+from dinov3_jax.engine import config_from_reference_cfg
+from dinov3_jax.train.train import build_schedulers, get_args_parser
+
+
+def test_defaults_follow_reference_yaml_and_scaling_rule():
+    cfg = setup_config(DinoV3SetupArgs())
+    assert cfg.dino.head_n_prototypes == 65536 and cfg.crops.local_crops_number == 8 and cfg.optim.clip_grad == 3.0
+    assert abs(cfg.optim.lr - 0.001 * 4 * math.sqrt(64 / 1024.0)) < 1e-12          # sqrt_wrt_1024 (configs/config.py:52-54)
+    e = config_from_reference_cfg(cfg)
+    assert (e.embed_dim, e.depth, e.heads) == (1024, 24, 16)
+
+
+def test_overrides_and_linear_rule():
+    cfg = setup_config(DinoV3SetupArgs(opts=["optim.scaling_rule=linear_wrt_256", "train.batch_size_per_gpu=32", "student.arch=vit_base"]))
+    assert abs(cfg.optim.lr - 0.001 * 32 / 256) < 1e-12 and config_from_reference_cfg(cfg).embed_dim == 768
+    with pytest.raises(ValueError):
+        setup_config(DinoV3SetupArgs(opts=["novalue"]))
+
+
+def test_schedulers_match_reference_construction():
+    cfg = setup_config(DinoV3SetupArgs())
+    lr, wd, mom, temp, last = build_schedulers(cfg)
+    L = cfg.train.OFFICIAL_EPOCH_LENGTH
+    assert len(lr.schedule) == 100 * L and len(temp.schedule) == 30 * L
+    assert lr[0] == 0.0 and abs(lr[10 * L - 1] - cfg.optim.lr) < 1e-12
+    assert (last.schedule[:L] == 0).all() and last[L] == lr[L]                      # frozen first epoch (train.py:169-173)
+    assert abs(temp[0] - 0.04) < 1e-12 and abs(temp[10 ** 9] - 0.07) < 1e-12 and abs(mom[0] - 0.992) < 1e-12
+    assert abs(wd[0] - 0.04) < 1e-12 and wd[100 * L - 1] < 0.4 + 1e-9
+
+
+def test_cli_surface():
+    a = get_args_parser().parse_args(["--config-file", "x.yaml", "--opts", "a.b=1", "c=2", "--output-dir", "out"])
+    assert a.config_file == "x.yaml" and a.opts == ["a.b=1", "c=2"] and a.output_dir == "out"
