@@ -15,6 +15,9 @@ namespace d3 {
 constexpr float LOG2E = 1.4426950408889634f;
 
 struct AttnShape {
+  int G;         // crops packed per CTA (block-diagonal attention inside one 128-row tile when G*N <= 128)
+  int span;      // G*N: token rows owned by one CTA (grid.z = ceil(n_crops / G))
+  int n_crops;
   int N;         // tokens per crop
   int Nkp;       // keys padded (multiple of 16 * nbox)
   int nbox;      // TMA boxes per K / V tile
@@ -58,7 +61,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int ch = threadIdx.x >> 7;
   const int qt = blockIdx.x, h = blockIdx.y, c = blockIdx.z;
   const int q0 = qt * 128;
-  const int row_base = c * sh.N;  // first token row of this crop in [T, ...]
+  const int row_base = c * sh.span;  // first token row of this CTA's crop group in [T, ...]
+  // this thread's query row, its crop inside the group and that crop's key range [klo, khi)
+  const int q_abs = q0 + r;
+  const int g = min(q_abs / sh.N, sh.G - 1);
+  const int klo = g * sh.N, khi = klo + sh.N;
+  const bool q_valid = (q_abs < sh.span) && (c * sh.G + g < sh.n_crops);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ);
@@ -112,7 +120,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tmem_ld_wait();
 #pragma unroll
     for (int j = 0; j < 16; ++j)
-      if (c0 + j < sh.N) mx = fmaxf(mx, __uint_as_float(v[j]));
+      if (c0 + j >= klo && c0 + j < khi) mx = fmaxf(mx, __uint_as_float(v[j]));
   }
   red[ch * 128 + r] = mx;
   __syncthreads();
@@ -128,7 +136,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     float p[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      p[j] = (c0 + j < sh.N) ? exp2f(__uint_as_float(v[j]) * cs - mxs) : 0.f;
+      p[j] = (c0 + j >= klo && c0 + j < khi) ? exp2f(__uint_as_float(v[j]) * cs - mxs) : 0.f;
       sum += p[j];
     }
     uint8_t* chunk = sP + (c0 >> 6) * 16384;
@@ -160,13 +168,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   mbar_wait(bar_mma, 1);
   tc_fence_after();
 
-  const int q = q0 + r;
   const float inv = 1.f / sum;
   uint32_t o[32];
   tmem_ld32(t_row + ch * 32, o);
   tmem_ld_wait();
-  if (q < sh.N) {
-    __nv_bfloat16* dst = O + (size_t)(row_base + q) * sh.D + h * 64 + ch * 32;
+  if (q_valid) {
+    __nv_bfloat16* dst = O + (size_t)(row_base + q_abs) * sh.D + h * 64 + ch * 32;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       reinterpret_cast<uint4*>(dst)[j] = make_uint4(
@@ -175,7 +182,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           pack_bf16(__uint_as_float(o[8 * j + 4]) * inv, __uint_as_float(o[8 * j + 5]) * inv),
           pack_bf16(__uint_as_float(o[8 * j + 6]) * inv, __uint_as_float(o[8 * j + 7]) * inv));
     }
-    if (LSE && ch == 0) LSE[((size_t)c * sh.H + h) * sh.N + q] = mx * sh.scale + logf(sum);   // natural-log LSE
+    if (LSE && ch == 0)   // natural-log LSE of the scaled scores, indexed [crop, head, token]
+      LSE[((size_t)(c * sh.G + g) * sh.H + h) * sh.N + (q_abs - klo)] = mx * sh.scale + logf(sum);
   }
   tc_fence_before();
   __syncthreads();
@@ -262,8 +270,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const int r = threadIdx.x & 127;
   const int ch = threadIdx.x >> 7;
   const int h = blockIdx.x, c = blockIdx.y;
-  const int row_base = c * sh.N;
-  const int nQ = (sh.N + 127) / 128, nK = nQ;
+  const int row_base = c * sh.span;
+  const int nQ = (sh.span + 127) / 128, nK = nQ;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQKV);
@@ -321,8 +329,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 
       // ---- elementwise: this thread owns query row q = qt*128 + r and key columns [64 ch, 64 ch + 64)
       const int q = qt * 128 + r;
-      const bool q_ok = q < sh.N;
-      const size_t stat = ((size_t)c * sh.H + h) * sh.N + (q_ok ? q : 0);
+      const int g = min(q / sh.N, sh.G - 1);
+      const int klo = g * sh.N, khi = klo + sh.N;      // keys of the same crop (block-diagonal when crops are packed)
+      const bool q_ok = (q < sh.span) && (c * sh.G + g < sh.n_crops);
+      const size_t stat = ((size_t)(c * sh.G + g) * sh.H + h) * sh.N + (q_ok ? q - klo : 0);
       const float lse2 = q_ok ? LSE[stat] * LOG2E : 0.f;
       const float dl = q_ok ? Delta[stat] : 0.f;
       uint8_t* pc = sP + ch * 16384;
@@ -337,7 +347,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         float p[16], ds[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const bool ok = q_ok && (kt * 128 + c0 + j < sh.N);
+          const int kk = kt * 128 + c0 + j;
+          const bool ok = q_ok && kk >= klo && kk < khi;
           p[j] = ok ? exp2f(__uint_as_float(s[j]) * cs - lse2) : 0.f;
           ds[j] = ok ? p[j] * (__uint_as_float(dp[j]) - dl) * sh.scale : 0.f;
         }
@@ -385,11 +396,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     // ---- dK (ch 0) / dV (ch 1) of this key tile: thread owns key row kt*128 + r
     {
       const int key = kt * 128 + r;
+      const int kg = min(key / sh.N, sh.G - 1);
+      const int tok = key - kg * sh.N;                 // token index inside its crop
       float a[64];
       load_row64((ch ? tDV : tDK) + t_lane, a);
-      if (key < sh.N) {
-        if (!ch && sh.sin_t && key >= sh.prefix)
-          rope_inverse_row(a, sh.sin_t + (size_t)(key - sh.prefix) * 64, sh.cos_t + (size_t)(key - sh.prefix) * 64);
+      if (key < sh.span && c * sh.G + kg < sh.n_crops) {
+        if (!ch && sh.sin_t && tok >= sh.prefix)
+          rope_inverse_row(a, sh.sin_t + (size_t)(tok - sh.prefix) * 64, sh.cos_t + (size_t)(tok - sh.prefix) * 64);
         store_row64_bf16(dQKV + (size_t)(row_base + key) * (3 * sh.D) + (ch ? 2 : 1) * sh.D + h * 64, a);
       }
     }
@@ -401,11 +414,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   // ---- dQ: query tile qt is written by the threads with ch == (qt & 1)
   for (int qt = ch; qt < nQ; qt += 2) {
     const int q = qt * 128 + r;
+    const int qg = min(q / sh.N, sh.G - 1);
+    const int tok = q - qg * sh.N;
     float a[64];
     load_row64(tDQ + qt * 64 + t_lane, a);
-    if (q < sh.N) {
-      if (sh.sin_t && q >= sh.prefix)
-        rope_inverse_row(a, sh.sin_t + (size_t)(q - sh.prefix) * 64, sh.cos_t + (size_t)(q - sh.prefix) * 64);
+    if (q < sh.span && c * sh.G + qg < sh.n_crops) {
+      if (sh.sin_t && tok >= sh.prefix)
+        rope_inverse_row(a, sh.sin_t + (size_t)(tok - sh.prefix) * 64, sh.cos_t + (size_t)(tok - sh.prefix) * 64);
       store_row64_bf16(dQKV + (size_t)(row_base + q) * (3 * sh.D) + h * 64, a);
     }
   }
@@ -422,13 +437,17 @@ static int make_map(CUtensorMap* map, const void* ptr, long rows, int cols, int 
   return encode_tensor_map_2d_bf16(map, ptr, dims, strides, box, estr);
 }
 
-static int attn_shape(AttnShape* s, int N, int D, int H) {
+static int attn_shape(AttnShape* s, int n_crops, int N, int D, int H) {
   if (D != H * 64) return set_error(D3_ERR_ARG, "attention: head_dim must be 64");
-  s->N = N; s->D = D; s->H = H; s->scale = 0.125f;
+  if (N <= 0 || n_crops <= 0) return set_error(D3_ERR_ARG, "attention: empty problem");
+  s->N = N; s->D = D; s->H = H; s->scale = 0.125f; s->n_crops = n_crops;
   s->sin_t = nullptr; s->cos_t = nullptr; s->prefix = 0;
-  s->nbox = (N + 255) / 256;
+  s->G = (N <= 64) ? (128 / N) : 1;                 // short crops: several per 128-row tile, block-diagonal mask
+  if (s->G > n_crops) s->G = n_crops;
+  s->span = s->G * N;
+  s->nbox = (s->span + 255) / 256;
   const int q = 16 * s->nbox;
-  s->Nkp = (N + q - 1) / q * q;
+  s->Nkp = (s->span + q - 1) / q * q;
   s->box_rows = s->Nkp / s->nbox;
   if (s->Nkp > 448) return set_error(D3_ERR_ARG, "attention: N > 448 tokens per crop not supported by the single-pass kernel");
   return D3_OK;
@@ -442,7 +461,7 @@ extern "C" {
 
 int d3_attn_fwd(const void* qkv, void* o, float* lse, int n_crops, int N, int D, int H, void* stream) {
   AttnShape s;
-  int rc = attn_shape(&s, N, D, H);
+  int rc = attn_shape(&s, n_crops, N, D, H);
   if (rc) return rc;
   const long T = (long)n_crops * N;
   CUtensorMap tq, tkv;
@@ -452,7 +471,7 @@ int d3_attn_fwd(const void* qkv, void* o, float* lse, int n_crops, int N, int D,
   const int p_chunks = (s.Nkp + 63) / 64;
   const int regA = max(16384 + kv_bytes, p_chunks * 16384);
   const int smem = regA + kv_bytes + 64 + 1024 + 1024;
-  dim3 grid((N + 127) / 128, H, n_crops);
+  dim3 grid((s.span + 127) / 128, H, (n_crops + s.G - 1) / s.G);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (s.Nkp <= 256) {
     static bool cfg = false;
@@ -471,7 +490,7 @@ int d3_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* ls
                 int n_crops, int N, int D, int H, const float* rope_sin, const float* rope_cos, int rope_prefix,
                 void* stream) {
   AttnShape s;
-  int rc = attn_shape(&s, N, D, H);
+  int rc = attn_shape(&s, n_crops, N, D, H);
   if (rc) return rc;
   if (N > 256) return set_error(D3_ERR_ARG, "d3_attn_bwd: N > 256 not supported yet");
   if ((rope_sin == nullptr) != (rope_cos == nullptr)) return set_error(D3_ERR_ARG, "d3_attn_bwd: sin/cos tables");
@@ -490,7 +509,7 @@ int d3_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* ls
   static bool cfg = false;
   if (!cfg) { cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); cfg = true; }
   const int smem = 163840 + 64 + 1024;
-  dim3 grid(H, n_crops);
+  dim3 grid(H, (n_crops + s.G - 1) / s.G);
   attn_bwd_kernel<<<grid, 256, smem, st>>>(tqkv, tdo, lse, delta_scratch, (__nv_bfloat16*)dqkv, s);
   D3_CHECK_LAUNCH();
   return D3_OK;
