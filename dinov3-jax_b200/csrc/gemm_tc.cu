@@ -191,30 +191,60 @@ __device__ __forceinline__ void epilogue_tile(const GemmEpilogue& ep, uint32_t t
 __device__ __forceinline__ uint32_t stg128(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
 __device__ __forceinline__ uint32_t stg64(int row, int chunk) { return (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4)); }
 
+// Per-warp epilogue pipeline state: two staging buffers (out 4 KB + aux 2 KB each); unit u uses buffer u & 1, the
+// residual / GELU' tiles of unit u+1 are prefetched by TMA while unit u is processed, and a buffer is rewritten only
+// after the bulk-store group that read it has drained (cp.async.bulk.wait_group.read 1).
+struct EpiPipe {
+  uint8_t* buf;          // 2 x (4096 + 2048) bytes, 1024-aligned
+  uint64_t* ld_bar;      // [2] one per buffer
+  uint32_t phase[2];
+  uint32_t unit;         // running unit counter of this warp
+};
+
 template <int BN>
 __device__ __forceinline__ void epilogue_tile_tma(const GemmEpilogue& ep, const CUtensorMap* tmOut,
                                                   const CUtensorMap* tmAux, const CUtensorMap* tmRes, uint32_t t_addr,
-                                                  int row0, int n0, int M, int N, int half, uint8_t* sOut, uint8_t* sAux,
-                                                  uint64_t* ld_bar, uint32_t& ld_phase) {
+                                                  int row0, int n0, int M, int N, int half, EpiPipe& pp) {
   const int lane = threadIdx.x & 31;
   const bool out_f32 = (ep.flags & EP_OUT_F32) != 0;
   const bool has_res = (ep.flags & EP_RESID) != 0;
   const bool has_auxin = (ep.flags & EP_MUL_DGELU) != 0;
   const bool store_pre = (ep.flags & EP_STORE_PRE) != 0;
   const bool fast_act = (ep.flags & EP_FAST_ACT) != 0;
+  const bool has_loads = has_res || has_auxin;
+  const uint32_t ld_bytes = (has_res ? 4096u : 0u) + (has_auxin ? 2048u : 0u);
   constexpr int CHUNKS = BN / 64;
   if (row0 >= M) return;   // warp-uniform: this warp's 32 rows are all padding
+  const int c_beg = half * CHUNKS;
+  int c_end = (half + 1) * CHUNKS;
+  while (c_end > c_beg && n0 + (c_end - 1) * 32 >= N) --c_end;   // warp-uniform clipping at the N edge
+  if (c_end <= c_beg) return;
+
+  auto issue_loads = [&](int c, uint32_t u) {   // lane 0 only
+    const uint32_t b = u & 1;
+    uint8_t* sOut = pp.buf + b * 6144;
+    mbar_expect_tx(&pp.ld_bar[b], ld_bytes);
+    if (has_res) tma_load_2d_cta(tmRes, &pp.ld_bar[b], sOut, n0 + c * 32, row0);
+    if (has_auxin) tma_load_2d_cta(tmAux, &pp.ld_bar[b], sOut + 4096, n0 + c * 32, row0);
+  };
+  // prologue: the first unit's buffer was last used two units ago -> its store group has drained after wait<1>
+  if (lane == 0) {
+    tma_store_wait_read1();
+    if (has_loads) issue_loads(c_beg, pp.unit);
+  }
 #pragma unroll 1
-  for (int c = half * CHUNKS; c < (half + 1) * CHUNKS; ++c) {
+  for (int c = c_beg; c < c_end; ++c) {
+    const uint32_t u = pp.unit;
+    const uint32_t b = u & 1;
+    uint8_t* sOut = pp.buf + b * 6144;
+    uint8_t* sAux = sOut + 4096;
     const int nc = n0 + c * 32;
-    if (nc >= N) break;
-    if (lane == 0) tma_store_wait_read();      // staging buffers free again
-    __syncwarp();
-    if ((has_res || has_auxin) && lane == 0) {
-      mbar_expect_tx(ld_bar, (has_res ? 4096u : 0u) + (has_auxin ? 2048u : 0u));
-      if (has_res) tma_load_2d_cta(tmRes, ld_bar, sOut, nc, row0);
-      if (has_auxin) tma_load_2d_cta(tmAux, ld_bar, sAux, nc, row0);
+    if (lane == 0 && c + 1 < c_end) {
+      // buffer (u+1)&1 was used by unit u-1: allow only the most recent store group (none issued since) to be pending
+      tma_store_wait_read0();
+      if (has_loads) issue_loads(c + 1, u + 1);
     }
+    __syncwarp();
     uint32_t r[32];
     tmem_ld32(t_addr + c * 32, r);
     tmem_ld_wait();
@@ -224,8 +254,8 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmEpilogue& ep, const 
     if (ep.flags & EP_BIAS) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
-        float4 b = *reinterpret_cast<const float4*>(ep.bias + nc + j);
-        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+        float4 bb = *reinterpret_cast<const float4*>(ep.bias + nc + j);
+        v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
       }
     }
     if (store_pre) {
@@ -244,17 +274,17 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmEpilogue& ep, const 
         for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
       }
     }
-    if (has_res || has_auxin) {
-      mbar_wait(ld_bar, ld_phase);
-      ld_phase ^= 1;
+    if (has_loads) {
+      mbar_wait(&pp.ld_bar[b], pp.phase[b]);
+      pp.phase[b] ^= 1;
     }
     if (has_auxin) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const uint4 u = *reinterpret_cast<const uint4*>(sAux + stg64(lane, j));
-        const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), cc = unpack_bf16(u.z), d = unpack_bf16(u.w);
+        const uint4 uu = *reinterpret_cast<const uint4*>(sAux + stg64(lane, j));
+        const float2 a = unpack_bf16(uu.x), bq = unpack_bf16(uu.y), cc = unpack_bf16(uu.z), d = unpack_bf16(uu.w);
         v[8 * j] *= gelu_tanh_grad_fast(a.x); v[8 * j + 1] *= gelu_tanh_grad_fast(a.y);
-        v[8 * j + 2] *= gelu_tanh_grad_fast(b.x); v[8 * j + 3] *= gelu_tanh_grad_fast(b.y);
+        v[8 * j + 2] *= gelu_tanh_grad_fast(bq.x); v[8 * j + 3] *= gelu_tanh_grad_fast(bq.y);
         v[8 * j + 4] *= gelu_tanh_grad_fast(cc.x); v[8 * j + 5] *= gelu_tanh_grad_fast(cc.y);
         v[8 * j + 6] *= gelu_tanh_grad_fast(d.x); v[8 * j + 7] *= gelu_tanh_grad_fast(d.y);
       }
@@ -291,6 +321,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmEpilogue& ep, const 
       if (store_pre) tma_store_2d(tmAux, sAux, nc, row0);
       tma_store_commit();
     }
+    pp.unit = u + 1;
   }
 }
 
@@ -445,24 +476,27 @@ gemm1sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 // ---------------------------------------------------------------------------------------------------------------
 // CTA-pair kernel: 256 x 256 tile per cluster; per CTA and stage: A 128x64 (16 KB) + B 128x64 (16 KB)
+// TMA_EPI: TMA-store epilogue (4 operand stages + 96 KB of double-buffered staging); otherwise direct / atomic
+// epilogue (weight gradients) with 6 operand stages.
+template <int TMA_EPI>
 struct Cfg2 {
   static constexpr int BN = 256;
-  static constexpr int STAGES = 5;
+  static constexpr int STAGES = TMA_EPI ? 4 : 6;
   static constexpr int A_BYTES = 128 * BK * 2;
   static constexpr int B_BYTES = 128 * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 512;
-  static constexpr int STG_WARP = 4096 + 2048;                 // per epilogue warp: out tile + aux tile
-  static constexpr int STG_BYTES = EPI_WARPS * STG_WARP;
+  static constexpr int STG_WARP = 2 * (4096 + 2048);           // per epilogue warp: two (out tile + aux tile) buffers
+  static constexpr int STG_BYTES = TMA_EPI ? EPI_WARPS * STG_WARP : 0;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024 + 256;
 };
 
-template <int A_MN, int B_MN>
+template <int A_MN, int B_MN, int TMA_EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAux,
                const __grid_constant__ CUtensorMap tmRes, const GemmEpilogue ep, int M, int N, int K, int splits) {
-  using Cfg = Cfg2;
+  using Cfg = Cfg2<TMA_EPI>;
   constexpr int BN = Cfg::BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -472,8 +506,8 @@ gemm2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty_bar = bars + Cfg::STAGES;           // per CTA, signalled by the leader's multicast commit
   uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;       // per CTA, multicast commit
   uint64_t* tempty_bar = bars + 2 * Cfg::STAGES + 2;  // leader: 2 x EPI_WARPS arrivals
-  uint64_t* ld_bar = bars + 2 * Cfg::STAGES + 4;      // [EPI_WARPS] epilogue TMA loads (residual / GELU' operand)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4 + EPI_WARPS);
+  uint64_t* ld_bar = bars + 2 * Cfg::STAGES + 4;      // [2 * EPI_WARPS] epilogue TMA loads (residual / GELU' operand)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4 + 2 * EPI_WARPS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -485,8 +519,8 @@ gemm2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 2 * EPI_WARPS); }
-    for (int s = 0; s < EPI_WARPS; ++s) mbar_init(&ld_bar[s], 1);
-    if (ep.flags & EP_TMA_EPI) { tma_prefetch_desc(&tmOut); tma_prefetch_desc(&tmAux); tma_prefetch_desc(&tmRes); }
+    for (int s = 0; s < 2 * EPI_WARPS; ++s) mbar_init(&ld_bar[s], 1);
+    if (TMA_EPI) { tma_prefetch_desc(&tmOut); tma_prefetch_desc(&tmAux); tma_prefetch_desc(&tmRes); }
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc_2sm<Cfg::TMEM_COLS>(tmem_slot);
@@ -569,10 +603,12 @@ gemm2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp >= 4) {
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;
-    uint8_t* sOut = staging + (warp - 4) * Cfg::STG_WARP;
-    uint8_t* sAux = sOut + 4096;
-    uint32_t ld_phase = 0;
-    const bool tma_epi = (ep.flags & EP_TMA_EPI) != 0;
+    EpiPipe pp;
+    pp.buf = staging + (warp - 4) * Cfg::STG_WARP;
+    pp.ld_bar = &ld_bar[2 * (warp - 4)];
+    pp.phase[0] = pp.phase[1] = 0;
+    pp.unit = 0;
+    constexpr bool tma_epi = TMA_EPI != 0;
     int local = 0;
     for (int w = cluster_id; w < num_work; w += num_clusters, ++local) {
       const WorkRange wr = work_item(w, num_m, num_n, num_k, splits, 256, BN, ep.flags & EP_M_FASTEST);
@@ -583,8 +619,7 @@ gemm2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (wr.kb1 > wr.kb0) {
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
         if (tma_epi)
-          epilogue_tile_tma<BN>(ep, &tmOut, &tmAux, &tmRes, t_addr, wr.m0 + rank * 128 + q * 32, wr.n0, M, N, half, sOut,
-                                sAux, &ld_bar[warp - 4], ld_phase);
+          epilogue_tile_tma<BN>(ep, &tmOut, &tmAux, &tmRes, t_addr, wr.m0 + rank * 128 + q * 32, wr.n0, M, N, half, pp);
         else
           epilogue_tile<BN>(ep, t_addr, wr.m0 + rank * 128 + q * 32 + lane, wr.n0, M, N, half);
       }
@@ -643,10 +678,11 @@ static int launch1(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilo
 
 struct EpiMaps { CUtensorMap out, aux, res; };
 
-template <int A_MN, int B_MN>
+template <int A_MN, int B_MN, int TMA_EPI>
 static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, const GemmEpilogue& ep, int M, int N,
                    int K, int splits, cudaStream_t stream) {
-  auto kern = gemm2sm_kernel<A_MN, B_MN>;
+  using Cfg2 = Cfg2<TMA_EPI>;
+  auto kern = gemm2sm_kernel<A_MN, B_MN, TMA_EPI>;
   static bool configured = false;
   int rc = configure_once(kern, Cfg2::SMEM_BYTES, &configured);
   if (rc) return rc;
@@ -670,10 +706,16 @@ static int dispatch1(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMa
 }
 static int dispatch2(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em,
                      const GemmEpilogue& ep, int M, int N, int K, int splits, cudaStream_t s) {
-  if (!a_mn && !b_mn) return launch2<0, 0>(ta, tb, em, ep, M, N, K, splits, s);
-  if (!a_mn && b_mn) return launch2<0, 1>(ta, tb, em, ep, M, N, K, splits, s);
-  if (a_mn && !b_mn) return launch2<1, 0>(ta, tb, em, ep, M, N, K, splits, s);
-  return launch2<1, 1>(ta, tb, em, ep, M, N, K, splits, s);
+  if (ep.flags & EP_TMA_EPI) {
+    if (!a_mn && !b_mn) return launch2<0, 0, 1>(ta, tb, em, ep, M, N, K, splits, s);
+    if (!a_mn && b_mn) return launch2<0, 1, 1>(ta, tb, em, ep, M, N, K, splits, s);
+    if (a_mn && !b_mn) return launch2<1, 0, 1>(ta, tb, em, ep, M, N, K, splits, s);
+    return launch2<1, 1, 1>(ta, tb, em, ep, M, N, K, splits, s);
+  }
+  if (!a_mn && !b_mn) return launch2<0, 0, 0>(ta, tb, em, ep, M, N, K, splits, s);
+  if (!a_mn && b_mn) return launch2<0, 1, 0>(ta, tb, em, ep, M, N, K, splits, s);
+  if (a_mn && !b_mn) return launch2<1, 0, 0>(ta, tb, em, ep, M, N, K, splits, s);
+  return launch2<1, 1, 0>(ta, tb, em, ep, M, N, K, splits, s);
 }
 
 // tile_n: 0 = auto; 64/128/256 force the single-CTA kernel with that tile; 512 forces the CTA-pair kernel.
