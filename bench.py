@@ -38,6 +38,25 @@ def peaks():
     return 1590.0, 1400.0, 6650.0, "fallback"
 
 
+def ncu_traffic():
+    """dram read+write bytes per launch of the GEMM kernel from the committed `ncu --set full` capture (mean over the
+    captured launches), or None when no capture summary is present."""
+    p = os.path.join(ROOT, "profiles", "r01_ncu_full_gemm2sm.txt")
+    if not os.path.exists(p):
+        return None
+    vals = []
+    for line in open(p):
+        if "traffic = dram read + write" in line:
+            f = line.split()
+            try:
+                v = float(f[-2]); unit = f[-1]
+                vals.append(v * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}.get(unit, 1.0))
+            except Exception:
+                pass
+    return {"bytes_per_launch_mean": sum(vals) / len(vals), "launches": len(vals),
+            "source": "profiles/r01_ncu_full_gemm2sm.txt (ncu --set full, 4 consecutive block GEMMs of a step)"} if vals else None
+
+
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -233,6 +252,7 @@ def main():
     g_ms = sum(p[2].elapsed_time(p[3]) for p in prof)
     burst, sustained, hbm, how = peaks()
     gemm_tf = g_flops / (g_ms * 1e-3) / 1e12 if g_ms else 0.0
+    traffic = ncu_traffic()
     value = 2 * B * world / (ms * 1e-3)
     e2e_value = 2 * B * world / (ms_e2e * 1e-3)
     step_tf = value * flops_per_gcrop / world / 1e12
@@ -242,9 +262,9 @@ def main():
         "dtype": "bf16", "data": "synthetic", "config": cfg_desc, "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": "global-crops/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 32,
                 "ms_per_step": ms_e2e, "loss": loss},
-        "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tc_kernel (all tcgen05 GEMM launches of one step)",
+        "roofline": {"bound": "tensor", "kernel": "gemm2sm_kernel + gemm1sm_kernel (every tcgen05 GEMM launch of one step)",
                      "achieved": gemm_tf, "peak": sustained, "unit": "TFLOP/s", "frac": gemm_tf / sustained,
-                     "traffic": None, "peak_source": f"bf16_tflops_sustained ({how})", "launches": len(prof),
+                     "traffic": traffic, "peak_source": f"bf16_tflops_sustained ({how})", "launches": len(prof),
                      "share_of_step": g_ms / ms if ms else None},
         "step_roofline": {"achieved": step_tf, "peak": sustained, "unit": "TFLOP/s", "frac": step_tf / sustained,
                           "note": "attention+MLP algorithmic FLOPs (BASELINE.md §3) / step time / GPU"},
