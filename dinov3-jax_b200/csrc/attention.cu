@@ -252,13 +252,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                 const AttnShape sh) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                 // [2][128 x 64] 32 KB (both query tiles stay resident)
-  uint8_t* sDO = smem + 32768;        // [2][128 x 64] 32 KB
-  uint8_t* sK = smem + 65536;         // 16 KB (current key tile)
-  uint8_t* sV = smem + 81920;         // 16 KB
-  uint8_t* sP = smem + 98304;         // [2 chunks of 64 keys][128 q x 128 B] 32 KB
-  uint8_t* sDS = smem + 131072;       // 32 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 163840);
+  const int nQ_ = (sh.span + 127) / 128;       // query tiles (all stay resident): 1..3
+  uint8_t* sQ = smem;                          // [nQ][128 x 64]
+  uint8_t* sDO = sQ + nQ_ * 16384;             // [nQ][128 x 64]
+  uint8_t* sK = sDO + nQ_ * 16384;             // 16 KB (current key tile)
+  uint8_t* sV = sK + 16384;                    // 16 KB
+  uint8_t* sP = sV + 16384;                    // [2 chunks of 64 keys][128 q x 128 B] 32 KB
+  uint8_t* sDS = sP + 32768;                   // 32 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + 32768);
   uint64_t* bar_q = bars;             // Q / dO tiles
   uint64_t* bar_kv = bars + 1;
   uint64_t* bar_mma = bars + 2;
@@ -287,7 +288,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   // TMEM columns: S [0,128) | dP [128,256) | dK [256,320) | dV [320,384) | dQ[qt] [384 + 64 qt, ...)
-  const uint32_t tS = tmem, tDP = tmem + 128, tDK = tmem + 256, tDV = tmem + 320, tDQ = tmem + 384;
+  // with three query tiles (256 < N <= 384) dP reuses the S columns (S is turned into P first) and everything moves down
+  const bool alias = nQ > 2;
+  const uint32_t tS = tmem, tDP = alias ? tmem : tmem + 128, tDK = tmem + (alias ? 128 : 256),
+                 tDV = tmem + (alias ? 192 : 320), tDQ = tmem + (alias ? 256 : 384);
   const uint32_t t_lane = (uint32_t)((warp & 3) * 32) << 16;
 
   if (threadIdx.x == 0) {
@@ -317,9 +321,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_bf16(tS, umma_desc_sw128(qa + k * 32, 16, 1024), umma_desc_sw128(ka + k * 32, 16, 1024), idesc, k > 0);
+        if (!alias) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tDP, umma_desc_sw128(doa + k * 32, 16, 1024), umma_desc_sw128(va + k * 32, 16, 1024), idesc, k > 0);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tDP, umma_desc_sw128(doa + k * 32, 16, 1024), umma_desc_sw128(va + k * 32, 16, 1024), idesc, k > 0);
+        }
         umma_commit(bar_mma);
       }
       __syncwarp();
@@ -337,29 +343,81 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       const float dl = q_ok ? Delta[stat] : 0.f;
       uint8_t* pc = sP + ch * 16384;
       uint8_t* dc = sDS + ch * 16384;
+      if (!alias) {
 #pragma unroll 1
-      for (int cc = 0; cc < 64; cc += 16) {
-        const int c0 = ch * 64 + cc;
-        uint32_t s[16], dp[16];
-        tmem_ld16(tS + t_lane + c0, s);
-        tmem_ld16(tDP + t_lane + c0, dp);
-        tmem_ld_wait();
-        float p[16], ds[16];
+        for (int cc = 0; cc < 64; cc += 16) {
+          const int c0 = ch * 64 + cc;
+          uint32_t s[16], dp[16];
+          tmem_ld16(tS + t_lane + c0, s);
+          tmem_ld16(tDP + t_lane + c0, dp);
+          tmem_ld_wait();
+          float p[16], ds[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int kk = kt * 128 + c0 + j;
-          const bool ok = q_ok && kk >= klo && kk < khi;
-          p[j] = ok ? exp2f(__uint_as_float(s[j]) * cs - lse2) : 0.f;
-          ds[j] = ok ? p[j] * (__uint_as_float(dp[j]) - dl) * sh.scale : 0.f;
+          for (int j = 0; j < 16; ++j) {
+            const int kk = kt * 128 + c0 + j;
+            const bool ok = q_ok && kk >= klo && kk < khi;
+            p[j] = ok ? exp2f(__uint_as_float(s[j]) * cs - lse2) : 0.f;
+            ds[j] = ok ? p[j] * (__uint_as_float(dp[j]) - dl) * sh.scale : 0.f;
+          }
+          *reinterpret_cast<uint4*>(pc + sw128_offset(r, cc)) =
+              make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
+          *reinterpret_cast<uint4*>(pc + sw128_offset(r, cc + 8)) =
+              make_uint4(pack_bf16(p[8], p[9]), pack_bf16(p[10], p[11]), pack_bf16(p[12], p[13]), pack_bf16(p[14], p[15]));
+          *reinterpret_cast<uint4*>(dc + sw128_offset(r, cc)) =
+              make_uint4(pack_bf16(ds[0], ds[1]), pack_bf16(ds[2], ds[3]), pack_bf16(ds[4], ds[5]), pack_bf16(ds[6], ds[7]));
+          *reinterpret_cast<uint4*>(dc + sw128_offset(r, cc + 8)) = make_uint4(
+              pack_bf16(ds[8], ds[9]), pack_bf16(ds[10], ds[11]), pack_bf16(ds[12], ds[13]), pack_bf16(ds[14], ds[15]));
         }
-        *reinterpret_cast<uint4*>(pc + sw128_offset(r, cc)) =
-            make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
-        *reinterpret_cast<uint4*>(pc + sw128_offset(r, cc + 8)) =
-            make_uint4(pack_bf16(p[8], p[9]), pack_bf16(p[10], p[11]), pack_bf16(p[12], p[13]), pack_bf16(p[14], p[15]));
-        *reinterpret_cast<uint4*>(dc + sw128_offset(r, cc)) =
-            make_uint4(pack_bf16(ds[0], ds[1]), pack_bf16(ds[2], ds[3]), pack_bf16(ds[4], ds[5]), pack_bf16(ds[6], ds[7]));
-        *reinterpret_cast<uint4*>(dc + sw128_offset(r, cc + 8)) = make_uint4(
-            pack_bf16(ds[8], ds[9]), pack_bf16(ds[10], ds[11]), pack_bf16(ds[12], ds[13]), pack_bf16(ds[14], ds[15]));
+      } else {
+        // pass 1: P from S (kept in registers as bf16 pairs, 64 columns -> 32 words), written to sP
+        uint32_t pk[32];
+#pragma unroll
+        for (int cc = 0; cc < 64; cc += 16) {
+          const int c0 = ch * 64 + cc;
+          uint32_t s[16];
+          tmem_ld16(tS + t_lane + c0, s);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            const int kk = kt * 128 + c0 + j;
+            const float p0 = (q_ok && kk >= klo && kk < khi) ? exp2f(__uint_as_float(s[j]) * cs - lse2) : 0.f;
+            const float p1 = (q_ok && kk + 1 >= klo && kk + 1 < khi) ? exp2f(__uint_as_float(s[j + 1]) * cs - lse2) : 0.f;
+            pk[(cc + j) >> 1] = pack_bf16(p0, p1);
+          }
+          *reinterpret_cast<uint4*>(pc + sw128_offset(r, cc)) = make_uint4(pk[cc / 2], pk[cc / 2 + 1], pk[cc / 2 + 2], pk[cc / 2 + 3]);
+          *reinterpret_cast<uint4*>(pc + sw128_offset(r, cc + 8)) = make_uint4(pk[cc / 2 + 4], pk[cc / 2 + 5], pk[cc / 2 + 6], pk[cc / 2 + 7]);
+        }
+        tc_fence_before();
+        __syncthreads();          // every thread has consumed S: the dP MMA may overwrite those columns
+        if (threadIdx.x == 0) {
+          tc_fence_after();
+          const uint32_t doa = smem_u32(sDO + qt * 16384), va = smem_u32(sV);
+          const uint32_t idesc = umma_idesc_bf16(128, 128, 0, 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tDP, umma_desc_sw128(doa + k * 32, 16, 1024), umma_desc_sw128(va + k * 32, 16, 1024), idesc, k > 0);
+          umma_commit(bar_mma);
+        }
+        __syncwarp();
+        mbar_wait(bar_mma, mma_phase);
+        mma_phase ^= 1;
+        tc_fence_after();
+        // pass 2: dS = P * (dP - Delta) * scale
+#pragma unroll
+        for (int cc = 0; cc < 64; cc += 16) {
+          const int c0 = ch * 64 + cc;
+          uint32_t dp[16];
+          tmem_ld16(tDP + t_lane + c0, dp);
+          tmem_ld_wait();
+          uint32_t dsw[8];
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            const float2 pp = unpack_bf16(pk[(cc + j) >> 1]);
+            dsw[j >> 1] = pack_bf16(pp.x * (__uint_as_float(dp[j]) - dl) * sh.scale, pp.y * (__uint_as_float(dp[j + 1]) - dl) * sh.scale);
+          }
+          *reinterpret_cast<uint4*>(dc + sw128_offset(r, cc)) = make_uint4(dsw[0], dsw[1], dsw[2], dsw[3]);
+          *reinterpret_cast<uint4*>(dc + sw128_offset(r, cc + 8)) = make_uint4(dsw[4], dsw[5], dsw[6], dsw[7]);
+        }
       }
       fence_proxy_async_smem();
       tc_fence_before();
@@ -492,7 +550,7 @@ int d3_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* ls
   AttnShape s;
   int rc = attn_shape(&s, n_crops, N, D, H);
   if (rc) return rc;
-  if (N > 256) return set_error(D3_ERR_ARG, "d3_attn_bwd: N > 256 not supported yet");
+  if (N > 384) return set_error(D3_ERR_ARG, "d3_attn_bwd: N > 384 tokens per crop not supported (3 query tiles of 128)");
   if ((rope_sin == nullptr) != (rope_cos == nullptr)) return set_error(D3_ERR_ARG, "d3_attn_bwd: sin/cos tables");
   s.sin_t = rope_sin; s.cos_t = rope_cos; s.prefix = rope_prefix;
   const long T = (long)n_crops * N;
@@ -508,7 +566,8 @@ int d3_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* ls
   if ((rc = make_map(&tdo, d_o, T, D, D, 128))) return rc;
   static bool cfg = false;
   if (!cfg) { cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); cfg = true; }
-  const int smem = 163840 + 64 + 1024;
+  const int nq = (s.span + 127) / 128;
+  const int smem = 2 * nq * 16384 + 32768 + 65536 + 64 + 1024;
   dim3 grid(H, (n_crops + s.G - 1) / s.G);
   attn_bwd_kernel<<<grid, 256, smem, st>>>(tqkv, tdo, lse, delta_scratch, (__nv_bfloat16*)dqkv, s);
   D3_CHECK_LAUNCH();

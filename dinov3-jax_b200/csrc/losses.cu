@@ -96,6 +96,36 @@ __global__ void sk_probs_kernel(const float* __restrict__ L, const float* __rest
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ softmax centering
+// Optional teacher normalisation (loss/dino_clstoken_loss.py:24-33,91-95; loss/ibot_patch_loss.py:28-36,69-73):
+//   center <- m*center + (1-m)*mean_rows(L)  (mean all-reduced over ranks), probs = softmax((L - center)/temp).
+// With s[k] = exp((center[k]-cmax)/temp)/K the existing row-sum kernel yields a[b] such that
+// Btot*E*a[b]/(K*s[k]) = softmax((L-center)/temp): the cross-entropy kernel is shared with the Sinkhorn path.
+__global__ void colsum_f32_kernel(const float* __restrict__ L, float* __restrict__ out, int R, int K) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int slab = (R + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * slab, r1 = min(R, r0 + slab);
+  if (k >= K) return;
+  float acc = 0.f;
+  for (int b = r0; b < r1; ++b) acc += L[(long)b * K + k];
+  atomicAdd(&out[k], acc);
+}
+__global__ void center_update_kernel(float* __restrict__ center, const float* __restrict__ colsum,
+                                     const float* __restrict__ total_rows, float momentum, float inv_temp,
+                                     float* __restrict__ s_out, int K) {
+  __shared__ float sh[32];
+  const float inv_rows = 1.f / *total_rows;
+  float mx = -CUDART_INF_F;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float c = center[k] * momentum + colsum[k] * inv_rows * (1.f - momentum);
+    center[k] = c;
+    mx = fmaxf(mx, c);
+  }
+  mx = block_max(mx, sh);
+  for (int k = threadIdx.x; k < K; k += blockDim.x) s_out[k] = __expf((center[k] - mx) * inv_temp) / (float)K;
+}
+
 // ------------------------------------------------------------------------------------------------ cross-entropy
 // per student row i (logits S[i,:]):  loss_i = - sum_p sum_k Q_p[k] * log_softmax(S[i,:]/ts)[k]   over its teacher
 // rows p in {t0[i], t1[i]} (-1 = none), Q_p from the Sinkhorn scalings above.
@@ -255,6 +285,19 @@ int d3_sinkhorn_probs(const float* L, const float* mx, float temp, const float* 
   long n = (long)R * K;
   sk_probs_kernel<<<(int)min((n + 255) / 256, (long)sm_count() * 16), 256, 0, STREAM(stream)>>>(L, mx, 1.f / temp, s, a,
                                                                                              btot, Q, R, K);
+  D3_CHECK_LAUNCH();
+  return D3_OK;
+}
+int d3_colsum_f32(const float* L, float* out /*[K] zeroed, +=*/, int R, int K, void* stream) {
+  if (R <= 0) return D3_OK;
+  dim3 grid((K + 255) / 256, max(1, min(R / 8, 64)));
+  colsum_f32_kernel<<<grid, 256, 0, STREAM(stream)>>>(L, out, R, K);
+  D3_CHECK_LAUNCH();
+  return D3_OK;
+}
+int d3_center_update(float* center, const float* colsum, const float* total_rows, float momentum, float temp,
+                     float* s_out, int K, void* stream) {
+  center_update_kernel<<<1, 1024, 0, STREAM(stream)>>>(center, colsum, total_rows, momentum, 1.f / temp, s_out, K);
   D3_CHECK_LAUNCH();
   return D3_OK;
 }

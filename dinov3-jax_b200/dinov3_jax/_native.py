@@ -58,6 +58,8 @@ SIGNATURES = {
     "d3_sinkhorn_colsum": [P, P, F, P, P, I, I, P],
     "d3_sinkhorn_rowsum": [P, P, F, P, P, P, I, I, P],
     "d3_sinkhorn_probs": [P, P, F, P, P, P, P, I, I, P],
+    "d3_colsum_f32": [P, P, I, I, P],
+    "d3_center_update": [P, P, P, F, F, P, I, P],
     "d3_ce_fwd_bwd": [P, F, P, P, F, P, P, P, P, P, P, P, P, P, P, I, I, P],
     "d3_koleo_fwd_bwd": [P, P, P, P, P, P, P, I, I, F, F, F, P],
     "d3_sumsq": [P, LL, P, P],

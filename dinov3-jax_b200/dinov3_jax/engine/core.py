@@ -124,8 +124,11 @@ class Engine:
     (default: the collate upper bound, data/collate.py:47-61) and the live M comes from `mask_indices_list`.
     """
 
-    def __init__(self, cfg: EngineConfig, B: int, device="cuda", max_masked: int | None = None, comm=None):
+    def __init__(self, cfg: EngineConfig, B: int, device="cuda", max_masked: int | None = None, comm=None,
+                 centering: str = "sinkhorn_knopp", center_momentum: float = 0.9):
         assert cfg.head_dim == 64, "kernels are specialised for head_dim 64 (every BASELINE arch)"
+        assert centering in ("sinkhorn_knopp", "softmax")
+        self.centering, self.center_momentum = centering, center_momentum
         self.cfg, self.B, self.device = cfg, B, torch.device(device)
         self.comm = comm  # fsdp.runtime.Comm (None = single GPU)
         self.world = 1 if comm is None else comm.world
@@ -156,6 +159,10 @@ class Engine:
         self.h_t_ibot = HeadBufs(cfg, self.max_masked, dev, stash=False)
         self.sk_dino = SinkhornBufs(ng, K, dev)
         self.sk_ibot = SinkhornBufs(self.max_masked, K, dev)
+        # centers of the optional softmax-centering path ("state" collection of the reference: dino_clstoken_loss.py:19-22)
+        self.center_dino = torch.zeros(K, dtype=f32, device=dev)
+        self.center_ibot = torch.zeros(K, dtype=f32, device=dev)
+        self._colsum = torch.zeros(K, dtype=f32, device=dev)
         i32 = torch.int32
         self.rows_masked_t = torch.empty(self.max_masked, dtype=i32, device=dev)
         self.rows_cls_t = torch.empty(ng, dtype=i32, device=dev)
@@ -308,6 +315,22 @@ class Engine:
             ops.sinkhorn_rowsum(L, sk.mx, temp, sk.s, sk.btot, sk.a[:R])
             a = sk.a[:R]
 
+    def _softmax_center(self, sk: SinkhornBufs, center, logits, R: int, temp: float, rows_local: float):
+        """softmax((x - center)/temp) after the center EMA update (loss/dino_clstoken_loss.py:24-33,91-95), expressed
+        through the same (mx, s, a, btot) scalings the cross-entropy kernel consumes."""
+        L = logits[:R]
+        sk.mx.fill_(float("-inf"))
+        sk.btot.fill_(float(rows_local))
+        ops.absmax(L, sk.mx)
+        self._colsum.zero_()
+        ops.colsum_f32(L, self._colsum)
+        if self.comm is not None:
+            self.comm.all_reduce_max(sk.mx)
+            self.comm.all_reduce_sum(sk.btot)
+            self.comm.all_reduce_sum(self._colsum)        # pmean of the local centers over "dp" (:93)
+        ops.center_update(center, self._colsum, sk.btot, self.center_momentum, temp, sk.s)
+        ops.sinkhorn_rowsum(L, sk.mx, temp, sk.s, sk.btot, sk.a[:R])
+
     # ------------------------------------------------------------------------------------------------ backward pieces
     def _head_bwd(self, hb: HeadBufs, module: str, R: int):
         hd = self.params.mods[module]
@@ -405,8 +428,12 @@ class Engine:
         ops.gather_rows(T_.Xn, self.rows_masked_t, M, D, dst_bf16=self.h_t_ibot.A0)
         self._head_fwd(self.h_t_dino, "dino_head", ng, teacher=True, stash=False)
         self._head_fwd(self.h_t_ibot, "ibot_head", M, teacher=True, stash=False)
-        self._sinkhorn(self.sk_dino, self.h_t_dino.logits, ng, teacher_temp, btot_local=ng)
-        self._sinkhorn(self.sk_ibot, self.h_t_ibot.logits, M, teacher_temp, btot_local=M)
+        if self.centering == "sinkhorn_knopp":
+            self._sinkhorn(self.sk_dino, self.h_t_dino.logits, ng, teacher_temp, btot_local=ng)
+            self._sinkhorn(self.sk_ibot, self.h_t_ibot.logits, M, teacher_temp, btot_local=M)
+        else:
+            self._softmax_center(self.sk_dino, self.center_dino, self.h_t_dino.logits, ng, teacher_temp, ng)
+            self._softmax_center(self.sk_ibot, self.center_ibot, self.h_t_ibot.logits, M, teacher_temp, M)
         # ---- student (train/ssl_meta_arch.py:406-460)
         S_ = self.student
         self._backbone_fwd(S_, [self.g_img, self.l_img], [self.masks_u8, None], teacher=False)

@@ -211,6 +211,16 @@ def sinkhorn_probs(L, mx, temp, s, a, btot, Q):
             "d3_sinkhorn_probs")
 
 
+def colsum_f32(L, out):
+    R, K = L.shape
+    N.check(N.init().d3_colsum_f32(_p(L), _p(out), R, K, _s()), "d3_colsum_f32")
+
+
+def center_update(center, colsum, total_rows, momentum, temp, s_out):
+    N.check(N.init().d3_center_update(_p(center), _p(colsum), _p(total_rows), momentum, temp, _p(s_out), center.numel(), _s()),
+            "d3_center_update")
+
+
 def ce_fwd_bwd(S, student_temp, Lt, mx, teacher_temp, s_t, a_t, btot, t0, t1, wm, wg, slot, metric, dS):
     Rs, K = S.shape
     assert S.dtype == f32 and Lt.dtype == f32 and (dS is None or dS.dtype == bf16) and t0.dtype == torch.int32

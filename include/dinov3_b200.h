@@ -90,7 +90,7 @@ int d3_layernorm_bwd(const void* dy, int dy_is_f32, const float* x, const float*
 int d3_rope(void* qkv_bf16, const float* sin_t /*[P,hd]*/, const float* cos_t, long long T, int tokens_per_crop,
             int prefix, int D, int head_dim, int inverse, void* stream);
 
-/* ---- attention (layers/attention.py:116 nn.dot_product_attention; head_dim 64, N <= 448 fwd / 256 bwd) ------------ */
+/* ---- attention (layers/attention.py:116 nn.dot_product_attention; head_dim 64, N <= 448 fwd / 384 bwd) ------------ */
 int d3_attn_fwd(const void* qkv_bf16 /*[n*N,3D] post-RoPE*/, void* o_bf16 /*[n*N,D]*/, float* lse /*[n,H,N] or NULL*/,
                 int n_crops, int N, int D, int H, void* stream);
 /* rope_sin / rope_cos ([P,64] fp32, or NULL): when given, the inverse rotation (transpose of layers/attention.py:19-20)
@@ -131,6 +131,13 @@ int d3_sinkhorn_rowsum(const float* L, const float* mx, float temp, const float*
                        float* a /*[R]*/, int R, int K, void* stream);
 int d3_sinkhorn_probs(const float* L, const float* mx, float temp, const float* s, const float* a, const float* btot,
                       float* Q /*[R,K]*/, int R, int K, void* stream);
+
+/* ---- softmax centering (optional teacher normalisation; loss/dino_clstoken_loss.py:24-33,91-95, ibot :28-36,69-73) ----
+ * center <- m*center + (1-m)*colsum/total_rows; s_out[k] = exp((center[k]-max center)/temp)/K.  One d3_sinkhorn_rowsum
+ * with this s then gives a[] such that the teacher probabilities are softmax((L-center)/temp) for d3_ce_fwd_bwd.   */
+int d3_colsum_f32(const float* L /*[R,K]*/, float* out /*[K] zeroed, +=*/, int R, int K, void* stream);
+int d3_center_update(float* center /*[K]*/, const float* colsum /*[K] (all-reduced)*/, const float* total_rows /*device*/,
+                     float momentum, float temp, float* s_out /*[K]*/, int K, void* stream);
 
 /* ---- cross-entropy over prototypes, forward + backward fused (loss/dino_clstoken_loss.py:66-89,
  * loss/ibot_patch_loss.py:13-14,55-67; weights train/ssl_meta_arch.py:480-525) ---------------------------------------

@@ -12,7 +12,7 @@ STUDENT_MODULES = ("student_backbone", "student_dino_head", "student_ibot_head")
 
 
 def ssl_forward(params: dict, batch: dict, teacher_temp: float, cfg: ModelCfg, emu: Emu = Emu(False),
-                world: int = 1, allreduce=None, dtype=torch.float32, return_aux: bool = False):
+                world: int = 1, allreduce=None, dtype=torch.float32, return_aux: bool = False, centers=None):
     """train/ssl_meta_arch.py:289-363 (__call__), :366-402 (teacher), :406-460 (student), :463-557 (losses).
 
     Single-device semantics: `batch` holds this rank's B images, crop-major.
@@ -33,12 +33,21 @@ def ssl_forward(params: dict, batch: dict, teacher_temp: float, cfg: ModelCfg, e
         t_buf = t_patch.reshape(-1, t_patch.shape[-1])[idx]                 # :377
         t_patch_logits = head_forward(sub(params, "teacher_ibot_head"), t_buf, emu)      # :378
         t_cls_logits = head_forward(sub(params, "teacher_dino_head"), t_cls, emu)        # :380
-        cls_centered = sinkhorn_knopp(t_cls_logits, teacher_temp, B_total=t_cls_logits.shape[0] * world,
-                                      allreduce=allreduce).reshape(n_g, B, K)            # :382-386
-        n_masked = batch["n_masked_patches"].sum().to(dtype)
-        if allreduce is not None:
-            n_masked = allreduce(n_masked)
-        patch_centered = sinkhorn_knopp(t_patch_logits, teacher_temp, B_total=n_masked, allreduce=allreduce)  # :388-393
+        if centers is None:
+            cls_centered = sinkhorn_knopp(t_cls_logits, teacher_temp, B_total=t_cls_logits.shape[0] * world,
+                                          allreduce=allreduce).reshape(n_g, B, K)            # :382-386
+            n_masked = batch["n_masked_patches"].sum().to(dtype)
+            if allreduce is not None:
+                n_masked = allreduce(n_masked)
+            patch_centered = sinkhorn_knopp(t_patch_logits, teacher_temp, B_total=n_masked, allreduce=allreduce)  # :388-393
+        else:
+            # optional softmax-centering path (train.centering != sinkhorn_knopp; disabled by the reference's assert,
+            # ssl_meta_arch.py:49): update the center first, then softmax((x - center)/temp) (dino_clstoken_loss.py:24-33)
+            from .losses import center_update, softmax_center_teacher
+            centers["dino"] = center_update(centers["dino"], t_cls_logits, centers.get("momentum", 0.9))
+            centers["ibot"] = center_update(centers["ibot"], t_patch_logits, centers.get("momentum", 0.9))
+            cls_centered = softmax_center_teacher(t_cls_logits, centers["dino"], teacher_temp).reshape(n_g, B, K)
+            patch_centered = softmax_center_teacher(t_patch_logits, centers["ibot"], teacher_temp)
 
     # ---- student
     s_g, s_l = backbone_forward(sub(params, "student_backbone"), [g, l], [masks, None], cfg, emu)   # :414-418

@@ -120,3 +120,37 @@ def test_batch_from_reference_collate_contract():
     eng.train_step(batch, **HYPER)
     m = eng.read_metrics()
     assert abs(m["dino_local_crops_loss"] - 5.545) < 0.01      # log(256) at init
+
+
+def test_softmax_centering_path_matches_oracle():
+    """Optional teacher normalisation of the north_star list: center EMA + softmax((x-c)/temp) instead of Sinkhorn."""
+    from dinov3_jax.engine import Engine, from_oracle_cfg
+    from oracle import tiny_cfg
+    from oracle.batch import synthetic_batch
+    from oracle.model import init_params
+    from oracle.step import ssl_forward
+    cfg = tiny_cfg(layerscale=0.5)
+    B = 3
+    P = init_params(cfg, 0, perturb=0.05)
+    batch = synthetic_batch(cfg, B, 2)
+    eng = Engine(from_oracle_cfg(cfg), B, max_masked=int(batch["mask_indices_list"].shape[0]), centering="softmax")
+    eng.params.load_reference_tree(P)
+    K = cfg.n_prototypes
+    c0 = torch.randn(K) * 0.01
+    eng.center_dino.copy_(c0); eng.center_ibot.copy_(-c0)
+    eng.set_batch(batch)
+    eng.forward_backward(0.05)
+    met = eng.read_metrics()
+    centers = {"dino": c0.clone().reshape(1, K), "ibot": (-c0).reshape(1, K), "momentum": 0.9}
+    student = {k: v.clone().requires_grad_(True) for k, v in P.items() if k.startswith("student_")}
+    full = dict(P); full.update(student)
+    loss, m = ssl_forward(full, batch, 0.05, cfg, centers=centers)
+    assert abs(met["total_loss"] - loss.item()) < 1e-3 * abs(loss.item())
+    assert torch.allclose(eng.center_dino.cpu(), centers["dino"].reshape(-1), atol=1e-5)
+    assert torch.allclose(eng.center_ibot.cpu(), centers["ibot"].reshape(-1), atol=1e-5)
+    keys = list(student)
+    gl = torch.autograd.grad(loss, [student[k] for k in keys], allow_unused=True)
+    ge = eng.params.export_reference_tree("grad")
+    num = sum(((ge[k].cpu().reshape(g.shape) - g) ** 2).sum() for k, g in zip(keys, gl) if g is not None)
+    den = sum((g ** 2).sum() for g in gl if g is not None)
+    assert float(torch.sqrt(num / den)) < 3e-2

@@ -123,7 +123,7 @@ def test_attention_forward(n, N, H):
     assert rel(o, ro) < BF16_TOL and rel(lse, rl) < 1e-5
 
 
-@pytest.mark.parametrize("n,N,H", [(2, 128, 1), (3, 197, 2), (5, 37, 2), (4, 50, 3), (2, 256, 1), (2, 17, 6)])
+@pytest.mark.parametrize("n,N,H", [(2, 128, 1), (3, 197, 2), (5, 37, 2), (4, 50, 3), (2, 256, 1), (2, 17, 6), (2, 257, 2), (1, 384, 1), (3, 300, 1)])
 def test_attention_backward(n, N, H):
     from dinov3_jax import ops
     D = 64 * H
