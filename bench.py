@@ -135,6 +135,8 @@ def main():
     ap.add_argument("--arch", default="vit_large")
     ap.add_argument("--batch", type=int, default=64, help="images per GPU (ssl_default_config.yaml:75)")
     ap.add_argument("--prototypes", type=int, default=65536)
+    ap.add_argument("--patch", type=int, default=16)
+    ap.add_argument("--local-size", type=int, default=96, help="98 for patch 14 (96 is not divisible, layers/patch_embed.py:48-49)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-batch", type=int, default=1)
     args = ap.parse_args()
@@ -145,9 +147,9 @@ def main():
 
     from dinov3_jax.engine.config import ARCHS
     D, L, H = ARCHS[args.arch]
-    Ng, Nl = (224 // 16) ** 2 + 1, (96 // 16) ** 2 + 1
+    Ng, Nl = (224 // args.patch) ** 2 + 1, (args.local_size // args.patch) ** 2 + 1
     flops_per_gcrop = f_img(D, L, Ng, Nl) / 2
-    cfg_desc = {"workload": f"{args.arch}/16 student+teacher, 2x224^2 + 8x96^2 crops, {args.batch} img/GPU, "
+    cfg_desc = {"workload": f"{args.arch}/{args.patch} student+teacher, 2x224^2 + 8x{args.local_size}^2 crops, {args.batch} img/GPU, "
                             f"K={args.prototypes} prototypes, DINO+iBOT+KoLeo, clip+AdamW+EMA (BASELINE configs[3] per-GPU shape)",
                 "global_batch": args.batch * world, "parallelism": f"fsdp{world}" if world > 1 else "single",
                 "l2": "inputs+activations per step >> 126 MB L2 (no flush needed)"}
@@ -182,7 +184,7 @@ def main():
     from dinov3_jax.engine import Engine, config_for
     from dinov3_jax.engine.synth import synthetic_batch, init_reference_like
     _native.init(local_rank)
-    cfg = config_for(args.arch, n_prototypes=args.prototypes)
+    cfg = config_for(args.arch, n_prototypes=args.prototypes, patch=args.patch, local_size=args.local_size)
     B = args.batch
     log(f"building synthetic batch B={B}")
     batch = synthetic_batch(cfg, B, seed=rank, pin=True)

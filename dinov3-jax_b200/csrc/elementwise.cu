@@ -21,7 +21,7 @@ __device__ __forceinline__ float warp_max(float v) {
 // layers/patch_embed.py:38-51: conv with kernel == stride == p is a GEMM over flattened patches.
 // img bf16 [n, H, W, 3] -> out bf16 [n*Hp*Wp, p*p*3], k = (a*p + b)*3 + c  (kernel layout [p,p,3,D]).
 __global__ void im2col_kernel(const __nv_bfloat16* __restrict__ img, __nv_bfloat16* __restrict__ out, int n, int H,
-                              int W, int p) {
+                              int W, int p, int ld) {
   const int Hp = H / p, Wp = W / p;
   const int rowlen = p * 3;              // contiguous run in the image per (patch row a)
   const long total = (long)n * Hp * Wp * p;   // one work item = one contiguous run
@@ -32,8 +32,10 @@ __global__ void im2col_kernel(const __nv_bfloat16* __restrict__ img, __nv_bfloat
     const int i = (int)((r / Wp) % Hp);
     const long c = r / ((long)Wp * Hp);
     const __nv_bfloat16* src = img + ((c * H + (long)i * p + a) * W + (long)j * p) * 3;
-    __nv_bfloat16* dst = out + r * (long)(p * rowlen) + (long)a * rowlen;
+    __nv_bfloat16* dst = out + r * (long)ld + (long)a * rowlen;
     for (int e = threadIdx.x & 31; e < rowlen; e += 32) dst[e] = src[e];
+    if (a == p - 1)   // zero the alignment padding of the row (ld may exceed p*p*3)
+      for (int e = p * rowlen + (threadIdx.x & 31); e < ld; e += 32) out[r * (long)ld + e] = __float2bfloat16(0.f);
   }
 }
 
@@ -455,11 +457,12 @@ static void launch_ln_bwd_fused(const void* dy, int dy_is_f32, const float* x, c
 
 extern "C" {
 
-int d3_im2col(const void* img, void* out, int n, int H, int W, int p, void* stream) {
+int d3_im2col(const void* img, void* out, int ld_out, int n, int H, int W, int p, void* stream) {
   if (!img || !out || H % p || W % p) return set_error(D3_ERR_ARG, "d3_im2col: bad args (H, W must divide by p)");
+  if (ld_out < p * p * 3) return set_error(D3_ERR_ARG, "d3_im2col: ld_out < p*p*3");
   long runs = (long)n * (H / p) * (W / p) * p;
   int blocks = (int)min((runs + 7) / 8, (long)sm_count() * 16);
-  im2col_kernel<<<blocks, 256, 0, STREAM(stream)>>>((const __nv_bfloat16*)img, (__nv_bfloat16*)out, n, H, W, p);
+  im2col_kernel<<<blocks, 256, 0, STREAM(stream)>>>((const __nv_bfloat16*)img, (__nv_bfloat16*)out, n, H, W, p, ld_out);
   D3_CHECK_LAUNCH();
   return D3_OK;
 }

@@ -38,7 +38,7 @@ P, I, LL, F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 SIGNATURES = {
     "d3_init": [I],
     "d3_gemm_bf16": [P, I, I, P, I, I, I, I, I, C.POINTER(GemmEpilogue), I, I, P],
-    "d3_im2col": [P, P, I, I, I, I, P],
+    "d3_im2col": [P, P, I, I, I, I, I, P],
     "d3_assemble_tokens": [P, P, P, P, P, I, I, I, P],
     "d3_assemble_tokens_bwd": [P, P, P, P, P, I, I, I, P],
     "d3_layernorm_fwd": [P, P, P, P, I, P, P, I, I, F, P],

@@ -48,7 +48,9 @@ class CropSet:
         self.T = n_crops * self.N
         self.row0 = row0
         self.sin, self.cos = rope_tables(self.Hp, self.Hp, cfg.head_dim, cfg.rope_base, device)
-        self.patches = torch.empty(n_crops * self.P, cfg.patch * cfg.patch * 3, dtype=bf16, device=device)
+        kdim = cfg.patch * cfg.patch * 3
+        kpad = (kdim + 7) // 8 * 8             # TMA needs 16-byte row strides (patch 14: 588 -> 592, padding zeroed)
+        self.patches = torch.empty(n_crops * self.P, kpad, dtype=bf16, device=device)[:, :kdim]
         self.tok = torch.empty(n_crops * self.P, cfg.embed_dim, dtype=f32, device=device)
         self.lse = None
 

@@ -57,7 +57,8 @@ class PatchEmbed:
         if H % self.p or W % self.p:
             raise AssertionError(f"Input image height {H} / width {W} is not a multiple of patch size {self.p}")   # :48-49
         P = (H // self.p) * (W // self.p)
-        patches = torch.empty(n * P, self.p * self.p * c, dtype=bf16, device=x.device)
+        kdim = self.p * self.p * c
+        patches = torch.empty(n * P, (kdim + 7) // 8 * 8, dtype=bf16, device=x.device)[:, :kdim]
         ops.im2col(x.to(bf16).contiguous(), patches, self.p)
         out = torch.empty(n * P, self.D, dtype=f32, device=x.device)
         ops.gemm(patches, self.kernel, out, b_mn=True, bias=self.bias)

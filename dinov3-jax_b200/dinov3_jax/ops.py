@@ -87,8 +87,8 @@ def _s():
 
 def im2col(img: torch.Tensor, out: torch.Tensor, patch: int) -> torch.Tensor:
     n, H, W, c = img.shape
-    assert c == 3 and img.dtype == bf16 and img.is_contiguous() and out.dtype == bf16 and out.is_contiguous()
-    N.check(N.init().d3_im2col(_p(img), _p(out), n, H, W, patch, _s()), "d3_im2col")
+    assert c == 3 and img.dtype == bf16 and img.is_contiguous() and out.dtype == bf16 and out.stride(1) == 1
+    N.check(N.init().d3_im2col(_p(img), _p(out), out.stride(0), n, H, W, patch, _s()), "d3_im2col")
     return out
 
 

@@ -70,8 +70,8 @@ int d3_gemm_bf16(const void* A, int lda, int a_major, const void* B, int ldb, in
 /* ---- patch embedding / token assembly ---------------------------------------------------------------------------
  * layers/patch_embed.py:38-51: the stride==kernel conv is im2col + GEMM (d3_gemm_bf16 with the kernel viewed as
  * [p*p*3, D]); models/vision_transformer.py:173-203: where(mask, mask_token, x), prepend cls.                        */
-int d3_im2col(const void* img_bf16 /*[n,H,W,3]*/, void* out_bf16 /*[n*Hp*Wp, p*p*3]*/, int n, int H, int W, int p,
-              void* stream);
+int d3_im2col(const void* img_bf16 /*[n,H,W,3]*/, void* out_bf16 /*[n*Hp*Wp, ld_out >= p*p*3], padding zeroed*/,
+              int ld_out, int n, int H, int W, int p, void* stream);
 int d3_assemble_tokens(const float* tok /*[n*P,D]*/, const float* cls /*[D]*/, const float* mask_token /*[D]*/,
                        const unsigned char* masks /*[n*P] or NULL*/, float* X /*[n,1+P,D]*/, int n, int P, int D,
                        void* stream);

@@ -42,7 +42,7 @@ def test_argument_errors_are_reported_without_gpu():
     ep = _native.GemmEpilogue()
     rc = lib.d3_gemm_bf16(None, 8, 0, None, 8, 0, 128, 128, 64, ctypes.byref(ep), 0, 0, None)
     assert rc == -1 and b"null" in lib.d3_last_error()
-    rc = lib.d3_im2col(None, None, 1, 30, 30, 16, None)
+    rc = lib.d3_im2col(None, None, 768, 1, 30, 30, 16, None)
     assert rc == -1
 
 

@@ -77,6 +77,12 @@ def test_ragged_shapes_three_heads_odd_batch():
     check(run_pair(cfg, 3, seed=1))
 
 
+def test_patch14_configuration():
+    """ViT-g/14-style geometry: patch 14 (im2col rows of 588 elements, padded to 592 for TMA), 4x4 / 2x2 patch grids."""
+    from oracle import tiny_cfg
+    check(run_pair(tiny_cfg(patch=14, global_size=56, local_size=28, layerscale=0.3), 2, seed=2))
+
+
 def test_updates_move_parameters_like_the_oracle():
     """AdamW step 1 is lr*sign(g): compare the sign pattern where the gradient is well above the noise floor, and the
     teacher EMA identity teacher' = m*teacher + (1-m)*student' exactly (fp32)."""
