@@ -1,6 +1,7 @@
 // C ABI glue: library state, error reporting, tensor-map encoding, extern "C" wrappers.
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include "d3_internal.h"
 
@@ -18,7 +19,11 @@ int set_error(int code, const char* msg) {
   snprintf(g_err, sizeof(g_err), "%s", msg ? msg : "");
   return code;
 }
-int sm_count() { return g_sm_count > 0 ? g_sm_count : 148; }
+static int g_sm_limit = 0;
+int sm_count() {
+  const int n = g_sm_count > 0 ? g_sm_count : 148;
+  return (g_sm_limit > 0 && g_sm_limit < n) ? g_sm_limit : n;
+}
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int encode_tensor_map_2d_bf16(CUtensorMap* map, const void* ptr, const cuuint64_t dims[2],
@@ -64,6 +69,11 @@ using namespace d3;
 extern "C" {
 
 int d3_abi_version(void) { return 1; }
+int d3_set_sm_limit(int n) {
+  if (n < 0) return set_error(D3_ERR_ARG, "d3_set_sm_limit: n < 0");
+  g_sm_limit = n & ~1;   // CTA pairs: keep it even
+  return D3_OK;
+}
 const char* d3_last_error(void) { return g_err; }
 long long d3_launch_count(void) { return g_launches.load(); }
 void d3_reset_launch_count(void) { g_launches.store(0); }
@@ -81,6 +91,7 @@ int d3_init(int device) {
     return set_error(D3_ERR_DEVICE, buf);
   }
   g_sm_count = prop.multiProcessorCount;
+  if (const char* e = getenv("D3_GEMM_SMS")) g_sm_limit = atoi(e) & ~1;
   if (!g_encode) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult q;

@@ -14,6 +14,12 @@ namespace d3 {
 
 constexpr float LOG2E = 1.4426950408889634f;
 
+__device__ long long* g_attn_dbg = nullptr;   // optional clock64() trace of CTA (0,0) (tools/attn_trace.py)
+__device__ __forceinline__ void dbg_mark(int slot) {
+  if (g_attn_dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (threadIdx.x == 0 || threadIdx.x == 200))
+    g_attn_dbg[slot * 2 + (threadIdx.x == 0 ? 0 : 1)] = clock64();
+}
+
 struct AttnShape {
   int G;         // crops packed per CTA (block-diagonal attention inside one 128-row tile when G*N <= 128)
   int span;      // G*N: token rows owned by one CTA (grid.z = ceil(n_crops / G))
@@ -247,7 +253,7 @@ __device__ __forceinline__ void load_row64(uint32_t taddr, float (&a)[64]) {
 }
 
 __global__ void __launch_bounds__(256)
-attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+attn_bwd_alias_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                 const float* __restrict__ LSE, const float* __restrict__ Delta, __nv_bfloat16* __restrict__ dQKV,
                 const AttnShape sh) {
   extern __shared__ uint8_t smem_raw[];
@@ -487,6 +493,243 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   if (warp == 0) tmem_free<512>(tmem);
 }
 
+__global__ void __launch_bounds__(256)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                const float* __restrict__ LSE, const float* __restrict__ Delta, __nv_bfloat16* __restrict__ dQKV,
+                const AttnShape sh) {
+  // Pipelined variant for up to two query / key tiles (span <= 256): one tensor-core commit per (kt, qt) iteration —
+  // the accumulate MMAs of iteration i and the S / dP MMAs of iteration i+1 are issued back to back, K / V tiles are
+  // double-buffered, and every MMA / column loop is trimmed to the valid extent of the (ragged) last tile.
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int nQ = (sh.span + 127) / 128, nK = nQ;
+  uint8_t* sQ = smem;                          // [nQ][128 x 64]
+  uint8_t* sDO = sQ + nQ * 16384;              // [nQ][128 x 64]
+  uint8_t* sK = sDO + nQ * 16384;              // [2][128 x 64] double-buffered key tile
+  uint8_t* sV = sK + 32768;                    // [2][128 x 64]
+  uint8_t* sP = sV + 32768;                    // [2 chunks of 64 keys][128 q x 128 B] 32 KB
+  uint8_t* sDS = sP + 32768;                   // 32 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + 32768);
+  uint64_t* bar_q = bars;
+  uint64_t* bar_kv = bars + 1;                 // [2]
+  uint64_t* bar_mma = bars + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int r = threadIdx.x & 127;
+  const int ch = threadIdx.x >> 7;
+  const int h = blockIdx.x, c = blockIdx.y;
+  const int row_base = c * sh.span;
+  const int n_it = nK * nQ;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmDO);
+    mbar_init(bar_q, 1);
+    mbar_init(&bar_kv[0], 1);
+    mbar_init(&bar_kv[1], 1);
+    mbar_init(bar_mma, 1);
+    fence_mbar_init();
+  }
+  dbg_mark(0);
+  if (warp == 0) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  dbg_mark(1);
+  const uint32_t tS = tmem, tDP = tmem + 128, tDK = tmem + 256, tDV = tmem + 320, tDQ = tmem + 384;
+  const uint32_t t_lane = (uint32_t)((warp & 3) * 32) << 16;
+  const float cs = sh.scale * LOG2E;
+
+  auto tile_extent = [&](int t) { return min(128, ((sh.span - t * 128) + 15) & ~15); };   // valid rows/cols, multiple of 16
+  auto load_kv = [&](int kt) {     // thread 0
+    const int bsel = kt & 1;
+    mbar_expect_tx(&bar_kv[bsel], 2 * 16384);
+    tma_load_2d(&tmQKV, &bar_kv[bsel], sK + bsel * 16384, sh.D + h * 64, row_base + kt * 128);
+    tma_load_2d(&tmQKV, &bar_kv[bsel], sV + bsel * 16384, 2 * sh.D + h * 64, row_base + kt * 128);
+  };
+  auto issue_sdp = [&](int kt, int qt) {   // thread 0: S = Q K^T and dP = dO V^T for this tile pair, N trimmed
+    const uint64_t qd = umma_desc_sw128(smem_u32(sQ + qt * 16384), 16, 1024), dod = umma_desc_sw128(smem_u32(sDO + qt * 16384), 16, 1024);
+    const uint64_t kd = umma_desc_sw128(smem_u32(sK + (kt & 1) * 16384), 16, 1024), vd = umma_desc_sw128(smem_u32(sV + (kt & 1) * 16384), 16, 1024);
+    const uint32_t idesc = umma_idesc_bf16(128, tile_extent(kt), 0, 0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {   // S and dP are independent accumulator chains: interleave them
+      umma_bf16(tS, qd + (uint64_t)(k * 2), kd + (uint64_t)(k * 2), idesc, k > 0 ? 1u : 0u);
+      umma_bf16(tDP, dod + (uint64_t)(k * 2), vd + (uint64_t)(k * 2), idesc, k > 0 ? 1u : 0u);
+    }
+  };
+  auto store_dkdv = [&](int kt) {          // all threads: dK (ch 0) / dV (ch 1) rows of key tile kt
+    const int key = kt * 128 + r;
+    const int kg = min(key / sh.N, sh.G - 1);
+    const int tok = key - kg * sh.N;
+    float a[64];
+    load_row64((ch ? tDV : tDK) + t_lane, a);
+    if (key < sh.span && c * sh.G + kg < sh.n_crops) {
+      if (!ch && sh.sin_t && tok >= sh.prefix)
+        rope_inverse_row(a, sh.sin_t + (size_t)(tok - sh.prefix) * 64, sh.cos_t + (size_t)(tok - sh.prefix) * 64);
+      store_row64_bf16(dQKV + (size_t)(row_base + key) * (3 * sh.D) + (ch ? 2 : 1) * sh.D + h * 64, a);
+    }
+  };
+
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar_q, nQ * 2 * 16384);
+    for (int qt = 0; qt < nQ; ++qt) {
+      tma_load_2d(&tmQKV, bar_q, sQ + qt * 16384, h * 64, row_base + qt * 128);
+      tma_load_2d(&tmDO, bar_q, sDO + qt * 16384, h * 64, row_base + qt * 128);
+    }
+    load_kv(0);
+    if (nK > 1) load_kv(1);
+    mbar_wait(bar_q, 0);
+    mbar_wait(&bar_kv[0], 0);
+    dbg_mark(2);
+    tc_fence_after();
+    issue_sdp(0, 0);
+    umma_commit(bar_mma);
+  }
+  uint32_t mma_phase = 0;
+
+#pragma unroll 1
+  for (int it = 0; it < n_it; ++it) {
+    const int kt = it / nQ, qt = it - kt * nQ;
+    __syncwarp();
+    dbg_mark(3 + it * 4);
+    mbar_wait(bar_mma, mma_phase);     // S / dP of this iteration ready; accumulate MMAs of the previous one retired
+    mma_phase ^= 1;
+    tc_fence_after();
+    dbg_mark(4 + it * 4);
+    if (qt == 0 && kt > 0) {
+      store_dkdv(kt - 1);              // previous key tile complete (its K / V buffer is free again)
+      // (nK <= 2 here, so no further key tile needs that buffer)
+    }
+    // ---- elementwise: query row q = qt*128 + r, this thread's half of the valid key columns
+    const int kcols = tile_extent(kt);
+    const int csplit = ((kcols / 16 + 1) / 2) * 16;
+    const int cbeg = ch ? csplit : 0, cend = ch ? kcols : csplit;
+    const int q = qt * 128 + r;
+    const int g = min(q / sh.N, sh.G - 1);
+    const int klo = g * sh.N, khi = klo + sh.N;
+    const bool q_ok = (q < sh.span) && (c * sh.G + g < sh.n_crops);
+    const size_t stat = ((size_t)(c * sh.G + g) * sh.H + h) * sh.N + (q_ok ? q - klo : 0);
+    const float lse2 = q_ok ? LSE[stat] * LOG2E : 0.f;
+    const float dl = q_ok ? Delta[stat] : 0.f;
+    {
+      // 16-column chunks, explicit register ping-pong: the TMEM loads of the next chunk are in flight while the current
+      // one is computed (tcgen05.wait::ld waits for every outstanding load of the thread)
+      auto compute = [&](const uint32_t (&sv)[16], const uint32_t (&dp)[16], int c0) {
+        uint32_t pw[8], dw[8];
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+          const int kk = kt * 128 + c0 + j;
+          const bool ok0 = q_ok && kk >= klo && kk < khi, ok1 = q_ok && kk + 1 >= klo && kk + 1 < khi;
+          const float p0 = ok0 ? exp2f(__uint_as_float(sv[j]) * cs - lse2) : 0.f;
+          const float p1 = ok1 ? exp2f(__uint_as_float(sv[j + 1]) * cs - lse2) : 0.f;
+          pw[j >> 1] = pack_bf16(p0, p1);
+          dw[j >> 1] = pack_bf16(p0 * (__uint_as_float(dp[j]) - dl) * sh.scale, p1 * (__uint_as_float(dp[j + 1]) - dl) * sh.scale);
+        }
+        uint8_t* pc = sP + (c0 >> 6) * 16384;
+        uint8_t* dc = sDS + (c0 >> 6) * 16384;
+        const int cc = c0 & 63;
+        *reinterpret_cast<uint4*>(pc + sw128_offset(r, cc)) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+        *reinterpret_cast<uint4*>(pc + sw128_offset(r, cc + 8)) = make_uint4(pw[4], pw[5], pw[6], pw[7]);
+        *reinterpret_cast<uint4*>(dc + sw128_offset(r, cc)) = make_uint4(dw[0], dw[1], dw[2], dw[3]);
+        *reinterpret_cast<uint4*>(dc + sw128_offset(r, cc + 8)) = make_uint4(dw[4], dw[5], dw[6], dw[7]);
+      };
+      uint32_t svA[16], dpA[16], svB[16], dpB[16];
+      if (cbeg < cend) {
+        tmem_ld16(tS + t_lane + cbeg, svA);
+        tmem_ld16(tDP + t_lane + cbeg, dpA);
+      }
+      tmem_ld_wait();
+#pragma unroll 1
+      for (int c0 = cbeg; c0 < cend; c0 += 32) {
+        const bool hasB = c0 + 16 < cend;
+        if (hasB) {
+          tmem_ld16(tS + t_lane + c0 + 16, svB);
+          tmem_ld16(tDP + t_lane + c0 + 16, dpB);
+        }
+        compute(svA, dpA, c0);
+        tmem_ld_wait();
+        if (hasB) {
+          if (c0 + 32 < cend) {
+            tmem_ld16(tS + t_lane + c0 + 32, svA);
+            tmem_ld16(tDP + t_lane + c0 + 32, dpA);
+          }
+          compute(svB, dpB, c0 + 16);
+          tmem_ld_wait();
+        }
+      }
+    }
+    dbg_mark(5 + it * 4);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    dbg_mark(6 + it * 4);
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+      // descriptors are built once; each UMMA_K step only adds a constant to the 14-bit start-address field
+      const uint64_t dP_mn = umma_desc_sw128(smem_u32(sP), 16384, 1024);            // P  as MN-major A (keys x query rows)
+      const uint64_t dS_mn = umma_desc_sw128(smem_u32(sDS), 16384, 1024);           // dS as MN-major A
+      const uint64_t dS_k = umma_desc_sw128(smem_u32(sDS), 16, 1024);               // dS as K-major A (query rows x keys)
+      const uint64_t dO_mn = umma_desc_sw128(smem_u32(sDO + qt * 16384), 8192, 1024);
+      const uint64_t dQ_mn = umma_desc_sw128(smem_u32(sQ + qt * 16384), 8192, 1024);
+      const uint64_t dK_mn = umma_desc_sw128(smem_u32(sK + (kt & 1) * 16384), 8192, 1024);
+      const int qsteps = tile_extent(qt) / 16, ksteps = kcols / 16;
+      constexpr uint32_t id_tt = umma_idesc_bf16(128, 64, 1, 1);
+      constexpr uint32_t id_nt = umma_idesc_bf16(128, 64, 0, 1);
+      const uint32_t acc_kv = qt > 0 ? 1u : 0u, acc_q = kt > 0 ? 1u : 0u;
+      // dV[keys, 64] += P^T dO ; dK[keys, 64] += dS^T Q  (16 query rows per UMMA_K = 2048 B = 128 descriptor units)
+      // dQ[q, 64] += dS K  (A: 64-key chunks 16 KB apart, 32 B per UMMA_K inside a chunk; B: 2048 B per step).
+      // The three accumulators are independent dependency chains: their MMAs are interleaved so that back-to-back
+      // instructions never wait on each other's accumulate latency.
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (k < qsteps) {
+          umma_bf16(tDV, dP_mn + (uint64_t)(k * 128), dO_mn + (uint64_t)(k * 128), id_tt, k > 0 ? 1u : acc_kv);
+          umma_bf16(tDK, dS_mn + (uint64_t)(k * 128), dQ_mn + (uint64_t)(k * 128), id_tt, k > 0 ? 1u : acc_kv);
+        }
+        if (k < ksteps)
+          umma_bf16(tDQ + qt * 64, dS_k + (uint64_t)((k >> 2) * 1024 + (k & 3) * 2), dK_mn + (uint64_t)(k * 128), id_nt,
+                    k > 0 ? 1u : acc_q);
+      }
+      if (it + 1 < n_it) {             // S / dP of the next iteration ride on the same commit
+        const int kt2 = (it + 1) / nQ, qt2 = (it + 1) - kt2 * nQ;
+        if (kt2 != kt) {
+          mbar_wait(&bar_kv[kt2 & 1], (kt2 >> 1) & 1);
+          tc_fence_after();
+        }
+        issue_sdp(kt2, qt2);
+      }
+      umma_commit(bar_mma);
+    }
+  }
+  dbg_mark(20);
+  __syncwarp();
+  mbar_wait(bar_mma, mma_phase);
+  tc_fence_after();
+  dbg_mark(21);
+  store_dkdv(nK - 1);
+  dbg_mark(22);
+  // ---- dQ: query tile qt is written by the threads with ch == (qt & 1)
+  for (int qt = ch; qt < nQ; qt += 2) {
+    const int q = qt * 128 + r;
+    const int qg = min(q / sh.N, sh.G - 1);
+    const int tok = q - qg * sh.N;
+    float a[64];
+    load_row64(tDQ + qt * 64 + t_lane, a);
+    if (q < sh.span && c * sh.G + qg < sh.n_crops) {
+      if (sh.sin_t && tok >= sh.prefix)
+        rope_inverse_row(a, sh.sin_t + (size_t)(tok - sh.prefix) * 64, sh.cos_t + (size_t)(tok - sh.prefix) * 64);
+      store_row64_bf16(dQKV + (size_t)(row_base + q) * (3 * sh.D) + h * 64, a);
+    }
+  }
+  dbg_mark(23);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_free<512>(tmem);
+  dbg_mark(24);
+}
+
 static int make_map(CUtensorMap* map, const void* ptr, long rows, int cols, int ld, int box_rows) {
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
@@ -516,6 +759,11 @@ static int attn_shape(AttnShape* s, int n_crops, int N, int D, int H) {
 using namespace d3;
 
 extern "C" {
+
+int d3_debug_attn_trace(long long* buf /*device [64] or NULL*/) {
+  cudaError_t e = cudaMemcpyToSymbol(g_attn_dbg, &buf, sizeof(buf));
+  return e == cudaSuccess ? D3_OK : set_error(D3_ERR_CUDA, cudaGetErrorString(e));
+}
 
 int d3_attn_fwd(const void* qkv, void* o, float* lse, int n_crops, int N, int D, int H, void* stream) {
   AttnShape s;
@@ -565,11 +813,20 @@ int d3_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* ls
   if ((rc = make_map(&tqkv, qkv, T, 3 * D, 3 * D, 128))) return rc;
   if ((rc = make_map(&tdo, d_o, T, D, D, 128))) return rc;
   static bool cfg = false;
-  if (!cfg) { cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); cfg = true; }
+  if (!cfg) {
+    cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    cudaFuncSetAttribute(attn_bwd_alias_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    cfg = true;
+  }
   const int nq = (s.span + 127) / 128;
-  const int smem = 2 * nq * 16384 + 32768 + 65536 + 64 + 1024;
   dim3 grid(H, (n_crops + s.G - 1) / s.G);
-  attn_bwd_kernel<<<grid, 256, smem, st>>>(tqkv, tdo, lse, delta_scratch, (__nv_bfloat16*)dqkv, s);
+  if (nq > 2) {
+    const int smem = 2 * nq * 16384 + 32768 + 65536 + 64 + 1024;
+    attn_bwd_alias_kernel<<<grid, 256, smem, st>>>(tqkv, tdo, lse, delta_scratch, (__nv_bfloat16*)dqkv, s);
+  } else {
+    const int smem = 2 * nq * 16384 + 65536 + 65536 + 64 + 1024;
+    attn_bwd_kernel<<<grid, 256, smem, st>>>(tqkv, tdo, lse, delta_scratch, (__nv_bfloat16*)dqkv, s);
+  }
   D3_CHECK_LAUNCH();
   return D3_OK;
 }

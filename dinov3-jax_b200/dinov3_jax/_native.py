@@ -37,6 +37,7 @@ P, I, LL, F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 # name -> argtypes, mirrors include/dinov3_b200.h (tests/test_abi.py checks every declared symbol is exported)
 SIGNATURES = {
     "d3_init": [I],
+    "d3_set_sm_limit": [I],
     "d3_gemm_bf16": [P, I, I, P, I, I, I, I, I, C.POINTER(GemmEpilogue), I, I, P],
     "d3_im2col": [P, P, I, I, I, I, I, P],
     "d3_assemble_tokens": [P, P, P, P, P, I, I, I, P],
@@ -45,6 +46,7 @@ SIGNATURES = {
     "d3_layernorm_bwd": [P, I, P, P, P, P, P, P, P, P, I, I, P],
     "d3_rope": [P, P, P, LL, I, I, I, I, I, P],
     "d3_attn_fwd": [P, P, P, I, I, I, I, P],
+    "d3_debug_attn_trace": [P],
     "d3_attn_bwd": [P, P, P, P, P, P, I, I, I, I, P, P, I, P],
     "d3_token_rows": [P, P, I, I, I, P],
     "d3_gather_rows": [P, P, P, P, I, I, P],

@@ -57,6 +57,8 @@ class FsdpRuntime:
         self.side = torch.cuda.Stream(device=device) if (self.cuda and self.world > 1) else None
         self._pending = {}       # (module, unit, teacher) -> [works]
         self._grad_works = []
+        import os
+        self._debug = int(os.environ.get("D3_FSDP_DEBUG", "0"))   # diagnostics only: 1 = skip gathers, 2 = skip reduce-scatters
 
     # ------------------------------------------------------------------------------------------ parameter gathers
     def _issue_gather(self, module: str, unit, teacher: bool):
@@ -80,7 +82,7 @@ class FsdpRuntime:
     def prefetch(self, items):
         """items: iterable of (module, unit, teacher) in use order.  All gathers are queued on the side stream at once:
         NCCL executes them back to back while the compute stream works through earlier units."""
-        if self.world == 1:
+        if self.world == 1 or (self._debug & 1):
             return
         if self.side is not None:
             self.side.wait_stream(torch.cuda.current_stream())   # parameters come from the previous optimizer step
@@ -103,7 +105,7 @@ class FsdpRuntime:
     def grads_ready(self, module: str, unit_name: str):
         """Called right after the kernels of this unit's backward were enqueued: reduce-scatter (mean) its gradient
         ranges into the rank's gradient shard, on the side stream."""
-        if self.world == 1:
+        if self.world == 1 or (self._debug & 2):
             return
         st = self.stores[module]
         L = st.layout

@@ -29,6 +29,9 @@ typedef enum {
 int d3_init(int device);                /* bind to device, cache SM count, resolve cuTensorMapEncodeTiled */
 const char* d3_last_error(void);
 int d3_abi_version(void);
+/* Cap the grid of the persistent kernels (GEMMs) to n SMs (0 = all).  Multi-GPU runs leave a few SMs to the NCCL
+ * kernels of the FSDP all-gather / reduce-scatter so they run under the GEMMs instead of between them.              */
+int d3_set_sm_limit(int n);
 long long d3_launch_count(void);        /* kernels launched by this library since the last reset (bench: gpu_launches) */
 void d3_reset_launch_count(void);
 
@@ -99,6 +102,9 @@ int d3_attn_fwd(const void* qkv_bf16 /*[n*N,3D] post-RoPE*/, void* o_bf16 /*[n*N
 int d3_attn_bwd(const void* qkv_bf16, const void* o_bf16, const void* do_bf16, const float* lse,
                 float* delta_scratch /*[n,H,N]*/, void* dqkv_bf16 /*[n*N,3D]*/, int n_crops, int N, int D, int H,
                 const float* rope_sin, const float* rope_cos, int rope_prefix, void* stream);
+
+/* diagnostics: when buf != NULL, CTA (0,0) of d3_attn_bwd writes clock64() marks (2 threads x 32 slots) into it */
+int d3_debug_attn_trace(long long* buf);
 
 /* ---- row gather / scatter (train/ssl_meta_arch.py:377,432 patch.reshape(-1,D)[mask_indices_list]; cls = token 0) --- */
 int d3_token_rows(const long long* mask_indices /*int64 [count] (mode 0)*/, int* rows /*int32 [count]*/, int count,
