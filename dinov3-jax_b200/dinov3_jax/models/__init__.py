@@ -5,6 +5,7 @@ from __future__ import annotations
 from dataclasses import replace
 
 from ..engine.config import ARCHS, EngineConfig, config_for, config_from_reference_cfg
+from .vision_transformer import DinoVisionTransformer
 
 
 def _factory(name):

@@ -14,11 +14,15 @@ its third-party stack (jax 0.7.1 / flax 0.11.2 / optax 0.2.5) is not installable
 reference cannot be executed end to end here.  The oracle is pinned as far as that allows:
   * `data/masking.py`, `data/collate.py` (mask part), `train/cosine_lr_scheduler.py` are pure numpy/torch and ARE
     imported from /root/reference by `tests/golden/make_golden.py`; the oracle's restatement is bit-exact against them;
-  * the loss / RoPE / head / attention / block / ViT / SSLMetaArch modules of the reference are executed
-    *unmodified* under a small numpy-backed shim of the jax / flax API (`oracle/jaxshim`, semantics of the third-party
-    ops restated per SURVEY.md Appendix F) and their outputs are committed as fixtures under `tests/golden/`;
+  * the loss / RoPE / param-group files and the whole model side — `models/vision_transformer.py`
+    (DinoVisionTransformer on multi-crop input with iBOT masks) with every layer under it (patch_embed, block,
+    attention, ffn_layers, layer_scale, rope) and `layers/dino_head.py` — are executed *unmodified* under a small
+    numpy-backed shim of the jax / flax API (`oracle/jaxshim`: mini flax.linen Module tree + parameter naming,
+    semantics of the third-party ops restated per SURVEY.md Appendix F); outputs are committed as fixtures under
+    `tests/golden/` and the oracle matches them to 1e-11 in float64;
   * analytic micro-cases (uniform Sinkhorn, LN of constant rows, orthogonal KoLeo pairs ...) in `tests/`.
 What is therefore *not* pinned: the third-party op semantics themselves (flax gelu/LayerNorm/attention defaults,
-optax adamw) — "parity unpinned" for those, stated here and in DESIGN.md.
+optax adamw) and the loss assembly in SSLMetaArch.__call__ / train_step (not importable without omegaconf and jax
+transforms) — "parity unpinned" for those, stated here and in DESIGN.md.
 """
 from .arch import ARCHS, ModelCfg, tiny_cfg, cfg_for  # noqa: F401

@@ -96,31 +96,190 @@ class _Variable:
         self.value = value
 
 
-class Module:
-    """flax.linen.Module stand-in: annotated class attributes become constructor fields; setup() runs eagerly."""
+# --------------------------------------------------------------------------------------------------------------------
+# mini flax.linen: just enough of the Module system to execute the reference's layers / ViT / DINOHead unmodified with
+# externally supplied parameters.  PARAMS maps "path/to/leaf" -> array, paths follow flax naming: attribute name for
+# submodules created in setup(), "<attr>_<i>" for list attributes, "<Class>_<n>" for submodules created inside an
+# @nn.compact __call__, "layers_<i>" for nn.Sequential.
+PARAMS: dict = {}
+_STACK: list = []
 
+
+def _adopt(parent, child, name):
+    if isinstance(child, Module) and child.__dict__.get("_parent") is None and child is not parent:
+        object.__setattr__(child, "_parent", parent)
+        object.__setattr__(child, "_name", name)
+
+
+class Module:
     def __init_subclass__(cls, **kw):
         super().__init_subclass__(**kw)
+        if "__call__" in cls.__dict__:
+            inner = cls.__dict__["__call__"]
+
+            def wrapped(self, *a, __inner=inner, **k):
+                self._ensure_setup()
+                object.__setattr__(self, "_auto", {})
+                _STACK.append(self)
+                try:
+                    return __inner(self, *a, **k)
+                finally:
+                    _STACK.pop()
+            cls.__call__ = wrapped
 
     def __init__(self, *args, **kwargs):
+        d = self.__dict__
+        d.update(_parent=None, _name=None, _setup_done=False, _in_setup=False, _auto={})
         fields = []
         for klass in reversed(type(self).__mro__):
             fields += [n for n in getattr(klass, "__annotations__", {}) if n not in fields]
-        for n, v in zip(fields, args):
-            object.__setattr__(self, n, v)
-        given = set(fields[: len(args)])
+        values = dict(zip(fields, args))
+        values.update(kwargs)
         for n in fields:
-            if n in kwargs:
-                object.__setattr__(self, n, kwargs[n])
-            elif n not in given:
+            if n in values:
+                setattr(self, n, values[n])
+            else:
                 if not hasattr(type(self), n):
-                    raise TypeError(f"missing field {n}")
+                    raise TypeError(f"{type(self).__name__}: missing field {n}")
                 object.__setattr__(self, n, getattr(type(self), n))   # instance attribute: plain functions stay unbound
-        if hasattr(self, "setup"):
-            self.setup()
+        if _STACK and not _STACK[-1].__dict__.get("_in_setup"):          # created inside a compact __call__
+            parent = _STACK[-1]
+            cname = type(self).__name__
+            idx = parent._auto.get(cname, 0)
+            parent._auto[cname] = idx + 1
+            _adopt(parent, self, f"{cname}_{idx}")
+
+    def __setattr__(self, k, v):
+        if not k.startswith("_"):
+            if isinstance(v, Module):
+                _adopt(self, v, k)
+            elif isinstance(v, (list, tuple)):
+                for i, e in enumerate(v):
+                    _adopt(self, e, f"{k}_{i}")
+        object.__setattr__(self, k, v)
+
+    def __getattr__(self, k):          # only reached when normal lookup fails: attributes defined by setup()
+        d = self.__dict__
+        if k.startswith("__") or d.get("_setup_done") or d.get("_in_setup"):
+            raise AttributeError(k)
+        self._ensure_setup()
+        return object.__getattribute__(self, k)
+
+    def _ensure_setup(self):
+        d = self.__dict__
+        if not d["_setup_done"]:
+            d["_setup_done"] = True
+            if hasattr(type(self), "setup"):
+                d["_in_setup"] = True
+                _STACK.append(self)
+                try:
+                    self.setup()
+                finally:
+                    _STACK.pop()
+                    d["_in_setup"] = False
+
+    def _path(self):
+        node, parts = self, []
+        while node is not None and node.__dict__.get("_name") is not None:
+            parts.append(node._name)
+            node = node._parent
+        return list(reversed(parts))
+
+    def param(self, name, init_fn=None, *shape_args):
+        key = "/".join(self._path() + [name])
+        if key not in PARAMS:
+            raise KeyError(f"parameter {key!r} not supplied")
+        v = np.asarray(PARAMS[key], dtype=np.float64)
+        if shape_args and isinstance(shape_args[0], (tuple, list)) and tuple(shape_args[0]) != v.shape:
+            raise ValueError(f"{key}: shape {v.shape} != requested {tuple(shape_args[0])}")
+        return v.view(Arr)
 
     def variable(self, collection, name, init_fn, *a):
         return _Variable(_wrap(init_fn(*a)))
+
+    def make_rng(self, name):
+        raise RuntimeError("rng requested on the deterministic path")
+
+
+class Dense(Module):
+    features: int
+    use_bias: bool = True
+    kernel_init: object = None
+    bias_init: object = None
+    dtype: object = None
+    param_dtype: object = None
+
+    def __call__(self, x):
+        y = np.asarray(x) @ self.param("kernel", None, (np.shape(x)[-1], self.features))
+        if self.use_bias:
+            y = y + self.param("bias", None, (self.features,))
+        return _wrap(np.asarray(y))
+
+
+class LayerNorm(Module):
+    epsilon: float = 1e-6
+    use_bias: bool = True
+    use_scale: bool = True
+    dtype: object = None
+
+    def __call__(self, x):
+        x = np.asarray(x)
+        mean = x.mean(-1, keepdims=True)
+        var = np.maximum((x * x).mean(-1, keepdims=True) - mean * mean, 0.0)    # use_fast_variance
+        y = (x - mean) / np.sqrt(var + self.epsilon)
+        if self.use_scale:
+            y = y * self.param("scale", None, (x.shape[-1],))
+        if self.use_bias:
+            y = y + self.param("bias", None, (x.shape[-1],))
+        return _wrap(y)
+
+
+class Conv(Module):
+    features: int
+    kernel_size: object = None
+    strides: object = 1
+    padding: object = "SAME"
+    use_bias: bool = True
+
+    def __call__(self, x):
+        x = np.asarray(x)
+        kh, kw = self.kernel_size
+        assert tuple(self.strides) == (kh, kw), "shim Conv supports stride == kernel (patch embedding) only"
+        b, H, W, c = x.shape
+        assert H % kh == 0 and W % kw == 0
+        k = self.param("kernel", None, (kh, kw, c, self.features))
+        p = x.reshape(b, H // kh, kh, W // kw, kw, c).transpose(0, 1, 3, 2, 4, 5).reshape(b, H // kh, W // kw, kh * kw * c)
+        y = p @ np.asarray(k).reshape(kh * kw * c, self.features)
+        if self.use_bias:
+            y = y + self.param("bias", None, (self.features,))
+        return _wrap(y)
+
+
+class Dropout(Module):
+    rate: float = 0.0
+
+    def __call__(self, x, deterministic=True):
+        assert deterministic or self.rate == 0.0
+        return x
+
+
+class Sequential(Module):
+    layers: object = None
+
+    def __call__(self, x):
+        for l in self.layers:
+            x = l(x)
+        return x
+
+
+def _dot_product_attention(q, k, v, deterministic=True, **unused):
+    """flax.linen.dot_product_attention for [batch, len, heads, dim]: softmax((q / sqrt(dim)) k^T) v, no mask/dropout."""
+    q, k, v = np.asarray(q), np.asarray(k), np.asarray(v)
+    s = np.einsum("bqhd,bkhd->bhqk", q / np.sqrt(q.shape[-1]), k)
+    s = s - s.max(-1, keepdims=True)
+    a = np.exp(s)
+    a = a / a.sum(-1, keepdims=True)
+    return _wrap(np.einsum("bhqk,bkhd->bqhd", a, v))
 
 
 def _initializer(*a, **k):
@@ -169,11 +328,14 @@ def install():
     nn.softmax, nn.log_softmax, nn.gelu = _softmax, _log_softmax, _gelu
     nn.compact = lambda f: f
     inits = types.ModuleType("flax.linen.initializers")
-    for n in ("lecun_normal", "normal", "constant"):
+    for n in ("lecun_normal", "normal", "constant", "truncated_normal"):
         setattr(inits, n, _initializer)
+    inits.ones = _initializer()
     inits.zeros = _initializer()
     nn.initializers = inits
-    for n in ("Dense", "Dropout", "LayerNorm", "Conv", "Sequential", "BatchNorm", "Partitioned", "silu"):
+    nn.Dense, nn.LayerNorm, nn.Conv, nn.Dropout, nn.Sequential = Dense, LayerNorm, Conv, Dropout, Sequential
+    nn.dot_product_attention = _dot_product_attention
+    for n in ("BatchNorm", "Partitioned", "silu", "make_causal_mask", "map_variables"):
         setattr(nn, n, type(n, (), {}))
     flax.linen = nn
     tu = types.ModuleType("flax.traverse_util")

@@ -255,12 +255,15 @@ def backbone_forward(P: dict, x_list, masks_list, cfg: ModelCfg, emu: Emu = Emu(
     return outs
 
 
-def head_forward(P: dict, x, emu: Emu = Emu(False)):
-    """layers/dino_head.py:78-85: MLP(GELU) -> x / (||x|| + 1e-12) -> bias-free prototype layer."""
+def head_forward(P: dict, x, emu: Emu = Emu(False), last_layer: bool = True):
+    """layers/dino_head.py:78-85: MLP(GELU) -> x / (||x|| + 1e-12) -> bias-free prototype layer
+    (last_layer=False is the reference's `no_last_layer=True`)."""
     x = emu.act(x)
     u = emu.act(gelu(emu.grad(x @ emu.w(P["mlp/layers_0/kernel"]) + P["mlp/layers_0/bias"])))
     u = emu.act(gelu(emu.grad(u @ emu.w(P["mlp/layers_2/kernel"]) + P["mlp/layers_2/bias"])))
     u = u @ emu.w(P["mlp/layers_4/kernel"]) + P["mlp/layers_4/bias"]
     nrm = torch.linalg.norm(u, ord=2, dim=-1, keepdim=True)
     u = emu.act(u / (nrm + 1e-12))
+    if not last_layer:
+        return u
     return u @ emu.w(P["last_layer/kernel"])

@@ -6,6 +6,12 @@
     layers/attention.py (rope_rotate_half / rope_apply), train/param_groups.py
                                                        — imported UNMODIFIED under oracle.jaxshim (numpy stand-in for
                                                          jax / flax.linen; the real stack is not installable offline)
+  * models/vision_transformer.py (DinoVisionTransformer + every layer it pulls in: patch_embed, block, attention,
+    ffn_layers, layer_scale, rope) and layers/dino_head.py
+                                                       — imported UNMODIFIED as the package `dinov3_jax` under the shim's
+                                                         mini flax.linen (Module tree / param naming / Dense / LayerNorm /
+                                                         Conv / dot_product_attention restated in numpy float64) and run
+                                                         on a 2-block ViT with multi-crop input + iBOT masks
 Usage:  python tests/golden/make_golden.py      (writes next to this file; the .npz files are committed)
 """
 from __future__ import annotations
@@ -117,6 +123,46 @@ def main():
             names.append(f"{root}/{k}"); vals.append((v.lr_multiplier, v.wd_multiplier, float(v.is_last_layer)))
     out["pg_names"] = np.array(names)
     out["pg_values"] = np.array(vals, dtype=np.float64)
+
+    # ---- backbone + head wiring: the reference's own module code, parameters supplied by name
+    import importlib
+    from oracle import jaxshim
+    from oracle.arch import ModelCfg
+    from oracle.model import init_params, sub
+    for k in [k for k in sys.modules if k == "dinov3_jax" or k.startswith("dinov3_jax.")]:
+        del sys.modules[k]
+    sys.path.insert(0, "/root/reference")
+    vt = importlib.import_module("dinov3_jax.models.vision_transformer")
+    dh = importlib.import_module("dinov3_jax.layers.dino_head")
+    assert vt.__file__.startswith("/root/reference/") and dh.__file__.startswith("/root/reference/")
+    cfg = ModelCfg(embed_dim=128, depth=2, heads=2, global_size=64, local_size=32, n_prototypes=48, head_hidden=64,
+                   head_bottleneck=32, layerscale=0.5)
+    P = {k: v.double() for k, v in init_params(cfg, 3, perturb=0.05, dtype=torch.float32).items()}   # f32-representable
+    rng = np.random.default_rng(11)
+    g = rng.standard_normal((2, 64, 64, 3)).astype(np.float32).astype(np.float64)
+    l = rng.standard_normal((3, 32, 32, 3)).astype(np.float32).astype(np.float64)
+    vmask = rng.random((2, 16)) < 0.4
+    bp = sub(P, "student_backbone")
+    jaxshim.PARAMS.clear(); jaxshim.PARAMS.update({k: v.numpy() for k, v in bp.items()})
+    model = vt.DinoVisionTransformer(img_size=64, patch_size=16, embed_dim=cfg.embed_dim, n_blocks=cfg.depth, num_heads=cfg.heads,
+                                     ffn_ratio=cfg.ffn_ratio, qkv_bias=True, layerscale_init=cfg.layerscale,
+                                     norm_layer="layernorm", ffn_layer="mlp", pos_embed_rope_base=cfg.rope_base)
+    og, ol = model([J(g), J(l)], masks=[J(vmask), None], is_training=True)
+    for k, v in bp.items():
+        out[f"vit_param/{k}"] = v.numpy().astype(np.float32)
+    out.update(vit_global=g.astype(np.float32), vit_local=l.astype(np.float32), vit_masks=vmask,
+               vit_g_cls=np.asarray(og["x_norm_clstoken"]), vit_g_patch=np.asarray(og["x_norm_patchtokens"]),
+               vit_l_cls=np.asarray(ol["x_norm_clstoken"]), vit_l_patch=np.asarray(ol["x_norm_patchtokens"]))
+    # inference entry point (is_training=False returns the head(cls) path = Identity -> x_norm_clstoken)
+    hp = sub(P, "student_dino_head")
+    jaxshim.PARAMS.clear(); jaxshim.PARAMS.update({k: v.numpy() for k, v in hp.items()})
+    head = dh.DINOHead(in_dim=cfg.embed_dim, out_dim=cfg.n_prototypes, hidden_dim=cfg.head_hidden,
+                       bottleneck_dim=cfg.head_bottleneck, nlayers=3)
+    hx = rng.standard_normal((5, cfg.embed_dim)).astype(np.float32).astype(np.float64)
+    for k, v in hp.items():
+        out[f"head_param/{k}"] = v.numpy().astype(np.float32)
+    out.update(head_x=hx.astype(np.float32), head_logits=np.asarray(head(J(hx))),
+               head_bottleneck=np.asarray(head(J(hx), no_last_layer=True)))
     np.savez_compressed(os.path.join(HERE, "reference_vectors.npz"), **out)
     print("wrote", os.path.join(HERE, "reference_vectors.npz"), len(out), "arrays")
 

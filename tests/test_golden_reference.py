@@ -1,6 +1,7 @@
 """Pins the oracle (and the product's host-side mirrors) against golden vectors produced by EXECUTING reference files
 (tests/golden/make_golden.py): masks / collate / schedules directly, losses / RoPE / param groups under the numpy
-stand-in for jax+flax.  Nothing here reads /root/reference."""
+stand-in for jax+flax; DinoVisionTransformer (+ every layer under it) and DINOHead under the shim's mini flax.linen.
+Nothing here reads /root/reference."""
 import os
 import random
 
@@ -101,3 +102,32 @@ def test_param_group_multipliers_match_reference_code(impl):
         rows = [lr_wd_multipliers(n.split("/", 1)[0][len("student_"):], n.split("/", 1)[1], cfg) for n in names]
     for n, (lr, wd, last), want in zip(names, rows, vals):
         assert abs(lr - want[0]) < 1e-12 and wd == want[1] and float(last) == want[2], n
+
+
+def _golden_tree(prefix):
+    return {k[len(prefix):]: T(G[k]).double() for k in G.files if k.startswith(prefix)}
+
+
+def test_backbone_matches_reference_module_code():
+    """models/vision_transformer.py DinoVisionTransformer.__call__(is_training=True) on [global, local] crops with iBOT
+    masks, executed from the reference sources, vs the oracle restatement in float64."""
+    from oracle.arch import ModelCfg
+    from oracle.model import backbone_forward
+    cfg = ModelCfg(embed_dim=128, depth=2, heads=2, global_size=64, local_size=32, n_prototypes=48, head_hidden=64,
+                   head_bottleneck=32, layerscale=0.5)
+    bp = _golden_tree("vit_param/")
+    outs = backbone_forward(bp, [T(G["vit_global"]).double(), T(G["vit_local"]).double()], [T(G["vit_masks"]), None], cfg)
+    for o, tag in zip(outs, ("g", "l")):
+        assert np.abs(o["x_norm_clstoken"].numpy() - G[f"vit_{tag}_cls"]).max() < 1e-11
+        assert np.abs(o["x_norm_patchtokens"].numpy() - G[f"vit_{tag}_patch"]).max() < 1e-11
+    # the mask has to matter (mask_token substituted before the blocks) or the fixture pins nothing about a4
+    nomask = backbone_forward(bp, [T(G["vit_global"]).double()], [None], cfg)[0]
+    assert np.abs(nomask["x_norm_clstoken"].numpy() - G["vit_g_cls"]).max() > 1e-3
+
+
+def test_head_matches_reference_module_code():
+    from oracle.model import head_forward
+    hp = _golden_tree("head_param/")
+    x = T(G["head_x"]).double()
+    assert np.abs(head_forward(hp, x).numpy() - G["head_logits"]).max() < 1e-12
+    assert np.abs(head_forward(hp, x, last_layer=False).numpy() - G["head_bottleneck"]).max() < 1e-12

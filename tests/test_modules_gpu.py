@@ -118,3 +118,28 @@ def test_do_train_runs_three_iterations():
                                              "ibot.head_n_prototypes=1024", "dino.head_hidden_dim=256", "ibot.head_hidden_dim=256"]))
     m = do_train(cfg, SSLMetaArch(cfg), max_iters=3, print_freq=1)
     assert abs(m["dino_local_crops_loss"] - 6.93) < 0.05 and m["total_loss"] == m["total_loss"]
+
+
+def test_vit_and_head_against_reference_golden(native):
+    """CUDA forward (dinov3_jax.models.DinoVisionTransformer, dinov3_jax.layers.DINOHead) against vectors produced by
+    executing the reference's own module code (tests/golden/make_golden.py) — no oracle in between.  bf16-operand /
+    fp32-accumulate tolerance, norm-wise."""
+    import os
+    import numpy as np
+    from conftest import GOLDEN
+    from dinov3_jax.layers import DINOHead
+    from dinov3_jax.models import DinoVisionTransformer
+    G = np.load(os.path.join(GOLDEN, "reference_vectors.npz"))
+    tree = lambda prefix: nest({k[len(prefix):]: torch.from_numpy(G[k]) for k in G.files if k.startswith(prefix)})
+    model = DinoVisionTransformer(tree("vit_param/"), img_size=64, patch_size=16, embed_dim=128, n_blocks=2, num_heads=2,
+                                  layerscale_init=0.5)
+    og, ol = model([torch.from_numpy(G["vit_global"]), torch.from_numpy(G["vit_local"])],
+                   masks=[torch.from_numpy(G["vit_masks"]), None], is_training=True)
+    for o, tag in ((og, "g"), (ol, "l")):
+        assert rel(o["x_norm_clstoken"], torch.from_numpy(G[f"vit_{tag}_cls"])) < 2e-2
+        assert rel(o["x_norm_patchtokens"], torch.from_numpy(G[f"vit_{tag}_patch"])) < 2e-2
+    assert rel(model(torch.from_numpy(G["vit_global"])), torch.from_numpy(G["vit_g_cls"])) > 1e-2      # masks matter
+    head = DINOHead(tree("head_param/"), in_dim=128, out_dim=48, hidden_dim=64, bottleneck_dim=32)
+    x = torch.from_numpy(G["head_x"]).cuda()
+    assert rel(head(x), torch.from_numpy(G["head_logits"])) < 2e-2
+    assert rel(head(x, no_last_layer=True), torch.from_numpy(G["head_bottleneck"])) < 2e-2
