@@ -20,9 +20,13 @@ reference cannot be executed end to end here.  The oracle is pinned as far as th
     numpy-backed shim of the jax / flax API (`oracle/jaxshim`: mini flax.linen Module tree + parameter naming,
     semantics of the third-party ops restated per SURVEY.md Appendix F); outputs are committed as fixtures under
     `tests/golden/` and the oracle matches them to 1e-11 in float64;
+  * `train/ssl_meta_arch.py` SSLMetaArch.setup + __call__ (the forward of the training step: teacher / student passes,
+    heads, iBOT gathers, Sinkhorns, loss weights, metrics) runs unmodified under the same shim on the reference's
+    default YAML; `oracle.step.ssl_forward` matches its loss and metrics to 1e-9 (the oracle's gradients are torch
+    autograd of that function);
   * analytic micro-cases (uniform Sinkhorn, LN of constant rows, orthogonal KoLeo pairs ...) in `tests/`.
 What is therefore *not* pinned: the third-party op semantics themselves (flax gelu/LayerNorm/attention defaults,
-optax adamw) and the loss assembly in SSLMetaArch.__call__ / train_step (not importable without omegaconf and jax
-transforms) — "parity unpinned" for those, stated here and in DESIGN.md.
+optax adamw) and train/train.py::train_step (clip + optax update; imports optax / orbax) — "parity unpinned" for
+those, stated here and in DESIGN.md.
 """
 from .arch import ARCHS, ModelCfg, tiny_cfg, cfg_for  # noqa: F401

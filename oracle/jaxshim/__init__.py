@@ -1,5 +1,5 @@
-"""A minimal numpy-backed stand-in for the parts of jax / flax.linen that the reference's *loss, RoPE and
-param-group* modules touch — TEST INFRASTRUCTURE, used only by tests/golden/make_golden.py in the build container
+"""A minimal numpy-backed stand-in for the parts of jax / flax.linen that the reference's *loss, RoPE,
+param-group, layer, ViT, DINOHead and SSLMetaArch* modules touch — TEST INFRASTRUCTURE, used only by tests/golden/make_golden.py in the build container
 (where /root/reference exists and the real jax/flax cannot be installed) to execute those reference files UNMODIFIED
 and record golden vectors.  It is not a JAX implementation: only single-device, eager, float64 numpy semantics.
 Third-party semantics restated here: nn.softmax / nn.log_softmax are the max-subtracted
@@ -335,8 +335,10 @@ def install():
     nn.initializers = inits
     nn.Dense, nn.LayerNorm, nn.Conv, nn.Dropout, nn.Sequential = Dense, LayerNorm, Conv, Dropout, Sequential
     nn.dot_product_attention = _dot_product_attention
-    for n in ("BatchNorm", "Partitioned", "silu", "make_causal_mask", "map_variables"):
+    for n in ("BatchNorm", "Partitioned", "silu", "make_causal_mask"):
         setattr(nn, n, type(n, (), {}))
+    # one device: gather/shard of un-partitioned leaves is the identity, so the FSDP wrapper returns its target
+    nn.map_variables = lambda target, *a, **k: target
     flax.linen = nn
     tu = types.ModuleType("flax.traverse_util")
 
@@ -362,7 +364,14 @@ def install():
         return out
     tu.flatten_dict, tu.unflatten_dict = flatten_dict, unflatten_dict
     flax.traverse_util = tu
-    mods = {"jax": jax, "jax.numpy": jnp, "jax.lax": lax, "jax.nn": jnn, "jax.nn.initializers": jinit,
+    sharding = types.ModuleType("jax.sharding")
+    for n in ("NamedSharding", "PartitionSpec", "Mesh"):
+        setattr(sharding, n, type(n, (), {"__init__": lambda self, *a, **k: None}))
+    jax.sharding = sharding
+    jax.__path__ = []           # lets `import jax.<sub>` resolve through sys.modules
+    mods = {"jax.sharding": sharding}
+    sys.modules.update(mods)
+    mods = {"jax.sharding": sharding, "jax": jax, "jax.numpy": jnp, "jax.lax": lax, "jax.nn": jnn, "jax.nn.initializers": jinit,
             "jax.random": jrandom, "jax.tree_util": jtu, "flax": flax, "flax.linen": nn,
             "flax.linen.initializers": inits, "flax.traverse_util": tu}
     sys.modules.update(mods)

@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import math
 
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -102,6 +103,46 @@ def init_head(cfg: ModelCfg, gen: torch.Generator, dtype=torch.float32) -> dict:
 
 
 MODULES = ("backbone", "dino_head", "ibot_head")
+
+
+def hash_uniform(n: int, key: int) -> np.ndarray:
+    """n float64 values in [-1, 1), a pure function of (index, key): splitmix64 finaliser in uint64 arithmetic, so the
+    same numbers come out on every numpy / platform (fixtures that would be too large to commit are regenerated from
+    this instead of being stored)."""
+    with np.errstate(over="ignore"):
+        x = np.arange(n, dtype=np.uint64) + np.uint64(key % (1 << 32)) * np.uint64(0x9E3779B97F4A7C15)
+        x ^= x >> np.uint64(30); x *= np.uint64(0xBF58476D1CE4E5B9)
+        x ^= x >> np.uint64(27); x *= np.uint64(0x94D049BB133111EB)
+        x ^= x >> np.uint64(31)
+    return (x >> np.uint64(40)).astype(np.float64) / float(1 << 23) - 1.0
+
+
+def formula_params(cfg: ModelCfg, seed: int = 0, dtype=torch.float64) -> dict:
+    """Same tree as init_params, every leaf a closed-form function of (name, index, seed) — lecun-scaled kernels,
+    non-trivial biases / LN affine / LayerScale / tokens, and a teacher that differs from the student."""
+    import zlib
+    out = {}
+    for name, t in init_params(cfg, 0, dtype=torch.float32).items():
+        leaf = name.split("/", 1)[1]
+        u = hash_uniform(t.numel(), zlib.crc32(name.encode()) + 7919 * seed).reshape(tuple(t.shape))
+        if leaf.endswith("kernel"):
+            fan_in = t.numel() // t.shape[-1]
+            amp = (3.0 / fan_in) ** 0.5 * (2.0 if "head" in name else 1.0)
+            v = amp * u
+        elif leaf.endswith("scale"):
+            v = 1.0 + 0.1 * u
+        elif leaf.endswith("gamma"):
+            v = 0.5 + 0.2 * u
+        else:                                   # biases, cls_token, mask_token
+            v = 0.05 * u
+        out[name] = torch.from_numpy(v).to(dtype)
+    return out
+
+
+def formula_images(shape, key: int, dtype=torch.float64):
+    """Unit-variance synthetic crops from hash_uniform (see formula_params)."""
+    n = int(np.prod(shape))
+    return torch.from_numpy(hash_uniform(n, key).reshape(shape) * 3.0 ** 0.5).to(dtype)
 
 
 def init_params(cfg: ModelCfg, seed: int = 0, dtype=torch.float32, teacher_copy: bool = True,

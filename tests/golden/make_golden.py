@@ -12,6 +12,15 @@
                                                          mini flax.linen (Module tree / param naming / Dense / LayerNorm /
                                                          Conv / dot_product_attention restated in numpy float64) and run
                                                          on a 2-block ViT with multi-crop input + iBOT masks
+  * train/ssl_meta_arch.py (SSLMetaArch.setup + __call__: teacher / student passes, head routing, iBOT row gathers,
+    both Sinkhorns, loss weights and the metrics dict)  — imported UNMODIFIED under the shim; the generator stubs the
+                                                         absent `omegaconf` / `termcolor` imports, registers the package
+                                                         `dinov3_jax.train` without running its __init__ (that pulls
+                                                         train.py -> optax / orbax), reads the reference's own
+                                                         ssl_default_config.yaml with PyYAML and registers a 2-block
+                                                         `vit_test` factory next to the reference's vit_* factories.
+                                                         Parameters / crops are closed-form (oracle.model.formula_*),
+                                                         so the fixture stores only masks and results.
 Usage:  python tests/golden/make_golden.py      (writes next to this file; the .npz files are committed)
 """
 from __future__ import annotations
@@ -163,6 +172,53 @@ def main():
         out[f"head_param/{k}"] = v.numpy().astype(np.float32)
     out.update(head_x=hx.astype(np.float32), head_logits=np.asarray(head(J(hx))),
                head_bottleneck=np.asarray(head(J(hx), no_last_layer=True)))
+
+    # ---- SSLMetaArch.__call__: the whole forward of the training step as the reference assembles it
+    import types
+    import yaml
+    from oracle.batch import collate_masks, make_mask_generator
+    from oracle.model import formula_images, formula_params
+
+    def stub(name, **attrs):
+        mod = types.ModuleType(name); mod.__dict__.update(attrs); sys.modules[name] = mod
+    stub("omegaconf", OmegaConf=type("OmegaConf", (), {"create": staticmethod(lambda x=None: x)}), DictConfig=dict)
+    stub("termcolor", colored=lambda text, *a, **k: text)
+    trainpkg = types.ModuleType("dinov3_jax.train"); trainpkg.__path__ = [REF + "/train"]
+    sys.modules["dinov3_jax.train"] = trainpkg
+    arch_mod = importlib.import_module("dinov3_jax.train.ssl_meta_arch")
+    assert arch_mod.__file__.startswith("/root/reference/")
+    vt.vit_test = lambda patch_size=16, **kw: vt.DinoVisionTransformer(patch_size=patch_size, embed_dim=128, n_blocks=2,
+                                                                       num_heads=2, ffn_ratio=4, **kw)
+
+    class AD(dict):
+        __getattr__ = dict.__getitem__
+    ad = lambda x: AD({k: ad(v) for k, v in x.items()}) if isinstance(x, dict) else x
+    for case, (B, n_local, temp, seed) in {"a": (4, 3, 0.05, 1), "b": (3, 8, 0.07, 2)}.items():
+        rcfg = ad(yaml.safe_load(open(REF + "/configs/ssl_default_config.yaml")))
+        rcfg.student.arch = "vit_test"
+        rcfg.crops.global_crops_size, rcfg.crops.local_crops_size, rcfg.crops.local_crops_number = 64, 32, n_local
+        for h in (rcfg.dino, rcfg.ibot):
+            h.head_n_prototypes, h.head_hidden_dim, h.head_bottleneck_dim = 48, 64, 32
+        mc = ModelCfg(embed_dim=128, depth=2, heads=2, global_size=64, local_size=32, n_local=n_local, n_prototypes=48,
+                      head_hidden=64, head_bottleneck=32)
+        P = formula_params(mc, seed)
+        jaxshim.PARAMS.clear(); jaxshim.PARAMS.update({k: v.numpy() for k, v in P.items()})
+        random.seed(seed); np.random.seed(seed)
+        md = collate_masks(2 * B, mc.n_patches_global, mc.mask_ratio, mc.mask_probability, make_mask_generator(mc))
+        data = {"collated_global_crops": J(formula_images((2 * B, 64, 64, 3), 100 + seed).numpy()),
+                "collated_local_crops": J(formula_images((n_local * B, 32, 32, 3), 200 + seed).numpy()),
+                "collated_masks": J(md["collated_masks"].numpy()), "mask_indices_list": J(md["mask_indices_list"].numpy()),
+                "masks_weight": J(md["masks_weight"].numpy()), "n_masked_patches": J(md["n_masked_patches"].numpy()),
+                "upperbound": md["upperbound"], "global_batch_size": B}
+        loss, metrics = arch_mod.SSLMetaArch(rcfg)(data, teacher_temp=temp, iteration=0)
+        out[f"ssl_{case}_spec"] = np.array([B, n_local, seed], dtype=np.int64)
+        out[f"ssl_{case}_teacher_temp"] = np.array(temp)
+        out[f"ssl_{case}_masks"] = md["collated_masks"].numpy()
+        out[f"ssl_{case}_mask_indices"] = md["mask_indices_list"].numpy()
+        out[f"ssl_{case}_loss"] = np.asarray(loss, dtype=np.float64)
+        for k, v in metrics.items():
+            out[f"ssl_{case}_metric/{k}"] = np.asarray(v, dtype=np.float64)
+        print(f"SSLMetaArch case {case}: loss {float(loss):.12f}", {k: float(np.asarray(v)) for k, v in metrics.items()})
     np.savez_compressed(os.path.join(HERE, "reference_vectors.npz"), **out)
     print("wrote", os.path.join(HERE, "reference_vectors.npz"), len(out), "arrays")
 

@@ -160,3 +160,34 @@ def test_softmax_centering_path_matches_oracle():
     num = sum(((ge[k].cpu().reshape(g.shape) - g) ** 2).sum() for k, g in zip(keys, gl) if g is not None)
     den = sum((g ** 2).sum() for g in gl if g is not None)
     assert float(torch.sqrt(num / den)) < 3e-2
+
+
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_engine_loss_against_reference_meta_arch_golden(case):
+    """Engine forward vs numbers produced by the reference's own SSLMetaArch.__call__ (tests/golden/make_golden.py);
+    the oracle is not involved.  Loss terms 1e-3 rel would be the fp32 bar; these fixtures use large-amplitude head
+    weights (peaky softmax), so the bf16-operand tolerance 5e-3 is stated here."""
+    import os
+    import numpy as np
+    from conftest import GOLDEN
+    from dinov3_jax.engine import Engine, from_oracle_cfg
+    from test_golden_reference import ssl_case
+    G = np.load(os.path.join(GOLDEN, "reference_vectors.npz"))
+    cfg, P, batch, temp = ssl_case(case, dtype=torch.float32)
+    B = batch["global_batch_size"]
+    batch["collated_global_crops"] = batch["collated_global_crops"].to(torch.bfloat16)
+    batch["collated_local_crops"] = batch["collated_local_crops"].to(torch.bfloat16)
+    eng = Engine(from_oracle_cfg(cfg), B, max_masked=max(int(batch["mask_indices_list"].shape[0]), 1))
+    eng.params.load_reference_tree(P)
+    eng.set_batch(batch)
+    eng.forward_backward(temp)
+    torch.cuda.synchronize()
+    met = eng.read_metrics()
+    tol = 5e-3
+    want = float(G[f"ssl_{case}_loss"])
+    assert abs(met["total_loss"] - want) < tol * abs(want), (met["total_loss"], want)
+    for k in ("dino_local_crops_loss", "dino_global_crops_loss", "ibot_loss"):
+        w = float(G[f"ssl_{case}_metric/{k}"])
+        assert abs(met[k] - w) < tol * abs(w), (k, met[k], w)
+    w = float(G[f"ssl_{case}_metric/koleo_loss"])
+    assert abs(met["koleo_loss"] - w) < 2e-2 * max(abs(w), 0.05)

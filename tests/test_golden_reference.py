@@ -131,3 +131,37 @@ def test_head_matches_reference_module_code():
     x = T(G["head_x"]).double()
     assert np.abs(head_forward(hp, x).numpy() - G["head_logits"]).max() < 1e-12
     assert np.abs(head_forward(hp, x, last_layer=False).numpy() - G["head_bottleneck"]).max() < 1e-12
+
+
+def ssl_case(case, dtype=torch.float64):
+    """Rebuild the closed-form inputs of an SSLMetaArch fixture (tests/golden/make_golden.py)."""
+    from oracle.arch import ModelCfg
+    from oracle.model import formula_images, formula_params
+    B, n_local, seed = (int(v) for v in G[f"ssl_{case}_spec"])
+    cfg = ModelCfg(embed_dim=128, depth=2, heads=2, global_size=64, local_size=32, n_local=n_local, n_prototypes=48,
+                   head_hidden=64, head_bottleneck=32)
+    masks = T(G[f"ssl_{case}_masks"])
+    idx = T(G[f"ssl_{case}_mask_indices"])
+    batch = {"collated_global_crops": formula_images((2 * B, 64, 64, 3), 100 + seed, dtype),
+             "collated_local_crops": formula_images((n_local * B, 32, 32, 3), 200 + seed, dtype),
+             "collated_masks": masks, "mask_indices_list": idx,
+             "masks_weight": (1 / masks.sum(-1).clamp(min=1.0)).unsqueeze(-1).expand_as(masks)[masks].to(torch.float32),
+             "n_masked_patches": torch.tensor([idx.shape[0]]), "upperbound": int(idx.shape[0]), "global_batch_size": B}
+    return cfg, formula_params(cfg, seed, dtype), batch, float(G[f"ssl_{case}_teacher_temp"])
+
+
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_ssl_forward_matches_reference_meta_arch(case):
+    """train/ssl_meta_arch.py SSLMetaArch.__call__ executed from the reference sources (teacher + student passes, four
+    heads, iBOT gathers, both Sinkhorns, loss weights) vs oracle.step.ssl_forward, float64.  The gradient the oracle
+    hands to the GPU parity tests is torch autograd of exactly this function."""
+    from oracle.step import ssl_forward
+    cfg, P, batch, temp = ssl_case(case)
+    loss, metrics = ssl_forward(P, batch, temp, cfg, dtype=torch.float64)
+    assert abs(float(loss) - float(G[f"ssl_{case}_loss"])) < 1e-9 * abs(float(G[f"ssl_{case}_loss"]))
+    keys = [k.split("/", 1)[1] for k in G.files if k.startswith(f"ssl_{case}_metric/")]
+    assert set(keys) == {"local_batch_size", "dino_local_crops_loss", "dino_local_loss_weight", "dino_global_crops_loss",
+                         "koleo_loss", "ibot_loss"}
+    for k in keys:
+        want = float(G[f"ssl_{case}_metric/{k}"])
+        assert abs(float(metrics[k]) - want) < 1e-9 * max(abs(want), 1.0), k
