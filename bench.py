@@ -246,10 +246,14 @@ def main():
         ms, ms_e2e = t.tolist()
     h2d = sum(batch[k].numel() * batch[k].element_size() for k in ("collated_global_crops", "collated_local_crops", "collated_masks", "mask_indices_list"))
     # ---- roofline leg: one instrumented step, CUDA events around every tensor-core GEMM launch
+    # (single stream for this step: with the weight-gradient stream active a launch's event pair would also time its
+    # wait for SMs held by the other stream's kernel)
+    overlap, eng.wgrad_overlap = eng.wgrad_overlap, False
     ops.PROFILE = []
     step_device(0)
     torch.cuda.synchronize()
     prof, ops.PROFILE = ops.PROFILE, None
+    eng.wgrad_overlap = overlap
     g_flops = sum(p[1] for p in prof)
     g_ms = sum(p[2].elapsed_time(p[3]) for p in prof)
     burst, sustained, hbm, how = peaks()

@@ -255,6 +255,362 @@ layernorm_bwd_fused_kernel(const InT* __restrict__ dy, const float* __restrict__
   }
 }
 
+
+// LayerNorm backward fused with the LayerScale/GELU backward of the branch that *feeds on* its result.
+// The row gradient dx (fp32 residual-stream gradient) produced here is exactly the dX the next branch upstream
+// needs (block.py:198-199: x_out = x_in + gamma * act(u)), so the same pass also writes
+//     du = bf16(dx * gamma * act'(u)),   dgamma += colsum(dx * act(u)),   dbias += colsum(du)
+// and the separate ls_act_bwd pass (one more read of dx and u, one more launch) disappears.
+//   ls_u == nullptr : act = identity and dgamma is not produced here (it is recovered from the weight gradient:
+//                     dgamma_j = (sum_i W_ij dW_ij + b_j db_j) / gamma_j, see ls_gamma_from_wgrad_kernel)
+// Layout: a row is owned by 128 threads (4 warps, float4 chunks, NC = ceil(D / 512) chunks per thread), two rows in
+// flight per CTA; every thread keeps its columns' parameter-gradient partial sums in registers over all its rows.
+template <int NC, typename InT>
+__global__ void __launch_bounds__(256)
+ln_bwd_ls_kernel(const InT* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+                 const float* __restrict__ rstd, const float* __restrict__ scale, const float* __restrict__ dx_add,
+                 float* __restrict__ dx, float* __restrict__ dscale, float* __restrict__ dbias, int T, int D,
+                 const float* __restrict__ ls_gamma, const __nv_bfloat16* __restrict__ ls_u, int ls_gelu,
+                 __nv_bfloat16* __restrict__ ls_du, float* __restrict__ ls_dgamma, float* __restrict__ ls_dbias) {
+  extern __shared__ float part[];                 // [4][D] cross-group reduction of the column sums
+  __shared__ float red[2][2][4][2];               // [group][parity][warp][a | b]
+  const int grp = threadIdx.x >> 7, t = threadIdx.x & 127, wig = t >> 5, lane = threadIdx.x & 31;
+  const float invD = 1.f / (float)D;
+  const bool tail = ls_gamma != nullptr;
+  float sc[NC][4], gm[NC][4];
+  float ads[NC][4], adb[NC][4], tdg[NC][4], tdb[NC][4];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int col = (c * 128 + t) * 4;
+    const bool ok = col < D;
+    const float4 s4 = ok ? *reinterpret_cast<const float4*>(scale + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 g4 = (ok && tail) ? *reinterpret_cast<const float4*>(ls_gamma + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+    sc[c][0] = s4.x; sc[c][1] = s4.y; sc[c][2] = s4.z; sc[c][3] = s4.w;
+    gm[c][0] = g4.x; gm[c][1] = g4.y; gm[c][2] = g4.z; gm[c][3] = g4.w;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { ads[c][j] = 0.f; adb[c][j] = 0.f; tdg[c][j] = 0.f; tdb[c][j] = 0.f; }
+  }
+  int parity = 0;
+  for (long row = (long)blockIdx.x * 2 + grp; row < T; row += (long)gridDim.x * 2, parity ^= 1) {
+    const float mu = mean[row], rs = rstd[row];
+    float xh[NC][4], gs[NC][4];
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int col = (c * 128 + t) * 4;
+      if (col < D) {
+        const float4 xv = *reinterpret_cast<const float4*>(x + row * (long)D + col);
+        float g[4];
+        if constexpr (sizeof(InT) == 2) {
+          const uint2 u = *reinterpret_cast<const uint2*>(dy + row * (long)D + col);
+          const float2 g0 = unpack_bf16(u.x), g1 = unpack_bf16(u.y);
+          g[0] = g0.x; g[1] = g0.y; g[2] = g1.x; g[3] = g1.y;
+        } else {
+          const float4 gv = *reinterpret_cast<const float4*>(dy + row * (long)D + col);
+          g[0] = gv.x; g[1] = gv.y; g[2] = gv.z; g[3] = gv.w;
+        }
+        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          xh[c][j] = (xs[j] - mu) * rs;
+          gs[c][j] = g[j] * sc[c][j];
+          a += gs[c][j];
+          b += gs[c][j] * xh[c][j];
+          ads[c][j] += g[j] * xh[c][j];
+          adb[c][j] += g[j];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { xh[c][j] = 0.f; gs[c][j] = 0.f; }
+      }
+    }
+    a = warp_sum(a);
+    b = warp_sum(b);
+    if (lane == 0) { red[grp][parity][wig][0] = a; red[grp][parity][wig][1] = b; }
+    asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
+    a = (red[grp][parity][0][0] + red[grp][parity][1][0] + red[grp][parity][2][0] + red[grp][parity][3][0]) * invD;
+    b = (red[grp][parity][0][1] + red[grp][parity][1][1] + red[grp][parity][2][1] + red[grp][parity][3][1]) * invD;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int col = (c * 128 + t) * 4;
+      if (col < D) {
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = rs * (gs[c][j] - a - xh[c][j] * b);
+        if (dx_add) {
+          const float4 r4 = *reinterpret_cast<const float4*>(dx_add + row * (long)D + col);
+          o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
+        }
+        *reinterpret_cast<float4*>(dx + row * (long)D + col) = make_float4(o[0], o[1], o[2], o[3]);
+        if (tail) {
+          float d[4];
+          if (ls_u) {
+            const uint2 uu = *reinterpret_cast<const uint2*>(ls_u + row * (long)D + col);
+            const float2 u0 = unpack_bf16(uu.x), u1 = unpack_bf16(uu.y);
+            const float uv[4] = {u0.x, u0.y, u1.x, u1.y};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float act = ls_gelu ? gelu_tanh(uv[j]) : uv[j];
+              const float dact = ls_gelu ? gelu_tanh_grad(uv[j]) : 1.f;
+              d[j] = o[j] * gm[c][j] * dact;
+              tdg[c][j] += o[j] * act;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) d[j] = o[j] * gm[c][j];
+          }
+          const uint32_t p0 = pack_bf16(d[0], d[1]), p1 = pack_bf16(d[2], d[3]);
+          // dbias is the column sum of the values the wgrad GEMM sees (the bf16-rounded du)
+          const float2 r0 = unpack_bf16(p0), r1 = unpack_bf16(p1);
+          tdb[c][0] += r0.x; tdb[c][1] += r0.y; tdb[c][2] += r1.x; tdb[c][3] += r1.y;
+          *reinterpret_cast<uint2*>(ls_du + row * (long)D + col) = make_uint2(p0, p1);
+        }
+      }
+    }
+  }
+  // ---- column sums: group 1 -> shared, group 0 adds its own and issues one global atomic per column and quantity
+  const bool want_ln = dscale != nullptr;
+  if (!want_ln && !tail) return;
+  if (grp == 1) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int col = (c * 128 + t) * 4;
+      if (col < D) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          part[col + j] = ads[c][j]; part[D + col + j] = adb[c][j];
+          part[2 * D + col + j] = tdg[c][j]; part[3 * D + col + j] = tdb[c][j];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (grp == 0) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int col = (c * 128 + t) * 4;
+      if (col < D) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (want_ln) {
+            atomicAdd(&dscale[col + j], ads[c][j] + part[col + j]);
+            atomicAdd(&dbias[col + j], adb[c][j] + part[D + col + j]);
+          }
+          if (tail) {
+            if (ls_dgamma && ls_u) atomicAdd(&ls_dgamma[col + j], tdg[c][j] + part[2 * D + col + j]);
+            if (ls_dbias) atomicAdd(&ls_dbias[col + j], tdb[c][j] + part[3 * D + col + j]);
+          }
+        }
+      }
+    }
+  }
+}
+
+
+// ---- the same fused pass as ln_bwd_ls_kernel, organised for HBM throughput (D = 128 * VPL, VPL <= 8) -----------------
+// One persistent CTA per SM.  A producer warp streams whole rows (x | dx_add | dy | u) into a shared-memory ring with
+// 1-D bulk copies (cp.async.bulk + mbarrier complete_tx), so the bytes in flight are set by the ring (up to ~200 KB
+// per SM) and not by registers; seven consumer warps each take a row, make the two LayerNorm passes out of shared
+// memory, store dx / du straight to global with 512-byte warp stores and keep the four column-sum vectors
+// (dscale, dbias, ls_dgamma, ls_dbias) for their columns in registers until the end.
+constexpr int LNR_MAX_STAGES = 16;
+constexpr int LNR_CONSUMERS = 7;     // + 1 producer warp = 8 warps: two per SM sub-partition, so 255 registers stay available
+
+__device__ __forceinline__ void bulk_load_1d(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int VPL, typename InT>
+__global__ void __launch_bounds__(32 * (LNR_CONSUMERS + 1), 1)
+ln_bwd_ring_kernel(const InT* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+                   const float* __restrict__ rstd, const float* __restrict__ scale, const float* __restrict__ dx_add,
+                   float* __restrict__ dx, float* __restrict__ dscale, float* __restrict__ dbias, int T, int stages,
+                   const float* __restrict__ ls_gamma, const __nv_bfloat16* __restrict__ ls_u, int ls_gelu,
+                   __nv_bfloat16* __restrict__ ls_du, float* __restrict__ ls_dgamma, float* __restrict__ ls_dbias) {
+  constexpr int D = VPL * 128;
+  extern __shared__ __align__(128) uint8_t lnr_smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(lnr_smem);
+  uint64_t* empty = full + LNR_MAX_STAGES;
+  float* s_scale = reinterpret_cast<float*>(lnr_smem + 256);
+  float* s_gamma = s_scale + D;
+  uint8_t* ring = lnr_smem + 256 + 2 * D * sizeof(float);
+  const bool tail = ls_gamma != nullptr;
+  const uint32_t xB = D * 4, aB = dx_add ? D * 4 : 0, gB = D * sizeof(InT), uB = (tail && ls_u) ? D * 2 : 0;
+  const uint32_t stageB = xB + aB + gB + uB;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    fence_mbar_init();
+  }
+  for (int e = threadIdx.x; e < D; e += blockDim.x) { s_scale[e] = scale[e]; s_gamma[e] = tail ? ls_gamma[e] : 0.f; }
+  __syncthreads();
+  const long nrows = blockIdx.x < T ? ((long)T - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (warp == LNR_CONSUMERS) {
+    if (lane == 0) {
+      for (long k = 0; k < nrows; ++k) {
+        const int st = (int)(k % stages);
+        const long use = k / stages;
+        if (use > 0) mbar_wait(&empty[st], (uint32_t)((use - 1) & 1));
+        const long row = blockIdx.x + k * (long)gridDim.x;
+        uint8_t* dst = ring + (size_t)st * stageB;
+        mbar_expect_tx(&full[st], stageB);
+        bulk_load_1d(dst, x + row * (long)D, xB, &full[st]);
+        if (aB) bulk_load_1d(dst + xB, dx_add + row * (long)D, aB, &full[st]);
+        bulk_load_1d(dst + xB + aB, dy + row * (long)D, gB, &full[st]);
+        if (uB) bulk_load_1d(dst + xB + aB + gB, ls_u + row * (long)D, uB, &full[st]);
+      }
+    }
+    return;      // the producer warp takes no part in the consumers' named barriers below
+  }
+
+  float ads[VPL][4], adb[VPL][4], tdg[VPL][4], tdb[VPL][4];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { ads[k][j] = 0.f; adb[k][j] = 0.f; tdg[k][j] = 0.f; tdb[k][j] = 0.f; }
+
+  for (long k = warp; k < nrows; k += LNR_CONSUMERS) {
+    const int st = (int)(k % stages);
+    const long row = blockIdx.x + k * (long)gridDim.x;
+    const float mu = mean[row], rs = rstd[row];
+    mbar_wait(&full[st], (uint32_t)((k / stages) & 1));
+    const uint8_t* base = ring + (size_t)st * stageB;
+    const float* sx = reinterpret_cast<const float*>(base);
+    const float* sa = reinterpret_cast<const float*>(base + xB);
+    const InT* sg = reinterpret_cast<const InT*>(base + xB + aB);
+    const __nv_bfloat16* su = reinterpret_cast<const __nv_bfloat16*>(base + xB + aB + gB);
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int c = 0; c < VPL; ++c) {
+      const int e = (c * 32 + lane) * 4;
+      const float4 xv = *reinterpret_cast<const float4*>(sx + e);
+      const float4 sc = *reinterpret_cast<const float4*>(s_scale + e);
+      float g[4];
+      if constexpr (sizeof(InT) == 2) {
+        const uint2 u2 = *reinterpret_cast<const uint2*>(sg + e);
+        const float2 g0 = unpack_bf16(u2.x), g1 = unpack_bf16(u2.y);
+        g[0] = g0.x; g[1] = g0.y; g[2] = g1.x; g[3] = g1.y;
+      } else {
+        const float4 gv = *reinterpret_cast<const float4*>(sg + e);
+        g[0] = gv.x; g[1] = gv.y; g[2] = gv.z; g[3] = gv.w;
+      }
+      const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, scs[4] = {sc.x, sc.y, sc.z, sc.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float xh = (xs[j] - mu) * rs, gsv = g[j] * scs[j];
+        a += gsv;
+        b += gsv * xh;
+        ads[c][j] += g[j] * xh;
+        adb[c][j] += g[j];
+      }
+    }
+    a = warp_sum(a) * (1.f / D);
+    b = warp_sum(b) * (1.f / D);
+#pragma unroll
+    for (int c = 0; c < VPL; ++c) {
+      const int e = (c * 32 + lane) * 4;
+      const float4 xv = *reinterpret_cast<const float4*>(sx + e);
+      const float4 sc = *reinterpret_cast<const float4*>(s_scale + e);
+      float g[4];
+      if constexpr (sizeof(InT) == 2) {
+        const uint2 u2 = *reinterpret_cast<const uint2*>(sg + e);
+        const float2 g0 = unpack_bf16(u2.x), g1 = unpack_bf16(u2.y);
+        g[0] = g0.x; g[1] = g0.y; g[2] = g1.x; g[3] = g1.y;
+      } else {
+        const float4 gv = *reinterpret_cast<const float4*>(sg + e);
+        g[0] = gv.x; g[1] = gv.y; g[2] = gv.z; g[3] = gv.w;
+      }
+      const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, scs[4] = {sc.x, sc.y, sc.z, sc.w};
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = rs * (g[j] * scs[j] - a - (xs[j] - mu) * rs * b);
+      if (aB) {
+        const float4 r4 = *reinterpret_cast<const float4*>(sa + e);
+        o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w;
+      }
+      *reinterpret_cast<float4*>(dx + row * (long)D + e) = make_float4(o[0], o[1], o[2], o[3]);
+      if (tail) {
+        const float4 gm = *reinterpret_cast<const float4*>(s_gamma + e);
+        const float gms[4] = {gm.x, gm.y, gm.z, gm.w};
+        float d[4];
+        if (uB) {
+          const uint2 uu = *reinterpret_cast<const uint2*>(su + e);
+          const float2 u0 = unpack_bf16(uu.x), u1 = unpack_bf16(uu.y);
+          const float uv[4] = {u0.x, u0.y, u1.x, u1.y};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float act = ls_gelu ? gelu_tanh_fast(uv[j]) : uv[j];
+            const float dact = ls_gelu ? gelu_tanh_grad_fast(uv[j]) : 1.f;
+            d[j] = o[j] * gms[j] * dact;
+            tdg[c][j] += o[j] * act;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) d[j] = o[j] * gms[j];
+        }
+        const uint32_t p0 = pack_bf16(d[0], d[1]), p1 = pack_bf16(d[2], d[3]);
+        const float2 r0 = unpack_bf16(p0), r1 = unpack_bf16(p1);
+        tdb[c][0] += r0.x; tdb[c][1] += r0.y; tdb[c][2] += r1.x; tdb[c][3] += r1.y;
+        *reinterpret_cast<uint2*>(ls_du + row * (long)D + e) = make_uint2(p0, p1);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[st]);
+  }
+
+  // ---- column sums: every consumer warp has drained its rows; reuse the ring as [8 warps][D] slabs, one quantity at a time
+  float* slab = reinterpret_cast<float*>(ring);
+  const int ct = threadIdx.x;                 // consumer threads only
+#define LNR_REDUCE(ACC, DST)                                                                         \
+  {                                                                                                  \
+    float* dst__ = (DST);                                                                            \
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * LNR_CONSUMERS) : "memory");                           \
+    if (dst__) {                                                                                     \
+      _Pragma("unroll") for (int c = 0; c < VPL; ++c)                                                \
+        *reinterpret_cast<float4*>(slab + warp * D + (c * 32 + lane) * 4) =                          \
+            make_float4(ACC[c][0], ACC[c][1], ACC[c][2], ACC[c][3]);                                 \
+    }                                                                                                \
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * LNR_CONSUMERS) : "memory");                           \
+    if (dst__) {                                                                                     \
+      for (int e = ct; e < D; e += 32 * LNR_CONSUMERS) {                                             \
+        float tot = 0.f;                                                                             \
+        _Pragma("unroll") for (int w = 0; w < LNR_CONSUMERS; ++w) tot += slab[w * D + e];            \
+        atomicAdd(&dst__[e], tot);                                                                   \
+      }                                                                                              \
+    }                                                                                                \
+  }
+  LNR_REDUCE(ads, dscale)
+  LNR_REDUCE(adb, dscale ? dbias : nullptr)
+  LNR_REDUCE(tdg, (tail && uB) ? ls_dgamma : nullptr)
+  LNR_REDUCE(tdb, tail ? ls_dbias : nullptr)
+#undef LNR_REDUCE
+}
+
+// LayerScale gradient of a linear branch x + gamma * (a W + b) recovered from the weight gradient
+// (dW = a^T (dx * gamma), db = colsum(dx * gamma)):   dgamma_j += (sum_i W_ij dW_ij + b_j db_j) / gamma_j.
+// W bf16 [K, N] (the compute copy the forward used), dW fp32 [K, N]; one CTA per 32 columns.
+__global__ void ls_gamma_from_wgrad_kernel(const __nv_bfloat16* __restrict__ W, const float* __restrict__ dW,
+                                           const float* __restrict__ bias, const float* __restrict__ dbias,
+                                           const float* __restrict__ gamma, float* __restrict__ dgamma, int K, int N) {
+  __shared__ float acc[8][33];
+  const int col = blockIdx.x * 32 + (threadIdx.x & 31), wy = threadIdx.x >> 5;
+  float s = 0.f;
+  if (col < N)
+    for (int i = wy; i < K; i += 8) s += __bfloat162float(W[(long)i * N + col]) * dW[(long)i * N + col];
+  acc[wy][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (wy == 0 && col < N) {
+    float tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tot += acc[k][threadIdx.x];
+    const float g = gamma[col];
+    tot += bias[col] * dbias[col];
+    dgamma[col] += (g != 0.f) ? tot / g : 0.f;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ RoPE
 // layers/attention.py:14-20,69-90 + layers/rope_position_encoding.py:117-123.  In place on the q and k thirds of
 // qkv bf16 [T, 3D]; token t of each crop (N tokens) is rotated iff t >= prefix; math in fp32.
@@ -455,6 +811,59 @@ static void launch_ln_bwd_fused(const void* dy, int dy_is_f32, const float* x, c
 }
 
 
+template <int NC>
+static void launch_ln_bwd_ls(const void* dy, int dy_is_f32, const float* x, const float* mean, const float* rstd,
+                             const float* scale, const float* dx_add, float* dx, float* dscale, float* dbias, int T, int D,
+                             const float* ls_gamma, const void* ls_u, int ls_gelu, void* ls_du, float* ls_dgamma,
+                             float* ls_dbias, cudaStream_t st) {
+  const size_t smem = (size_t)4 * D * sizeof(float);
+  static int occ_bf16 = 0, occ_f32 = 0;
+  if (!occ_bf16) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_bf16, ln_bwd_ls_kernel<NC, __nv_bfloat16>, 256, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f32, ln_bwd_ls_kernel<NC, float>, 256, smem);
+    occ_bf16 = max(occ_bf16, 1); occ_f32 = max(occ_f32, 1);
+  }
+  if (dy_is_f32) {
+    const int blocks = min((T + 1) / 2, sm_count() * occ_f32);
+    ln_bwd_ls_kernel<NC, float><<<blocks, 256, smem, st>>>((const float*)dy, x, mean, rstd, scale, dx_add, dx, dscale, dbias,
+        T, D, ls_gamma, (const __nv_bfloat16*)ls_u, ls_gelu, (__nv_bfloat16*)ls_du, ls_dgamma, ls_dbias);
+  } else {
+    const int blocks = min((T + 1) / 2, sm_count() * occ_bf16);
+    ln_bwd_ls_kernel<NC, __nv_bfloat16><<<blocks, 256, smem, st>>>((const __nv_bfloat16*)dy, x, mean, rstd, scale, dx_add, dx,
+        dscale, dbias, T, D, ls_gamma, (const __nv_bfloat16*)ls_u, ls_gelu, (__nv_bfloat16*)ls_du, ls_dgamma, ls_dbias);
+  }
+}
+
+
+template <int VPL>
+static bool launch_ln_bwd_ring(const void* dy, int dy_is_f32, const float* x, const float* mean, const float* rstd,
+                               const float* scale, const float* dx_add, float* dx, float* dscale, float* dbias, int T,
+                               const float* ls_gamma, const void* ls_u, int ls_gelu, void* ls_du, float* ls_dgamma,
+                               float* ls_dbias, cudaStream_t st) {
+  constexpr int D = VPL * 128;
+  const size_t stageB = (size_t)D * 4 + (dx_add ? D * 4 : 0) + (size_t)D * (dy_is_f32 ? 4 : 2) + ((ls_gamma && ls_u) ? D * 2 : 0);
+  const size_t fixed = 256 + 2 * D * sizeof(float);
+  const size_t budget = 200 * 1024;
+  int stages = (int)min((size_t)LNR_MAX_STAGES, (budget - fixed) / stageB);
+  if (stages < 3) return false;
+  const size_t need = max(stageB * stages, (size_t)LNR_CONSUMERS * D * sizeof(float));    // ring doubles as the reduction slabs
+  const size_t smem = fixed + need;
+  static bool cfg_b = false, cfg_f = false;
+  const int grid = min(T, sm_count());
+  const int threads = 32 * (LNR_CONSUMERS + 1);
+  if (dy_is_f32) {
+    if (!cfg_f) { cudaFuncSetAttribute(ln_bwd_ring_kernel<VPL, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024); cfg_f = true; }
+    ln_bwd_ring_kernel<VPL, float><<<grid, threads, smem, st>>>((const float*)dy, x, mean, rstd, scale, dx_add, dx, dscale,
+        dbias, T, stages, ls_gamma, (const __nv_bfloat16*)ls_u, ls_gelu, (__nv_bfloat16*)ls_du, ls_dgamma, ls_dbias);
+  } else {
+    if (!cfg_b) { cudaFuncSetAttribute(ln_bwd_ring_kernel<VPL, __nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024); cfg_b = true; }
+    ln_bwd_ring_kernel<VPL, __nv_bfloat16><<<grid, threads, smem, st>>>((const __nv_bfloat16*)dy, x, mean, rstd, scale, dx_add,
+        dx, dscale, dbias, T, stages, ls_gamma, (const __nv_bfloat16*)ls_u, ls_gelu, (__nv_bfloat16*)ls_du, ls_dgamma, ls_dbias);
+  }
+  return true;
+}
+
+
 extern "C" {
 
 int d3_im2col(const void* img, void* out, int ld_out, int n, int H, int W, int p, void* stream) {
@@ -526,6 +935,53 @@ int d3_layernorm_bwd(const void* dy, int dy_is_f32, const float* x, const float*
   }
   D3_CHECK_LAUNCH();
   if (dscale) count_launch();
+  return D3_OK;
+}
+
+int d3_layernorm_bwd_ls(const void* dy, int dy_is_f32, const float* x, const float* mean, const float* rstd,
+                        const float* scale, const float* dx_add, float* dx, float* dscale, float* dbias, int T, int D,
+                        const float* ls_gamma, const void* ls_u, int ls_gelu, void* ls_du, float* ls_dgamma,
+                        float* ls_dbias, void* stream) {
+  if (T <= 0) return D3_OK;
+  if (D % 4 != 0 || D > 1536) return set_error(D3_ERR_ARG, "d3_layernorm_bwd_ls: D must be a multiple of 4 and <= 1536");
+  if (ls_gamma && !ls_du) return set_error(D3_ERR_ARG, "d3_layernorm_bwd_ls: ls_du required with ls_gamma");
+  if (((uintptr_t)dy | (uintptr_t)x | (uintptr_t)dx | (uintptr_t)scale | (uintptr_t)dx_add | (uintptr_t)ls_gamma |
+       (uintptr_t)ls_u | (uintptr_t)ls_du) % 8 != 0 || ((uintptr_t)x | (uintptr_t)dx | (uintptr_t)dx_add) % 16 != 0)
+    return set_error(D3_ERR_ARG, "d3_layernorm_bwd_ls: misaligned buffer");
+  cudaStream_t st = STREAM(stream);
+  const bool ring_ok = (((uintptr_t)dy | (uintptr_t)x | (uintptr_t)dx | (uintptr_t)dx_add | (uintptr_t)ls_u | (uintptr_t)ls_du) % 16 == 0) &&
+                       !getenv("D3_LN_NO_RING");
+#define LN_RING_ARGS dy, dy_is_f32, x, mean, rstd, scale, dx_add, dx, dscale, dbias, T, ls_gamma, ls_u, ls_gelu, ls_du, ls_dgamma, ls_dbias, st
+  if (ring_ok && D % 128 == 0 && D / 128 <= 8) {
+    bool done = false;
+    switch (D / 128) {
+      case 1: done = launch_ln_bwd_ring<1>(LN_RING_ARGS); break;
+      case 2: done = launch_ln_bwd_ring<2>(LN_RING_ARGS); break;
+      case 3: done = launch_ln_bwd_ring<3>(LN_RING_ARGS); break;
+      case 4: done = launch_ln_bwd_ring<4>(LN_RING_ARGS); break;
+      case 6: done = launch_ln_bwd_ring<6>(LN_RING_ARGS); break;
+      case 8: done = launch_ln_bwd_ring<8>(LN_RING_ARGS); break;
+      default: break;
+    }
+    if (done) { D3_CHECK_LAUNCH(); return D3_OK; }
+  }
+#undef LN_RING_ARGS
+  const int nc = (D + 511) / 512;
+#define LN_LS_ARGS dy, dy_is_f32, x, mean, rstd, scale, dx_add, dx, dscale, dbias, T, D, ls_gamma, ls_u, ls_gelu, ls_du, ls_dgamma, ls_dbias, st
+  if (nc == 1) launch_ln_bwd_ls<1>(LN_LS_ARGS);
+  else if (nc == 2) launch_ln_bwd_ls<2>(LN_LS_ARGS);
+  else launch_ln_bwd_ls<3>(LN_LS_ARGS);
+#undef LN_LS_ARGS
+  D3_CHECK_LAUNCH();
+  return D3_OK;
+}
+
+int d3_ls_gamma_from_wgrad(const void* W, const float* dW, const float* bias, const float* dbias, const float* gamma,
+                           float* dgamma, int K, int N, void* stream) {
+  if (K <= 0 || N <= 0) return D3_OK;
+  ls_gamma_from_wgrad_kernel<<<(N + 31) / 32, 256, 0, STREAM(stream)>>>((const __nv_bfloat16*)W, dW, bias, dbias, gamma,
+                                                                      dgamma, K, N);
+  D3_CHECK_LAUNCH();
   return D3_OK;
 }
 

@@ -44,6 +44,8 @@ SIGNATURES = {
     "d3_assemble_tokens_bwd": [P, P, P, P, P, I, I, I, P],
     "d3_layernorm_fwd": [P, P, P, P, I, P, P, I, I, F, P],
     "d3_layernorm_bwd": [P, I, P, P, P, P, P, P, P, P, I, I, P],
+    "d3_layernorm_bwd_ls": [P, I, P, P, P, P, P, P, P, P, I, I, P, P, I, P, P, P, P],
+    "d3_ls_gamma_from_wgrad": [P, P, P, P, P, P, I, I, P],
     "d3_rope": [P, P, P, LL, I, I, I, I, I, P],
     "d3_attn_fwd": [P, P, P, I, I, I, I, P],
     "d3_debug_attn_trace": [P],

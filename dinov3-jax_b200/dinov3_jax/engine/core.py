@@ -10,6 +10,7 @@ the crop structure.  Activations needed by the backward are stashed per block (b
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 
@@ -76,7 +77,6 @@ class Stream:
         self.Xn = e(T, D, dt=f32)
         self.LSE = [[e(s.n, cfg.heads, s.N, dt=f32) for s in sets] for _ in range(nb)]
         if stash:
-            self.Pst = [e(T, D) for _ in range(L)]
             self.U1 = [e(T, Hd) for _ in range(L)]
             self.U2 = [e(T, D) for _ in range(L)]
             self.stats = [[e(T, dt=f32) for _ in range(4)] for _ in range(L)]   # mean1, rstd1, mean2, rstd2
@@ -181,9 +181,20 @@ class Engine:
         e = lambda *shape, dt=bf16: torch.empty(*shape, dtype=dt, device=dev)
         self.dX = [e(T, D, dt=f32), e(T, D, dt=f32)]
         self.dXmid = e(T, D, dt=f32)
-        self.dU2, self.dP, self.dZ, self.dY, self.dO = e(T, D), e(T, D), e(T, D), e(T, D), e(T, D)
-        self.dU1 = e(T, Hd)
-        self.dQKV = e(T, 3 * D)
+        self.dZ, self.dY, self.dO = e(T, D), e(T, D), e(T, D)
+        # Weight-gradient GEMMs only feed the optimizer, so they run on a second stream and fill the tensor cores
+        # while the main stream is in its HBM-bound kernels (LN / LayerScale backward, column sums).  The operands
+        # they read (dU2, dU1, dP, dQKV) are double-buffered by block parity; events order reuse.
+        self.wgrad_overlap = os.environ.get("D3_WGRAD_STREAM", "1") != "0"
+        nbuf = 2 if self.wgrad_overlap else 1
+        self.dU2, self.dP = [e(T, D) for _ in range(nbuf)], [e(T, D) for _ in range(nbuf)]
+        self.dU1 = [e(T, Hd) for _ in range(nbuf)]
+        self.dQKV = [e(T, 3 * D) for _ in range(nbuf)]
+        if self.wgrad_overlap:
+            self.wstream = torch.cuda.Stream(device=self.device, priority=0)
+            self._ev_in = [[torch.cuda.Event() for _ in range(4)] for _ in range(2)]     # main -> wgrad stream
+            self._ev_done = [torch.cuda.Event() for _ in range(2)]                      # wgrad stream -> main
+            self._ev_done_live = [False, False]
         self.delta = [e(s.n, cfg.heads, s.N, dt=f32) for s in self.s_sets]
         self.dTok = [e(s.n * s.P, D) for s in self.s_sets]
         self._build_ce_tables()
@@ -265,8 +276,7 @@ class Engine:
             q = QKV[cs.row0: cs.row0 + cs.T]
             ops.rope(q, cs.sin, cs.cos, cs.N, 1, D, cfg.head_dim)
             ops.attn_fwd(q, O[cs.row0: cs.row0 + cs.T], lse if st.stash else None, cs.n, cs.N, D, H)
-        ops.gemm(O, w("attn/proj/kernel"), Xmid, b_mn=True, bias=v("attn/proj/bias"),
-                 store_pre=st.Pst[i] if st.stash else None, gamma=v("ls1/gamma"), resid=X)
+        ops.gemm(O, w("attn/proj/kernel"), Xmid, b_mn=True, bias=v("attn/proj/bias"), gamma=v("ls1/gamma"), resid=X)
         ops.layernorm_fwd(Xmid, v("norm2/scale"), v("norm2/bias"), Z, stats[2], stats[3], cfg.ln_eps)
         ops.gemm(Z, w("mlp/Dense_0/kernel"), Hh, b_mn=True, bias=v("mlp/Dense_0/bias"), gelu=True,
                  store_pre=st.U1[i] if st.stash else None)
@@ -356,36 +366,77 @@ class Engine:
         ops.gemm(r(hb.dUa), w("mlp/layers_0/kernel"), r(hb.dA0))                                 # fp32 [R, D]
         self.fsdp.grads_ready(module, "head")
 
+    def _ls_tail(self, i: int):
+        """Arguments that make a LayerNorm backward also emit the LayerScale/activation backward of block i's MLP
+        branch (x_out = x_mid + g2 * act(h W2 + b2)) from the residual gradient it produces: dU2 -> self.dU2[parity]."""
+        cfg, bb, st = self.cfg, self.params.mods["backbone"], self.student
+        p = f"blocks_{i}/"
+        par = (i & 1) if self.wgrad_overlap else 0
+        if self.wgrad_overlap and self._ev_done_live[par]:
+            torch.cuda.current_stream().wait_event(self._ev_done[par])   # weight gradients of block i+2 have read dU2[par]
+            self._ev_done_live[par] = False
+        return dict(ls_gamma=bb.vec(p + "ls2/gamma"), ls_u=st.U2[i], ls_gelu=cfg.mlp_second_act, ls_du=self.dU2[par],
+                    ls_dgamma=bb.gv(p + "ls2/gamma"), ls_dbias=bb.gv(p + "mlp/Dense_1/bias"))
+
     def _block_bwd(self, i: int, dX, dXprev):
+        """Backward of block i.  On entry dX is the gradient of the block output and self.dU2[parity(i)] already holds
+        dU2 = dX * g2 * act'(u2) (written by the LayerNorm backward that produced dX, see _ls_tail)."""
         cfg, bb, st = self.cfg, self.params.mods["backbone"], self.student
         D, H = cfg.embed_dim, cfg.heads
         p = f"blocks_{i}/"
         v, w, gw, gv = (lambda n: bb.vec(p + n)), (lambda n: bb.w(p + n)), (lambda n: bb.gw(p + n)), (lambda n: bb.gv(p + n))
         m1, r1, m2, r2 = st.stats[i]
+        par = (i & 1) if self.wgrad_overlap else 0
+        dU2, dU1, dP, dQKV = self.dU2[par], self.dU1[par], self.dP[par], self.dQKV[par]
+        main = torch.cuda.current_stream()
+
+        def on_wstream(slot, fn):
+            """Run fn on the weight-gradient stream once the main stream has reached this point."""
+            if not self.wgrad_overlap:
+                fn()
+                return
+            ev = self._ev_in[par][slot]
+            ev.record(main)
+            self.wstream.wait_event(ev)
+            with torch.cuda.stream(self.wstream):
+                fn()
+
+        wgrad = lambda slot, a, b, out: on_wstream(slot, lambda: ops.gemm(a, b, out, a_mn=True, b_mn=True, accum=True))
         # ---- MLP branch: x_out = x_mid + g2 * act(u2), u2 = h W2 + b2, h = gelu(u1), u1 = z W1 + b1
-        ops.ls_act_bwd(dX, st.U2[i], v("ls2/gamma"), self.dU2, gv("ls2/gamma"), gv("mlp/Dense_1/bias"), cfg.mlp_second_act)
-        ops.gemm(self.dU2, w("mlp/Dense_1/kernel"), self.dU1, dgelu_of=st.U1[i])                 # dU1 = (dU2 W2^T) * gelu'(u1)
-        ops.gemm(st.Hh[i], self.dU2, gw("mlp/Dense_1/kernel"), a_mn=True, b_mn=True, accum=True)            # dW2 = h^T dU2
-        ops.colsum_bf16(self.dU1, gv("mlp/Dense_0/bias"))
-        ops.gemm(self.dU1, w("mlp/Dense_0/kernel"), self.dZ)                                    # dZ = dU1 W1^T
-        ops.gemm(st.Z[i], self.dU1, gw("mlp/Dense_0/kernel"), a_mn=True, b_mn=True, accum=True)             # dW1 = z^T dU1
-        ops.layernorm_bwd(self.dZ, st.Xmid[i], m2, r2, v("norm2/scale"), self.dXmid, dx_add=dX,
-                          dscale=gv("norm2/scale"), dbias=gv("norm2/bias"))
-        # ---- attention branch: x_mid = x_in + g1 * (o Wp + bp)
-        ops.ls_act_bwd(self.dXmid, st.Pst[i], v("ls1/gamma"), self.dP, gv("ls1/gamma"), gv("attn/proj/bias"), False)
-        ops.gemm(self.dP, w("attn/proj/kernel"), self.dO)                                       # dO = dP Wp^T
-        ops.gemm(st.O[i], self.dP, gw("attn/proj/kernel"), a_mn=True, b_mn=True, accum=True)                # dWp = o^T dP
+        wgrad(0, st.Hh[i], dU2, gw("mlp/Dense_1/kernel"))                                      # dW2 = h^T dU2
+        ops.gemm(dU2, w("mlp/Dense_1/kernel"), dU1, dgelu_of=st.U1[i])                         # dU1 = (dU2 W2^T) * gelu'(u1)
+        wgrad(1, st.Z[i], dU1, gw("mlp/Dense_0/kernel"))                                       # dW1 = z^T dU1
+        ops.colsum_bf16(dU1, gv("mlp/Dense_0/bias"))
+        ops.gemm(dU1, w("mlp/Dense_0/kernel"), self.dZ)                                        # dZ = dU1 W1^T
+        # LN2 backward; its tail is the attention branch's LayerScale: x_mid = x_in + g1 * (o Wp + bp), dP = dXmid * g1
+        ops.layernorm_bwd_ls(self.dZ, st.Xmid[i], m2, r2, v("norm2/scale"), self.dXmid, dx_add=dX,
+                             dscale=gv("norm2/scale"), dbias=gv("norm2/bias"),
+                             ls_gamma=v("ls1/gamma"), ls_du=dP, ls_dbias=gv("attn/proj/bias"))
+
+        def proj_wgrad():
+            ops.gemm(st.O[i], dP, gw("attn/proj/kernel"), a_mn=True, b_mn=True, accum=True)    # dWp = o^T dP
+            # dg1 from dWp / dbp (no stash of the projection output needed)
+            ops.ls_gamma_from_wgrad(w("attn/proj/kernel"), gw("attn/proj/kernel"), v("attn/proj/bias"),
+                                    gv("attn/proj/bias"), v("ls1/gamma"), gv("ls1/gamma"))
+        on_wstream(2, proj_wgrad)
+        ops.gemm(dP, w("attn/proj/kernel"), self.dO)                                           # dO = dP Wp^T
         for cs, lse, delta in zip(st.sets, st.LSE[i], self.delta):
             sl = slice(cs.row0, cs.row0 + cs.T)
             # gradient w.r.t. the pre-RoPE projection: the inverse rotation is fused into the kernel's store stage
-            ops.attn_bwd(st.QKV[i][sl], st.O[i][sl], self.dO[sl], lse, delta, self.dQKV[sl], cs.n, cs.N, D, H,
+            ops.attn_bwd(st.QKV[i][sl], st.O[i][sl], self.dO[sl], lse, delta, dQKV[sl], cs.n, cs.N, D, H,
                          rope_sin=cs.sin, rope_cos=cs.cos, rope_prefix=1)
-        ops.colsum_bf16(self.dQKV, gv("attn/qkv/bias"))
-        ops.gemm(self.dQKV, w("attn/qkv/kernel"), self.dY)                                      # dY = dQKV Wqkv^T
-        ops.gemm(st.Y[i], self.dQKV, gw("attn/qkv/kernel"), a_mn=True, b_mn=True, accum=True)               # dWqkv = y^T dQKV
-        ops.layernorm_bwd(self.dY, st.X[i], m1, r1, v("norm1/scale"), dXprev, dx_add=self.dXmid,
-                          dscale=gv("norm1/scale"), dbias=gv("norm1/bias"))
-        self.fsdp.grads_ready("backbone", f"blocks_{i}")
+        wgrad(3, st.Y[i], dQKV, gw("attn/qkv/kernel"))                                         # dWqkv = y^T dQKV
+        ops.colsum_bf16(dQKV, gv("attn/qkv/bias"))
+        ops.gemm(dQKV, w("attn/qkv/kernel"), self.dY)                                          # dY = dQKV Wqkv^T
+        tail = self._ls_tail(i - 1) if i > 0 else {}
+        ops.layernorm_bwd_ls(self.dY, st.X[i], m1, r1, v("norm1/scale"), dXprev, dx_add=self.dXmid,
+                             dscale=gv("norm1/scale"), dbias=gv("norm1/bias"), **tail)
+        if self.wgrad_overlap:
+            self._ev_done[par].record(self.wstream)
+            self._ev_done_live[par] = True
+            self.fsdp.grads_ready("backbone", f"blocks_{i}", also_after=self._ev_done[par])
+        else:
+            self.fsdp.grads_ready("backbone", f"blocks_{i}")
 
     def _gather_schedule(self):
         """(module, unit, teacher) in the order the step uses them: teacher pass, then student pass (student parameters
@@ -469,8 +520,8 @@ class Engine:
         ops.scatter_add_rows(self.h_s_ibot.dA0, self.rows_masked_t, dXn, M, D)
         bb = self.params.mods["backbone"]
         dXL = self.dX[1]
-        ops.layernorm_bwd(dXn, S_.X[cfg.depth], S_.fstats[0], S_.fstats[1], bb.vec("norm/scale"), dXL,
-                          dscale=bb.gv("norm/scale"), dbias=bb.gv("norm/bias"))
+        ops.layernorm_bwd_ls(dXn, S_.X[cfg.depth], S_.fstats[0], S_.fstats[1], bb.vec("norm/scale"), dXL,
+                             dscale=bb.gv("norm/scale"), dbias=bb.gv("norm/bias"), **self._ls_tail(cfg.depth - 1))
         self.fsdp.grads_ready("backbone", "norm")
         cur, nxt = 1, 0
         for i in reversed(range(cfg.depth)):
@@ -486,6 +537,9 @@ class Engine:
             ops.gemm(cs.patches, dTok, bb.gw("patch_embed/proj/kernel"), a_mn=True, b_mn=True, accum=True)
             first = False
         self.fsdp.grads_ready("backbone", "embed")
+        if self.wgrad_overlap:
+            torch.cuda.current_stream().wait_stream(self.wstream)     # the optimizer reads every weight gradient
+            self._ev_done_live = [False, False]
 
     def optimizer_step(self, lr: float, wd: float, last_layer_lr: float, momentum: float):
         """Per-module clip (train/train.py:516-541) + AdamW (:95-106) + teacher EMA (ssl_meta_arch.py:650-652)."""

@@ -102,7 +102,7 @@ class FsdpRuntime:
                 w.wait()
 
     # ------------------------------------------------------------------------------------------ gradient reduction
-    def grads_ready(self, module: str, unit_name: str):
+    def grads_ready(self, module: str, unit_name: str, also_after=None):
         """Called right after the kernels of this unit's backward were enqueued: reduce-scatter (mean) its gradient
         ranges into the rank's gradient shard, on the side stream."""
         if self.world == 1 or (self._debug & 2):
@@ -121,9 +121,13 @@ class FsdpRuntime:
                         self._grad_works.append(w)
         if self.side is not None:
             self.side.wait_stream(torch.cuda.current_stream())
+            if also_after is not None:       # kernels of this unit enqueued on another stream (weight gradients)
+                self.side.wait_event(also_after)
             with torch.cuda.stream(self.side):
                 issue()
         else:
+            if also_after is not None:
+                torch.cuda.current_stream().wait_event(also_after)
             issue()
 
     def finish_grads(self):

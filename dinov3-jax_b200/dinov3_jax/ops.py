@@ -121,6 +121,23 @@ def layernorm_bwd(dy, x, mean, rstd, scale, dx, dx_add=None, dscale=None, dbias=
     return dx
 
 
+def layernorm_bwd_ls(dy, x, mean, rstd, scale, dx, dx_add=None, dscale=None, dbias=None, *, ls_gamma=None, ls_u=None,
+                     ls_gelu=False, ls_du=None, ls_dgamma=None, ls_dbias=None):
+    """LayerNorm backward + the LayerScale/activation backward of the branch upstream (d3_layernorm_bwd_ls)."""
+    T, D = x.shape
+    assert x.dtype == f32 and dx.dtype == f32 and (ls_du is None or ls_du.dtype == bf16)
+    N.check(N.init().d3_layernorm_bwd_ls(_p(dy), int(dy.dtype == f32), _p(x), _p(mean), _p(rstd), _p(scale), _p(dx_add),
+                                         _p(dx), _p(dscale), _p(dbias), T, D, _p(ls_gamma), _p(ls_u), int(ls_gelu),
+                                         _p(ls_du), _p(ls_dgamma), _p(ls_dbias), _s()), "d3_layernorm_bwd_ls")
+
+
+def ls_gamma_from_wgrad(W, dW, bias, dbias, gamma, dgamma):
+    K, Nn = W.shape
+    assert W.dtype == bf16 and dW.dtype == f32 and W.is_contiguous() and dW.is_contiguous()
+    N.check(N.init().d3_ls_gamma_from_wgrad(_p(W), _p(dW), _p(bias), _p(dbias), _p(gamma), _p(dgamma), K, Nn, _s()),
+            "d3_ls_gamma_from_wgrad")
+
+
 def rope(qkv, sin_t, cos_t, tokens_per_crop, prefix, D, head_dim, inverse=False):
     T = qkv.shape[0]
     assert qkv.dtype == bf16 and qkv.shape[1] == 3 * D and qkv.is_contiguous() and sin_t.dtype == f32

@@ -87,6 +87,20 @@ int d3_layernorm_fwd(const float* x /*[T,D]*/, const float* scale, const float* 
 int d3_layernorm_bwd(const void* dy, int dy_is_f32, const float* x, const float* mean, const float* rstd,
                      const float* scale, const float* dx_add /*residual-stream gradient or NULL*/, float* dx,
                      float* dscale /*[D] += or NULL*/, float* dbias /*[D] +=*/, int T, int D, void* stream);
+/* LayerNorm backward fused with the LayerScale (+GELU) backward of the branch upstream of it
+ * (layers/block.py:198-199 x_out = x_in + gamma * act(u); layers/layer_scale.py:17-21): with dx the row gradient it
+ * has just produced it also writes du = bf16(dx * gamma * act'(u)), ls_dbias += colsum(du) and, when the stash `ls_u`
+ * is given, ls_dgamma += colsum(dx * act(u)) (act = tanh-GELU if ls_gelu else identity).  ls_u == NULL: act =
+ * identity, dgamma comes from d3_ls_gamma_from_wgrad.  ls_gamma == NULL: plain LayerNorm backward.                   */
+int d3_layernorm_bwd_ls(const void* dy, int dy_is_f32, const float* x, const float* mean, const float* rstd,
+                        const float* scale, const float* dx_add, float* dx, float* dscale, float* dbias, int T, int D,
+                        const float* ls_gamma /*[D] or NULL*/, const void* ls_u_bf16 /*[T,D] or NULL*/, int ls_gelu,
+                        void* ls_du_bf16 /*[T,D]*/, float* ls_dgamma /*[D] += or NULL*/, float* ls_dbias /*[D] +=*/,
+                        void* stream);
+/* LayerScale gradient of a linear branch x + gamma * (a W + b) from that layer's weight gradient:
+ * dgamma_j += (sum_i W_ij dW_ij + b_j db_j) / gamma_j   (W bf16 [K,N] as used by the forward, dW fp32 [K,N]).        */
+int d3_ls_gamma_from_wgrad(const void* W_bf16, const float* dW, const float* bias, const float* dbias,
+                           const float* gamma, float* dgamma, int K, int N, void* stream);
 
 /* ---- RoPE (layers/attention.py:14-20,69-90; tables from layers/rope_position_encoding.py:117-123) -----------------
  * in place on the q and k thirds of qkv bf16 [T,3D]; tokens t < prefix of every crop are left untouched.             */

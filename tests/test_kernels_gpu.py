@@ -226,6 +226,70 @@ def test_layernorm_forward_backward(T, D):
     assert rel(dx, xr.grad + add) < 1e-4 and rel(ds, scr.grad) < 1e-4 and rel(db, bir.grad) < 1e-4
 
 
+@pytest.mark.parametrize("T,D", [(1000, 384), (333, 1024), (7, 128), (2051, 768), (301, 1536), (64, 192), (1, 1024)])
+@pytest.mark.parametrize("mode", ["plain", "linear_tail", "gelu_tail", "identity_tail_with_stash"])
+def test_layernorm_backward_with_layerscale_tail(T, D, mode):
+    """d3_layernorm_bwd_ls: LN backward + (optionally) du = dx*gamma*act'(u), dgamma, dbias of the upstream branch."""
+    from dinov3_jax import ops
+    from oracle.model import layer_norm
+    x = torch.randn(T, D, device="cuda") * 2 + 0.5
+    sc, bi = torch.randn(D, device="cuda"), torch.randn(D, device="cuda")
+    y = torch.empty(T, D, device="cuda", dtype=torch.bfloat16)
+    mean, rstd = torch.empty(T, device="cuda"), torch.empty(T, device="cuda")
+    ops.layernorm_fwd(x, sc, bi, y, mean, rstd)
+    xr, scr, bir = x.clone().requires_grad_(True), sc.clone().requires_grad_(True), bi.clone().requires_grad_(True)
+    dy = torch.randn(T, D, device="cuda").to(torch.bfloat16)
+    add = torch.randn(T, D, device="cuda")
+    layer_norm(xr, scr, bir, 1e-6).backward(dy.float())
+    dx_ref = xr.grad + add
+    dx, ds, db = torch.empty(T, D, device="cuda"), torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda")
+    gam = torch.randn(D, device="cuda")
+    ub = torch.randn(T, D, device="cuda").to(torch.bfloat16)
+    du = torch.empty(T, D, device="cuda", dtype=torch.bfloat16)
+    dg, dbl = torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda")
+    kw = {}
+    if mode == "linear_tail":
+        kw = dict(ls_gamma=gam, ls_du=du, ls_dbias=dbl)
+    elif mode == "gelu_tail":
+        kw = dict(ls_gamma=gam, ls_u=ub, ls_gelu=True, ls_du=du, ls_dgamma=dg, ls_dbias=dbl)
+    elif mode == "identity_tail_with_stash":
+        kw = dict(ls_gamma=gam, ls_u=ub, ls_gelu=False, ls_du=du, ls_dgamma=dg, ls_dbias=dbl)
+    ops.layernorm_bwd_ls(dy, x, mean, rstd, sc, dx, dx_add=add, dscale=ds, dbias=db, **kw)
+    assert rel(dx, dx_ref) < 1e-4 and rel(ds, scr.grad) < 1e-4 and rel(db, bir.grad) < 1e-4
+    if mode == "plain":
+        return
+    uu = ub.float()
+    if mode == "gelu_tail":
+        ur = uu.clone().requires_grad_(True)
+        act = torch.nn.functional.gelu(ur, approximate="tanh")
+        act.sum().backward()
+        dact, act = ur.grad, act.detach()
+    else:
+        dact, act = torch.ones_like(uu), uu
+    du_ref = dx_ref * gam * dact
+    assert rel(du, du_ref) < BF16_TOL
+    assert rel(dbl, du.float().sum(0)) < 1e-4          # bias gradient = column sum of the rounded du the wgrad GEMM sees
+    if mode != "linear_tail":
+        assert rel(dg, (dx_ref * act).sum(0)) < 1e-4
+
+
+def test_layerscale_gamma_from_weight_gradient():
+    """dgamma of x + gamma*(a W + b) recovered from dW, db (d3_ls_gamma_from_wgrad) equals the direct column sum."""
+    from dinov3_jax import ops
+    T, K, N = 900, 320, 200
+    a = torch.randn(T, K, device="cuda").to(torch.bfloat16)
+    W = (torch.randn(K, N, device="cuda") / K ** 0.5).to(torch.bfloat16)
+    b, gam = torch.randn(N, device="cuda") * 0.1, torch.randn(N, device="cuda") * 1e-3
+    dx = torch.randn(T, N, device="cuda")
+    du = dx * gam
+    dW = a.float().t() @ du
+    dbias = du.sum(0)
+    want = (dx * (a.float() @ W.float() + b)).sum(0)
+    got = torch.zeros(N, device="cuda")
+    ops.ls_gamma_from_wgrad(W, dW.contiguous(), b, dbias, gam, got)
+    assert rel(got, want) < 1e-4
+
+
 def test_rope_forward_and_adjoint():
     from dinov3_jax import ops
     from oracle.model import rope_apply, rope_sincos
