@@ -199,18 +199,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 // Delta[c,h,q] = sum_d dO[q, h, d] * O[q, h, d]    (backward softmax term)
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ O, const __nv_bfloat16* __restrict__ dO,
                                   float* __restrict__ delta, long T, int N, int D, int H) {
-  const long w = blockIdx.x * (long)(blockDim.x >> 5) + (threadIdx.x >> 5);   // one warp per (row, head)
-  const int lane = threadIdx.x & 31;
-  if (w >= T * H) return;
-  const long row = w / H;
-  const int h = (int)(w % H);
-  const uint32_t a = *reinterpret_cast<const uint32_t*>(O + row * D + h * 64 + lane * 2);
-  const uint32_t b = *reinterpret_cast<const uint32_t*>(dO + row * D + h * 64 + lane * 2);
-  const float2 fa = unpack_bf16(a), fb = unpack_bf16(b);
-  float s = fa.x * fb.x + fa.y * fb.y;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0) delta[((row / N) * H + h) * N + (row % N)] = s;
+  // 8 threads per (row, head): one 16-byte load of O and of dO each, 3 shuffle steps inside the 8-lane group
+  const long g = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  const int per_row = D >> 3;
+  const bool ok = g < T * per_row;
+  float s = 0.f;
+  long row = 0;
+  int c8 = 0;
+  if (ok) {
+    row = g / per_row;
+    c8 = (int)(g % per_row);
+    const uint4 a = *reinterpret_cast<const uint4*>(O + row * D + c8 * 8);
+    const uint4 b = *reinterpret_cast<const uint4*>(dO + row * D + c8 * 8);
+    const float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
+    const float2 b0 = unpack_bf16(b.x), b1 = unpack_bf16(b.y), b2 = unpack_bf16(b.z), b3 = unpack_bf16(b.w);
+    s = a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y + a2.x * b2.x + a2.y * b2.y + a3.x * b3.x + a3.y * b3.y;
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  if (ok && (c8 & 7) == 0) delta[((row / N) * H + (c8 >> 3)) * N + (row % N)] = s;
 }
 
 // ------------------------------------------------------------------------------------------------ backward
@@ -804,9 +812,9 @@ int d3_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* ls
   const long T = (long)n_crops * N;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   {
-    const long warps = T * H;
-    attn_delta_kernel<<<(int)((warps + 7) / 8), 256, 0, st>>>((const __nv_bfloat16*)o, (const __nv_bfloat16*)d_o,
-                                                            delta_scratch, T, N, D, H);
+    const long threads = T * (D / 8);
+    attn_delta_kernel<<<(int)((threads + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)o, (const __nv_bfloat16*)d_o,
+                                                                  delta_scratch, T, N, D, H);
     D3_CHECK_LAUNCH();
   }
   CUtensorMap tqkv, tdo;

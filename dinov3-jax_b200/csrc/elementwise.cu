@@ -594,20 +594,34 @@ ln_bwd_ring_kernel(const InT* __restrict__ dy, const float* __restrict__ x, cons
 __global__ void ls_gamma_from_wgrad_kernel(const __nv_bfloat16* __restrict__ W, const float* __restrict__ dW,
                                            const float* __restrict__ bias, const float* __restrict__ dbias,
                                            const float* __restrict__ gamma, float* __restrict__ dgamma, int K, int N) {
-  __shared__ float acc[8][33];
-  const int col = blockIdx.x * 32 + (threadIdx.x & 31), wy = threadIdx.x >> 5;
-  float s = 0.f;
-  if (col < N)
-    for (int i = wy; i < K; i += 8) s += __bfloat162float(W[(long)i * N + col]) * dW[(long)i * N + col];
-  acc[wy][threadIdx.x & 31] = s;
+  // grid (N / 64, K-slabs): a thread owns two adjacent columns of a slab of rows; the 8 warps of the CTA interleave rows
+  __shared__ float acc[8][64];
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  const int col = blockIdx.x * 64 + lane * 2;
+  const int slab = (K + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * slab, r1 = min(K, r0 + slab);
+  float s0 = 0.f, s1 = 0.f;
+  if (col + 1 < N) {
+    for (int i = r0 + wy; i < r1; i += 8) {
+      const float2 w = unpack_bf16(*reinterpret_cast<const uint32_t*>(W + (long)i * N + col));
+      const float2 g = *reinterpret_cast<const float2*>(dW + (long)i * N + col);
+      s0 += w.x * g.x; s1 += w.y * g.y;
+    }
+  } else if (col < N) {
+    for (int i = r0 + wy; i < r1; i += 8) s0 += __bfloat162float(W[(long)i * N + col]) * dW[(long)i * N + col];
+  }
+  acc[wy][lane * 2] = s0; acc[wy][lane * 2 + 1] = s1;
   __syncthreads();
-  if (wy == 0 && col < N) {
-    float tot = 0.f;
+  if (threadIdx.x < 64) {
+    const int c = blockIdx.x * 64 + threadIdx.x;
+    if (c < N) {
+      float tot = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) tot += acc[k][threadIdx.x];
-    const float g = gamma[col];
-    tot += bias[col] * dbias[col];
-    dgamma[col] += (g != 0.f) ? tot / g : 0.f;
+      for (int k = 0; k < 8; ++k) tot += acc[k][threadIdx.x];
+      if (blockIdx.y == 0) tot += bias[c] * dbias[c];
+      const float g = gamma[c];
+      if (g != 0.f) atomicAdd(&dgamma[c], tot / g);
+    }
   }
 }
 
@@ -979,8 +993,9 @@ int d3_layernorm_bwd_ls(const void* dy, int dy_is_f32, const float* x, const flo
 int d3_ls_gamma_from_wgrad(const void* W, const float* dW, const float* bias, const float* dbias, const float* gamma,
                            float* dgamma, int K, int N, void* stream) {
   if (K <= 0 || N <= 0) return D3_OK;
-  ls_gamma_from_wgrad_kernel<<<(N + 31) / 32, 256, 0, STREAM(stream)>>>((const __nv_bfloat16*)W, dW, bias, dbias, gamma,
-                                                                      dgamma, K, N);
+  if (N % 2) return set_error(D3_ERR_ARG, "d3_ls_gamma_from_wgrad: N must be even");
+  dim3 grid((N + 63) / 64, max(1, min(32, K / 32)));
+  ls_gamma_from_wgrad_kernel<<<grid, 256, 0, STREAM(stream)>>>((const __nv_bfloat16*)W, dW, bias, dbias, gamma, dgamma, K, N);
   D3_CHECK_LAUNCH();
   return D3_OK;
 }

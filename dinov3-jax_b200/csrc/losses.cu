@@ -41,6 +41,10 @@ __device__ __forceinline__ float block_max(float v, float* sh) {
   __syncthreads();
   return sh[0];
 }
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
 __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
   // ordered-int trick; *addr must be initialised to -inf
   if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
@@ -177,6 +181,124 @@ ce_fwd_bwd_kernel(const float* __restrict__ S, float inv_ts, const float* __rest
   if (threadIdx.x == 0) atomicAdd(&metric[slot[i]], wm[i] * loss);
 }
 
+
+// ---- 128-bit versions used when K % 4 == 0 and the rows are 16-byte aligned (every recipe: K = 65536) --------------
+__global__ void absmax_vec_kernel(const float4* __restrict__ L, long n4, float* __restrict__ out) {
+  __shared__ float sh[32];
+  float m = -CUDART_INF_F;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    const float4 v = L[i];
+    m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+  }
+  m = block_max(m, sh);
+  if (threadIdx.x == 0) atomic_max_float(out, m);
+}
+__global__ void sk_colsum_vec_kernel(const float* __restrict__ L, const float* __restrict__ mx, float inv_temp,
+                                     const float* __restrict__ a, float* __restrict__ s, int R, int K) {
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int slab = (R + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * slab, r1 = min(R, r0 + slab);
+  if (k >= K) return;
+  const float c = inv_temp * 1.4426950408889634f, mc = *mx * c;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int b = r0; b < r1; ++b) {
+    const float4 v = *reinterpret_cast<const float4*>(L + (long)b * K + k);
+    const float w = a ? a[b] : 1.f;
+    acc.x += exp2f(v.x * c - mc) * w; acc.y += exp2f(v.y * c - mc) * w;
+    acc.z += exp2f(v.z * c - mc) * w; acc.w += exp2f(v.w * c - mc) * w;
+  }
+  atomicAdd(&s[k], acc.x); atomicAdd(&s[k + 1], acc.y); atomicAdd(&s[k + 2], acc.z); atomicAdd(&s[k + 3], acc.w);
+}
+__global__ void sk_rowsum_vec_kernel(const float* __restrict__ L, const float* __restrict__ mx, float inv_temp,
+                                     const float* __restrict__ s, const float* __restrict__ btot, float* __restrict__ a,
+                                     int R, int K) {
+  __shared__ float sh[32];
+  const int b = blockIdx.x;
+  const float c = inv_temp * 1.4426950408889634f, mc = *mx * c;
+  const float4* Lb = reinterpret_cast<const float4*>(L + (long)b * K);
+  const float4* s4 = reinterpret_cast<const float4*>(s);
+  float acc = 0.f;
+#pragma unroll 4
+  for (int k = threadIdx.x; k < K / 4; k += blockDim.x) {
+    const float4 v = Lb[k], sv = s4[k];
+    acc += __fdividef(exp2f(v.x * c - mc), sv.x) + __fdividef(exp2f(v.y * c - mc), sv.y) +
+           __fdividef(exp2f(v.z * c - mc), sv.z) + __fdividef(exp2f(v.w * c - mc), sv.w);
+  }
+  acc = block_sum(acc, sh) / (float)K;
+  if (threadIdx.x == 0) a[b] = 1.f / (*btot * acc);
+}
+
+// vectorised cross-entropy: same contract as ce_fwd_bwd_kernel; the second pass re-reads the student row from L2
+__global__ void __launch_bounds__(512)
+ce_fwd_bwd_vec_kernel(const float* __restrict__ S, float inv_ts, const float* __restrict__ Lt,
+                      const float* __restrict__ mx, float inv_tt, const float* __restrict__ s_t,
+                      const float* __restrict__ a_t, const float* __restrict__ btot, const int* __restrict__ t0,
+                      const int* __restrict__ t1, const float* __restrict__ wm, const float* __restrict__ wg,
+                      const int* __restrict__ slot, float* __restrict__ metric, __nv_bfloat16* __restrict__ dS, int K) {
+  __shared__ float sh[32];
+  const int i = blockIdx.x;
+  const int K4 = K >> 2;
+  const float LOG2E = 1.4426950408889634f;
+  const float4* Si = reinterpret_cast<const float4*>(S + (long)i * K);
+  const float cs = inv_ts * LOG2E;
+  // online max / sum of 2^(cs * s) per thread, one float4 at a time
+  float m = -CUDART_INF_F, z = 0.f;
+#pragma unroll 2
+  for (int k = threadIdx.x; k < K4; k += blockDim.x) {
+    const float4 v = Si[k];
+    const float m4 = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)) * cs;
+    if (m4 > m) { z *= exp2f(m - m4); m = m4; }
+    z += exp2f(v.x * cs - m) + exp2f(v.y * cs - m) + exp2f(v.z * cs - m) + exp2f(v.w * cs - m);
+  }
+  const float gm = block_max(m, sh);
+  z = block_sum(z * exp2f(m - gm), sh);
+  const float lse2 = gm + log2f(z);                 // log2-domain logsumexp of the scaled row
+  const int p0 = t0[i], p1 = t1[i];
+  const float np = (p0 >= 0 ? 1.f : 0.f) + (p1 >= 0 ? 1.f : 0.f);
+  const float ct = inv_tt * LOG2E;
+  const float mt = s_t ? *mx * ct : 0.f, bt = s_t ? *btot : 1.f;
+  const float invK = 1.f / (float)K;
+  const float c0 = (s_t && p0 >= 0) ? bt * a_t[p0] * invK : 0.f;
+  const float c1 = (s_t && p1 >= 0) ? bt * a_t[p1] * invK : 0.f;
+  const float4* L0 = reinterpret_cast<const float4*>(Lt + (long)(p0 >= 0 ? p0 : 0) * K);
+  const float4* L1 = reinterpret_cast<const float4*>(Lt + (long)(p1 >= 0 ? p1 : 0) * K);
+  const float4* st4 = reinterpret_cast<const float4*>(s_t);
+  const float g = wg[i] * inv_ts;
+  const float LN2 = 0.6931471805599453f;
+  uint2* dSi = dS ? reinterpret_cast<uint2*>(dS + (long)i * K) : nullptr;
+  float loss = 0.f;
+#pragma unroll 2
+  for (int k = threadIdx.x; k < K4; k += blockDim.x) {
+    const float4 v = Si[k];
+    const float l2[4] = {v.x * cs - lse2, v.y * cs - lse2, v.z * cs - lse2, v.w * cs - lse2};   // log2 softmax
+    float q[4] = {0.f, 0.f, 0.f, 0.f};
+    if (s_t) {
+      const float4 sv = st4[k];
+      const float r[4] = {__fdividef(1.f, sv.x), __fdividef(1.f, sv.y), __fdividef(1.f, sv.z), __fdividef(1.f, sv.w)};
+      if (p0 >= 0) {
+        const float4 t = L0[k];
+        q[0] += c0 * exp2f(t.x * ct - mt) * r[0]; q[1] += c0 * exp2f(t.y * ct - mt) * r[1];
+        q[2] += c0 * exp2f(t.z * ct - mt) * r[2]; q[3] += c0 * exp2f(t.w * ct - mt) * r[3];
+      }
+      if (p1 >= 0) {
+        const float4 t = L1[k];
+        q[0] += c1 * exp2f(t.x * ct - mt) * r[0]; q[1] += c1 * exp2f(t.y * ct - mt) * r[1];
+        q[2] += c1 * exp2f(t.z * ct - mt) * r[2]; q[3] += c1 * exp2f(t.w * ct - mt) * r[3];
+      }
+    } else {
+      if (p0 >= 0) { const float4 t = L0[k]; q[0] += t.x; q[1] += t.y; q[2] += t.z; q[3] += t.w; }
+      if (p1 >= 0) { const float4 t = L1[k]; q[0] += t.x; q[1] += t.y; q[2] += t.z; q[3] += t.w; }
+    }
+    loss -= (q[0] * l2[0] + q[1] * l2[1] + q[2] * l2[2] + q[3] * l2[3]) * LN2;
+    if (dSi)
+      dSi[k] = make_uint2(pack2(g * (np * exp2f(l2[0]) - q[0]), g * (np * exp2f(l2[1]) - q[1])),
+                          pack2(g * (np * exp2f(l2[2]) - q[2]), g * (np * exp2f(l2[3]) - q[3])));
+  }
+  loss = block_sum(loss, sh);
+  if (threadIdx.x == 0) atomicAdd(&metric[slot[i]], wm[i] * loss);
+}
+
 // ------------------------------------------------------------------------------------------------ KoLeo
 // loss/koleo_loss.py:16-35:  xn = x/(||x||+eps); nn(i) = argmax_{j!=i} xn_i.xn_j; L = -mean_i log(||xn_i - xn_nn(i)|| + 2 eps)
 __global__ void koleo_norm_kernel(const float* __restrict__ x, float* __restrict__ xn, float* __restrict__ nrm, int D,
@@ -260,22 +382,36 @@ extern "C" {
 
 int d3_absmax(const float* L, long long n, float* out /* pre-set to -inf */, void* stream) {
   if (n <= 0) return D3_OK;
-  absmax_kernel<<<(int)min((n + 1023) / 1024, (long long)sm_count() * 8), 256, 0, STREAM(stream)>>>(L, n, out);
+  if (n % 4 == 0 && (uintptr_t)L % 16 == 0)
+    absmax_vec_kernel<<<(int)min((n / 4 + 1023) / 1024, (long long)sm_count() * 8), 256, 0, STREAM(stream)>>>(
+        reinterpret_cast<const float4*>(L), n / 4, out);
+  else
+    absmax_kernel<<<(int)min((n + 1023) / 1024, (long long)sm_count() * 8), 256, 0, STREAM(stream)>>>(L, n, out);
   D3_CHECK_LAUNCH();
   return D3_OK;
 }
 int d3_sinkhorn_colsum(const float* L, const float* mx, float temp, const float* a, float* s /* zeroed */, int R, int K,
                        void* stream) {
   if (R <= 0) return D3_OK;
-  dim3 grid((K + 255) / 256, max(1, min(R / 8, 64)));
-  sk_colsum_kernel<<<grid, 256, 0, STREAM(stream)>>>(L, mx, 1.f / temp, a, s, R, K);
+  if (K % 4 == 0 && (uintptr_t)L % 16 == 0) {
+    // (K/4)/128 column CTAs x row slabs: aim at ~8 CTAs per SM
+    const int cx = (K / 4 + 127) / 128;
+    dim3 grid(cx, max(1, min(R / 8, max(1, sm_count() * 8 / cx))));
+    sk_colsum_vec_kernel<<<grid, 128, 0, STREAM(stream)>>>(L, mx, 1.f / temp, a, s, R, K);
+  } else {
+    dim3 grid((K + 255) / 256, max(1, min(R / 8, 64)));
+    sk_colsum_kernel<<<grid, 256, 0, STREAM(stream)>>>(L, mx, 1.f / temp, a, s, R, K);
+  }
   D3_CHECK_LAUNCH();
   return D3_OK;
 }
 int d3_sinkhorn_rowsum(const float* L, const float* mx, float temp, const float* s, const float* btot, float* a, int R,
                        int K, void* stream) {
   if (R <= 0) return D3_OK;
-  sk_rowsum_kernel<<<R, 256, 0, STREAM(stream)>>>(L, mx, 1.f / temp, s, btot, a, R, K);
+  if (K % 4 == 0 && ((uintptr_t)L | (uintptr_t)s) % 16 == 0)
+    sk_rowsum_vec_kernel<<<R, 256, 0, STREAM(stream)>>>(L, mx, 1.f / temp, s, btot, a, R, K);
+  else
+    sk_rowsum_kernel<<<R, 256, 0, STREAM(stream)>>>(L, mx, 1.f / temp, s, btot, a, R, K);
   D3_CHECK_LAUNCH();
   return D3_OK;
 }
@@ -305,8 +441,12 @@ int d3_ce_fwd_bwd(const float* S, float student_temp, const float* Lt, const flo
                   const float* s_t, const float* a_t, const float* btot, const int* t0, const int* t1, const float* wm,
                   const float* wg, const int* slot, float* metric, void* dS, int Rs, int K, void* stream) {
   if (Rs <= 0) return D3_OK;
-  ce_fwd_bwd_kernel<<<Rs, 256, 0, STREAM(stream)>>>(S, 1.f / student_temp, Lt, mx, 1.f / teacher_temp, s_t, a_t, btot, t0,
-                                                   t1, wm, wg, slot, metric, (__nv_bfloat16*)dS, K);
+  if (K % 4 == 0 && ((uintptr_t)S | (uintptr_t)Lt | (uintptr_t)s_t | (uintptr_t)dS) % 16 == 0)
+    ce_fwd_bwd_vec_kernel<<<Rs, 512, 0, STREAM(stream)>>>(S, 1.f / student_temp, Lt, mx, 1.f / teacher_temp, s_t, a_t, btot,
+                                                         t0, t1, wm, wg, slot, metric, (__nv_bfloat16*)dS, K);
+  else
+    ce_fwd_bwd_kernel<<<Rs, 256, 0, STREAM(stream)>>>(S, 1.f / student_temp, Lt, mx, 1.f / teacher_temp, s_t, a_t, btot, t0,
+                                                     t1, wm, wg, slot, metric, (__nv_bfloat16*)dS, K);
   D3_CHECK_LAUNCH();
   return D3_OK;
 }

@@ -46,3 +46,21 @@ cs = torch.zeros(3 * D, device=dev); q = torch.randn(T, 3 * D, device=dev).to(bf
 timeit("colsum_bf16 [T,3D]", lambda: ops.colsum_bf16(q, cs), TD * 3 * 2)
 h = torch.randn(T, 4 * D, device=dev).to(bf); cs4 = torch.zeros(4 * D, device=dev)
 timeit("colsum_bf16 [T,4D]", lambda: ops.colsum_bf16(h, cs4), TD * 4 * 2)
+
+# ---- head / loss kernels at the iBOT shape (M = 3771 masked tokens, K = 65536 prototypes)
+if len(sys.argv) <= 2:
+    M, K = 3771, 65536
+    Lt = torch.randn(M, K, device=dev) * 0.3; S = torch.randn(M, K, device=dev)
+    mx = torch.full((1,), float("-inf"), device=dev); sv = torch.zeros(K, device=dev); a = torch.ones(M, device=dev)
+    btot = torch.full((1,), float(M), device=dev)
+    MK = M * K
+    print(f"M={M} K={K}")
+    timeit("absmax", lambda: ops.absmax(Lt, mx), MK * 4)
+    timeit("sinkhorn_colsum", lambda: ops.sinkhorn_colsum(Lt, mx, 0.05, a, sv), MK * 4)
+    sv.fill_(1.0)
+    timeit("sinkhorn_rowsum", lambda: ops.sinkhorn_rowsum(Lt, mx, 0.05, sv, btot, a), MK * 4)
+    t0 = torch.arange(M, device=dev, dtype=torch.int32); t1 = torch.full((M,), -1, device=dev, dtype=torch.int32)
+    wm = torch.ones(M, device=dev); wg = torch.ones(M, device=dev); slot = torch.zeros(M, device=dev, dtype=torch.int32)
+    metric = torch.zeros(8, device=dev); dS = torch.empty(M, K, device=dev, dtype=bf)
+    timeit("ce_fwd_bwd (iBOT: 1 teacher row per student row)", lambda: ops.ce_fwd_bwd(S, 0.1, Lt, mx, 0.05, sv, a, btot, t0, t1, wm, wg, slot, metric, dS), MK * (4 + 4 + 2))
+    dOo = torch.randn(T, D, device=dev).to(bf); dl = torch.empty(T // 197, 16, 197, device=dev)
