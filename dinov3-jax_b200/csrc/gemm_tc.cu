@@ -488,15 +488,45 @@ struct Cfg2 {
   static constexpr int TMEM_COLS = 512;
   static constexpr int STG_WARP = 2 * (4096 + 2048);           // per epilogue warp: two (out tile + aux tile) buffers
   static constexpr int STG_BYTES = TMA_EPI ? EPI_WARPS * STG_WARP : 0;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024 + 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024 + 256 + 256;   // + CLC ring
 };
 
-template <int A_MN, int B_MN, int TMA_EPI>
+// Dynamic tile scheduling (SCHED = 1): the grid has one cluster per work item; a resident cluster finishes its own item
+// and then takes over not-yet-launched clusters with clusterlaunchcontrol.try_cancel, so work follows whichever SMs are
+// actually free (NCCL or the other stream's kernels may hold some) instead of a static stride that leaves a late
+// cluster with a full share.  One scheduler warp in the leader CTA issues the queries; the 16-byte responses are
+// multicast into a small ring in both CTAs and consumed by every role (TMA producers, MMA issuer, epilogue warps).
+__device__ int g_gemm_stagger_ns = 0;   // optional de-phasing of the clusters' tile loops (D3_GEMM_STAGGER_NS)
+constexpr int CLC_STAGES = 4;
+struct ClcRing {
+  uint8_t* resp;      // [CLC_STAGES][16]
+  uint64_t* full;     // [CLC_STAGES] local: 1 arrival (expect_tx) + 16 transaction bytes
+  uint64_t* empty;    // [CLC_STAGES] in the leader CTA: one arrival per consumer role of both CTAs
+  uint32_t it;
+};
+constexpr int CLC_CONSUMERS = 2 /*TMA producers*/ + 1 /*MMA issuer*/ + 2 * EPI_WARPS;
+// next work index for a consumer role.  WARP = true: called by all 32 lanes of a warp (lane 0 releases the slot after
+// every lane has read it); WARP = false: called by a single elected thread.
+template <bool WARP>
+__device__ __forceinline__ int clc_next(ClcRing& r, bool arrive) {
+  const uint32_t slot = r.it % CLC_STAGES, ph = (r.it / CLC_STAGES) & 1;
+  mbar_wait(&r.full[slot], ph);
+  uint32_t x;
+  const bool valid = clc_query(r.resp + slot * 16, x);
+  fence_proxy_async_smem();
+  if (WARP) __syncwarp();
+  if (arrive) mbar_arrive_cluster(&r.empty[slot], 0);
+  ++r.it;
+  return valid ? (int)(x >> 1) : -1;
+}
+
+template <int A_MN, int B_MN, int TMA_EPI, int SCHED>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAux,
                const __grid_constant__ CUtensorMap tmRes, const GemmEpilogue ep, int M, int N, int K, int splits) {
   using Cfg = Cfg2<TMA_EPI>;
+  static_assert(2 * Cfg::STAGES + 4 + 2 * EPI_WARPS + 1 <= 40, "barrier block");
   constexpr int BN = Cfg::BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -508,6 +538,9 @@ gemm2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tempty_bar = bars + 2 * Cfg::STAGES + 2;  // leader: 2 x EPI_WARPS arrivals
   uint64_t* ld_bar = bars + 2 * Cfg::STAGES + 4;      // [2 * EPI_WARPS] epilogue TMA loads (residual / GELU' operand)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4 + 2 * EPI_WARPS);
+  uint64_t* clc_full = bars + 40;
+  uint64_t* clc_empty = clc_full + CLC_STAGES;
+  uint8_t* clc_resp = reinterpret_cast<uint8_t*>(clc_empty + CLC_STAGES);      // 16-byte aligned (bars is 1024-aligned)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -520,6 +553,7 @@ gemm2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 2 * EPI_WARPS); }
     for (int s = 0; s < 2 * EPI_WARPS; ++s) mbar_init(&ld_bar[s], 1);
+    if (SCHED) for (int s = 0; s < CLC_STAGES; ++s) { mbar_init(&clc_full[s], 1); mbar_init(&clc_empty[s], CLC_CONSUMERS); }
     if (TMA_EPI) { tma_prefetch_desc(&tmOut); tma_prefetch_desc(&tmAux); tma_prefetch_desc(&tmRes); }
     fence_mbar_init();
   }
@@ -540,7 +574,9 @@ gemm2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = cluster_id; w < num_work; w += num_clusters) {
+      ClcRing ring{clc_resp, clc_full, clc_empty, 0};
+      if (g_gemm_stagger_ns > 0 && num_work > num_clusters) __nanosleep((unsigned)(cluster_id * g_gemm_stagger_ns));
+      for (int w = cluster_id; w >= 0 && w < num_work; w = SCHED ? clc_next<false>(ring, true) : w + num_clusters) {
         const WorkRange wr = work_item(w, num_m, num_n, num_k, splits, 256, BN, ep.flags & EP_M_FASTEST);
         const int m0 = wr.m0 + rank * 128;     // this CTA's 128 A rows
         const int n0 = wr.n0 + rank * 128;     // this CTA's half of the B tile
@@ -575,7 +611,8 @@ gemm2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
-      for (int w = cluster_id; w < num_work; w += num_clusters, ++local) {
+      ClcRing ring{clc_resp, clc_full, clc_empty, 0};
+      for (int w = cluster_id; w >= 0 && w < num_work; w = SCHED ? clc_next<false>(ring, true) : w + num_clusters, ++local) {
         const WorkRange wr = work_item(w, num_m, num_n, num_k, splits, 256, BN, ep.flags & EP_M_FASTEST);
         const int acc = local & 1;
         const uint32_t acc_phase = (local >> 1) & 1;
@@ -600,6 +637,20 @@ gemm2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     __syncwarp();
+  } else if (SCHED && warp == 3) {
+    if (leader) {
+      for (uint32_t it = 0;; ++it) {
+        const uint32_t slot = it % CLC_STAGES, ph = (it / CLC_STAGES) & 1;
+        if (it >= CLC_STAGES) mbar_wait(&clc_empty[slot], ph ^ 1);          // every consumer has read the old response
+        if (lane < 2) mbar_arrive_expect_tx_cluster(&clc_full[slot], lane, 16);
+        __syncwarp();
+        if (lane == 0) clc_try_cancel_multicast(clc_resp + slot * 16, &clc_full[slot]);
+        mbar_wait(&clc_full[slot], ph);
+        uint32_t x;
+        if (!clc_query(clc_resp + slot * 16, x)) break;                     // nothing left: no further queries allowed
+      }
+    }
+    __syncwarp();
   } else if (warp >= 4) {
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;
@@ -610,7 +661,8 @@ gemm2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     pp.unit = 0;
     constexpr bool tma_epi = TMA_EPI != 0;
     int local = 0;
-    for (int w = cluster_id; w < num_work; w += num_clusters, ++local) {
+    ClcRing ring{clc_resp, clc_full, clc_empty, 0};
+    for (int w = cluster_id; w >= 0 && w < num_work; w = SCHED ? clc_next<true>(ring, lane == 0) : w + num_clusters, ++local) {
       const WorkRange wr = work_item(w, num_m, num_n, num_k, splits, 256, BN, ep.flags & EP_M_FASTEST);
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
@@ -678,17 +730,17 @@ static int launch1(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilo
 
 struct EpiMaps { CUtensorMap out, aux, res; };
 
-template <int A_MN, int B_MN, int TMA_EPI>
+template <int A_MN, int B_MN, int TMA_EPI, int SCHED>
 static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, const GemmEpilogue& ep, int M, int N,
                    int K, int splits, cudaStream_t stream) {
   using Cfg2 = Cfg2<TMA_EPI>;
-  auto kern = gemm2sm_kernel<A_MN, B_MN, TMA_EPI>;
+  auto kern = gemm2sm_kernel<A_MN, B_MN, TMA_EPI, SCHED>;
   static bool configured = false;
   int rc = configure_once(kern, Cfg2::SMEM_BYTES, &configured);
   if (rc) return rc;
   const int work = ((M + 255) / 256) * ((N + 255) / 256) * splits;
   const int max_clusters = sm_count() / 2;
-  const int clusters = work < max_clusters ? work : max_clusters;
+  const int clusters = SCHED ? work : (work < max_clusters ? work : max_clusters);
   kern<<<2 * clusters, GEMM_THREADS, Cfg2::SMEM_BYTES, stream>>>(ta, tb, em.out, em.aux, em.res, ep, M, N, K, splits);
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) return set_error(D3_ERR_CUDA, cudaGetErrorString(e));
@@ -704,18 +756,38 @@ static int dispatch1(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMa
   if (a_mn && !b_mn) return launch1<BN, 1, 0>(ta, tb, ep, M, N, K, splits, s);
   return launch1<BN, 1, 1>(ta, tb, ep, M, N, K, splits, s);
 }
+static void apply_stagger_env() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  const char* e = getenv("D3_GEMM_STAGGER_NS");
+  const int ns = e ? atoi(e) : 0;
+  if (ns > 0) cudaMemcpyToSymbol(g_gemm_stagger_ns, &ns, sizeof(ns));
+}
+static bool clc_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("D3_GEMM_CLC"); v = (e && e[0] == '1') ? 1 : 0; }   // measured slower in-step: opt-in
+  return v == 1;
+}
+template <int SCHED>
+static int dispatch2s(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em,
+                      const GemmEpilogue& ep, int M, int N, int K, int splits, cudaStream_t s) {
+  if (ep.flags & EP_TMA_EPI) {
+    if (!a_mn && !b_mn) return launch2<0, 0, 1, SCHED>(ta, tb, em, ep, M, N, K, splits, s);
+    if (!a_mn && b_mn) return launch2<0, 1, 1, SCHED>(ta, tb, em, ep, M, N, K, splits, s);
+    if (a_mn && !b_mn) return launch2<1, 0, 1, SCHED>(ta, tb, em, ep, M, N, K, splits, s);
+    return launch2<1, 1, 1, SCHED>(ta, tb, em, ep, M, N, K, splits, s);
+  }
+  if (!a_mn && !b_mn) return launch2<0, 0, 0, SCHED>(ta, tb, em, ep, M, N, K, splits, s);
+  if (!a_mn && b_mn) return launch2<0, 1, 0, SCHED>(ta, tb, em, ep, M, N, K, splits, s);
+  if (a_mn && !b_mn) return launch2<1, 0, 0, SCHED>(ta, tb, em, ep, M, N, K, splits, s);
+  return launch2<1, 1, 0, SCHED>(ta, tb, em, ep, M, N, K, splits, s);
+}
 static int dispatch2(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em,
                      const GemmEpilogue& ep, int M, int N, int K, int splits, cudaStream_t s) {
-  if (ep.flags & EP_TMA_EPI) {
-    if (!a_mn && !b_mn) return launch2<0, 0, 1>(ta, tb, em, ep, M, N, K, splits, s);
-    if (!a_mn && b_mn) return launch2<0, 1, 1>(ta, tb, em, ep, M, N, K, splits, s);
-    if (a_mn && !b_mn) return launch2<1, 0, 1>(ta, tb, em, ep, M, N, K, splits, s);
-    return launch2<1, 1, 1>(ta, tb, em, ep, M, N, K, splits, s);
-  }
-  if (!a_mn && !b_mn) return launch2<0, 0, 0>(ta, tb, em, ep, M, N, K, splits, s);
-  if (!a_mn && b_mn) return launch2<0, 1, 0>(ta, tb, em, ep, M, N, K, splits, s);
-  if (a_mn && !b_mn) return launch2<1, 0, 0>(ta, tb, em, ep, M, N, K, splits, s);
-  return launch2<1, 1, 0>(ta, tb, em, ep, M, N, K, splits, s);
+  apply_stagger_env();
+  return clc_enabled() ? dispatch2s<1>(a_mn, b_mn, ta, tb, em, ep, M, N, K, splits, s)
+                       : dispatch2s<0>(a_mn, b_mn, ta, tb, em, ep, M, N, K, splits, s);
 }
 
 // tile_n: 0 = auto; 64/128/256 force the single-CTA kernel with that tile; 512 forces the CTA-pair kernel.

@@ -239,6 +239,41 @@ __device__ __forceinline__ float gelu_tanh_grad_fast(float u) {
   return 0.5f * (1.0f + t) + 0.5f * u * (1.0f - t * t) * dz;
 }
 
+
+// ------------------------------------------------------------------ cluster launch control (dynamic tile scheduling)
+// arrive + expect_tx on the mbarrier at the same offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint64_t* bar, uint32_t cta, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.expect_tx.shared::cluster.b64 _, [ra], %2;\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta), "r"(bytes)
+      : "memory");
+}
+// Try to cancel the launch of a not-yet-started cluster of this grid; the 16-byte response is written to `resp` and
+// 16 transaction bytes are completed on `bar`, at the same shared-memory offsets in EVERY CTA of the cluster.
+__device__ __forceinline__ void clc_try_cancel_multicast(void* resp, uint64_t* bar) {
+  asm volatile(
+      "clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.multicast::cluster::all.b128 [%0], [%1];"
+      ::"r"(smem_u32(resp)), "r"(smem_u32(bar))
+      : "memory");
+}
+// Decode a response: true + ctaid.x of the first CTA of the cancelled cluster, or false when nothing was left to cancel.
+__device__ __forceinline__ bool clc_query(const void* resp, uint32_t& ctaid_x) {
+  uint32_t valid = 0, x = 0;
+  asm volatile(
+      "{\n\t.reg .pred p1;\n\t.reg .b128 r;\n\t"
+      "ld.shared.b128 r, [%2];\n\t"
+      "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, r;\n\t"
+      "selp.u32 %1, 1, 0, p1;\n\t"
+      "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid.v4.b32.b128 {%0, _, _, _}, r;\n\t}"
+      : "+r"(x), "=r"(valid)
+      : "r"(smem_u32(resp))
+      : "memory");
+  ctaid_x = x;
+  return valid != 0;
+}
+
 // ------------------------------------------------------------------ math helpers
 __device__ __forceinline__ float gelu_tanh(float u) {
   // 0.5 u (1 + tanh(sqrt(2/pi)(u + 0.044715 u^3)))  -- flax.linen.gelu(approximate=True)
