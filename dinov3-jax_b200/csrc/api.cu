@@ -68,7 +68,7 @@ using namespace d3;
 
 extern "C" {
 
-int d3_abi_version(void) { return 1; }
+int d3_abi_version(void) { return 2; }   // 2: d3_gemm_epilogue gained the sc_* scatter fields
 int d3_set_sm_limit(int n) {
   if (n < 0) return set_error(D3_ERR_ARG, "d3_set_sm_limit: n < 0");
   g_sm_limit = n & ~1;   // CTA pairs: keep it even
@@ -113,7 +113,12 @@ int d3_gemm_bf16(const void* A, int lda, int a_major, const void* B, int ldb, in
   g.aux_in = reinterpret_cast<const __nv_bfloat16*>(ep->aux_in);
   g.aux_out = reinterpret_cast<__nv_bfloat16*>(ep->aux_out);
   g.out = ep->out; g.ld_out = ep->ld_out; g.ld_aux = ep->ld_aux; g.ld_resid = ep->ld_resid;
-  g.flags = ep->flags & 0xFF; g.alpha = ep->alpha;
+  g.flags = ep->flags & 0x1FF; g.alpha = ep->alpha;
+  for (int i = 0; i < 8; ++i) g.sc_peer[i] = ep->sc_peer[i];
+  g.sc_off = ep->sc_off; g.sc_shard = ep->sc_shard; g.sc_world = ep->sc_world;
+  if (g.flags & EP_SCATTER)
+    for (int i = 0; i < g.sc_world && i < 8; ++i)
+      if (!g.sc_peer[i]) return set_error(D3_ERR_ARG, "scatter flag without peer pointers");
   if ((g.flags & EP_BIAS) && !g.bias) return set_error(D3_ERR_ARG, "bias flag without pointer");
   if ((g.flags & EP_GAMMA) && !g.gamma) return set_error(D3_ERR_ARG, "gamma flag without pointer");
   if ((g.flags & EP_RESID) && !g.resid) return set_error(D3_ERR_ARG, "resid flag without pointer");

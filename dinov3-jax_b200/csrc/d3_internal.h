@@ -18,6 +18,7 @@ enum : int {
   EP_RESID = D3_EP_RESID,
   EP_OUT_F32 = D3_EP_OUT_F32,
   EP_ACCUM = D3_EP_ACCUM,
+  EP_SCATTER = D3_EP_SCATTER,
   EP_SLOW = 1 << 30,      // internal: force the bounds-checked scalar epilogue
   EP_ATOMIC = 1 << 29,    // internal: split-K partial sums, fp32 atomic reduction into out
   EP_DEBUG_NOSTORE = 1 << 27,  // internal (D3_GEMM_DEBUG=1): skip epilogue global traffic
@@ -36,6 +37,12 @@ struct GemmEpilogue {
   int ld_out, ld_aux, ld_resid;
   int flags;
   float alpha;
+  // EP_SCATTER: the fp32 result is not stored at `out` but added (red.add over NVLink peer mappings) into the rank
+  // that owns it: element e of the output ([row*ld_out + col]) has global index g = sc_off + e inside a flat range cut
+  // into sc_world slices of sc_shard elements; it goes to sc_peer[g / sc_shard][g % sc_shard].
+  float* sc_peer[8];
+  long long sc_off;
+  int sc_shard, sc_world;
 };
 
 int set_error(int code, const char* msg);

@@ -806,6 +806,22 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat1
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ peer reduce-scatter
+// Push-style reduce-scatter of a flat fp32 gradient range over NVLink peer mappings (replaces psum_scatter / pmean,
+// fsdp/utils.py:61-64,108): element g of src (g = off + i) is added, scaled by alpha, into rank g / shard's slice.
+struct PeerPtrs { float* p[8]; };
+__global__ void scatter_add_peers_kernel(const float* __restrict__ src, long n4, PeerPtrs peers, unsigned long long off,
+                                         unsigned shard, float alpha) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    const unsigned long long g = off + (unsigned long long)i * 4;
+    const unsigned r = (unsigned)(g / shard);
+    atomicAdd(reinterpret_cast<float4*>(peers.p[r] + (g - (unsigned long long)r * shard)),
+              make_float4(v.x * alpha, v.y * alpha, v.z * alpha, v.w * alpha));
+  }
+}
+
 }  // namespace d3
 
 using namespace d3;
@@ -996,6 +1012,21 @@ int d3_ls_gamma_from_wgrad(const void* W, const float* dW, const float* bias, co
   if (N % 2) return set_error(D3_ERR_ARG, "d3_ls_gamma_from_wgrad: N must be even");
   dim3 grid((N + 63) / 64, max(1, min(32, K / 32)));
   ls_gamma_from_wgrad_kernel<<<grid, 256, 0, STREAM(stream)>>>((const __nv_bfloat16*)W, dW, bias, dbias, gamma, dgamma, K, N);
+  D3_CHECK_LAUNCH();
+  return D3_OK;
+}
+
+int d3_scatter_add_peers(const float* src, long long n, float* const* peers /*host array [world]*/, int world,
+                         long long off, int shard, float alpha, void* stream) {
+  if (n <= 0) return D3_OK;
+  if (world < 1 || world > 8 || shard <= 0 || (shard % 4) || (off % 4) || (n % 4) || ((uintptr_t)src % 16))
+    return set_error(D3_ERR_ARG, "d3_scatter_add_peers: 1..8 ranks, 4-element aligned range");
+  if ((unsigned long long)off + n > (unsigned long long)shard * world) return set_error(D3_ERR_ARG, "d3_scatter_add_peers: range exceeds shards");
+  PeerPtrs pp;
+  for (int i = 0; i < 8; ++i) pp.p[i] = i < world ? peers[i] : nullptr;
+  const long n4 = n / 4;
+  const int blocks = (int)min((n4 + 255) / 256, (long)sm_count() * 4);
+  scatter_add_peers_kernel<<<blocks, 256, 0, STREAM(stream)>>>(src, n4, pp, (unsigned long long)off, (unsigned)shard, alpha);
   D3_CHECK_LAUNCH();
   return D3_OK;
 }

@@ -35,6 +35,27 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, size_t ro
                                                bool full) {
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] *= ep.alpha;
+  if (ep.flags & EP_SCATTER) {  // fused reduce-scatter: add into the owning rank's shard slice (NVLink peer mapping)
+    const unsigned long long g0 = (unsigned long long)ep.sc_off + ro * ep.ld_out + nc;
+    const unsigned shard = (unsigned)ep.sc_shard;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (!full && nc + j + 3 >= N) {
+        for (int t = 0; t < 4; ++t)
+          if (nc + j + t < N) {
+            const unsigned long long g = g0 + j + t;
+            const unsigned r = (unsigned)(g / shard);
+            atomicAdd(ep.sc_peer[r] + (g - (unsigned long long)r * shard), v[j + t]);
+          }
+        continue;
+      }
+      const unsigned long long g = g0 + j;                      // a float4 never straddles two owners (shard % 4 == 0)
+      const unsigned r = (unsigned)(g / shard);
+      atomicAdd(reinterpret_cast<float4*>(ep.sc_peer[r] + (g - (unsigned long long)r * shard)),
+                make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+    }
+    return;
+  }
   if (ep.flags & EP_ATOMIC) {   // split-K partial: fp32 reduction into a zero-initialised output
     float* o = reinterpret_cast<float*>(ep.out) + ro * ep.ld_out + nc;
     if (full) {
@@ -835,6 +856,14 @@ int gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn
       if (splits > num_k / 4) splits = num_k / 4;
       if (splits < 1) splits = 1;
     }
+  }
+  if (ep.flags & EP_SCATTER) {
+    if (!plain_f32) return set_error(D3_ERR_ARG, "gemm: SCATTER needs a plain fp32 output");
+    if (ep.sc_world < 1 || ep.sc_world > 8 || ep.sc_shard <= 0 || (ep.sc_shard % 4) || (ep.sc_off % 4) || (ep.ld_out % 4))
+      return set_error(D3_ERR_ARG, "gemm: SCATTER needs 1..8 ranks and 4-element aligned shard / offset / ld_out");
+    if ((unsigned long long)ep.sc_off + (unsigned long long)(M - 1) * ep.ld_out + N > (unsigned long long)ep.sc_shard * ep.sc_world)
+      return set_error(D3_ERR_ARG, "gemm: SCATTER output exceeds the sharded range");
+    ep.flags |= EP_ATOMIC;       // every contribution is an atomic add (other ranks add into the same slice)
   }
   if (splits > 1) {
     if (!plain_f32) return set_error(D3_ERR_ARG, "gemm: split-K needs a plain fp32 output");

@@ -19,6 +19,7 @@ LIB_PATH = PKG_ROOT / "libdinov3_b200.so"
 
 # epilogue flags (include/dinov3_b200.h)
 EP_BIAS, EP_GELU, EP_STORE_PRE, EP_MUL_DGELU, EP_GAMMA, EP_RESID, EP_OUT_F32, EP_ACCUM = 1, 2, 4, 8, 16, 32, 64, 128
+EP_SCATTER = 256
 
 
 class NativeError(RuntimeError):
@@ -30,6 +31,7 @@ class GemmEpilogue(C.Structure):
         ("bias", C.c_void_p), ("gamma", C.c_void_p), ("resid", C.c_void_p), ("aux_in", C.c_void_p),
         ("aux_out", C.c_void_p), ("out", C.c_void_p),
         ("ld_out", C.c_int), ("ld_aux", C.c_int), ("ld_resid", C.c_int), ("flags", C.c_int), ("alpha", C.c_float),
+        ("sc_peer", C.c_void_p * 8), ("sc_off", C.c_longlong), ("sc_shard", C.c_int), ("sc_world", C.c_int),
     ]
 
 
@@ -39,6 +41,7 @@ SIGNATURES = {
     "d3_init": [I],
     "d3_set_sm_limit": [I],
     "d3_gemm_bf16": [P, I, I, P, I, I, I, I, I, C.POINTER(GemmEpilogue), I, I, P],
+    "d3_scatter_add_peers": [P, LL, P, I, LL, I, F, P],
     "d3_im2col": [P, P, I, I, I, I, I, P],
     "d3_assemble_tokens": [P, P, P, P, P, I, I, I, P],
     "d3_assemble_tokens_bwd": [P, P, P, P, P, I, I, I, P],

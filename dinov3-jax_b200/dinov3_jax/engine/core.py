@@ -401,11 +401,19 @@ class Engine:
             with torch.cuda.stream(self.wstream):
                 fn()
 
-        wgrad = lambda slot, a, b, out: on_wstream(slot, lambda: ops.gemm(a, b, out, a_mn=True, b_mn=True, accum=True))
+        # multi-GPU: the three large weight gradients are reduce-scattered by the GEMM epilogue itself (each tile is
+        # added into the owning rank's gradient shard over NVLink); the rest of the unit is pushed in grads_ready
+        fused = ("mlp/Dense_1/kernel", "mlp/Dense_0/kernel", "attn/qkv/kernel") if self.fsdp.push else ()
+        inv_world = 1.0 / self.fsdp.world
+
+        def wgrad(slot, a, b, name):
+            spec = self.fsdp.scatter_spec("backbone", f"blocks_{i}", p + name) if name in fused else None
+            on_wstream(slot, lambda: ops.gemm(a, b, gw(name), a_mn=True, b_mn=True, accum=True, scatter=spec,
+                                              alpha=inv_world if spec else 1.0))
         # ---- MLP branch: x_out = x_mid + g2 * act(u2), u2 = h W2 + b2, h = gelu(u1), u1 = z W1 + b1
-        wgrad(0, st.Hh[i], dU2, gw("mlp/Dense_1/kernel"))                                      # dW2 = h^T dU2
+        wgrad(0, st.Hh[i], dU2, "mlp/Dense_1/kernel")                                          # dW2 = h^T dU2
         ops.gemm(dU2, w("mlp/Dense_1/kernel"), dU1, dgelu_of=st.U1[i])                         # dU1 = (dU2 W2^T) * gelu'(u1)
-        wgrad(1, st.Z[i], dU1, gw("mlp/Dense_0/kernel"))                                       # dW1 = z^T dU1
+        wgrad(1, st.Z[i], dU1, "mlp/Dense_0/kernel")                                           # dW1 = z^T dU1
         ops.colsum_bf16(dU1, gv("mlp/Dense_0/bias"))
         ops.gemm(dU1, w("mlp/Dense_0/kernel"), self.dZ)                                        # dZ = dU1 W1^T
         # LN2 backward; its tail is the attention branch's LayerScale: x_mid = x_in + g1 * (o Wp + bp), dP = dXmid * g1
@@ -425,18 +433,25 @@ class Engine:
             # gradient w.r.t. the pre-RoPE projection: the inverse rotation is fused into the kernel's store stage
             ops.attn_bwd(st.QKV[i][sl], st.O[i][sl], self.dO[sl], lse, delta, dQKV[sl], cs.n, cs.N, D, H,
                          rope_sin=cs.sin, rope_cos=cs.cos, rope_prefix=1)
-        wgrad(3, st.Y[i], dQKV, gw("attn/qkv/kernel"))                                         # dWqkv = y^T dQKV
+        wgrad(3, st.Y[i], dQKV, "attn/qkv/kernel")                                             # dWqkv = y^T dQKV
         ops.colsum_bf16(dQKV, gv("attn/qkv/bias"))
         ops.gemm(dQKV, w("attn/qkv/kernel"), self.dY)                                          # dY = dQKV Wqkv^T
         tail = self._ls_tail(i - 1) if i > 0 else {}
         ops.layernorm_bwd_ls(self.dY, st.X[i], m1, r1, v("norm1/scale"), dXprev, dx_add=self.dXmid,
                              dscale=gv("norm1/scale"), dbias=gv("norm1/bias"), **tail)
+        scattered = tuple(p + n for n in fused)
         if self.wgrad_overlap:
-            self._ev_done[par].record(self.wstream)
+            if self.fsdp.push:
+                # the remaining ranges are pushed from the weight-gradient stream, after the main stream's last
+                # contribution to this unit (the LayerNorm backward above)
+                on_wstream(0, lambda: self.fsdp.grads_ready("backbone", f"blocks_{i}", scattered=scattered))
+                self._ev_done[par].record(self.wstream)
+            else:
+                self._ev_done[par].record(self.wstream)
+                self.fsdp.grads_ready("backbone", f"blocks_{i}", also_after=self._ev_done[par])
             self._ev_done_live[par] = True
-            self.fsdp.grads_ready("backbone", f"blocks_{i}", also_after=self._ev_done[par])
         else:
-            self.fsdp.grads_ready("backbone", f"blocks_{i}")
+            self.fsdp.grads_ready("backbone", f"blocks_{i}", scattered=scattered)
 
     def _gather_schedule(self):
         """(module, unit, teacher) in the order the step uses them: teacher pass, then student pass (student parameters
@@ -473,6 +488,7 @@ class Engine:
         self.metrics.zero_()
         for st in self.params.mods.values():
             st.zero_grads()
+        self.fsdp.begin_step()
         self.fsdp.prefetch(self._gather_schedule())
         # ---- teacher (train/ssl_meta_arch.py:366-402)
         T_ = self.teacher

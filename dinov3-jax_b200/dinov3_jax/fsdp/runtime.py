@@ -59,6 +59,73 @@ class FsdpRuntime:
         self._grad_works = []
         import os
         self._debug = int(os.environ.get("D3_FSDP_DEBUG", "0"))   # diagnostics only: 1 = skip gathers, 2 = skip reduce-scatters
+        # Gradient reduce-scatter without NCCL: every rank ADDS its contribution straight into the owner's gradient
+        # shard through NVLink peer mappings (torch symmetric memory provides the mappings) — from the weight-gradient
+        # GEMM's epilogue for the big matrices (ops.gemm(scatter=...)), from d3_scatter_add_peers for the rest.
+        self.push = False
+        self._peer_ptrs = {}
+        if self.cuda and self.world > 1 and comm.backend == "nccl" and os.environ.get("D3_FSDP_PUSH", "1") != "0":
+            self._setup_push()
+
+    def _setup_push(self):
+        import torch.distributed._symmetric_memory as symm_mem
+        try:
+            for name, st in self.stores.items():
+                shard = symm_mem.empty(st.grad_shard.numel(), dtype=torch.float32, device=st.grad_shard.device)
+                hdl = symm_mem.rendezvous(shard, self.comm.group)
+                shard.zero_()
+                st.grad_shard = shard
+                self._peer_ptrs[name] = [int(p) for p in hdl.buffer_ptrs]
+                st._symm_handle = hdl
+            torch.cuda.synchronize()
+            torch.distributed.barrier(group=self.comm.group)
+            self.push = True
+        except Exception as e:            # no peer access on this box: keep the NCCL reduce-scatter
+            import warnings
+            warnings.warn(f"symmetric-memory gradient push disabled ({type(e).__name__}: {e}); using NCCL reduce-scatter")
+            self.push = False
+
+    def scatter_spec(self, module: str, unit_name: str, tensor: str):
+        """(peer pointers at this unit's shard slice, offset of the tensor inside the unit's matrix range, shard length)
+        for ops.gemm(scatter=...), or None when gradients go through NCCL."""
+        if not self.push:
+            return None
+        st = self.stores[module]
+        L = st.layout
+        unit = next(u for u in L.units if u.name == unit_name)
+        a, b = unit.mat
+        s = (b - a) // self.world
+        so, _ = L.shard_range(unit, "mat")
+        return [p + 4 * so for p in self._peer_ptrs[module]], L.offsets[tensor] - a, s
+
+    def begin_step(self):
+        """Gradient shards accumulate pushes from every rank, so they start each step at zero.  Safe without a barrier:
+        a peer can only push after its forward, which needs this rank's all-gathers, which are queued after this."""
+        if self.push:
+            for st in self.stores.values():
+                st.grad_shard.zero_()
+
+    def _push_ranges(self, module: str, unit, skip: tuple):
+        """Push every gradient range of the unit that the GEMM epilogues did not already scatter."""
+        from .. import ops
+        st = self.stores[module]
+        L = st.layout
+        inv = 1.0 / self.world
+        peers = self._peer_ptrs[module]
+        for region in ("mat", "vec"):
+            a, b = getattr(unit, region)
+            if b <= a:
+                continue
+            s = (b - a) // self.world
+            so, _ = L.shard_range(unit, region)
+            pp = [p + 4 * so for p in peers]
+            # maximal runs of the region not covered by `skip` tensors
+            holes = sorted((L.offsets[t], L.offsets[t] + L.padded[t]) for t in skip if L.kinds[t] == ("mat" if region == "mat" else "vec"))
+            cur = a
+            for ha, hb in holes + [(b, b)]:
+                if ha > cur:
+                    ops.scatter_add_peers(st.grad[cur:ha], pp, cur - a, s, inv)
+                cur = max(cur, hb)
 
     # ------------------------------------------------------------------------------------------ parameter gathers
     def _issue_gather(self, module: str, unit, teacher: bool):
@@ -102,7 +169,7 @@ class FsdpRuntime:
                 w.wait()
 
     # ------------------------------------------------------------------------------------------ gradient reduction
-    def grads_ready(self, module: str, unit_name: str, also_after=None):
+    def grads_ready(self, module: str, unit_name: str, also_after=None, scattered=()):
         """Called right after the kernels of this unit's backward were enqueued: reduce-scatter (mean) its gradient
         ranges into the rank's gradient shard, on the side stream."""
         if self.world == 1 or (self._debug & 2):
@@ -110,6 +177,12 @@ class FsdpRuntime:
         st = self.stores[module]
         L = st.layout
         unit = next(u for u in L.units if u.name == unit_name)
+        if self.push:
+            cur = torch.cuda.current_stream()
+            if also_after is not None:
+                cur.wait_event(also_after)
+            self._push_ranges(module, unit, tuple(scattered))
+            return
 
         def issue():
             for region in ("mat", "vec"):
@@ -134,6 +207,13 @@ class FsdpRuntime:
         for w in self._grad_works:
             w.wait()
         self._grad_works = []
+        if self.push:
+            # every rank's pushes are complete once its stream reaches this collective; the all-reduce completes on a
+            # rank only after all ranks have joined, so afterwards every contribution has landed in the local shard
+            self._fence = getattr(self, "_fence", None)
+            if self._fence is None:
+                self._fence = torch.zeros(1, device=next(iter(self.stores.values())).grad_shard.device)
+            self.comm.all_reduce_sum(self._fence)
 
     # ------------------------------------------------------------------------------------------ utilities
     def gather_full(self, module: str, what: str, teacher: bool = False) -> torch.Tensor:

@@ -27,7 +27,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, a_mn: bool = Fa
          bias: torch.Tensor | None = None, gelu: bool = False, store_pre: torch.Tensor | None = None,
          dgelu_of: torch.Tensor | None = None, gamma: torch.Tensor | None = None,
          resid: torch.Tensor | None = None, accum: bool = False, alpha: float = 1.0, tile_n: int = 0,
-         split_k: int = 0) -> torch.Tensor:
+         split_k: int = 0, scatter=None) -> torch.Tensor:
     """out[M,N] = epilogue(alpha * A.B) on the tcgen05 tensor cores (d3_gemm_bf16).
 
     A is [M,K] (a_mn=False) or stored transposed [K,M] (a_mn=True); B is [N,K] (b_mn=False) or [K,N] (b_mn=True).
@@ -63,6 +63,14 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, *, a_mn: bool = Fa
     if accum:
         assert out.dtype == f32
         flags |= N.EP_ACCUM
+    if scatter is not None:
+        # fused reduce-scatter: (peer_ptrs, offset of out[0,0] in the sharded range, shard_len); `out` gives the geometry
+        peers, sc_off, sc_shard = scatter
+        assert out.dtype == f32 and out.is_contiguous() and 1 <= len(peers) <= 8
+        flags |= N.EP_SCATTER
+        for i, ptr in enumerate(peers):
+            ep.sc_peer[i] = ptr
+        ep.sc_off, ep.sc_shard, ep.sc_world = int(sc_off), int(sc_shard), len(peers)
     ep.flags = flags
     ep.alpha = float(alpha)
     if PROFILE is not None:
@@ -129,6 +137,14 @@ def layernorm_bwd_ls(dy, x, mean, rstd, scale, dx, dx_add=None, dscale=None, dbi
     N.check(N.init().d3_layernorm_bwd_ls(_p(dy), int(dy.dtype == f32), _p(x), _p(mean), _p(rstd), _p(scale), _p(dx_add),
                                          _p(dx), _p(dscale), _p(dbias), T, D, _p(ls_gamma), _p(ls_u), int(ls_gelu),
                                          _p(ls_du), _p(ls_dgamma), _p(ls_dbias), _s()), "d3_layernorm_bwd_ls")
+
+
+def scatter_add_peers(src, peers, off, shard, alpha):
+    """alpha * src (flat fp32) added into the owners' shard slices over peer mappings (d3_scatter_add_peers)."""
+    assert src.dtype == f32 and src.is_contiguous()
+    arr = (C.c_void_p * len(peers))(*peers)
+    N.check(N.init().d3_scatter_add_peers(_p(src), src.numel(), arr, len(peers), int(off), int(shard), float(alpha), _s()),
+            "d3_scatter_add_peers")
 
 
 def ls_gamma_from_wgrad(W, dW, bias, dbias, gamma, dgamma):

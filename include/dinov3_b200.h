@@ -52,6 +52,7 @@ enum {
   D3_EP_RESID = 32,     /* v += resid[m,n]                    fp32 residual stream */
   D3_EP_OUT_F32 = 64,   /* out is fp32 (default bf16) */
   D3_EP_ACCUM = 128,    /* out += v (fp32 out only; weight-gradient accumulation over crop sets) */
+  D3_EP_SCATTER = 256, /* add the result into peer-mapped shard slices (see d3_gemm_epilogue.sc_*) */
 };
 typedef struct {
   const float* bias;
@@ -63,6 +64,14 @@ typedef struct {
   int ld_out, ld_aux, ld_resid;
   int flags;
   float alpha;
+  /* D3_EP_SCATTER (fused weight-gradient reduce-scatter, replaces jax.lax.psum_scatter at fsdp/utils.py:61-64): the fp32
+   * result, scaled by alpha (= 1/world for the mean), is ADDED into the rank that owns each element instead of being
+   * stored at `out`: output element e = row*ld_out + col has index g = sc_off + e in a flat range split into sc_world
+   * slices of sc_shard elements; it is accumulated at sc_peer[g / sc_shard] + g % sc_shard, where sc_peer[r] is rank
+   * r's (peer-mapped, zero-initialised) shard slice for that range.  `out` is only used for its alignment.           */
+  float* sc_peer[8];
+  long long sc_off;
+  int sc_shard, sc_world;
 } d3_gemm_epilogue;
 /* tile_n : 0 = auto; 64 / 128 / 256 = single-CTA kernel with that tile width; 512 = CTA-pair (cta_group::2) 256x256 kernel.
  * split_k: 0 = auto (used only for plain fp32 outputs with D3_EP_ACCUM, i.e. weight gradients: partial sums are reduced
@@ -101,6 +110,13 @@ int d3_layernorm_bwd_ls(const void* dy, int dy_is_f32, const float* x, const flo
  * dgamma_j += (sum_i W_ij dW_ij + b_j db_j) / gamma_j   (W bf16 [K,N] as used by the forward, dW fp32 [K,N]).        */
 int d3_ls_gamma_from_wgrad(const void* W_bf16, const float* dW, const float* bias, const float* dbias,
                            const float* gamma, float* dgamma, int K, int N, void* stream);
+
+/* ---- FSDP gradient reduce-scatter without NCCL (fsdp/utils.py:61-64 psum_scatter/n, :108 pmean) ---------------------
+ * adds alpha * src[i] into the rank owning flat index off + i of a range split into `world` slices of `shard` elements;
+ * peers[r] = rank r's zero-initialised slice (a pointer valid in THIS process: NVLink peer mapping, peers[rank] local).
+ * The caller orders the step with a cross-rank barrier before the slices are consumed.                               */
+int d3_scatter_add_peers(const float* src, long long n, float* const* peers /*host array [world]*/, int world,
+                         long long off, int shard, float alpha, void* stream);
 
 /* ---- RoPE (layers/attention.py:14-20,69-90; tables from layers/rope_position_encoding.py:117-123) -----------------
  * in place on the q and k thirds of qkv bf16 [T,3D]; tokens t < prefix of every crop are left untouched.             */

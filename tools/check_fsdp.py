@@ -27,6 +27,8 @@ def main():
     hyper = dict(lr=1e-3, wd=0.04, last_layer_lr=5e-4, momentum=0.99, teacher_temp=0.05)
     eng = Engine(from_oracle_cfg(cfg), B, device=f"cuda:{lr_}", max_masked=max(int(b["mask_indices_list"].shape[0]) for b in batches), comm=Comm())
     eng.params.load_reference_tree(P)
+    if rank == 0:
+        print("gradient reduce-scatter path:", "push over NVLink peer memory (GEMM epilogue + d3_scatter_add_peers)" if eng.fsdp.push else "NCCL reduce_scatter", flush=True)
     eng.set_batch(batches[rank])
     eng.forward_backward(hyper["teacher_temp"])
     eng.fsdp.finish_grads()
