@@ -787,7 +787,11 @@ int d3_attn_fwd(const void* qkv, void* o, float* lse, int n_crops, int N, int D,
   const int smem = regA + kv_bytes + 64 + 1024 + 1024;
   dim3 grid((s.span + 127) / 128, H, (n_crops + s.G - 1) / s.G);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (s.Nkp <= 256) {
+  if (s.Nkp <= 128) {        // short crops (local 96^2: three crops per tile): 128 TMEM columns -> four CTAs per SM
+    static bool cfg = false;
+    if (!cfg) { cudaFuncSetAttribute(attn_fwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); cfg = true; }
+    attn_fwd_kernel<128><<<grid, 256, smem, st>>>(tq, tkv, (__nv_bfloat16*)o, lse, s);
+  } else if (s.Nkp <= 256) {
     static bool cfg = false;
     if (!cfg) { cudaFuncSetAttribute(attn_fwd_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); cfg = true; }
     attn_fwd_kernel<256><<<grid, 256, smem, st>>>(tq, tkv, (__nv_bfloat16*)o, lse, s);

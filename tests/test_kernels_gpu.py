@@ -402,3 +402,30 @@ def test_adamw_ema_clip_matches_optax_formula():
     ops.adamw_ema(p, g, m, v, t, pb, tb, 8192, segs, 3, ss, maxn, lr, llr, wd, step, mom)
     assert rel(p, P1) < 1e-6 and rel(m, M1) < 1e-6 and rel(v, V1) < 1e-6 and rel(t, T1) < 1e-6
     assert torch.equal(pb, p[:8192].to(torch.bfloat16)) and torch.equal(tb, t[:8192].to(torch.bfloat16))
+
+
+# --------------------------------------------------------------------------------------------------- fused reduce-scatter
+@pytest.mark.parametrize("M,N,K,world", [(512, 768, 4096, 2), (1024, 1024, 8192, 4), (296, 264, 2048, 8)])
+def test_gemm_scatter_epilogue_and_peer_push(M, N, K, world):
+    """D3_EP_SCATTER: the weight-gradient tile is added into the slice owner's buffer (here `world` local buffers stand
+    in for the peers' NVLink mappings); d3_scatter_add_peers does the same for a flat range.  Two "ranks" contribute."""
+    from dinov3_jax import ops
+    total = ((M * N + 8 * world - 1) // (8 * world)) * 8 * world + 64 * world     # tensor sits at offset 64 in the range
+    shard = total // world
+    shards = [torch.zeros(shard, device="cuda") for _ in range(world)]
+    peers = [t.data_ptr() for t in shards]
+    ref = torch.zeros(total, device="cuda")
+    for seed in (0, 1):
+        g = torch.Generator(device="cuda").manual_seed(seed)
+        a = torch.randn(K, M, device="cuda", generator=g).to(torch.bfloat16)       # a^T b with a stored [K, M]
+        b = torch.randn(K, N, device="cuda", generator=g).to(torch.bfloat16)
+        geom = torch.empty(M, N, device="cuda")
+        ops.gemm(a, b, geom, a_mn=True, b_mn=True, accum=True, scatter=(peers, 64, shard), alpha=0.5)
+        ref[64:64 + M * N] += 0.5 * (a.float().t() @ b.float()).reshape(-1)
+    got = torch.cat(shards)
+    assert rel(got, ref) < 2e-3
+    # flat push of a vector range at an offset
+    src = torch.randn(8 * world * 5, device="cuda")
+    ops.scatter_add_peers(src, peers, 8 * world, shard, 0.25)
+    ref[8 * world: 8 * world + src.numel()] += 0.25 * src
+    assert rel(torch.cat(shards), ref) < 2e-3
