@@ -120,7 +120,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int cbeg = ch ? csplit : 0, cend = ch ? sh.Nkp : csplit;
   const float cs = sh.scale * LOG2E;
   float mx = -3.0e38f;
-  for (int c0 = cbeg; c0 < cend; c0 += 16) {
+  // warps whose 32 query rows all lie beyond the crop group (ragged last tile: 197 = 128 + 69) skip the row math; their
+  // P rows stay undefined, which only feeds output rows that are never stored
+  const bool warp_live = q0 + (warp & 3) * 32 < sh.span;
+  for (int c0 = cbeg; warp_live && c0 < cend; c0 += 16) {
     uint32_t v[16];
     tmem_ld16(t_row + c0, v);
     tmem_ld_wait();
@@ -135,7 +138,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const float mxs = mx * cs;
   float sum = 0.f;
   // the MMA that read sQ / sK has completed (bar_mma), so region A may now be overwritten with P
-  for (int c0 = cbeg; c0 < cend; c0 += 16) {
+  for (int c0 = cbeg; warp_live && c0 < cend; c0 += 16) {
     uint32_t v[16];
     tmem_ld16(t_row + c0, v);
     tmem_ld_wait();

@@ -217,6 +217,16 @@ class ParamStore:
                 pre = f"{who}_{m}/"
                 st.load({k[len(pre):]: v for k, v in params.items() if k.startswith(pre)}, teacher)
 
+    def load_optimizer_tree(self, mu: dict, nu: dict):
+        """Adam moments with the reference's names ('student_backbone/...'): fills this rank's m / v shards."""
+        for m, st in self.mods.items():
+            pre = f"student_{m}/"
+            for tree, dst in ((mu, st.m), (nu, st.v)):
+                full = torch.zeros(st.n, dtype=torch.float32, device=dst.device)
+                for name in st.offsets:
+                    st._view(full, name).copy_(tree[pre + name].to(device=dst.device, dtype=torch.float32).reshape(st.shapes[name]))
+                dst.copy_(full if st.world == 1 else full[st.shard_index()])
+
     def export_reference_tree(self, what: str = "param") -> dict:
         """Full (un-sharded) tensors with the reference's names; under FSDP this all-gathers the shards."""
         out = {}

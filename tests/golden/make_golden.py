@@ -21,6 +21,9 @@
                                                          `vit_test` factory next to the reference's vit_* factories.
                                                          Parameters / crops are closed-form (oracle.model.formula_*),
                                                          so the fixture stores only masks and results.
+  * hubconf.py: the function `setup_checkpoint` (torch-hub state-dict key mapper, :40-70) is exec'ed from its source
+    text (the module body around it downloads a model) on a synthetic state dict with Meta's key names; the produced
+    key list and transpose decisions pin dinov3_jax.checkpointer.convert_torch_hub_state_dict.
 Usage:  python tests/golden/make_golden.py      (writes next to this file; the .npz files are committed)
 """
 from __future__ import annotations
@@ -219,6 +222,33 @@ def main():
         for k, v in metrics.items():
             out[f"ssl_{case}_metric/{k}"] = np.asarray(v, dtype=np.float64)
         print(f"SSLMetaArch case {case}: loss {float(loss):.12f}", {k: float(np.asarray(v)) for k, v in metrics.items()})
+
+    # ---- torch-hub key mapping (hubconf.py:40-70)
+    import re as _re
+    src = open("/root/reference/hubconf.py").read()
+    fn_src = src[src.index("def setup_checkpoint("): src.index("checkpoint = setup_checkpoint(")]
+    ns = {"re": _re, "t2j": lambda x: x.detach().cpu().numpy()}
+    exec(fn_src, ns)
+    D, p_ = 8, 2
+    sd = {"cls_token": torch.zeros(1, 1, D), "mask_token": torch.zeros(1, D), "storage_tokens": torch.zeros(1, 4, D),
+          "patch_embed.proj.weight": torch.arange(D * 3 * p_ * p_, dtype=torch.float32).reshape(D, 3, p_, p_),
+          "patch_embed.proj.bias": torch.zeros(D), "rope_embed.periods": torch.zeros(2),
+          "norm.weight": torch.ones(D), "norm.bias": torch.zeros(D)}
+    for i in range(2):
+        b = f"blocks.{i}."
+        sd.update({b + "norm1.weight": torch.ones(D), b + "norm1.bias": torch.zeros(D),
+                   b + "attn.qkv.weight": torch.arange(3 * D * D, dtype=torch.float32).reshape(3 * D, D),
+                   b + "attn.qkv.bias": torch.zeros(3 * D), b + "attn.qkv.bias_mask": torch.zeros(3 * D),
+                   b + "attn.proj.weight": torch.zeros(D, D), b + "attn.proj.bias": torch.zeros(D),
+                   b + "ls1.gamma": torch.ones(D), b + "norm2.weight": torch.ones(D), b + "norm2.bias": torch.zeros(D),
+                   b + "mlp.fc1.weight": torch.arange(4 * D * D, dtype=torch.float32).reshape(4 * D, D),
+                   b + "mlp.fc1.bias": torch.zeros(4 * D), b + "mlp.fc2.weight": torch.zeros(D, 4 * D),
+                   b + "mlp.fc2.bias": torch.zeros(D), b + "ls2.gamma": torch.ones(D)})
+    mapped = ns["setup_checkpoint"](sd, {})
+    out["hub_torch_keys"] = np.array(sorted(sd))
+    out["hub_jax_keys"] = np.array(sorted(mapped))
+    out["hub_qkv_kernel_b0"] = np.asarray(mapped["blocks_0.attn.qkv.kernel"])
+    out["hub_fc1_kernel_b1"] = np.asarray(mapped["blocks_1.mlp.Dense_0.kernel"])
     np.savez_compressed(os.path.join(HERE, "reference_vectors.npz"), **out)
     print("wrote", os.path.join(HERE, "reference_vectors.npz"), len(out), "arrays")
 
