@@ -84,9 +84,30 @@ def do_train(config, model: SSLMetaArch, resume: bool = False, data_loader=None,
     if data_loader is None:
         fixed = synthetic_batch(engine.cfg, config.train.batch_size_per_gpu, seed=distributed.get_rank(), pin=True)
         data_loader = (fixed for _ in range(n_iters))
+    # ---- resume / periodic checkpoints (train/train.py:447-469,695-706; <output_dir>/ckpt/<iteration>)
+    from ..checkpointer import (engine_state, find_latest_checkpoint, keep_checkpoint_copy, keep_last_n_checkpoints,
+                                load_checkpoint, load_engine_state, save_checkpoint)
+    ckpt_dir = os.path.join(getattr(config.train, "output_dir", None) or ".", "ckpt")
+    ck_cfg = config.get("checkpointing", None) if hasattr(config, "get") else getattr(config, "checkpointing", None)
+    start_iter = 0
+    last = find_latest_checkpoint(ckpt_dir) if resume else None
+    if last is not None:
+        ck = load_checkpoint(last, strict_loading=False)
+        load_engine_state(engine, ck["model_params"], ck.get("optimizer_state"))
+        start_iter = int(ck["iteration"]) + 1
+        if distributed.is_main_process():
+            print(f"checkpoint found {last}: resuming at iteration {start_iter}", flush=True)
     meters, nan_streak, t0 = {}, 0, time.time()
-    for it, data in zip(range(n_iters), data_loader):
+    for it, data in zip(range(start_iter, n_iters), data_loader):
         train_step(engine, data, schedules[3][it], it, schedules)
+        if ck_cfg is not None and (it + 1) % int(ck_cfg.period) == 0:
+            params_tree, opt_tree = engine_state(engine)                 # collective under FSDP (all-gathers the shards)
+            if distributed.is_main_process():
+                save_checkpoint(os.path.join(ckpt_dir, str(it)), iteration=it, params=params_tree,
+                                optimizer_state=opt_tree, overwrite=True)
+                keep_last_n_checkpoints(ckpt_dir, ck_cfg.max_to_keep)
+                if "keep_every" in ck_cfg and (it + 1) % int(ck_cfg.keep_every) == 0:
+                    keep_checkpoint_copy(os.path.join(ckpt_dir, str(it)))
         if it % print_freq == 0 or it == n_iters - 1:
             m = engine.read_metrics()                  # the only device->host sync of the loop
             if math.isnan(m["total_loss"]):            # NaN guard of train/train.py:656-667, evaluated on read

@@ -120,6 +120,20 @@ def test_do_train_runs_three_iterations():
     assert abs(m["dino_local_crops_loss"] - 6.93) < 0.05 and m["total_loss"] == m["total_loss"]
 
 
+def test_do_train_checkpoints_and_resumes(tmp_path):
+    from dinov3_jax.checkpointer import find_all_checkpoints
+    from dinov3_jax.configs import DinoV3SetupArgs, setup_config
+    from dinov3_jax.train import SSLMetaArch
+    from dinov3_jax.train.train import do_train
+    opts = ["student.arch=vit_small", "train.batch_size_per_gpu=2", "dino.head_n_prototypes=1024", "ibot.head_n_prototypes=1024",
+            "dino.head_hidden_dim=256", "ibot.head_hidden_dim=256", "checkpointing.period=2", "checkpointing.max_to_keep=1"]
+    cfg = setup_config(DinoV3SetupArgs(opts=opts, output_dir=str(tmp_path)))
+    do_train(cfg, SSLMetaArch(cfg), max_iters=4, print_freq=1)
+    assert [p.name for p in find_all_checkpoints(tmp_path / "ckpt")] == ["3"]          # period 2, keep last 1
+    m = do_train(cfg, SSLMetaArch(cfg), resume=True, max_iters=5, print_freq=1)        # runs iteration 4 only
+    assert m["total_loss"] == m["total_loss"]
+
+
 def test_vit_and_head_against_reference_golden(native):
     """CUDA forward (dinov3_jax.models.DinoVisionTransformer, dinov3_jax.layers.DINOHead) against vectors produced by
     executing the reference's own module code (tests/golden/make_golden.py) — no oracle in between.  bf16-operand /
