@@ -40,43 +40,50 @@ __global__ void im2col_kernel(const __nv_bfloat16* __restrict__ img, __nv_bfloat
 }
 
 // ------------------------------------------------------------------------------------------------ tokens
-// models/vision_transformer.py:173-203: where(mask, mask_token, x); prepend cls (+0*mask_token).
-// tok fp32 [n*P, D] -> X fp32 [n, 1+P, D]
+// models/vision_transformer.py:173-203: where(mask, mask_token, x); prepend cls (+0*mask_token) and the R storage
+// (register) tokens.  tok fp32 [n*P, D] -> X fp32 [n, 1+R+P, D]
 __global__ void assemble_tokens_kernel(const float* __restrict__ tok, const float* __restrict__ cls,
-                                       const float* __restrict__ mask_token, const uint8_t* __restrict__ masks,
-                                       float* __restrict__ X, int n, int P, int D) {
-  const long rows = (long)n * (P + 1);
+                                       const float* __restrict__ storage, const float* __restrict__ mask_token,
+                                       const uint8_t* __restrict__ masks, float* __restrict__ X, int n, int P, int R,
+                                       int D) {
+  const int N = P + 1 + R;
+  const long rows = (long)n * N;
   const int D4 = D / 4;
   for (long r = blockIdx.x; r < rows; r += gridDim.x) {
-    const long c = r / (P + 1);
-    const int t = (int)(r % (P + 1));
+    const long c = r / N;
+    const int t = (int)(r % N);
     const float4* src;
     if (t == 0) src = reinterpret_cast<const float4*>(cls);
-    else if (masks && masks[c * P + (t - 1)]) src = reinterpret_cast<const float4*>(mask_token);
-    else src = reinterpret_cast<const float4*>(tok + (c * P + (t - 1)) * (long)D);
+    else if (t <= R) src = reinterpret_cast<const float4*>(storage + (long)(t - 1) * D);
+    else if (masks && masks[c * P + (t - 1 - R)]) src = reinterpret_cast<const float4*>(mask_token);
+    else src = reinterpret_cast<const float4*>(tok + (c * P + (t - 1 - R)) * (long)D);
     float4* dst = reinterpret_cast<float4*>(X + r * (long)D);
     for (int e = threadIdx.x; e < D4; e += blockDim.x) dst[e] = src[e];
   }
 }
-// backward: dX fp32 [n,1+P,D] -> dTok bf16 [n*P, D] (0 where masked); dcls[D] += sum_c dX[c,0]; dmask[D] += masked rows
+// backward: dX fp32 [n,1+R+P,D] -> dTok bf16 [n*P, D] (0 where masked); dcls[D] += sum_c dX[c,0];
+// dstorage[R,D] += sum_c dX[c,1..R]; dmask[D] += masked rows
 __global__ void assemble_tokens_bwd_kernel(const float* __restrict__ dX, const uint8_t* __restrict__ masks,
                                            __nv_bfloat16* __restrict__ dTok, float* __restrict__ dcls,
-                                           float* __restrict__ dmask, int n, int P, int D) {
-  // grid.x = column chunks of 128 floats (threads 128: one column each), grid.y = row slabs
+                                           float* __restrict__ dstorage, float* __restrict__ dmask, int n, int P, int R,
+                                           int D) {
+  // grid.x = column chunks of 128 floats (threads 128: one column each), grid.y = slabs of whole crops
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  const long rows = (long)n * (P + 1);
-  const long slab = (rows + gridDim.y - 1) / gridDim.y;
-  const long r0 = blockIdx.y * slab, r1 = min(rows, r0 + slab);
+  const int N = P + 1 + R;
+  const long slab = ((long)n + gridDim.y - 1) / gridDim.y;
+  const long c0 = blockIdx.y * slab, c1 = min((long)n, c0 + slab);
   if (col >= D) return;
   float acc_cls = 0.f, acc_mask = 0.f;
-  for (long r = r0; r < r1; ++r) {
-    const long c = r / (P + 1);
-    const int t = (int)(r % (P + 1));
-    const float g = dX[r * (long)D + col];
-    if (t == 0) { acc_cls += g; continue; }
-    const bool m = masks && masks[c * P + (t - 1)];
-    if (m) acc_mask += g;
-    dTok[(c * P + (t - 1)) * (long)D + col] = __float2bfloat16(m ? 0.f : g);
+  for (long c = c0; c < c1; ++c) {
+    const float* row = dX + c * N * (long)D + col;
+    acc_cls += row[0];
+    for (int t = 1; t <= R; ++t) atomicAdd(&dstorage[(long)(t - 1) * D + col], row[(long)t * D]);
+    for (int t = 0; t < P; ++t) {
+      const float g = row[(long)(1 + R + t) * D];
+      const bool m = masks && masks[c * P + t];
+      if (m) acc_mask += g;
+      dTok[(c * P + t) * (long)D + col] = __float2bfloat16(m ? 0.f : g);
+    }
   }
   atomicAdd(&dcls[col], acc_cls);
   if (masks) atomicAdd(&dmask[col], acc_mask);
@@ -680,14 +687,15 @@ __global__ void rope_kernel(__nv_bfloat16* __restrict__ qkv, const float* __rest
 // ------------------------------------------------------------------------------------------------ gather / scatter
 // train/ssl_meta_arch.py:377,432: patch.reshape(-1, D)[mask_indices_list]; cls rows = token 0 of each crop.
 // mode 0: rows[i] = idx[i]/P*(P+1) + 1 + idx[i]%P (masked patch i -> token row); mode 1: rows[i] = i*(P+1) (cls)
-__global__ void token_rows_kernel(const long long* __restrict__ idx, int* __restrict__ rows, int count, int P, int mode) {
+__global__ void token_rows_kernel(const long long* __restrict__ idx, int* __restrict__ rows, int count, int P, int prefix,
+                                  int mode) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
   if (mode == 0) {
     const long long m = idx[i];
-    rows[i] = (int)(m / P * (P + 1) + 1 + m % P);
+    rows[i] = (int)(m / P * (P + prefix) + prefix + m % P);
   } else {
-    rows[i] = i * (P + 1);
+    rows[i] = i * (P + prefix);
   }
 }
 __global__ void gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ rows,
@@ -906,20 +914,23 @@ int d3_im2col(const void* img, void* out, int ld_out, int n, int H, int W, int p
   return D3_OK;
 }
 
-int d3_assemble_tokens(const float* tok, const float* cls, const float* mask_token, const unsigned char* masks,
-                       float* X, int n, int P, int D, void* stream) {
+int d3_assemble_tokens(const float* tok, const float* cls, const float* storage, const float* mask_token,
+                       const unsigned char* masks, float* X, int n, int P, int R, int D, void* stream) {
   if (D % 4) return set_error(D3_ERR_ARG, "d3_assemble_tokens: D % 4");
-  long rows = (long)n * (P + 1);
-  assemble_tokens_kernel<<<(int)min(rows, (long)sm_count() * 16), 128, 0, STREAM(stream)>>>(tok, cls, mask_token, masks,
-                                                                                           X, n, P, D);
+  if (R < 0 || (R > 0 && !storage)) return set_error(D3_ERR_ARG, "d3_assemble_tokens: storage tokens pointer");
+  long rows = (long)n * (P + 1 + R);
+  assemble_tokens_kernel<<<(int)min(rows, (long)sm_count() * 16), 128, 0, STREAM(stream)>>>(tok, cls, storage, mask_token,
+                                                                                           masks, X, n, P, R, D);
   D3_CHECK_LAUNCH();
   return D3_OK;
 }
 
-int d3_assemble_tokens_bwd(const float* dX, const unsigned char* masks, void* dTok, float* dcls, float* dmask, int n,
-                           int P, int D, void* stream) {
-  dim3 grid((D + 127) / 128, 64);
-  assemble_tokens_bwd_kernel<<<grid, 128, 0, STREAM(stream)>>>(dX, masks, (__nv_bfloat16*)dTok, dcls, dmask, n, P, D);
+int d3_assemble_tokens_bwd(const float* dX, const unsigned char* masks, void* dTok, float* dcls, float* dstorage,
+                           float* dmask, int n, int P, int R, int D, void* stream) {
+  if (R < 0 || (R > 0 && !dstorage)) return set_error(D3_ERR_ARG, "d3_assemble_tokens_bwd: storage gradient pointer");
+  dim3 grid((D + 127) / 128, max(1, min(n, 128)));
+  assemble_tokens_bwd_kernel<<<grid, 128, 0, STREAM(stream)>>>(dX, masks, (__nv_bfloat16*)dTok, dcls, dstorage, dmask, n, P,
+                                                              R, D);
   D3_CHECK_LAUNCH();
   return D3_OK;
 }
@@ -1042,9 +1053,10 @@ int d3_rope(void* qkv, const float* sin_t, const float* cos_t, long long T, int 
   return D3_OK;
 }
 
-int d3_token_rows(const long long* idx, int* rows, int count, int P, int mode, void* stream) {
+int d3_token_rows(const long long* idx, int* rows, int count, int P, int prefix, int mode, void* stream) {
   if (count <= 0) return D3_OK;
-  token_rows_kernel<<<(count + 255) / 256, 256, 0, STREAM(stream)>>>(idx, rows, count, P, mode);
+  if (prefix < 1) return set_error(D3_ERR_ARG, "d3_token_rows: prefix >= 1 (cls token)");
+  token_rows_kernel<<<(count + 255) / 256, 256, 0, STREAM(stream)>>>(idx, rows, count, P, prefix, mode);
   D3_CHECK_LAUNCH();
   return D3_OK;
 }

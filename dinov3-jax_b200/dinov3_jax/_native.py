@@ -43,8 +43,8 @@ SIGNATURES = {
     "d3_gemm_bf16": [P, I, I, P, I, I, I, I, I, C.POINTER(GemmEpilogue), I, I, P],
     "d3_scatter_add_peers": [P, LL, P, I, LL, I, F, P],
     "d3_im2col": [P, P, I, I, I, I, I, P],
-    "d3_assemble_tokens": [P, P, P, P, P, I, I, I, P],
-    "d3_assemble_tokens_bwd": [P, P, P, P, P, I, I, I, P],
+    "d3_assemble_tokens": [P, P, P, P, P, P, I, I, I, I, P],
+    "d3_assemble_tokens_bwd": [P, P, P, P, P, P, I, I, I, I, P],
     "d3_layernorm_fwd": [P, P, P, P, I, P, P, I, I, F, P],
     "d3_layernorm_bwd": [P, I, P, P, P, P, P, P, P, P, I, I, P],
     "d3_layernorm_bwd_ls": [P, I, P, P, P, P, P, P, P, P, I, I, P, P, I, P, P, P, P],
@@ -53,7 +53,7 @@ SIGNATURES = {
     "d3_attn_fwd": [P, P, P, I, I, I, I, P],
     "d3_debug_attn_trace": [P],
     "d3_attn_bwd": [P, P, P, P, P, P, I, I, I, I, P, P, I, P],
-    "d3_token_rows": [P, P, I, I, I, P],
+    "d3_token_rows": [P, P, I, I, I, I, P],
     "d3_gather_rows": [P, P, P, P, I, I, P],
     "d3_scatter_add_rows": [P, I, P, P, I, I, P],
     "d3_l2norm_fwd": [P, P, P, I, I, F, P],

@@ -38,7 +38,8 @@ class EngineConfig:
     koleo_loss_weight: float = 0.1
     ibot_loss_weight: float = 1.0
     clip_grad: float = 3.0
-    ln_eps: float = 1e-6
+    ln_eps: float = 1e-6             # norm_layer layernorm: 1e-6, layernormbf16: 1e-5 (models/vision_transformer.py:38-42)
+    n_storage: int = 0               # student.n_storage_tokens (register tokens after cls, vision_transformer.py:106-111)
     mlp_second_act: bool = True      # reference applies GELU after fc2 too (layers/ffn_layers.py:47)
     layerwise_decay: float = 0.9
     patch_embed_lr_mult: float = 0.2
@@ -59,8 +60,13 @@ class EngineConfig:
     def patches(self, size: int) -> int:
         return (size // self.patch) ** 2
 
+    @property
+    def prefix(self) -> int:
+        """Tokens in front of the patch tokens (cls + storage): they are not rotated by RoPE."""
+        return 1 + self.n_storage
+
     def tokens(self, size: int) -> int:
-        return self.patches(size) + 1
+        return self.patches(size) + self.prefix
 
 
 def config_for(arch: str, **kw) -> EngineConfig:
@@ -83,8 +89,10 @@ def config_from_reference_cfg(cfg) -> EngineConfig:
         raise NotImplementedError("ibot.separate_head must be true (ssl_meta_arch.py:48)")
     if cfg.crops.local_crops_number <= 0:
         raise ValueError("crops.local_crops_number must be > 0 (ssl_meta_arch.py:47)")
-    if cfg.student.ffn_layer != "mlp" or cfg.student.norm_layer != "layernorm" or cfg.student.n_storage_tokens != 0:
-        raise NotImplementedError("only ffn_layer=mlp, norm_layer=layernorm, n_storage_tokens=0 are on the B200 path (SURVEY 8f)")
+    if cfg.student.ffn_layer != "mlp" or cfg.student.norm_layer not in ("layernorm", "layernormbf16"):
+        raise NotImplementedError("only ffn_layer=mlp and norm_layer=layernorm|layernormbf16 are on the B200 path (SURVEY 8f)")
+    if cfg.student.get("mask_k_bias", False):
+        raise NotImplementedError("student.mask_k_bias is not on the B200 path (SURVEY 8f)")
     if cfg.gram.use_loss or cfg.dino.koleo_loss_distributed or cfg.dino.reweight_dino_local_loss:
         raise NotImplementedError("gram loss / distributed KoLeo / local-loss reweighting are not on the B200 path yet")
     arch = cfg.student.arch
@@ -103,4 +111,5 @@ def config_from_reference_cfg(cfg) -> EngineConfig:
         clip_grad=cfg.optim.clip_grad, layerwise_decay=cfg.optim.layerwise_decay,
         patch_embed_lr_mult=cfg.optim.patch_embed_lr_mult, dino_head_wd_multiplier=cfg.optim.dino_head_wd_multiplier,
         adamw_beta1=cfg.optim.adamw_beta1, adamw_beta2=cfg.optim.adamw_beta2,
-        mask_probability=cfg.ibot.mask_sample_probability, mask_ratio=tuple(cfg.ibot.mask_ratio_min_max))
+        mask_probability=cfg.ibot.mask_sample_probability, mask_ratio=tuple(cfg.ibot.mask_ratio_min_max),
+        n_storage=int(cfg.student.n_storage_tokens), ln_eps=1e-5 if cfg.student.norm_layer == "layernormbf16" else 1e-6)

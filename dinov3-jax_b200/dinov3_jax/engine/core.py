@@ -45,7 +45,7 @@ class CropSet:
         self.size = size
         self.Hp = size // cfg.patch
         self.P = self.Hp * self.Hp
-        self.N = self.P + 1
+        self.N = self.P + cfg.prefix
         self.T = n_crops * self.N
         self.row0 = row0
         self.sin, self.cos = rope_tables(self.Hp, self.Hp, cfg.head_dim, cfg.rope_base, device)
@@ -207,7 +207,7 @@ class Engine:
     # ------------------------------------------------------------------------------------------------ static tables
     def _build_rows(self):
         sg, sl = self.s_sets
-        ops.token_rows(None, self.rows_cls_t, self.t_sets[0].n, self.t_sets[0].P, 1)
+        ops.token_rows(None, self.rows_cls_t, self.t_sets[0].n, self.t_sets[0].P, 1, prefix=self.cfg.prefix)
         # student cls rows: global crops then local crops (local rows offset by the global part)
         rows_g = torch.arange(sg.n, dtype=torch.int32) * sg.N
         rows_l = torch.arange(sl.n, dtype=torch.int32) * sl.N + sl.row0
@@ -257,7 +257,8 @@ class Engine:
             ops.im2col(img, cs.patches, cfg.patch)
             ops.gemm(cs.patches, Wpe, cs.tok, b_mn=True, bias=bb.vec("patch_embed/proj/bias", teacher))
             ops.assemble_tokens(cs.tok, bb.vec("cls_token", teacher), bb.vec("mask_token", teacher), masks,
-                                X0[cs.row0: cs.row0 + cs.T], cs.n, cs.P, cfg.embed_dim)
+                                X0[cs.row0: cs.row0 + cs.T], cs.n, cs.P, cfg.embed_dim,
+                                storage=bb.vec("storage_tokens", teacher) if cfg.n_storage else None)
 
     def _block_fwd(self, st: Stream, i: int, teacher: bool):
         cfg, bb = self.cfg, self.params.mods["backbone"]
@@ -274,7 +275,7 @@ class Engine:
         lses = st.b(st.LSE, i)
         for cs, lse in zip(st.sets, lses):
             q = QKV[cs.row0: cs.row0 + cs.T]
-            ops.rope(q, cs.sin, cs.cos, cs.N, 1, D, cfg.head_dim)
+            ops.rope(q, cs.sin, cs.cos, cs.N, cfg.prefix, D, cfg.head_dim)
             ops.attn_fwd(q, O[cs.row0: cs.row0 + cs.T], lse if st.stash else None, cs.n, cs.N, D, H)
         ops.gemm(O, w("attn/proj/kernel"), Xmid, b_mn=True, bias=v("attn/proj/bias"), gamma=v("ls1/gamma"), resid=X)
         ops.layernorm_fwd(Xmid, v("norm2/scale"), v("norm2/bias"), Z, stats[2], stats[3], cfg.ln_eps)
@@ -432,7 +433,7 @@ class Engine:
             sl = slice(cs.row0, cs.row0 + cs.T)
             # gradient w.r.t. the pre-RoPE projection: the inverse rotation is fused into the kernel's store stage
             ops.attn_bwd(st.QKV[i][sl], st.O[i][sl], self.dO[sl], lse, delta, dQKV[sl], cs.n, cs.N, D, H,
-                         rope_sin=cs.sin, rope_cos=cs.cos, rope_prefix=1)
+                         rope_sin=cs.sin, rope_cos=cs.cos, rope_prefix=cfg.prefix)
         wgrad(3, st.Y[i], dQKV, "attn/qkv/kernel")                                             # dWqkv = y^T dQKV
         ops.colsum_bf16(dQKV, gv("attn/qkv/bias"))
         ops.gemm(dQKV, w("attn/qkv/kernel"), self.dY)                                          # dY = dQKV Wqkv^T
@@ -479,7 +480,7 @@ class Engine:
         self.M = int(idx.shape[0])
         assert self.M <= self.max_masked, f"M={self.M} exceeds max_masked={self.max_masked}"
         self.mask_idx[: self.M].copy_(idx, non_blocking=True)
-        ops.token_rows(self.mask_idx, self.rows_masked_t, self.M, self.s_sets[0].P, 0)
+        ops.token_rows(self.mask_idx, self.rows_masked_t, self.M, self.s_sets[0].P, 0, prefix=self.cfg.prefix)
 
     def forward_backward(self, teacher_temp: float):
         cfg, B, M = self.cfg, self.B, self.M
@@ -548,7 +549,8 @@ class Engine:
         first = True
         for cs, masks, dTok in zip(S_.sets, [self.masks_u8, None], self.dTok):
             ops.assemble_tokens_bwd(dX0[cs.row0: cs.row0 + cs.T], masks, dTok, bb.gv("cls_token"),
-                                    bb.gv("mask_token"), cs.n, cs.P, D)
+                                    bb.gv("mask_token"), cs.n, cs.P, D,
+                                    dstorage=bb.gv("storage_tokens") if cfg.n_storage else None)
             ops.colsum_bf16(dTok, bb.gv("patch_embed/proj/bias"))
             ops.gemm(cs.patches, dTok, bb.gw("patch_embed/proj/kernel"), a_mn=True, b_mn=True, accum=True)
             first = False

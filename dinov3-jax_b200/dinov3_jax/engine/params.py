@@ -29,6 +29,8 @@ def backbone_spec(cfg: EngineConfig):
     D, p, Hd = cfg.embed_dim, cfg.patch, cfg.hidden
     spec = [("patch_embed/proj/kernel", (p, p, 3, D), "mat"), ("patch_embed/proj/bias", (D,), "vec"),
             ("cls_token", (1, 1, D), "vec"), ("mask_token", (1, D), "vec")]
+    if cfg.n_storage:
+        spec.insert(3, ("storage_tokens", (1, cfg.n_storage, D), "vec"))
     for i in range(cfg.depth):
         b = f"blocks_{i}/"
         spec += [(b + "norm1/scale", (D,), "vec"), (b + "norm1/bias", (D,), "vec"),

@@ -55,7 +55,7 @@ def reference_like_params(cfg: EngineConfig, seed: int = 0) -> dict:
                 t = torch.full(shape, cfg.layerscale)
             elif name.endswith("/bias") or name == "mask_token":
                 t = torch.zeros(shape)
-            elif name == "cls_token":
+            elif name in ("cls_token", "storage_tokens"):
                 t = torch.randn(shape, generator=gen) * 0.02
             elif module == "backbone":
                 fan_in = int(np.prod(shape[:-1]))

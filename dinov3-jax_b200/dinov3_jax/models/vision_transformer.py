@@ -26,9 +26,11 @@ class DinoVisionTransformer:
                  ffn_layer: str = "mlp", ffn_bias: bool = True, proj_bias: bool = True, n_storage_tokens: int = 0,
                  mask_k_bias: bool = False, untie_cls_and_patch_norms: bool = False,
                  untie_global_and_local_cls_norm: bool = False, device="cuda"):
-        if norm_layer != "layernorm" or ffn_layer != "mlp" or n_storage_tokens or mask_k_bias \
+        if norm_layer not in ("layernorm", "layernormbf16") or ffn_layer != "mlp" or mask_k_bias \
                 or untie_cls_and_patch_norms or untie_global_and_local_cls_norm:
-            raise NotImplementedError("B200 path: layernorm + mlp blocks, no storage tokens / untied norms (SURVEY §8f.1)")
+            raise NotImplementedError("B200 path: layernorm(bf16) + mlp blocks, tied norms, no mask_k_bias (SURVEY §8f.1)")
+        self.eps = 1e-5 if norm_layer == "layernormbf16" else 1e-6        # models/vision_transformer.py:38-42
+        self.n_storage_tokens = n_storage_tokens
         if drop_path_rate:
             raise NotImplementedError("stochastic depth is not on the B200 path (reference default 0 is asserted upstream)")
         dev = torch.device(device)
@@ -40,11 +42,12 @@ class DinoVisionTransformer:
                                       embed_dim=embed_dim)
         self.cls_token = params["cls_token"].to(f32).reshape(-1).contiguous()
         self.mask_token = params["mask_token"].to(f32).reshape(-1).contiguous()
+        self.storage_tokens = params["storage_tokens"].to(f32).reshape(-1).contiguous() if n_storage_tokens else None
         self.rope_embed = RopePositionEmbedding(embed_dim=embed_dim, num_heads=num_heads, base=pos_embed_rope_base,
                                                 min_period=pos_embed_rope_min_period, max_period=pos_embed_rope_max_period,
                                                 normalize_coords=pos_embed_rope_normalize_coords)
         self.blocks = [SelfAttentionBlock(params[f"blocks_{i}"], dim=embed_dim, num_heads=num_heads, ffn_ratio=ffn_ratio,
-                                          qkv_bias=qkv_bias, proj_bias=proj_bias, ffn_bias=ffn_bias)
+                                          qkv_bias=qkv_bias, proj_bias=proj_bias, ffn_bias=ffn_bias, eps=self.eps)
                        for i in range(n_blocks)]
         self.norm = (params["norm"]["scale"].to(f32).reshape(-1).contiguous(),
                      params["norm"]["bias"].to(f32).reshape(-1).contiguous())
@@ -55,9 +58,10 @@ class DinoVisionTransformer:
         x = torch.as_tensor(x).to(self.device)
         tok = self.patch_embed(x)
         n, Hp, Wp, D = tok.shape
-        X = torch.empty(n, 1 + Hp * Wp, D, dtype=f32, device=self.device)
+        X = torch.empty(n, 1 + self.n_storage_tokens + Hp * Wp, D, dtype=f32, device=self.device)
         m8 = None if masks is None else torch.as_tensor(masks).to(self.device).reshape(n, Hp * Wp).to(torch.uint8).contiguous()
-        ops.assemble_tokens(tok.view(n * Hp * Wp, D), self.cls_token, self.mask_token, m8, X, n, Hp * Wp, D)
+        ops.assemble_tokens(tok.view(n * Hp * Wp, D), self.cls_token, self.mask_token, m8, X, n, Hp * Wp, D,
+                            storage=self.storage_tokens)
         return X, (Hp, Wp)
 
     # models/vision_transformer.py:205-247
@@ -70,9 +74,10 @@ class DinoVisionTransformer:
                 X = blk(X, rope=rope)
             n, N, D = X.shape
             Y = torch.empty(n * N, D, dtype=f32, device=self.device)
-            ops.layernorm_fwd(X.view(n * N, D), self.norm[0], self.norm[1], Y)
+            ops.layernorm_fwd(X.view(n * N, D), self.norm[0], self.norm[1], Y, eps=self.eps)
             Y = Y.view(n, N, D)
-            out.append({"x_norm_clstoken": Y[:, 0], "x_storage_tokens": Y[:, 1:1], "x_norm_patchtokens": Y[:, 1:],
+            R = self.n_storage_tokens
+            out.append({"x_norm_clstoken": Y[:, 0], "x_storage_tokens": Y[:, 1:1 + R], "x_norm_patchtokens": Y[:, 1 + R:],
                         "x_prenorm": X, "masks": masks})
         return out
 

@@ -100,17 +100,20 @@ def im2col(img: torch.Tensor, out: torch.Tensor, patch: int) -> torch.Tensor:
     return out
 
 
-def assemble_tokens(tok, cls, mask_token, masks_u8, X, n, P, D):
+def assemble_tokens(tok, cls, mask_token, masks_u8, X, n, P, D, storage=None):
+    """X [n, 1+R+P, D] = [cls | R storage tokens | patches (mask_token where masked)]; storage fp32 [R*D] or None."""
     assert tok.dtype == f32 and X.dtype == f32 and (masks_u8 is None or masks_u8.dtype == torch.uint8)
-    N.check(N.init().d3_assemble_tokens(_p(tok), _p(cls), _p(mask_token), _p(masks_u8), _p(X), n, P, D, _s()),
+    R = 0 if storage is None else storage.numel() // D
+    N.check(N.init().d3_assemble_tokens(_p(tok), _p(cls), _p(storage), _p(mask_token), _p(masks_u8), _p(X), n, P, R, D, _s()),
             "d3_assemble_tokens")
     return X
 
 
-def assemble_tokens_bwd(dX, masks_u8, dTok, dcls, dmask, n, P, D):
+def assemble_tokens_bwd(dX, masks_u8, dTok, dcls, dmask, n, P, D, dstorage=None):
     assert dX.dtype == f32 and dTok.dtype == bf16 and dcls.dtype == f32
-    N.check(N.init().d3_assemble_tokens_bwd(_p(dX), _p(masks_u8), _p(dTok), _p(dcls), _p(dmask), n, P, D, _s()),
-            "d3_assemble_tokens_bwd")
+    R = 0 if dstorage is None else dstorage.numel() // D
+    N.check(N.init().d3_assemble_tokens_bwd(_p(dX), _p(masks_u8), _p(dTok), _p(dcls), _p(dstorage), _p(dmask), n, P, R, D,
+                                            _s()), "d3_assemble_tokens_bwd")
 
 
 def layernorm_fwd(x, scale, bias, y, mean=None, rstd=None, eps=1e-6):
@@ -175,9 +178,9 @@ def attn_bwd(qkv, o, do, lse, delta, dqkv, n_crops, Ntok, D, H, rope_sin=None, r
     return dqkv
 
 
-def token_rows(mask_indices, rows, count, P, mode):
+def token_rows(mask_indices, rows, count, P, mode, prefix=1):
     assert rows.dtype == torch.int32 and (mask_indices is None or mask_indices.dtype == torch.int64)
-    N.check(N.init().d3_token_rows(_p(mask_indices), _p(rows), count, P, mode, _s()), "d3_token_rows")
+    N.check(N.init().d3_token_rows(_p(mask_indices), _p(rows), count, P, prefix, mode, _s()), "d3_token_rows")
     return rows
 
 

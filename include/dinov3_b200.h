@@ -84,11 +84,12 @@ int d3_gemm_bf16(const void* A, int lda, int a_major, const void* B, int ldb, in
  * [p*p*3, D]); models/vision_transformer.py:173-203: where(mask, mask_token, x), prepend cls.                        */
 int d3_im2col(const void* img_bf16 /*[n,H,W,3]*/, void* out_bf16 /*[n*Hp*Wp, ld_out >= p*p*3], padding zeroed*/,
               int ld_out, int n, int H, int W, int p, void* stream);
-int d3_assemble_tokens(const float* tok /*[n*P,D]*/, const float* cls /*[D]*/, const float* mask_token /*[D]*/,
-                       const unsigned char* masks /*[n*P] or NULL*/, float* X /*[n,1+P,D]*/, int n, int P, int D,
-                       void* stream);
+int d3_assemble_tokens(const float* tok /*[n*P,D]*/, const float* cls /*[D]*/, const float* storage /*[R,D] or NULL*/,
+                       const float* mask_token /*[D]*/, const unsigned char* masks /*[n*P] or NULL*/,
+                       float* X /*[n,1+R+P,D]: cls, R storage tokens, patches*/, int n, int P, int R, int D, void* stream);
 int d3_assemble_tokens_bwd(const float* dX, const unsigned char* masks, void* dTok_bf16 /*[n*P,D]*/,
-                           float* dcls /*[D] +=*/, float* dmask_token /*[D] +=*/, int n, int P, int D, void* stream);
+                           float* dcls /*[D] +=*/, float* dstorage /*[R,D] += or NULL*/, float* dmask_token /*[D] +=*/,
+                           int n, int P, int R, int D, void* stream);
 
 /* ---- LayerNorm (models/vision_transformer.py:40: eps 1e-6, biased variance E[x^2]-E[x]^2, fp32 statistics) ------- */
 int d3_layernorm_fwd(const float* x /*[T,D]*/, const float* scale, const float* bias, void* y, int y_is_f32,
@@ -138,7 +139,8 @@ int d3_debug_attn_trace(long long* buf);
 
 /* ---- row gather / scatter (train/ssl_meta_arch.py:377,432 patch.reshape(-1,D)[mask_indices_list]; cls = token 0) --- */
 int d3_token_rows(const long long* mask_indices /*int64 [count] (mode 0)*/, int* rows /*int32 [count]*/, int count,
-                  int P, int mode /*0: masked patch -> token row, 1: cls row of crop i*/, void* stream);
+                  int P, int prefix /*tokens before the patches: 1 + n_storage_tokens*/,
+                  int mode /*0: masked patch -> token row, 1: cls row of crop i*/, void* stream);
 int d3_gather_rows(const float* src /*[*,D]*/, const int* rows, void* dst_bf16 /*or NULL*/, float* dst_f32 /*or NULL*/,
                    int R, int D, void* stream);
 int d3_scatter_add_rows(const void* src, int src_is_f32, const int* rows, float* dst /*+=*/, int R, int D, void* stream);

@@ -39,7 +39,8 @@ class ModelCfg:
     mask_probability: float = 0.5   # ibot.mask_sample_probability  :44
     mask_ratio: tuple = (0.1, 0.5)  # ibot.mask_ratio_min_max       :43
     clip_grad: float = 3.0          # optim.clip_grad               :148
-    ln_eps: float = 1e-6            # models/vision_transformer.py:40
+    ln_eps: float = 1e-6            # models/vision_transformer.py:40 (layernormbf16: 1e-5, :41)
+    n_storage: int = 0              # student.n_storage_tokens (models/vision_transformer.py:106-111)
     mlp_second_act: bool = True     # layers/ffn_layers.py:47 applies GELU after fc2 as well
 
     @property
@@ -50,8 +51,12 @@ class ModelCfg:
     def hidden(self) -> int:
         return int(self.embed_dim * self.ffn_ratio)
 
+    @property
+    def prefix(self) -> int:
+        return 1 + self.n_storage
+
     def tokens(self, size: int) -> int:
-        return (size // self.patch) ** 2 + 1
+        return (size // self.patch) ** 2 + self.prefix
 
     @property
     def n_patches_global(self) -> int:

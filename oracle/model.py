@@ -69,6 +69,8 @@ def init_backbone(cfg: ModelCfg, gen: torch.Generator, dtype=torch.float32) -> d
     P["patch_embed/proj/bias"] = torch.zeros(D, dtype=dtype)
     P["cls_token"] = (torch.randn((1, 1, D), generator=gen, dtype=torch.float64) * 0.02).to(dtype)  # :95-99
     P["mask_token"] = torch.zeros((1, D), dtype=dtype)                                             # :165-169
+    if cfg.n_storage:                                                                              # :106-111
+        P["storage_tokens"] = (torch.randn((1, cfg.n_storage, D), generator=gen, dtype=torch.float64) * 0.02).to(dtype)
     for i in range(cfg.depth):
         b = f"blocks_{i}/"
         P[b + "norm1/scale"] = torch.ones(D, dtype=dtype)
@@ -160,7 +162,7 @@ def init_params(cfg: ModelCfg, seed: int = 0, dtype=torch.float32, teacher_copy:
     if perturb > 0:
         for sub in student.values():
             for k, v in sub.items():
-                if k.endswith("/bias") or k.endswith("/scale") or k.endswith("/gamma") or k in ("mask_token",):
+                if k.endswith("/bias") or k.endswith("/scale") or k.endswith("/gamma") or k in ("mask_token", "storage_tokens"):
                     v.add_(torch.randn(v.shape, generator=gen, dtype=torch.float64).to(dtype) * perturb)
     for m in MODULES:
         for k, v in student[m].items():
@@ -283,7 +285,10 @@ def backbone_forward(P: dict, x_list, masks_list, cfg: ModelCfg, emu: Emu = Emu(
             cls = P["cls_token"]
         else:                                                   # :185-187
             cls = P["cls_token"] + 0 * P["mask_token"]
-        t = torch.cat([cls.expand(t.shape[0], -1, -1), t], dim=1)   # :197-201 (no storage tokens by default)
+        parts = [cls.expand(t.shape[0], -1, -1)]
+        if cfg.n_storage:                                       # :189-201 register tokens between cls and patches
+            parts.append(P["storage_tokens"].to(t.dtype).expand(t.shape[0], -1, -1))
+        t = torch.cat(parts + [t], dim=1)
         toks.append(t)
         sc = rope_sincos(Hp, Wp, cfg.head_dim, cfg.rope_base, t.dtype)
         ropes.append((sc[0].to(t.device), sc[1].to(t.device)))
@@ -292,7 +297,9 @@ def backbone_forward(P: dict, x_list, masks_list, cfg: ModelCfg, emu: Emu = Emu(
     outs = []
     for t in toks:
         xn = layer_norm(t, P["norm/scale"], P["norm/bias"], cfg.ln_eps)      # :234
-        outs.append({"x_norm_clstoken": xn[:, 0], "x_norm_patchtokens": xn[:, 1:], "x_prenorm": t})
+        R = cfg.n_storage                                                    # :231-245
+        outs.append({"x_norm_clstoken": xn[:, 0], "x_storage_tokens": xn[:, 1:1 + R], "x_norm_patchtokens": xn[:, 1 + R:],
+                     "x_prenorm": t})
     return outs
 
 

@@ -165,6 +165,20 @@ def main():
     out.update(vit_global=g.astype(np.float32), vit_local=l.astype(np.float32), vit_masks=vmask,
                vit_g_cls=np.asarray(og["x_norm_clstoken"]), vit_g_patch=np.asarray(og["x_norm_patchtokens"]),
                vit_l_cls=np.asarray(ol["x_norm_clstoken"]), vit_l_patch=np.asarray(ol["x_norm_patchtokens"]))
+    # same network with 4 storage (register) tokens and norm_layer="layernormbf16" (eps 1e-5); closed-form parameters
+    from oracle.model import formula_images, formula_params
+    cfg_r = ModelCfg(embed_dim=128, depth=2, heads=2, global_size=64, local_size=32, n_prototypes=48, head_hidden=64,
+                     head_bottleneck=32, n_storage=4, ln_eps=1e-5)
+    Pr = sub(formula_params(cfg_r, 9), "student_backbone")
+    jaxshim.PARAMS.clear(); jaxshim.PARAMS.update({k: v.numpy() for k, v in Pr.items()})
+    model_r = vt.DinoVisionTransformer(img_size=64, patch_size=16, embed_dim=128, n_blocks=2, num_heads=2, ffn_ratio=4.0,
+                                       qkv_bias=True, layerscale_init=0.5, norm_layer="layernormbf16", ffn_layer="mlp",
+                                       n_storage_tokens=4)
+    gr, lr_ = formula_images((2, 64, 64, 3), 31).numpy(), formula_images((3, 32, 32, 3), 32).numpy()
+    ogr, olr = model_r([J(gr), J(lr_)], masks=[J(vmask), None], is_training=True)
+    out.update(vitr_g_cls=np.asarray(ogr["x_norm_clstoken"]), vitr_g_storage=np.asarray(ogr["x_storage_tokens"]),
+               vitr_g_patch=np.asarray(ogr["x_norm_patchtokens"]), vitr_l_cls=np.asarray(olr["x_norm_clstoken"]),
+               vitr_l_storage=np.asarray(olr["x_storage_tokens"]), vitr_l_patch=np.asarray(olr["x_norm_patchtokens"]))
     # inference entry point (is_training=False returns the head(cls) path = Identity -> x_norm_clstoken)
     hp = sub(P, "student_dino_head")
     jaxshim.PARAMS.clear(); jaxshim.PARAMS.update({k: v.numpy() for k, v in hp.items()})
@@ -196,14 +210,16 @@ def main():
     class AD(dict):
         __getattr__ = dict.__getitem__
     ad = lambda x: AD({k: ad(v) for k, v in x.items()}) if isinstance(x, dict) else x
-    for case, (B, n_local, temp, seed) in {"a": (4, 3, 0.05, 1), "b": (3, 8, 0.07, 2)}.items():
+    for case, (B, n_local, temp, seed, n_storage, norm) in {"a": (4, 3, 0.05, 1, 0, "layernorm"), "b": (3, 8, 0.07, 2, 0, "layernorm"),
+                                                            "c": (2, 4, 0.06, 3, 4, "layernormbf16")}.items():
         rcfg = ad(yaml.safe_load(open(REF + "/configs/ssl_default_config.yaml")))
         rcfg.student.arch = "vit_test"
+        rcfg.student.n_storage_tokens, rcfg.student.norm_layer = n_storage, norm      # register tokens / eps 1e-5 (§8f.1)
         rcfg.crops.global_crops_size, rcfg.crops.local_crops_size, rcfg.crops.local_crops_number = 64, 32, n_local
         for h in (rcfg.dino, rcfg.ibot):
             h.head_n_prototypes, h.head_hidden_dim, h.head_bottleneck_dim = 48, 64, 32
         mc = ModelCfg(embed_dim=128, depth=2, heads=2, global_size=64, local_size=32, n_local=n_local, n_prototypes=48,
-                      head_hidden=64, head_bottleneck=32)
+                      head_hidden=64, head_bottleneck=32, n_storage=n_storage, ln_eps=1e-5 if norm == "layernormbf16" else 1e-6)
         P = formula_params(mc, seed)
         jaxshim.PARAMS.clear(); jaxshim.PARAMS.update({k: v.numpy() for k, v in P.items()})
         random.seed(seed); np.random.seed(seed)
@@ -214,7 +230,7 @@ def main():
                 "masks_weight": J(md["masks_weight"].numpy()), "n_masked_patches": J(md["n_masked_patches"].numpy()),
                 "upperbound": md["upperbound"], "global_batch_size": B}
         loss, metrics = arch_mod.SSLMetaArch(rcfg)(data, teacher_temp=temp, iteration=0)
-        out[f"ssl_{case}_spec"] = np.array([B, n_local, seed], dtype=np.int64)
+        out[f"ssl_{case}_spec"] = np.array([B, n_local, seed, n_storage, int(norm == "layernormbf16")], dtype=np.int64)
         out[f"ssl_{case}_teacher_temp"] = np.array(temp)
         out[f"ssl_{case}_masks"] = md["collated_masks"].numpy()
         out[f"ssl_{case}_mask_indices"] = md["mask_indices_list"].numpy()

@@ -162,7 +162,7 @@ def test_softmax_centering_path_matches_oracle():
     assert float(torch.sqrt(num / den)) < 3e-2
 
 
-@pytest.mark.parametrize("case", ["a", "b"])
+@pytest.mark.parametrize("case", ["a", "b", "c"])
 def test_engine_loss_against_reference_meta_arch_golden(case):
     """Engine forward vs numbers produced by the reference's own SSLMetaArch.__call__ (tests/golden/make_golden.py);
     the oracle is not involved.  Loss terms 1e-3 rel would be the fp32 bar; these fixtures use large-amplitude head
@@ -224,3 +224,13 @@ def test_checkpoint_round_trip_resumes_identically(tmp_path):
     pa, pb = a.params.export_reference_tree("param"), b.params.export_reference_tree("param")
     worst = max(float((pa[k] - pb[k]).abs().max()) for k in pa)
     assert worst < 1e-5            # fp32 atomics in the gradient reductions are the only source of run-to-run difference
+
+
+def test_step_with_storage_tokens_and_layernormbf16():
+    """4 register tokens (N = 1 + 4 + P, RoPE prefix 5, storage-token gradients) and eps 1e-5."""
+    from oracle import tiny_cfg
+    r = run_pair(tiny_cfg(n_storage=4, ln_eps=1e-5, layerscale=0.5), 3, seed=2)
+    check(r)
+    g = r["grads"]["student_backbone/storage_tokens"]
+    e = float((r["grads_e"]["student_backbone/storage_tokens"].reshape(g.shape) - g).norm() / g.norm())
+    assert e < 6e-2

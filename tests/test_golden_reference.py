@@ -137,9 +137,9 @@ def ssl_case(case, dtype=torch.float64):
     """Rebuild the closed-form inputs of an SSLMetaArch fixture (tests/golden/make_golden.py)."""
     from oracle.arch import ModelCfg
     from oracle.model import formula_images, formula_params
-    B, n_local, seed = (int(v) for v in G[f"ssl_{case}_spec"])
+    B, n_local, seed, n_storage, norm_bf16 = (int(v) for v in G[f"ssl_{case}_spec"])
     cfg = ModelCfg(embed_dim=128, depth=2, heads=2, global_size=64, local_size=32, n_local=n_local, n_prototypes=48,
-                   head_hidden=64, head_bottleneck=32)
+                   head_hidden=64, head_bottleneck=32, n_storage=n_storage, ln_eps=1e-5 if norm_bf16 else 1e-6)
     masks = T(G[f"ssl_{case}_masks"])
     idx = T(G[f"ssl_{case}_mask_indices"])
     batch = {"collated_global_crops": formula_images((2 * B, 64, 64, 3), 100 + seed, dtype),
@@ -150,7 +150,23 @@ def ssl_case(case, dtype=torch.float64):
     return cfg, formula_params(cfg, seed, dtype), batch, float(G[f"ssl_{case}_teacher_temp"])
 
 
-@pytest.mark.parametrize("case", ["a", "b"])
+def test_backbone_with_storage_tokens_matches_reference_module_code():
+    """DinoVisionTransformer(n_storage_tokens=4, norm_layer="layernormbf16") from the reference sources:
+    register tokens sit between cls and the patches, are not rotated by RoPE and come back as x_storage_tokens."""
+    from oracle.arch import ModelCfg
+    from oracle.model import backbone_forward, formula_images, formula_params, sub
+    cfg = ModelCfg(embed_dim=128, depth=2, heads=2, global_size=64, local_size=32, n_prototypes=48, head_hidden=64,
+                   head_bottleneck=32, n_storage=4, ln_eps=1e-5)
+    bp = sub(formula_params(cfg, 9), "student_backbone")
+    outs = backbone_forward(bp, [formula_images((2, 64, 64, 3), 31), formula_images((3, 32, 32, 3), 32)],
+                            [T(G["vit_masks"]), None], cfg)
+    for o, tag in zip(outs, ("g", "l")):
+        assert o["x_storage_tokens"].shape[1] == 4
+        for key, name in (("x_norm_clstoken", "cls"), ("x_storage_tokens", "storage"), ("x_norm_patchtokens", "patch")):
+            assert np.abs(o[key].numpy() - G[f"vitr_{tag}_{name}"]).max() < 1e-10, (tag, name)
+
+
+@pytest.mark.parametrize("case", ["a", "b", "c"])
 def test_ssl_forward_matches_reference_meta_arch(case):
     """train/ssl_meta_arch.py SSLMetaArch.__call__ executed from the reference sources (teacher + student passes, four
     heads, iBOT gathers, both Sinkhorns, loss weights) vs oracle.step.ssl_forward, float64.  The gradient the oracle

@@ -429,3 +429,27 @@ def test_gemm_scatter_epilogue_and_peer_push(M, N, K, world):
     ops.scatter_add_peers(src, peers, 8 * world, shard, 0.25)
     ref[8 * world: 8 * world + src.numel()] += 0.25 * src
     assert rel(torch.cat(shards), ref) < 2e-3
+
+
+def test_token_assembly_with_storage_tokens_bit_exact():
+    from dinov3_jax import ops
+    n, P, R, D = 3, 16, 4, 128
+    tok = torch.randn(n * P, D, device="cuda"); cls = torch.randn(D, device="cuda"); st = torch.randn(R * D, device="cuda")
+    mt = torch.randn(D, device="cuda"); masks = (torch.rand(n, P, device="cuda") < 0.4)
+    X = torch.empty(n, 1 + R + P, D, device="cuda")
+    ops.assemble_tokens(tok, cls, mt, masks.to(torch.uint8).contiguous(), X, n, P, D, storage=st)
+    ref = torch.cat([cls.expand(n, 1, D), st.view(1, R, D).expand(n, R, D),
+                     torch.where(masks[..., None], mt.view(1, 1, D), tok.view(n, P, D))], dim=1)
+    assert torch.equal(X, ref)
+    dX = torch.randn(n, 1 + R + P, D, device="cuda")
+    dTok = torch.empty(n * P, D, device="cuda", dtype=torch.bfloat16)
+    dcls, dst, dm = torch.zeros(D, device="cuda"), torch.zeros(R * D, device="cuda"), torch.zeros(D, device="cuda")
+    ops.assemble_tokens_bwd(dX, masks.to(torch.uint8).contiguous(), dTok, dcls, dm, n, P, D, dstorage=dst)
+    assert rel(dcls, dX[:, 0].sum(0)) < 1e-6 and rel(dst.view(R, D), dX[:, 1:1 + R].sum(0)) < 1e-6
+    dp = dX[:, 1 + R:]
+    assert rel(dm, (dp * masks[..., None]).sum((0, 1))) < 1e-6
+    assert torch.equal(dTok.view(n, P, D), torch.where(masks[..., None], torch.zeros_like(dp), dp).to(torch.bfloat16))
+    idx = masks.flatten().nonzero().flatten()
+    rows = torch.empty(idx.numel(), dtype=torch.int32, device="cuda")
+    ops.token_rows(idx, rows, idx.numel(), P, 0, prefix=1 + R)
+    assert torch.equal(X.view(-1, D)[rows.long()], mt.expand(idx.numel(), D))        # masked rows hold the mask token
