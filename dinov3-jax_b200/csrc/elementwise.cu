@@ -128,6 +128,48 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* _
   }
 }
 
+
+// D = 128 * VPL known at compile time: the row stays in registers between the statistics and the normalisation (one
+// read of x), all VPL 16-byte loads of a lane are in flight together.
+template <int VPL, typename OutT>
+__global__ void __launch_bounds__(256)
+layernorm_fwd_reg_kernel(const float* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ bias,
+                         OutT* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int T, float eps) {
+  constexpr int D = VPL * 128;
+  const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
+  for (long row = (long)blockIdx.x * warps + (threadIdx.x >> 5); row < T; row += (long)gridDim.x * warps) {
+    const float4* xr = reinterpret_cast<const float4*>(x + row * (long)D);
+    float4 v[VPL];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) v[k] = xr[k * 32 + lane];
+    float s = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      s += v[k].x + v[k].y + v[k].z + v[k].w;
+      s2 += v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z + v[k].w * v[k].w;
+    }
+    s = warp_sum(s);
+    s2 = warp_sum(s2);
+    const float mean = s * (1.f / D);
+    const float var = fmaxf(s2 * (1.f / D) - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    if (lane == 0 && mean_out) { mean_out[row] = mean; rstd_out[row] = rstd; }
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int e = k * 32 + lane;
+      const float4 g = reinterpret_cast<const float4*>(scale)[e];
+      const float4 b = reinterpret_cast<const float4*>(bias)[e];
+      const float o0 = (v[k].x - mean) * rstd * g.x + b.x, o1 = (v[k].y - mean) * rstd * g.y + b.y;
+      const float o2 = (v[k].z - mean) * rstd * g.z + b.z, o3 = (v[k].w - mean) * rstd * g.w + b.w;
+      if constexpr (sizeof(OutT) == 2) {
+        reinterpret_cast<uint2*>(y + row * (long)D)[e] = make_uint2(pack_bf16(o0, o1), pack_bf16(o2, o3));
+      } else {
+        reinterpret_cast<float4*>(y + row * (long)D)[e] = make_float4(o0, o1, o2, o3);
+      }
+    }
+  }
+}
+
 // backward: dx = rstd * (g*scale - mean_D(g*scale) - xhat * mean_D(g*scale*xhat));   dx_out = dx (+ dx_add)
 // One warp per row (row pass); parameter gradients come from a second, column-major pass (coalesced, no atomics in
 // the inner loop): dscale[D] += sum_rows g*xhat ; dbias[D] += sum_rows g.
@@ -803,6 +845,38 @@ __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* _
   }
 }
 
+
+// 128-bit version: a thread owns 8 adjacent columns; blockDim = (32, 8): 8 row phases per CTA, reduced in shared memory
+__global__ void __launch_bounds__(256)
+colsum_bf16_vec_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long T, int N, int ld) {
+  __shared__ float red[8][32][9];
+  const int col = (blockIdx.x * 32 + threadIdx.x) * 8;
+  const long slab = (T + gridDim.y - 1) / gridDim.y;
+  const long r0 = blockIdx.y * slab, r1 = min(T, r0 + slab);
+  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (col < N) {
+#pragma unroll 4
+    for (long r = r0 + threadIdx.y; r < r1; r += 8) {
+      const uint4 v = *reinterpret_cast<const uint4*>(x + r * ld + col);
+      const float2 f0 = unpack_bf16(v.x), f1 = unpack_bf16(v.y), f2 = unpack_bf16(v.z), f3 = unpack_bf16(v.w);
+      a[0] += f0.x; a[1] += f0.y; a[2] += f1.x; a[3] += f1.y; a[4] += f2.x; a[5] += f2.y; a[6] += f3.x; a[7] += f3.y;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[threadIdx.y][threadIdx.x][j] = a[j];
+  __syncthreads();
+  // 256 threads -> 256 columns of this CTA
+  const int t = threadIdx.y * 32 + threadIdx.x;
+  const int lc = t >> 3, j = t & 7;
+  const int c = (blockIdx.x * 32 + lc) * 8 + j;
+  if (c < N) {
+    float tot = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) tot += red[y][lc][j];
+    atomicAdd(&out[c], tot);
+  }
+}
+
 // dst bf16 <- src fp32 (compute copy of weight matrices)
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long n) {
   const long i4 = (blockIdx.x * (long)blockDim.x + threadIdx.x) * 4;
@@ -939,6 +1013,20 @@ int d3_layernorm_fwd(const float* x, const float* scale, const float* bias, void
                      float* rstd, int T, int D, float eps, void* stream) {
   if (D % 4) return set_error(D3_ERR_ARG, "d3_layernorm_fwd: D % 4");
   int blocks = min((T + 7) / 8, sm_count() * 8);
+  if (D % 128 == 0 && D / 128 <= 12 && ((uintptr_t)x | (uintptr_t)y | (uintptr_t)scale | (uintptr_t)bias) % 16 == 0) {
+#define LN_FWD_REG(V)                                                                                                   \
+  case V:                                                                                                               \
+    if (y_is_f32) layernorm_fwd_reg_kernel<V, float><<<blocks, 256, 0, STREAM(stream)>>>(x, scale, bias, (float*)y, mean, rstd, T, eps); \
+    else layernorm_fwd_reg_kernel<V, __nv_bfloat16><<<blocks, 256, 0, STREAM(stream)>>>(x, scale, bias, (__nv_bfloat16*)y, mean, rstd, T, eps); \
+    break;
+    bool done = true;
+    switch (D / 128) {
+      LN_FWD_REG(1) LN_FWD_REG(2) LN_FWD_REG(3) LN_FWD_REG(4) LN_FWD_REG(6) LN_FWD_REG(8) LN_FWD_REG(12)
+      default: done = false;
+    }
+#undef LN_FWD_REG
+    if (done) { D3_CHECK_LAUNCH(); return D3_OK; }
+  }
   if (y_is_f32)
     layernorm_fwd_kernel<float><<<blocks, 256, 0, STREAM(stream)>>>(x, scale, bias, (float*)y, mean, rstd, T, D, eps);
   else
@@ -1107,6 +1195,13 @@ int d3_ls_act_bwd(const float* dX, const void* u, const float* gamma, void* du, 
 int d3_colsum_bf16(const void* x, float* out, long long T, int N, int ld, void* stream) {
   if (T <= 0) return D3_OK;
   if (ld % 2) return set_error(D3_ERR_ARG, "d3_colsum_bf16: ld % 2");
+  if (N % 8 == 0 && ld % 8 == 0 && (uintptr_t)x % 16 == 0 && T >= 64) {
+    const int gx = (N / 8 + 31) / 32;
+    const int gy = (int)max(1LL, min(T / 32, (long long)(sm_count() * 8 + gx - 1) / gx));
+    colsum_bf16_vec_kernel<<<dim3(gx, gy), dim3(32, 8), 0, STREAM(stream)>>>((const __nv_bfloat16*)x, out, T, N, ld);
+    D3_CHECK_LAUNCH();
+    return D3_OK;
+  }
   dim3 grid((N / 2 + 127) / 128 + ((N / 2) % 128 == 0 && N % 2 ? 1 : 0), (int)min(256LL, max(1LL, T / 64)));
   if (((N + 1) / 2 + 127) / 128 > (int)grid.x) grid.x = ((N + 1) / 2 + 127) / 128;
   colsum_bf16_kernel<<<grid, 128, 0, STREAM(stream)>>>((const __nv_bfloat16*)x, out, T, N, ld);
