@@ -127,9 +127,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint32_t v[16];
     tmem_ld16(t_row + c0, v);
     tmem_ld_wait();
+    if (c0 >= klo && c0 + 16 <= khi) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j)
-      if (c0 + j >= klo && c0 + j < khi) mx = fmaxf(mx, __uint_as_float(v[j]));
+      for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (c0 + j >= klo && c0 + j < khi) mx = fmaxf(mx, __uint_as_float(v[j]));
+    }
   }
   red[ch * 128 + r] = mx;
   __syncthreads();
@@ -143,10 +148,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tmem_ld16(t_row + c0, v);
     tmem_ld_wait();
     float p[16];
+    if (c0 >= klo && c0 + 16 <= khi) {          // whole chunk inside this row's crop
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      p[j] = (c0 + j >= klo && c0 + j < khi) ? exp2f(__uint_as_float(v[j]) * cs - mxs) : 0.f;
-      sum += p[j];
+      for (int j = 0; j < 16; ++j) {
+        p[j] = ex2_approx(fmaf(__uint_as_float(v[j]), cs, -mxs));
+        sum += p[j];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        p[j] = (c0 + j >= klo && c0 + j < khi) ? ex2_approx(fmaf(__uint_as_float(v[j]), cs, -mxs)) : 0.f;
+        sum += p[j];
+      }
     }
     uint8_t* chunk = sP + (c0 >> 6) * 16384;
     const int cc = c0 & 63;
@@ -629,14 +642,26 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       // one is computed (tcgen05.wait::ld waits for every outstanding load of the thread)
       auto compute = [&](const uint32_t (&sv)[16], const uint32_t (&dp)[16], int c0) {
         uint32_t pw[8], dw[8];
+        const int kk0 = kt * 128 + c0;
+        if (q_ok && kk0 >= klo && kk0 + 16 <= khi) {
+          // all 16 keys belong to this row's crop: no per-element masking, SFU exponent
 #pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          const int kk = kt * 128 + c0 + j;
-          const bool ok0 = q_ok && kk >= klo && kk < khi, ok1 = q_ok && kk + 1 >= klo && kk + 1 < khi;
-          const float p0 = ok0 ? exp2f(__uint_as_float(sv[j]) * cs - lse2) : 0.f;
-          const float p1 = ok1 ? exp2f(__uint_as_float(sv[j + 1]) * cs - lse2) : 0.f;
-          pw[j >> 1] = pack_bf16(p0, p1);
-          dw[j >> 1] = pack_bf16(p0 * (__uint_as_float(dp[j]) - dl) * sh.scale, p1 * (__uint_as_float(dp[j + 1]) - dl) * sh.scale);
+          for (int j = 0; j < 16; j += 2) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(sv[j]), cs, -lse2));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(sv[j + 1]), cs, -lse2));
+            pw[j >> 1] = pack_bf16(p0, p1);
+            dw[j >> 1] = pack_bf16((p0 * sh.scale) * (__uint_as_float(dp[j]) - dl), (p1 * sh.scale) * (__uint_as_float(dp[j + 1]) - dl));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            const int kk = kk0 + j;
+            const bool ok0 = q_ok && kk >= klo && kk < khi, ok1 = q_ok && kk + 1 >= klo && kk + 1 < khi;
+            const float p0 = ok0 ? ex2_approx(fmaf(__uint_as_float(sv[j]), cs, -lse2)) : 0.f;
+            const float p1 = ok1 ? ex2_approx(fmaf(__uint_as_float(sv[j + 1]), cs, -lse2)) : 0.f;
+            pw[j >> 1] = pack_bf16(p0, p1);
+            dw[j >> 1] = pack_bf16((p0 * sh.scale) * (__uint_as_float(dp[j]) - dl), (p1 * sh.scale) * (__uint_as_float(dp[j + 1]) - dl));
+          }
         }
         uint8_t* pc = sP + (c0 >> 6) * 16384;
         uint8_t* dc = sDS + (c0 >> 6) * 16384;

@@ -221,6 +221,12 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
       ::"r"(smem_u32(bar)), "h"((uint16_t)3)
       : "memory");
 }
+// 2^x on the SFU (ex2.approx, rel. error 2^-22; -inf -> 0)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
