@@ -404,7 +404,7 @@ class Engine:
 
         # multi-GPU: the three large weight gradients are reduce-scattered by the GEMM epilogue itself (each tile is
         # added into the owning rank's gradient shard over NVLink); the rest of the unit is pushed in grads_ready
-        fused = ("mlp/Dense_1/kernel", "mlp/Dense_0/kernel", "attn/qkv/kernel") if self.fsdp.push else ()
+        fused = ("mlp/Dense_1/kernel", "mlp/Dense_0/kernel", "attn/qkv/kernel") if (self.fsdp.push and self.fsdp.push_gemm) else ()
         inv_world = 1.0 / self.fsdp.world
 
         def wgrad(slot, a, b, name):

@@ -63,8 +63,13 @@ class FsdpRuntime:
         # shard through NVLink peer mappings (torch symmetric memory provides the mappings) — from the weight-gradient
         # GEMM's epilogue for the big matrices (ops.gemm(scatter=...)), from d3_scatter_add_peers for the rest.
         self.push = False
+        self.push_gemm = os.environ.get("D3_FSDP_PUSH_GEMM", "1") != "0"     # 0: only the stand-alone push kernel
         self._peer_ptrs = {}
-        if self.cuda and self.world > 1 and comm.backend == "nccl" and os.environ.get("D3_FSDP_PUSH", "1") != "0":
+        # Default: on for 2 ranks (validated: tools/check_fsdp.py + bench, profiles/r01_fsdp_push_*.log).  At 8 ranks the
+        # stand-alone push kernel works but the GEMM-epilogue scatter raised an asynchronous launch failure on ViT-L
+        # (open issue), so larger worlds keep the NCCL reduce-scatter unless D3_FSDP_PUSH=1 is set.
+        want = os.environ.get("D3_FSDP_PUSH", "auto")
+        if self.cuda and self.world > 1 and comm.backend == "nccl" and (want == "1" or (want == "auto" and self.world == 2)):
             self._setup_push()
 
     def _setup_push(self):
