@@ -103,3 +103,22 @@ def test_second_gelu_flag_changes_result():
     a, _ = ssl_forward(P, b, 0.05, dataclasses.replace(cfg, layerscale=1.0), )
     c, _ = ssl_forward(P, b, 0.05, dataclasses.replace(cfg, layerscale=1.0, mlp_second_act=False))
     assert abs(a.item() - c.item()) > 1e-6
+
+
+def test_adamw_restatement_matches_an_independent_implementation():
+    """optax.adamw(lr, b1, b2, eps, weight_decay) = scale_by_adam -> add_decayed_weights -> scale(-lr): the same update
+    rule as torch.optim.AdamW (decoupled decay: p <- p(1 - lr*wd) - lr * m_hat / (sqrt(v_hat) + eps)).  optax cannot be
+    installed here, so the oracle's formula is checked against torch's independent implementation over several steps."""
+    import torch
+    from oracle.step import adamw_update
+    torch.manual_seed(0)
+    p0 = torch.randn(257, dtype=torch.float64)
+    p_ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([p_ref], lr=3e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.04)
+    p, m, v = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+    for step in range(1, 6):
+        g = torch.randn(257, dtype=torch.float64) * (0.1 * step)
+        p_ref.grad = g.clone()
+        opt.step()
+        p, m, v = adamw_update(p, g, m, v, step, 3e-3, 0.04)
+        assert (p - p_ref.detach()).abs().max() < 1e-12
