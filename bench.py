@@ -190,6 +190,9 @@ def main():
     batch = synthetic_batch(cfg, B, seed=rank, pin=True)
     M = int(batch["mask_indices_list"].shape[0])
     eng = Engine(cfg, B, device=f"cuda:{local_rank}", max_masked=M, comm=comm)
+    if world > 1:
+        cfg_desc["grad_reduce_scatter"] = ("push over NVLink peer memory (GEMM epilogue + d3_scatter_add_peers)" if eng.fsdp.push else "nccl reduce_scatter")
+    cfg_desc["wgrad_stream"] = bool(eng.wgrad_overlap)
     log(f"engine allocated ({torch.cuda.memory_allocated() / 2**30:.1f} GiB); initialising {eng.params.n_params() / 1e6:.1f} M student params")
     init_reference_like(eng, seed=0)
     log("params loaded")
