@@ -252,11 +252,13 @@ def main():
     # (single stream for this step: with the weight-gradient stream active a launch's event pair would also time its
     # wait for SMs held by the other stream's kernel)
     overlap, eng.wgrad_overlap = eng.wgrad_overlap, False
+    fwd_overlap, eng.fwd_overlap = eng.fwd_overlap, False
     ops.PROFILE = []
     step_device(0)
     torch.cuda.synchronize()
     prof, ops.PROFILE = ops.PROFILE, None
     eng.wgrad_overlap = overlap
+    eng.fwd_overlap = fwd_overlap
     g_flops = sum(p[1] for p in prof)
     g_ms = sum(p[2].elapsed_time(p[3]) for p in prof)
     burst, sustained, hbm, how = peaks()

@@ -190,6 +190,10 @@ class Engine:
         self.dU2, self.dP = [e(T, D) for _ in range(nbuf)], [e(T, D) for _ in range(nbuf)]
         self.dU1 = [e(T, Hd) for _ in range(nbuf)]
         self.dQKV = [e(T, 3 * D) for _ in range(nbuf)]
+        self.fwd_overlap = os.environ.get("D3_FWD_STREAMS", "0") == "1"   # measured: no gain (step is power-capped), off by default
+        if self.fwd_overlap:
+            self.tstream = torch.cuda.Stream(device=self.device)
+            self._ev_fwd = [torch.cuda.Event(), torch.cuda.Event()]
         if self.wgrad_overlap:
             self.wstream = torch.cuda.Stream(device=self.device, priority=0)
             self._ev_in = [[torch.cuda.Event() for _ in range(4)] for _ in range(2)]     # main -> wgrad stream
@@ -491,19 +495,32 @@ class Engine:
             st.zero_grads()
         self.fsdp.begin_step()
         self.fsdp.prefetch(self._gather_schedule())
-        # ---- teacher (train/ssl_meta_arch.py:366-402)
+        # ---- teacher (train/ssl_meta_arch.py:366-402).  It shares nothing with the student pass until the losses, so
+        # it runs on its own stream: the HBM-bound kernels of one pass overlap the tensor-bound kernels of the other.
         T_ = self.teacher
-        self._backbone_fwd(T_, [self.g_img], [None], teacher=True)
-        ops.gather_rows(T_.Xn, self.rows_cls_t, ng, D, dst_bf16=self.h_t_dino.A0)
-        ops.gather_rows(T_.Xn, self.rows_masked_t, M, D, dst_bf16=self.h_t_ibot.A0)
-        self._head_fwd(self.h_t_dino, "dino_head", ng, teacher=True, stash=False)
-        self._head_fwd(self.h_t_ibot, "ibot_head", M, teacher=True, stash=False)
-        if self.centering == "sinkhorn_knopp":
-            self._sinkhorn(self.sk_dino, self.h_t_dino.logits, ng, teacher_temp, btot_local=ng)
-            self._sinkhorn(self.sk_ibot, self.h_t_ibot.logits, M, teacher_temp, btot_local=M)
+
+        def teacher_pass():
+            self._backbone_fwd(T_, [self.g_img], [None], teacher=True)
+            ops.gather_rows(T_.Xn, self.rows_cls_t, ng, D, dst_bf16=self.h_t_dino.A0)
+            ops.gather_rows(T_.Xn, self.rows_masked_t, M, D, dst_bf16=self.h_t_ibot.A0)
+            self._head_fwd(self.h_t_dino, "dino_head", ng, teacher=True, stash=False)
+            self._head_fwd(self.h_t_ibot, "ibot_head", M, teacher=True, stash=False)
+            if self.centering == "sinkhorn_knopp":
+                self._sinkhorn(self.sk_dino, self.h_t_dino.logits, ng, teacher_temp, btot_local=ng)
+                self._sinkhorn(self.sk_ibot, self.h_t_ibot.logits, M, teacher_temp, btot_local=M)
+            else:
+                self._softmax_center(self.sk_dino, self.center_dino, self.h_t_dino.logits, ng, teacher_temp, ng)
+                self._softmax_center(self.sk_ibot, self.center_ibot, self.h_t_ibot.logits, M, teacher_temp, M)
+
+        if self.fwd_overlap:
+            main = torch.cuda.current_stream()
+            self._ev_fwd[0].record(main)
+            self.tstream.wait_event(self._ev_fwd[0])          # batch, zeroed metrics, parameters of the last update
+            with torch.cuda.stream(self.tstream):
+                teacher_pass()
+                self._ev_fwd[1].record(self.tstream)
         else:
-            self._softmax_center(self.sk_dino, self.center_dino, self.h_t_dino.logits, ng, teacher_temp, ng)
-            self._softmax_center(self.sk_ibot, self.center_ibot, self.h_t_ibot.logits, M, teacher_temp, M)
+            teacher_pass()
         # ---- student (train/ssl_meta_arch.py:406-460)
         S_ = self.student
         self._backbone_fwd(S_, [self.g_img, self.l_img], [self.masks_u8, None], teacher=False)
@@ -512,6 +529,8 @@ class Engine:
         self._head_fwd(self.h_s_dino, "dino_head", self.Rc, teacher=False, stash=True)
         self._head_fwd(self.h_s_ibot, "ibot_head", M, teacher=False, stash=True)
         # ---- losses + d(logits) (train/ssl_meta_arch.py:463-525)
+        if self.fwd_overlap:
+            torch.cuda.current_stream().wait_event(self._ev_fwd[1])      # teacher targets ready
         t0, t1, wm, wg, slot = self.ce_dino
         ops.ce_fwd_bwd(self.h_s_dino.logits, cfg.student_temp, self.h_t_dino.logits, self.sk_dino.mx, teacher_temp,
                        self.sk_dino.s, self.sk_dino.a, self.sk_dino.btot, t0, t1, wm, wg, slot, self.metrics,
