@@ -124,3 +124,66 @@ def test_gloo_world2_gather_and_reduce_scatter():
     for r in range(world):
         ok_gather, ok_rs, s, m = ret[r]
         assert ok_gather and ok_rs and s == 3.0 and m == 1.0
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_push_reduce_scatter_addresses_cover_every_gradient_once(world, monkeypatch):
+    """The push reduce-scatter (fsdp/runtime.py: scatter_spec for the GEMM epilogue + _push_ranges for the rest) must add
+    every element of a unit's gradient exactly once into the shard slice that full_to_shard_index assigns to it.
+    The D3_EP_SCATTER / d3_scatter_add_peers address rule (owner = g // shard, slot = g % shard) is emulated in numpy."""
+    from dinov3_jax import ops
+    from dinov3_jax.fsdp.runtime import FsdpRuntime
+    spec = backbone_spec(CFG)
+    L, offsets, padded = build_layout("backbone", spec, world)
+    grad = torch.arange(1, L.n + 1, dtype=torch.float32)            # element i carries value i+1
+    shards = [np.zeros(L.n_shard, dtype=np.float64) for _ in range(world)]
+    base = [r * 10**9 for r in range(world)]                         # fake, disjoint "peer pointers" (byte addresses)
+
+    def emulate(peers, off, shard, values):
+        for i, v in enumerate(values):
+            g = off + i
+            r, slot = g // shard, g % shard
+            byte = peers[r] + 4 * slot
+            owner = next(k for k in range(world) if base[k] <= byte < base[k] + 10**9)
+            shards[owner][(byte - base[owner]) // 4] += v
+
+    class Store:
+        pass
+    st = Store()
+    st.layout, st.grad = L, grad
+    rt = FsdpRuntime.__new__(FsdpRuntime)
+    rt.world, rt.push, rt.stores, rt._peer_ptrs = world, True, {"backbone": st}, {"backbone": base}
+    monkeypatch.setattr(ops, "scatter_add_peers",
+                        lambda src, peers, off, shard, alpha: emulate(peers, off, shard, (src.double() * alpha).tolist()))
+    for u in L.units:
+        fused = tuple(t for t in u.tensors if t.endswith(("mlp/Dense_1/kernel", "mlp/Dense_0/kernel", "attn/qkv/kernel")))
+        for t in fused:                                              # what the GEMM epilogue would do for this tensor
+            peers, off, shard = rt.scatter_spec("backbone", u.name, t)
+            n = int(np.prod(dict((nm, sh) for nm, sh, _ in spec)[t]))
+            emulate(peers, off, shard, grad[offsets[t]: offsets[t] + n].double().tolist())
+        rt._push_ranges("backbone", u, fused)
+    scale = 1.0 / world
+    for r in range(world):
+        idx = L.full_to_shard_index(r)
+        want = grad.double().numpy()[idx]
+        pad = np.ones(L.n, dtype=bool)
+        for nm, sh, _ in spec:
+            pad[offsets[nm]: offsets[nm] + int(np.prod(sh))] = False
+        got = shards[r]
+        fused_mask = np.zeros(L.n, dtype=bool)
+        for nm, sh, _ in spec:
+            if nm.endswith(("mlp/Dense_1/kernel", "mlp/Dense_0/kernel", "attn/qkv/kernel")):
+                fused_mask[offsets[nm]: offsets[nm] + int(np.prod(sh))] = True
+        # fused tensors were emulated unscaled, the pushed ranges carry 1/world; alignment padding of fused tensors is
+        # never pushed (its gradient is identically zero)
+        expect = np.where(fused_mask[idx], want, want * scale)
+        expect = np.where(pad[idx] & _fused_padding(L, offsets, padded, spec)[idx], 0.0, expect)
+        assert np.allclose(got, expect), r
+
+
+def _fused_padding(L, offsets, padded, spec):
+    m = np.zeros(L.n, dtype=bool)
+    for nm, sh, _ in spec:
+        if nm.endswith(("mlp/Dense_1/kernel", "mlp/Dense_0/kernel", "attn/qkv/kernel")):
+            m[offsets[nm] + int(np.prod(sh)): offsets[nm] + padded[nm]] = True
+    return m
