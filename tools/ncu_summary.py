@@ -20,8 +20,12 @@ def main(path):
             if w in idx:
                 print(f"    {w:68s} {r[idx[w]]:>16s} {units[idx[w]]}")
         try:
-            rd, wr = float(r[idx["dram__bytes_read.sum"]]), float(r[idx["dram__bytes_write.sum"]])
-            print(f"    {'traffic = dram read + write':68s} {rd + wr:16.1f} {units[idx['dram__bytes_read.sum']]}")
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+            rd = float(r[idx["dram__bytes_read.sum"]]) * scale[units[idx["dram__bytes_read.sum"]]]
+            wr = float(r[idx["dram__bytes_write.sum"]]) * scale[units[idx["dram__bytes_write.sum"]]]
+            print(f"    {'traffic = dram read + write':68s} {(rd + wr) / 1e6:16.1f} Mbyte")
+            t = float(r[idx["gpu__time_duration.sum"]]) * {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}.get(units[idx["gpu__time_duration.sum"]], 1e-6)
+            print(f"    {'dram traffic / duration':68s} {(rd + wr) / t / 1e9:16.1f} GB/s")
         except Exception:
             pass
 
