@@ -1,7 +1,11 @@
 """iBOT block-mask generator with the reference's interface (dinov3_jax/data/masking.py:14-100).
 
 Own implementation; it consumes the `random` / `numpy.random` streams in exactly the reference's order, so equal
-seeds give bit-identical masks (tests/test_masks.py checks this against golden vectors produced by the reference file).
+seeds give bit-identical masks (tests/test_golden_reference.py checks this against vectors produced by the reference
+file).  The draw order that has to be preserved, per rectangle attempt: area ~ U(min, budget) and log-aspect ~ U(lo, hi)
+from `random.uniform`, then the top and the left corner from `random.randint` — only when the rectangle fits strictly
+inside the grid; a rectangle is accepted when it adds between 1 and `budget` new cells; the remainder up to the
+requested count is filled with one `numpy.random.choice` over the still-free cells (flattened, row-major).
 """
 from __future__ import annotations
 
@@ -23,8 +27,8 @@ class MaskingGenerator:
         self.log_aspect_ratio = (math.log(min_aspect), math.log(hi))
 
     def __repr__(self):
-        return (f"Generator({self.height}, {self.width} -> [{self.min_num_patches} ~ {self.max_num_patches}], "
-                f"max = {self.num_masking_patches}, {self.log_aspect_ratio[0]:.3f} ~ {self.log_aspect_ratio[1]:.3f})")
+        lo, hi = self.log_aspect_ratio
+        return f"MaskingGenerator(grid={self.height}x{self.width}, block={self.min_num_patches}..{self.max_num_patches}, log_aspect=[{lo:.3f}, {hi:.3f}])"
 
     def get_shape(self):
         return self.height, self.width
