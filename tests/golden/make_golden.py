@@ -24,6 +24,8 @@
   * hubconf.py: the function `setup_checkpoint` (torch-hub state-dict key mapper, :40-70) is exec'ed from its source
     text (the module body around it downloads a model) on a synthetic state dict with Meta's key names; the produced
     key list and transpose decisions pin dinov3_jax.checkpointer.convert_torch_hub_state_dict.
+  * train/train.py: `build_schedulers` (:124-182) exec'ed from its source text with the reference CosineScheduler on the
+    reference's default YAML (epoch length / epochs shortened).
 Usage:  python tests/golden/make_golden.py      (writes next to this file; the .npz files are committed)
 """
 from __future__ import annotations
@@ -209,6 +211,7 @@ def main():
 
     class AD(dict):
         __getattr__ = dict.__getitem__
+        __setattr__ = dict.__setitem__
     ad = lambda x: AD({k: ad(v) for k, v in x.items()}) if isinstance(x, dict) else x
     for case, (B, n_local, temp, seed, n_storage, norm) in {"a": (4, 3, 0.05, 1, 0, "layernorm"), "b": (3, 8, 0.07, 2, 0, "layernorm"),
                                                             "c": (2, 4, 0.06, 3, 4, "layernormbf16")}.items():
@@ -265,6 +268,22 @@ def main():
     out["hub_jax_keys"] = np.array(sorted(mapped))
     out["hub_qkv_kernel_b0"] = np.asarray(mapped["blocks_0.attn.qkv.kernel"])
     out["hub_fc1_kernel_b1"] = np.asarray(mapped["blocks_1.mlp.Dense_0.kernel"])
+
+    # ---- build_schedulers (train/train.py:124-182): the function text is exec'ed (the module imports optax / orbax)
+    tsrc = open(REF + "/train/train.py").read()
+    fn_src = tsrc[tsrc.index("def build_schedulers(config):"):]
+    fn_src = fn_src[: fn_src.index("\n    return (")] + "\n    return (lr_schedule, wd_schedule, momentum_schedule, teacher_temp_schedule, last_layer_lr_schedule)\n"
+    import logging as _logging
+    ns2 = {"CosineScheduler": sched.CosineScheduler, "logger": _logging.getLogger("dinov3")}
+    exec(fn_src, ns2)
+    scfg = ad(yaml.safe_load(open(REF + "/configs/ssl_default_config.yaml")))
+    scfg.train.OFFICIAL_EPOCH_LENGTH = 20
+    scfg.optim.epochs, scfg.optim.warmup_epochs, scfg.optim.freeze_last_layer_epochs = 12, 3, 1
+    scfg.teacher.warmup_teacher_temp_epochs = 4
+    scfg.pop("schedules", None)
+    for nm, sc_ in zip(("lr", "wd", "momentum", "teacher_temp", "last_layer_lr"), ns2["build_schedulers"](scfg)):
+        out[f"bs_{nm}"] = np.asarray(sc_.schedule, dtype=np.float64)
+        out[f"bs_{nm}_probe"] = np.array([sc_[0], sc_[7], sc_[10 ** 6]], dtype=np.float64)     # __getitem__ incl. past-the-end
     np.savez_compressed(os.path.join(HERE, "reference_vectors.npz"), **out)
     print("wrote", os.path.join(HERE, "reference_vectors.npz"), len(out), "arrays")
 

@@ -181,3 +181,15 @@ def test_ssl_forward_matches_reference_meta_arch(case):
     for k in keys:
         want = float(G[f"ssl_{case}_metric/{k}"])
         assert abs(float(metrics[k]) - want) < 1e-9 * max(abs(want), 1.0), k
+
+
+def test_build_schedulers_bit_exact_against_reference_function():
+    """dinov3_jax.train.train.build_schedulers vs the reference's function (train/train.py:124-182) executed on its own
+    default YAML with OFFICIAL_EPOCH_LENGTH=20, epochs=12, warmup 3, freeze-last-layer 1, teacher-temp warm-up 4."""
+    from dinov3_jax.configs import DinoV3SetupArgs, setup_config
+    from dinov3_jax.train.train import build_schedulers
+    cfg = setup_config(DinoV3SetupArgs(opts=["train.OFFICIAL_EPOCH_LENGTH=20", "optim.epochs=12", "optim.warmup_epochs=3",
+                                             "optim.freeze_last_layer_epochs=1", "teacher.warmup_teacher_temp_epochs=4"]))
+    for name, sc in zip(("lr", "wd", "momentum", "teacher_temp", "last_layer_lr"), build_schedulers(cfg)):
+        assert np.array_equal(np.asarray(sc.schedule, dtype=np.float64), G[f"bs_{name}"]), name
+        assert np.array_equal(np.array([sc[0], sc[7], sc[10 ** 6]], dtype=np.float64), G[f"bs_{name}_probe"]), name
