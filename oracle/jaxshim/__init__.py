@@ -319,6 +319,12 @@ def install():
             return {k: tree_map(fn, v, *[r[k] for r in rest], is_leaf=is_leaf) for k, v in tree.items()}
         return fn(tree, *rest)
     jtu.tree_map = tree_map
+
+    def tree_leaves(tree):
+        if isinstance(tree, dict):
+            return [l for v in tree.values() for l in tree_leaves(v)]
+        return [tree]
+    jtu.tree_leaves = tree_leaves
     jax.tree_util = jtu
     jax.vmap = lambda f: (lambda x: np.stack([f(r) for r in x]))
 

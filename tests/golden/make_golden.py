@@ -26,6 +26,8 @@
     key list and transpose decisions pin dinov3_jax.checkpointer.convert_torch_hub_state_dict.
   * train/train.py: `build_schedulers` (:124-182) exec'ed from its source text with the reference CosineScheduler on the
     reference's default YAML (epoch length / epochs shortened).
+  * train/train.py: the per-submodule gradient clipping block of train_step (:516-541, nested helpers `global_norm`,
+    `clip_grads` and the loop over student submodules) exec'ed from its source text on a random gradient tree.
 Usage:  python tests/golden/make_golden.py      (writes next to this file; the .npz files are committed)
 """
 from __future__ import annotations
@@ -284,6 +286,24 @@ def main():
     for nm, sc_ in zip(("lr", "wd", "momentum", "teacher_temp", "last_layer_lr"), ns2["build_schedulers"](scfg)):
         out[f"bs_{nm}"] = np.asarray(sc_.schedule, dtype=np.float64)
         out[f"bs_{nm}_probe"] = np.array([sc_[0], sc_[7], sc_[10 ** 6]], dtype=np.float64)     # __getitem__ incl. past-the-end
+
+    # ---- per-submodule gradient clipping (train/train.py:516-541): the two nested helpers + the loop, exec'ed from text
+    blk = tsrc[tsrc.index("        def global_norm(grads):"): tsrc.index("        def min_rank_1(v):")]
+    import textwrap
+    import jax as _jax, jax.numpy as _jnp
+    crng = np.random.default_rng(5)
+    gtree = {m_: {"a": {"kernel": J(crng.standard_normal((7, 5)) * s_), "bias": J(crng.standard_normal(5) * s_)},
+                  "b": J(crng.standard_normal(11) * s_)}
+             for m_, s_ in (("student_backbone", 2.0), ("student_dino_head", 0.05), ("student_ibot_head", 0.6))}
+    flat3 = lambda t: np.concatenate([np.asarray(t["a"]["kernel"]).ravel(), np.asarray(t["a"]["bias"]).ravel(), np.asarray(t["b"]).ravel()])
+    clip_inputs = {m_: flat3(gtree[m_]).copy() for m_ in gtree}        # the reference loop overwrites grads[k] in place
+    ns3 = {"jnp": _jnp, "jax": _jax, "config": ad({"optim": {"clip_grad": 3.0}}), "grads": gtree,
+           "student_params": {k: None for k in gtree}, "metrics_dict": {}}
+    exec(textwrap.dedent(blk), ns3)
+    for m_ in gtree:
+        out[f"clip_in/{m_}"] = clip_inputs[m_]
+        out[f"clip_out/{m_}"] = flat3(ns3["grads"][m_])
+        out[f"clip_norm/{m_}"] = np.asarray(ns3["metrics_dict"][f"{m_}_grad_norm"], dtype=np.float64)
     np.savez_compressed(os.path.join(HERE, "reference_vectors.npz"), **out)
     print("wrote", os.path.join(HERE, "reference_vectors.npz"), len(out), "arrays")
 

@@ -193,3 +193,22 @@ def test_build_schedulers_bit_exact_against_reference_function():
     for name, sc in zip(("lr", "wd", "momentum", "teacher_temp", "last_layer_lr"), build_schedulers(cfg)):
         assert np.array_equal(np.asarray(sc.schedule, dtype=np.float64), G[f"bs_{name}"]), name
         assert np.array_equal(np.array([sc[0], sc[7], sc[10 ** 6]], dtype=np.float64), G[f"bs_{name}_probe"]), name
+
+
+def test_gradient_clipping_matches_reference_block():
+    """train/train.py:516-541 (per top-level student submodule: g * min(1, 3 / (||g|| + 1e-6)), norm reported as
+    `{module}_grad_norm`) executed from the reference text vs oracle.step.clip_by_module.  One module is above the
+    threshold (scaled), one far below (untouched), one in between."""
+    from oracle.step import clip_by_module
+    grads = {}
+    for m in ("student_backbone", "student_dino_head", "student_ibot_head"):
+        flat = T(G[f"clip_in/{m}"])
+        grads[f"{m}/a/kernel"], grads[f"{m}/a/bias"], grads[f"{m}/b"] = flat[:35].reshape(7, 5), flat[35:40], flat[40:]
+    out, norms = clip_by_module(grads, 3.0)
+    scaled = 0
+    for m in ("student_backbone", "student_dino_head", "student_ibot_head"):
+        got = torch.cat([out[f"{m}/a/kernel"].reshape(-1), out[f"{m}/a/bias"], out[f"{m}/b"]]).numpy()
+        assert np.abs(got - G[f"clip_out/{m}"]).max() < 1e-12
+        assert abs(float(norms[f"{m}_grad_norm"]) - float(G[f"clip_norm/{m}"])) < 1e-12
+        scaled += int(float(G[f"clip_norm/{m}"]) > 3.0)
+    assert scaled >= 1
