@@ -24,9 +24,12 @@ reference cannot be executed end to end here.  The oracle is pinned as far as th
     heads, iBOT gathers, Sinkhorns, loss weights, metrics) runs unmodified under the same shim on the reference's
     default YAML; `oracle.step.ssl_forward` matches its loss and metrics to 1e-9 (the oracle's gradients are torch
     autograd of that function);
-  * analytic micro-cases (uniform Sinkhorn, LN of constant rows, orthogonal KoLeo pairs ...) in `tests/`.
+  * `build_schedulers` and the gradient-clipping block of `train_step` (train/train.py:124-182,516-541) are exec'ed from
+    their source text; the schedules are reproduced bit-exactly, the clipping to 1e-12;
+  * analytic micro-cases (uniform Sinkhorn, LN of constant rows, orthogonal KoLeo pairs ...) in `tests/`, and the AdamW
+    rule against torch.optim.AdamW.
 What is therefore *not* pinned: the third-party op semantics themselves (flax gelu/LayerNorm/attention defaults,
-optax adamw) and train/train.py::train_step (clip + optax update; imports optax / orbax) — "parity unpinned" for
-those, stated here and in DESIGN.md.
+optax adamw) and the optax.multi_transform wiring / update application of train/train.py (imports optax) — "parity
+unpinned" for those, stated here and in DESIGN.md.
 """
 from .arch import ARCHS, ModelCfg, tiny_cfg, cfg_for  # noqa: F401
