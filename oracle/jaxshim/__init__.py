@@ -370,6 +370,15 @@ def install():
         return out
     tu.flatten_dict, tu.unflatten_dict = flatten_dict, unflatten_dict
     flax.traverse_util = tu
+    dlpack = types.ModuleType("jax.dlpack")
+
+    def from_dlpack(capsule):
+        import torch
+        t = torch.utils.dlpack.from_dlpack(capsule)
+        return _wrap((t.float() if t.dtype == torch.bfloat16 else t).numpy())
+    dlpack.from_dlpack = from_dlpack
+    jax.dlpack = dlpack
+    sys.modules["jax.dlpack"] = dlpack
     sharding = types.ModuleType("jax.sharding")
     for n in ("NamedSharding", "PartitionSpec", "Mesh"):
         setattr(sharding, n, type(n, (), {"__init__": lambda self, *a, **k: None}))

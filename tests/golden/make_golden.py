@@ -28,6 +28,8 @@
     reference's default YAML (epoch length / epochs shortened).
   * train/train.py: the per-submodule gradient clipping block of train_step (:516-541, nested helpers `global_norm`,
     `clip_grads` and the loop over student submodules) exec'ed from its source text on a random gradient tree.
+  * data/collate.py: `collate_data_and_cast` called as it is (crop stacking order, bf16 cast, NCHW -> NHWC, masks,
+    indices, weights, dlpack hand-over through the shim).
 Usage:  python tests/golden/make_golden.py      (writes next to this file; the .npz files are committed)
 """
 from __future__ import annotations
@@ -270,6 +272,19 @@ def main():
     out["hub_jax_keys"] = np.array(sorted(mapped))
     out["hub_qkv_kernel_b0"] = np.asarray(mapped["blocks_0.attn.qkv.kernel"])
     out["hub_fc1_kernel_b1"] = np.asarray(mapped["blocks_1.mlp.Dense_0.kernel"])
+
+    # ---- collate_data_and_cast (data/collate.py:16-93): the reference function itself, reference mask generator,
+    #      bf16 cast, NCHW -> NHWC, dlpack hand-over (the shim turns the capsule into a numpy array)
+    collate = load("ref_collate", "data/collate.py")
+    crng = torch.Generator().manual_seed(21)
+    nB, gs, ls = 3, 32, 16
+    samples = [({"global_crops": [torch.randn(3, gs, gs, generator=crng) for _ in range(2)],
+                 "local_crops": [torch.randn(3, ls, ls, generator=crng) for _ in range(4)]}, None) for _ in range(nB)]
+    random.seed(13); np.random.seed(13)
+    cgen = masking.MaskingGenerator(input_size=(gs // 16 * 2, gs // 16 * 2), max_num_patches=0.5 * 16)
+    cd = collate.collate_data_and_cast(samples, (0.1, 0.5), 0.5, torch.bfloat16, n_tokens=16, mask_generator=cgen)
+    for k, v in cd.items():
+        out[f"collate/{k}"] = np.asarray(v)
 
     # ---- build_schedulers (train/train.py:124-182): the function text is exec'ed (the module imports optax / orbax)
     tsrc = open(REF + "/train/train.py").read()

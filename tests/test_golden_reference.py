@@ -212,3 +212,27 @@ def test_gradient_clipping_matches_reference_block():
         assert abs(float(norms[f"{m}_grad_norm"]) - float(G[f"clip_norm/{m}"])) < 1e-12
         scaled += int(float(G[f"clip_norm/{m}"]) > 3.0)
     assert scaled >= 1
+
+
+def test_collate_data_and_cast_matches_reference_function():
+    """dinov3_jax.data.collate.collate_data_and_cast vs the reference function called on the same samples / seeds:
+    crop-major stacking, bf16 cast, NHWC layout, masks / flat indices / weights / counters — bit-exact."""
+    from dinov3_jax.data.collate import collate_data_and_cast
+    from dinov3_jax.data.masking import MaskingGenerator
+    gen = torch.Generator().manual_seed(21)
+    nB, gs, ls = 3, 32, 16
+    samples = [({"global_crops": [torch.randn(3, gs, gs, generator=gen) for _ in range(2)],
+                 "local_crops": [torch.randn(3, ls, ls, generator=gen) for _ in range(4)]}, None) for _ in range(nB)]
+    random.seed(13); np.random.seed(13)
+    mg = MaskingGenerator(input_size=(4, 4), max_num_patches=0.5 * 16)
+    d = collate_data_and_cast(samples, (0.1, 0.5), 0.5, torch.bfloat16, n_tokens=16, mask_generator=mg)
+    keys = {k.split("/", 1)[1] for k in G.files if k.startswith("collate/")}
+    assert keys == set(d.keys())
+    for k in keys:
+        want = G[f"collate/{k}"]
+        got = d[k]
+        if torch.is_tensor(got):
+            assert tuple(got.shape) == tuple(want.shape), k
+            got = got.float().numpy() if got.dtype == torch.bfloat16 else got.numpy()
+        assert np.array_equal(np.asarray(got), want), k
+    assert d["collated_global_crops"].shape == (2 * nB, gs, gs, 3) and d["collated_global_crops"].dtype == torch.bfloat16
