@@ -303,6 +303,12 @@ def install():
     lax.pmean = lambda x, axis_name=None: x
     lax.cond = lambda pred, t, f, operand=None: (t if pred else f)(operand)
     lax.axis_index = lambda name: 0
+
+    def dynamic_slice_in_dim(operand, start_index, slice_size, axis=0):
+        idx = [slice(None)] * np.ndim(operand)
+        idx[axis] = slice(int(start_index), int(start_index) + int(slice_size))
+        return _wrap(np.asarray(operand)[tuple(idx)])
+    lax.dynamic_slice_in_dim = dynamic_slice_in_dim
     jax.lax = lax
     jnn = types.ModuleType("jax.nn")
     jinit = types.ModuleType("jax.nn.initializers")
@@ -341,8 +347,13 @@ def install():
     nn.initializers = inits
     nn.Dense, nn.LayerNorm, nn.Conv, nn.Dropout, nn.Sequential = Dense, LayerNorm, Conv, Dropout, Sequential
     nn.dot_product_attention = _dot_product_attention
-    for n in ("BatchNorm", "Partitioned", "silu", "make_causal_mask"):
+    for n in ("BatchNorm", "silu", "make_causal_mask"):
         setattr(nn, n, type(n, (), {}))
+
+    class Partitioned:                     # flax.linen.Partitioned: a boxed value plus its per-axis mesh names
+        def __init__(self, value=None, names=None, mesh=None):
+            self.value, self.names, self.mesh = value, names, mesh
+    nn.Partitioned = Partitioned
     # one device: gather/shard of un-partitioned leaves is the identity, so the FSDP wrapper returns its target
     nn.map_variables = lambda target, *a, **k: target
     flax.linen = nn

@@ -30,6 +30,7 @@
     `clip_grads` and the loop over student submodules) exec'ed from its source text on a random gradient tree.
   * data/collate.py: `collate_data_and_cast` called as it is (crop stacking order, bf16 cast, NCHW -> NHWC, masks,
     indices, weights, dlpack hand-over through the shim).
+  * fsdp/utils.py: `shard_params` (:19-53) called for every rank of a 2- and 3-device axis (axis_index / psum patched).
 Usage:  python tests/golden/make_golden.py      (writes next to this file; the .npz files are committed)
 """
 from __future__ import annotations
@@ -272,6 +273,26 @@ def main():
     out["hub_jax_keys"] = np.array(sorted(mapped))
     out["hub_qkv_kernel_b0"] = np.asarray(mapped["blocks_0.attn.qkv.kernel"])
     out["hub_fc1_kernel_b1"] = np.asarray(mapped["blocks_1.mlp.Dense_0.kernel"])
+
+    # ---- fsdp/utils.py shard_params (:19-53) for every rank of a 2- and a 3-device "dp" axis
+    import jax as _jx
+    futils = importlib.import_module("dinov3_jax.fsdp.utils")
+    assert futils.__file__.startswith("/root/reference/")
+    srng = np.random.default_rng(3)
+    ptree = {"w": J(srng.standard_normal((6, 8))), "odd": J(srng.standard_normal((3, 5))), "tiny": J(srng.standard_normal(4)),
+             "cube": {"k": J(srng.standard_normal((9, 6, 4))), "sq": J(srng.standard_normal((6, 6)))}}
+    for k_, v_ in (("w", ptree["w"]), ("odd", ptree["odd"]), ("tiny", ptree["tiny"]), ("cube/k", ptree["cube"]["k"]), ("cube/sq", ptree["cube"]["sq"])):
+        out[f"shard_in/{k_}"] = np.asarray(v_)
+    keep = (_jx.lax.axis_index, _jx.lax.psum)
+    for n_ in (2, 3):
+        for r_ in range(n_):
+            _jx.lax.axis_index, _jx.lax.psum = (lambda name, r_=r_: r_), (lambda x, name, n_=n_: x * n_)
+            sh = futils.shard_params(ptree, "dp", min_param_size=8)
+            for k_, v_ in (("w", sh["w"]), ("odd", sh["odd"]), ("tiny", sh["tiny"]), ("cube/k", sh["cube"]["k"]), ("cube/sq", sh["cube"]["sq"])):
+                boxed = hasattr(v_, "names")
+                out[f"shard_out/n{n_}r{r_}/{k_}"] = np.asarray(v_.value if boxed else v_)
+                out[f"shard_axis/n{n_}r{r_}/{k_}"] = np.array(v_.names.index("dp") if boxed else -1)
+    _jx.lax.axis_index, _jx.lax.psum = keep
 
     # ---- collate_data_and_cast (data/collate.py:16-93): the reference function itself, reference mask generator,
     #      bf16 cast, NCHW -> NHWC, dlpack hand-over (the shim turns the capsule into a numpy array)

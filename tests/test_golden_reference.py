@@ -236,3 +236,28 @@ def test_collate_data_and_cast_matches_reference_function():
             got = got.float().numpy() if got.dtype == torch.bfloat16 else got.numpy()
         assert np.array_equal(np.asarray(got), want), k
     assert d["collated_global_crops"].shape == (2 * nB, gs, gs, 3) and d["collated_global_crops"].dtype == torch.bfloat16
+
+
+@pytest.mark.parametrize("n", [2, 3])
+def test_shard_params_matches_reference_function(n, monkeypatch):
+    """dinov3_jax.fsdp.utils.shard_params vs the reference function (fsdp/utils.py:19-53) run for every rank of an
+    n-device "dp" axis: which axis is split (largest divisible; ties resolved like np.argsort(...)[::-1]), which leaves
+    stay replicated (too small / no divisible axis) and the slice each rank keeps."""
+    from dinov3_jax.fsdp import utils as fu
+    names = ("w", "odd", "tiny", "cube/k", "cube/sq")
+    tree = {"w": T(G["shard_in/w"]), "odd": T(G["shard_in/odd"]), "tiny": T(G["shard_in/tiny"]),
+            "cube": {"k": T(G["shard_in/cube/k"]), "sq": T(G["shard_in/cube/sq"])}}
+    for r in range(n):
+        monkeypatch.setattr(fu, "_axis_index", lambda axis_name="dp", r=r: r)
+        monkeypatch.setattr(fu, "_axis_size", lambda axis_name="dp": n)
+        sh = fu.shard_params(tree, "dp", min_param_size=8)
+        flat = {"w": sh["w"], "odd": sh["odd"], "tiny": sh["tiny"], "cube/k": sh["cube"]["k"], "cube/sq": sh["cube"]["sq"]}
+        for k in names:
+            want_axis = int(G[f"shard_axis/n{n}r{r}/{k}"])
+            got = flat[k]
+            if want_axis < 0:
+                assert not isinstance(got, fu.Partitioned), k
+                assert np.array_equal(got.numpy(), G[f"shard_out/n{n}r{r}/{k}"])
+            else:
+                assert isinstance(got, fu.Partitioned) and got.axis == want_axis, k
+                assert np.array_equal(got.value.numpy(), G[f"shard_out/n{n}r{r}/{k}"]), k
