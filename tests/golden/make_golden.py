@@ -106,6 +106,15 @@ def main():
     out.update(dino_t_logits=t_logits, dino_s_global=s_global, dino_s_local=s_local, dino_probs=np.asarray(probs),
                dino_loss_local=np.asarray(dl(J(s_local), J(probs).reshape(2, B, K))),
                dino_loss_global=np.asarray(dl(J(s_global), J(probs).reshape(2, B, K), ignore_diagonal=True)))
+    # optional softmax-centering path (dino_clstoken_loss.py:24-33,91-95): two successive calls, the center is state
+    crng2 = np.random.default_rng(17)
+    dlc = dino.DINOLoss(K)
+    c_logits1, c_logits2 = crng2.standard_normal((6, K)), crng2.standard_normal((6, K)) + 0.5
+    c_p1 = np.asarray(dlc.softmax_center_teacher(J(c_logits1), 0.05))
+    c_center1 = np.asarray(dlc.center.value).copy()
+    c_p2 = np.asarray(dlc.softmax_center_teacher(J(c_logits2), 0.07))
+    out.update(center_logits1=c_logits1, center_logits2=c_logits2, center_probs1=c_p1, center_probs2=c_p2,
+               center_state1=c_center1, center_state2=np.asarray(dlc.center.value))
     M = 11
     p_logits = rng.standard_normal((M, K)) * 0.3
     s_patch = rng.standard_normal((M, K))

@@ -261,3 +261,15 @@ def test_shard_params_matches_reference_function(n, monkeypatch):
             else:
                 assert isinstance(got, fu.Partitioned) and got.axis == want_axis, k
                 assert np.array_equal(got.value.numpy(), G[f"shard_out/n{n}r{r}/{k}"]), k
+
+
+def test_softmax_centering_matches_reference_code():
+    """DINOLoss.softmax_center_teacher / apply_center_update (loss/dino_clstoken_loss.py:24-33,91-95): the center EMA is
+    applied BEFORE the softmax of the same call; two successive calls pin the state evolution."""
+    from oracle.losses import center_update, softmax_center_teacher
+    c = torch.zeros(1, G["center_logits1"].shape[1], dtype=torch.float64)
+    for i, temp in ((1, 0.05), (2, 0.07)):
+        x = T(G[f"center_logits{i}"])
+        c = center_update(c, x, 0.9)
+        assert np.abs(c.numpy() - G[f"center_state{i}"]).max() < 1e-14
+        assert np.abs(softmax_center_teacher(x, c, temp).numpy() - G[f"center_probs{i}"]).max() < 1e-13
