@@ -275,7 +275,9 @@ def main():
                 "ms_per_step": ms_e2e, "loss": loss},
         "roofline": {"bound": "tensor", "kernel": "gemm2sm_kernel + gemm1sm_kernel (every tcgen05 GEMM launch of one step)",
                      "achieved": gemm_tf, "peak": sustained, "unit": "TFLOP/s", "frac": gemm_tf / sustained,
-                     "traffic": traffic, "peak_source": f"bf16_tflops_sustained ({how})", "launches": len(prof),
+                     "traffic": traffic["bytes_per_launch_mean"] if traffic else None,
+                     "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)",
+                     "traffic_source": traffic["source"] if traffic else None, "peak_source": f"bf16_tflops_sustained ({how})", "launches": len(prof),
                      "share_of_step": g_ms / ms if ms else None},
         "step_roofline": {"achieved": step_tf, "peak": sustained, "unit": "TFLOP/s", "frac": step_tf / sustained,
                           "note": "attention+MLP algorithmic FLOPs (BASELINE.md §3) / step time / GPU"},
