@@ -138,7 +138,7 @@ def main():
     ap.add_argument("--patch", type=int, default=16)
     ap.add_argument("--local-size", type=int, default=96, help="98 for patch 14 (96 is not divisible, layers/patch_embed.py:48-49)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-batch", type=int, default=1)
+    ap.add_argument("--cpu-sample-batch", type=int, default=2, help="images per CPU-baseline step (bounded sample: ~15-25 s of CPU work)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -285,11 +285,11 @@ def main():
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             log("cpu baseline (oracle port) ...")
-            v, dt, _, cores = cpu_reference_rate(args.arch, cores, args.cpu_sample_batch)
+            v, dt, _, cores = cpu_reference_rate(args.arch, cores, args.cpu_sample_batch, steps=2, warmup=0)
             log(f"cpu baseline: {dt:.1f} s/step")
             out["cpu_baseline"] = {"value": v, "unit": "global-crops/s", "cores": cores, "kind": "port",
                                    "sample": f"oracle train_step (torch-CPU fp32 restatement), {args.arch}, "
-                                             f"{args.cpu_sample_batch} images, 1 step of {dt:.1f} s"}
+                                             f"{args.cpu_sample_batch} images per step, 2 steps of {dt:.1f} s"}
         print(json.dumps(out))
     if world > 1:
         torch.distributed.destroy_process_group()
