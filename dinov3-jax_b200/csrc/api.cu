@@ -64,9 +64,20 @@ int encode_tensor_map_2d(CUtensorMap* map, const void* ptr, int elt_bytes, cuuin
 
 }  // namespace d3
 
+static int g_scatter_mode = -1;
+namespace d3 {
+int scatter_mode() {
+  if (g_scatter_mode < 0) { const char* e = getenv("D3_FSDP_PUSH_SYS"); g_scatter_mode = (e && e[0] == '1') ? 1 : 0; }
+  return g_scatter_mode;
+}
+void set_scatter_mode(int mode) { g_scatter_mode = mode ? 1 : 0; }
+}  // namespace d3
+
 using namespace d3;
 
 extern "C" {
+
+int d3_set_scatter_mode(int mode) { d3::set_scatter_mode(mode); return D3_OK; }
 
 int d3_abi_version(void) { return 2; }   // 2: d3_gemm_epilogue gained the sc_* scatter fields
 int d3_set_sm_limit(int n) {
@@ -115,7 +126,7 @@ int d3_gemm_bf16(const void* A, int lda, int a_major, const void* B, int ldb, in
   g.out = ep->out; g.ld_out = ep->ld_out; g.ld_aux = ep->ld_aux; g.ld_resid = ep->ld_resid;
   g.flags = ep->flags & 0x1FF; g.alpha = ep->alpha;
   for (int i = 0; i < 8; ++i) g.sc_peer[i] = ep->sc_peer[i];
-  g.sc_off = ep->sc_off; g.sc_shard = ep->sc_shard; g.sc_world = ep->sc_world;
+  g.sc_off = ep->sc_off; g.sc_shard = ep->sc_shard; g.sc_world = ep->sc_world; g.sc_sys = scatter_mode();
   if (g.flags & EP_SCATTER)
     for (int i = 0; i < g.sc_world && i < 8; ++i)
       if (!g.sc_peer[i]) return set_error(D3_ERR_ARG, "scatter flag without peer pointers");

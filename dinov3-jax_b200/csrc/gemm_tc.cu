@@ -51,8 +51,13 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, size_t ro
       }
       const unsigned long long g = g0 + j;                      // a float4 never straddles two owners (shard % 4 == 0)
       const unsigned r = (unsigned)(g / shard);
-      atomicAdd(reinterpret_cast<float4*>(ep.sc_peer[r] + (g - (unsigned long long)r * shard)),
-                make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+      float* dst = ep.sc_peer[r] + (g - (unsigned long long)r * shard);
+      if (ep.sc_sys) {
+        atomicAdd_system(dst, v[j]); atomicAdd_system(dst + 1, v[j + 1]);
+        atomicAdd_system(dst + 2, v[j + 2]); atomicAdd_system(dst + 3, v[j + 3]);
+      } else {
+        atomicAdd(reinterpret_cast<float4*>(dst), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+      }
     }
     return;
   }

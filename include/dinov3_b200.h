@@ -116,6 +116,9 @@ int d3_ls_gamma_from_wgrad(const void* W_bf16, const float* dW, const float* bia
  * adds alpha * src[i] into the rank owning flat index off + i of a range split into `world` slices of `shard` elements;
  * peers[r] = rank r's zero-initialised slice (a pointer valid in THIS process: NVLink peer mapping, peers[rank] local).
  * The caller orders the step with a cross-rank barrier before the slices are consumed.                               */
+/* 0 (default): one device-scope vector red per float4; 1: four scalar system-scope atomics (also env D3_FSDP_PUSH_SYS=1).
+ * Applies to D3_EP_SCATTER and d3_scatter_add_peers.                                                                   */
+int d3_set_scatter_mode(int mode);
 int d3_scatter_add_peers(const float* src, long long n, float* const* peers /*host array [world]*/, int world,
                          long long off, int shard, float alpha, void* stream);
 
