@@ -962,7 +962,11 @@ static bool launch_ln_bwd_ring(const void* dy, int dy_is_f32, const float* x, co
   const size_t fixed = 256 + 2 * D * sizeof(float);
   const size_t budget = 200 * 1024;
   int stages = (int)min((size_t)LNR_MAX_STAGES, (budget - fixed) / stageB);
-  if (stages < 3) return false;
+  // A multiple of the consumer count: then every use of a ring stage is handled by the same consumer warp, in order, so
+  // a warp can never start waiting for use u of a stage before use u-1 has completed (an mbarrier parity wait that is
+  // two phases ahead would return immediately).
+  stages = stages / LNR_CONSUMERS * LNR_CONSUMERS;
+  if (stages < LNR_CONSUMERS) return false;
   const size_t need = max(stageB * stages, (size_t)LNR_CONSUMERS * D * sizeof(float));    // ring doubles as the reduction slabs
   const size_t smem = fixed + need;
   static bool cfg_b = false, cfg_f = false;
