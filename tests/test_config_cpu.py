@@ -37,3 +37,28 @@ def test_schedulers_match_reference_construction():
 def test_cli_surface():
     a = get_args_parser().parse_args(["--config-file", "x.yaml", "--opts", "a.b=1", "c=2", "--output-dir", "out"])
     assert a.config_file == "x.yaml" and a.opts == ["a.b=1", "c=2"] and a.output_dir == "out"
+
+
+def test_storage_tokens_and_norm_layer_map_onto_the_engine_config():
+    """student.n_storage_tokens / student.norm_layer (models/vision_transformer.py:38-42,106-111) are on the B200 path;
+    SwiGLU / RMSNorm / mask_k_bias are not and are rejected loudly."""
+    cfg = setup_config(DinoV3SetupArgs(opts=["student.n_storage_tokens=4", "student.norm_layer=layernormbf16"]))
+    e = config_from_reference_cfg(cfg)
+    assert e.n_storage == 4 and e.prefix == 5 and e.ln_eps == 1e-5
+    assert e.tokens(224) == 196 + 5 and e.tokens(96) == 36 + 5
+    assert config_from_reference_cfg(setup_config(DinoV3SetupArgs())).ln_eps == 1e-6
+    for bad in ("student.ffn_layer=swiglu64", "student.norm_layer=rmsnorm", "student.mask_k_bias=true"):
+        with pytest.raises(NotImplementedError):
+            config_from_reference_cfg(setup_config(DinoV3SetupArgs(opts=[bad])))
+
+
+def test_parameter_spec_contains_storage_tokens_with_the_reference_multipliers():
+    from dinov3_jax.engine.config import config_for
+    from dinov3_jax.engine.params import backbone_spec, lr_wd_multipliers
+    cfg = config_for("vit_small", n_storage=4)
+    spec = {n: (s, k) for n, s, k in backbone_spec(cfg)}
+    assert spec["storage_tokens"] == ((1, 4, 384), "vec")
+    lr, wd, last = lr_wd_multipliers("backbone", "storage_tokens", cfg)
+    lr_cls, wd_cls, _ = lr_wd_multipliers("backbone", "cls_token", cfg)
+    assert (lr, wd, last) == (lr_cls, wd_cls, False)            # same layer-0 group as cls / mask tokens (param_groups.py:117-129)
+    assert abs(lr - cfg.layerwise_decay ** (cfg.depth + 1)) < 1e-12
