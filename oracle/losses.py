@@ -67,3 +67,23 @@ def koleo_loss(x, eps: float = 1e-8):
     idx = torch.argmax(dots, dim=1)
     dist = torch.linalg.norm(x - x[idx], ord=2, dim=-1) + eps      # pairwise_distance (:16-17)
     return -torch.log(dist + eps).mean()
+
+
+def gram_loss(output_feats, target_feats, apply_norm: bool = True, img_level: bool = True, remove_neg: bool = True,
+              remove_only_teacher_neg: bool = False):
+    """loss/gram_loss.py:13-50 (not on the round-1 GPU path): MSE between the patch-similarity (Gram)
+    matrices of student and gram-teacher features, per image ([B, N, D]) or over the whole batch ([B*N, D])."""
+    assert remove_neg != remove_only_teacher_neg
+    t, s = target_feats, output_feats
+    if apply_norm:
+        t = t / torch.linalg.norm(t, dim=-1, keepdim=True)
+        s = s / torch.linalg.norm(s, dim=-1, keepdim=True)
+    if not img_level:
+        t, s = t.reshape(-1, t.shape[-1]), s.reshape(-1, s.shape[-1])
+    t_sim, s_sim = t @ t.transpose(-1, -2), s @ s.transpose(-1, -2)
+    if remove_neg:
+        t_sim, s_sim = t_sim.clamp_min(0.0), s_sim.clamp_min(0.0)
+    else:
+        s_sim = torch.where((s_sim < 0) & (t_sim < 0), torch.zeros_like(s_sim), s_sim)
+        t_sim = t_sim.clamp_min(0.0)
+    return ((s_sim - t_sim) ** 2).mean()

@@ -115,6 +115,13 @@ def main():
     c_p2 = np.asarray(dlc.softmax_center_teacher(J(c_logits2), 0.07))
     out.update(center_logits1=c_logits1, center_logits2=c_logits2, center_probs1=c_p1, center_probs2=c_p2,
                center_state1=c_center1, center_state2=np.asarray(dlc.center.value))
+    # gram loss (loss/gram_loss.py:13-50; SURVEY 8f.2 — oracle groundwork only)
+    gram = load("ref_gram", "loss/gram_loss.py")
+    grng = np.random.default_rng(23)
+    g_s, g_t = grng.standard_normal((3, 9, 16)), grng.standard_normal((3, 9, 16))
+    gl = gram.GramLoss()
+    out.update(gram_s=g_s, gram_t=g_t, gram_img=np.asarray(gl(J(g_s), J(g_t), img_level=True)),
+               gram_batch=np.asarray(gl(J(g_s), J(g_t), img_level=False)))
     M = 11
     p_logits = rng.standard_normal((M, K)) * 0.3
     s_patch = rng.standard_normal((M, K))

@@ -273,3 +273,12 @@ def test_softmax_centering_matches_reference_code():
         c = center_update(c, x, 0.9)
         assert np.abs(c.numpy() - G[f"center_state{i}"]).max() < 1e-14
         assert np.abs(softmax_center_teacher(x, c, temp).numpy() - G[f"center_probs{i}"]).max() < 1e-13
+
+
+def test_gram_loss_matches_reference_code():
+    """loss/gram_loss.py GramLoss (defaults: normalised features, negatives removed) per image and over the batch —
+    oracle groundwork for SURVEY §8f.2; the gram teacher is not on the GPU path yet."""
+    from oracle.losses import gram_loss
+    s, t = T(G["gram_s"]), T(G["gram_t"])
+    assert abs(float(gram_loss(s, t, img_level=True)) - float(G["gram_img"])) < 1e-14
+    assert abs(float(gram_loss(s, t, img_level=False)) - float(G["gram_batch"])) < 1e-14
