@@ -31,6 +31,7 @@
   * data/collate.py: `collate_data_and_cast` called as it is (crop stacking order, bf16 cast, NCHW -> NHWC, masks,
     indices, weights, dlpack hand-over through the shim).
   * fsdp/utils.py: `shard_params` (:19-53) called for every rank of a 2- and 3-device axis (axis_index / psum patched).
+  * fsdp/ac_compile_parallelize.py: called with recording stand-ins for NamedSharding / PartitionSpec / device_put.
 Usage:  python tests/golden/make_golden.py      (writes next to this file; the .npz files are committed)
 """
 from __future__ import annotations
@@ -309,6 +310,31 @@ def main():
                 out[f"shard_out/n{n_}r{r_}/{k_}"] = np.asarray(v_.value if boxed else v_)
                 out[f"shard_axis/n{n_}r{r_}/{k_}"] = np.array(v_.names.index("dp") if boxed else -1)
     _jx.lax.axis_index, _jx.lax.psum = keep
+
+    # ---- fsdp/ac_compile_parallelize.py (:20-44): which axis every leaf is placed on, for 2 and 3 devices
+    acp = importlib.import_module("dinov3_jax.fsdp.ac_compile_parallelize")
+    assert acp.__file__.startswith("/root/reference/")
+
+    class _Spec:
+        def __init__(self, *axes): self.axes = axes
+    class _Named:
+        def __init__(self, mesh, spec): self.spec = spec
+    acp.NamedSharding, acp.P = _Named, _Spec
+    keep_j = {k_: getattr(_jx, k_, None) for k_ in ("device_count", "make_mesh", "device_put")}
+    _jx.make_mesh = lambda shape, names: None
+    _jx.device_put = lambda p_, sh_: ("placed", sh_.spec.axes)
+    atree = {"k": J(np.zeros((6, 8))), "bias": J(np.zeros(16384)), "odd": J(np.zeros((3, 5))), "cube": J(np.zeros((4, 6, 2))),
+             "sq": J(np.zeros((6, 6)))}
+    for n_ in (2, 3):
+        _jx.device_count = lambda n_=n_: n_
+        placed = acp.ac_compile_parallelize(atree, None, None)
+        for k_, v_ in placed.items():
+            axes = v_[1] if isinstance(v_, tuple) and v_[0] == "placed" else None
+            out[f"acp_axis/n{n_}/{k_}"] = np.array(-1 if axes is None or "dp" not in axes else axes.index("dp"))
+            out[f"acp_placed/n{n_}/{k_}"] = np.array(axes is not None)
+    for k_, v_ in keep_j.items():
+        if v_ is not None:
+            setattr(_jx, k_, v_)
 
     # ---- collate_data_and_cast (data/collate.py:16-93): the reference function itself, reference mask generator,
     #      bf16 cast, NCHW -> NHWC, dlpack hand-over (the shim turns the capsule into a numpy array)

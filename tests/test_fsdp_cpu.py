@@ -187,3 +187,23 @@ def _fused_padding(L, offsets, padded, spec):
         if nm.endswith(("mlp/Dense_1/kernel", "mlp/Dense_0/kernel", "attn/qkv/kernel")):
             m[offsets[nm] + int(np.prod(sh)): offsets[nm] + padded[nm]] = True
     return m
+
+
+def test_ac_compile_parallelize_policy(monkeypatch):
+    """fsdp/ac_compile_parallelize.py:20-44: >= 2-D leaves are split on their largest divisible axis whatever their
+    size, 1-D leaves never; the slices of all ranks tile the leaf."""
+    from dinov3_jax.fsdp import ac_compile_parallelize as acp
+    from dinov3_jax.fsdp.utils import Partitioned
+    tree = {"k": torch.arange(6 * 8, dtype=torch.float32).reshape(6, 8), "bias": torch.arange(4096 * 4, dtype=torch.float32),
+            "odd": torch.zeros(3, 5), "blk": {"cube": torch.arange(4 * 6 * 2, dtype=torch.float32).reshape(4, 6, 2)}}
+    parts = []
+    for r in range(2):
+        monkeypatch.setattr(acp, "_axis_index", lambda name="dp", r=r: r)
+        monkeypatch.setattr(acp, "_axis_size", lambda name="dp": 2)
+        parts.append(acp.ac_compile_parallelize(tree, None, None))
+    for p in parts:
+        assert isinstance(p["k"], Partitioned) and p["k"].axis == 1            # 8 is the largest axis
+        assert isinstance(p["blk"]["cube"], Partitioned) and p["blk"]["cube"].axis == 1
+        assert not isinstance(p["bias"], Partitioned) and not isinstance(p["odd"], Partitioned)
+    assert torch.equal(torch.cat([p["k"].value for p in parts], dim=1), tree["k"])
+    assert torch.equal(torch.cat([p["blk"]["cube"].value for p in parts], dim=1), tree["blk"]["cube"])

@@ -282,3 +282,22 @@ def test_gram_loss_matches_reference_code():
     s, t = T(G["gram_s"]), T(G["gram_t"])
     assert abs(float(gram_loss(s, t, img_level=True)) - float(G["gram_img"])) < 1e-14
     assert abs(float(gram_loss(s, t, img_level=False)) - float(G["gram_batch"])) < 1e-14
+
+
+@pytest.mark.parametrize("n", [2, 3])
+def test_ac_compile_parallelize_axes_match_reference_function(n, monkeypatch):
+    """fsdp/ac_compile_parallelize.py:20-44 executed with recording stand-ins for the jax placement API: same leaves
+    sharded, same axis chosen (1-D leaves never; >= 2-D leaves on the largest divisible axis, whatever their size)."""
+    from dinov3_jax.fsdp import ac_compile_parallelize as acp
+    from dinov3_jax.fsdp.utils import Partitioned
+    tree = {"k": torch.zeros(6, 8), "bias": torch.zeros(16384), "odd": torch.zeros(3, 5), "cube": torch.zeros(4, 6, 2),
+            "sq": torch.zeros(6, 6)}
+    monkeypatch.setattr(acp, "_axis_index", lambda name="dp": 0)
+    monkeypatch.setattr(acp, "_axis_size", lambda name="dp": n)
+    out = acp.ac_compile_parallelize(tree, None, None)
+    for k, v in out.items():
+        want = int(G[f"acp_axis/n{n}/{k}"])
+        if want < 0:
+            assert not isinstance(v, Partitioned), k
+        else:
+            assert isinstance(v, Partitioned) and v.axis == want, k
