@@ -145,7 +145,8 @@ def main():
     # ---- param groups (layer-wise decay etc.)
     pg = load("ref_pg", "train/param_groups.py")
     depth = 4
-    tree = {"patch_embed": {"proj": {"kernel": 0, "bias": 0}}, "cls_token": 0, "mask_token": 0, "norm": {"scale": 0, "bias": 0}}
+    tree = {"patch_embed": {"proj": {"kernel": 0, "bias": 0}}, "cls_token": 0, "mask_token": 0, "storage_tokens": 0,
+            "norm": {"scale": 0, "bias": 0}}
     for i in range(depth):
         tree[f"blocks_{i}"] = {"norm1": {"scale": 0, "bias": 0}, "attn": {"qkv": {"kernel": 0, "bias": 0}, "proj": {"kernel": 0, "bias": 0}},
                                "ls1": {"gamma": 0}, "norm2": {"scale": 0, "bias": 0},
