@@ -122,3 +122,38 @@ def test_adamw_restatement_matches_an_independent_implementation():
         opt.step()
         p, m, v = adamw_update(p, g, m, v, step, 3e-3, 0.04)
         assert (p - p_ref.detach()).abs().max() < 1e-12
+
+
+def test_oracle_gradient_is_the_derivative_of_the_pinned_forward():
+    """The gradient handed to the GPU parity tests is torch autograd of oracle.step.ssl_forward (itself pinned against
+    the reference's SSLMetaArch.__call__).  Central finite differences in float64 on a few student parameters of every
+    module confirm it is the derivative of that function with the teacher held fixed (train/train.py:501-513)."""
+    import torch
+    from oracle.arch import ModelCfg
+    from oracle.batch import synthetic_batch
+    from oracle.model import formula_params
+    from oracle.step import ssl_forward
+    cfg = ModelCfg(embed_dim=64, depth=1, heads=1, global_size=32, local_size=16, n_local=2, n_prototypes=24,
+                   head_hidden=32, head_bottleneck=16, layerscale=0.5)
+    P = formula_params(cfg, 4)
+    batch = synthetic_batch(cfg, 2, seed=1, dtype=torch.float64)
+    student = {k: v.clone().requires_grad_(True) for k, v in P.items() if k.startswith("student_")}
+    full = dict(P); full.update(student)
+    loss, _ = ssl_forward(full, batch, 0.05, cfg, dtype=torch.float64)
+    names = ["student_backbone/blocks_0/attn/qkv/kernel", "student_backbone/blocks_0/ls2/gamma", "student_backbone/cls_token",
+             "student_backbone/patch_embed/proj/kernel", "student_dino_head/last_layer/kernel", "student_ibot_head/mlp/layers_2/bias"]
+    grads = dict(zip(names, torch.autograd.grad(loss, [student[n] for n in names])))
+    h = 1e-6
+    for n in names:
+        flat = P[n].reshape(-1)
+        for idx in (0, flat.numel() // 2, flat.numel() - 1):
+            vals = []
+            for sgn in (+1, -1):
+                Q = dict(P)
+                q = P[n].clone().reshape(-1); q[idx] += sgn * h
+                Q[n] = q.reshape(P[n].shape)
+                with torch.no_grad():
+                    vals.append(float(ssl_forward(Q, batch, 0.05, cfg, dtype=torch.float64)[0]))
+            fd = (vals[0] - vals[1]) / (2 * h)
+            an = float(grads[n].reshape(-1)[idx])
+            assert abs(fd - an) <= 1e-5 * max(1.0, abs(an)) + 1e-7, (n, idx, fd, an)
