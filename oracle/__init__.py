@@ -26,6 +26,8 @@ reference cannot be executed end to end here.  The oracle is pinned as far as th
     autograd of that function);
   * `build_schedulers` and the gradient-clipping block of `train_step` (train/train.py:124-182,516-541) are exec'ed from
     their source text; the schedules are reproduced bit-exactly, the clipping to 1e-12;
+  * the ViT forward is cross-checked against an independent implementation of upstream DINOv3 (Hugging Face
+    transformers' DINOv3ViTModel) to 2e-6 — RoPE, attention, LayerScale, token order, register tokens, mask token;
   * analytic micro-cases (uniform Sinkhorn, LN of constant rows, orthogonal KoLeo pairs ...) in `tests/`, and the AdamW
     rule against torch.optim.AdamW.
 What is therefore *not* pinned: the third-party op semantics themselves (flax gelu/LayerNorm/attention defaults,
