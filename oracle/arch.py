@@ -41,6 +41,8 @@ class ModelCfg:
     clip_grad: float = 3.0          # optim.clip_grad               :148
     ln_eps: float = 1e-6            # models/vision_transformer.py:40 (layernormbf16: 1e-5, :41)
     n_storage: int = 0              # student.n_storage_tokens (models/vision_transformer.py:106-111)
+    ffn_layer: str = "mlp"          # "mlp" | "swiglu" (layers/ffn_layers.py:52-76; oracle only)
+    swiglu_align: int = 8           # swiglu / swiglu32 / swiglu64 / swiglu128 (models/vision_transformer.py:30-36)
     mlp_second_act: bool = True     # layers/ffn_layers.py:47 applies GELU after fc2 as well
 
     @property
@@ -50,6 +52,11 @@ class ModelCfg:
     @property
     def hidden(self) -> int:
         return int(self.embed_dim * self.ffn_ratio)
+
+    @property
+    def swiglu_hidden(self) -> int:
+        d = int(self.hidden * 2 / 3)                       # layers/ffn_layers.py:64-65
+        return d + (-d % self.swiglu_align)
 
     @property
     def prefix(self) -> int:

@@ -347,8 +347,9 @@ def install():
     nn.initializers = inits
     nn.Dense, nn.LayerNorm, nn.Conv, nn.Dropout, nn.Sequential = Dense, LayerNorm, Conv, Dropout, Sequential
     nn.dot_product_attention = _dot_product_attention
-    for n in ("BatchNorm", "silu", "make_causal_mask"):
+    for n in ("BatchNorm", "make_causal_mask"):
         setattr(nn, n, type(n, (), {}))
+    nn.silu = lambda x: _wrap(np.asarray(x) / (1.0 + np.exp(-np.asarray(x))))        # jax.nn.silu = x * sigmoid(x)
 
     class Partitioned:                     # flax.linen.Partitioned: a boxed value plus its per-axis mesh names
         def __init__(self, value=None, names=None, mesh=None):

@@ -82,10 +82,16 @@ def init_backbone(cfg: ModelCfg, gen: torch.Generator, dtype=torch.float32) -> d
         P[b + "ls1/gamma"] = torch.full((D,), cfg.layerscale, dtype=dtype)    # layers/layer_scale.py:12-21
         P[b + "norm2/scale"] = torch.ones(D, dtype=dtype)
         P[b + "norm2/bias"] = torch.zeros(D, dtype=dtype)
-        P[b + "mlp/Dense_0/kernel"] = _lecun_normal((D, Hd), D, gen, dtype)   # layers/ffn_layers.py:36-39
-        P[b + "mlp/Dense_0/bias"] = torch.zeros(Hd, dtype=dtype)
-        P[b + "mlp/Dense_1/kernel"] = _lecun_normal((Hd, D), Hd, gen, dtype)  # layers/ffn_layers.py:43-46
-        P[b + "mlp/Dense_1/bias"] = torch.zeros(D, dtype=dtype)
+        if cfg.ffn_layer == "swiglu":                                         # layers/ffn_layers.py:62-69
+            Hs = cfg.swiglu_hidden
+            for w_, (i_, o_) in (("w1", (D, Hs)), ("w2", (D, Hs)), ("w3", (Hs, D))):
+                P[b + f"mlp/{w_}/kernel"] = _lecun_normal((i_, o_), i_, gen, dtype)
+                P[b + f"mlp/{w_}/bias"] = torch.zeros(o_, dtype=dtype)
+        else:
+            P[b + "mlp/Dense_0/kernel"] = _lecun_normal((D, Hd), D, gen, dtype)   # layers/ffn_layers.py:36-39
+            P[b + "mlp/Dense_0/bias"] = torch.zeros(Hd, dtype=dtype)
+            P[b + "mlp/Dense_1/kernel"] = _lecun_normal((Hd, D), Hd, gen, dtype)  # layers/ffn_layers.py:43-46
+            P[b + "mlp/Dense_1/bias"] = torch.zeros(D, dtype=dtype)
         P[b + "ls2/gamma"] = torch.full((D,), cfg.layerscale, dtype=dtype)
     P["norm/scale"] = torch.ones(D, dtype=dtype)
     P["norm/bias"] = torch.zeros(D, dtype=dtype)
@@ -252,6 +258,12 @@ def block_forward(P: dict, b: str, x, sin, cos, cfg: ModelCfg, emu: Emu):
     p = o @ emu.w(P[b + "attn/proj/kernel"]) + P[b + "attn/proj/bias"]
     x = x + P[b + "ls1/gamma"] * emu.grad(p)
     z = emu.act(layer_norm(x, P[b + "norm2/scale"], P[b + "norm2/bias"], cfg.ln_eps))
+    if cfg.ffn_layer == "swiglu":                                                # layers/ffn_layers.py:71-76
+        x1 = emu.grad(z @ emu.w(P[b + "mlp/w1/kernel"]) + P[b + "mlp/w1/bias"])
+        x2 = emu.grad(z @ emu.w(P[b + "mlp/w2/kernel"]) + P[b + "mlp/w2/bias"])
+        h = emu.act(F.silu(x1) * x2)
+        m = emu.grad(h @ emu.w(P[b + "mlp/w3/kernel"]) + P[b + "mlp/w3/bias"])
+        return x + P[b + "ls2/gamma"] * m
     u1 = emu.grad(z @ emu.w(P[b + "mlp/Dense_0/kernel"]) + P[b + "mlp/Dense_0/bias"])
     h = emu.act(gelu(u1))                                                        # layers/ffn_layers.py:36-40
     u2 = emu.grad(h @ emu.w(P[b + "mlp/Dense_1/kernel"]) + P[b + "mlp/Dense_1/bias"])

@@ -204,6 +204,18 @@ def main():
     out.update(vitr_g_cls=np.asarray(ogr["x_norm_clstoken"]), vitr_g_storage=np.asarray(ogr["x_storage_tokens"]),
                vitr_g_patch=np.asarray(ogr["x_norm_patchtokens"]), vitr_l_cls=np.asarray(olr["x_norm_clstoken"]),
                vitr_l_storage=np.asarray(olr["x_storage_tokens"]), vitr_l_patch=np.asarray(olr["x_norm_patchtokens"]))
+    # SwiGLU FFN (layers/ffn_layers.py:52-76) called directly with explicit feature sizes (oracle groundwork)
+    ffn = importlib.import_module("dinov3_jax.layers.ffn_layers")
+    srng2 = np.random.default_rng(41)
+    sw = {"w1/kernel": srng2.standard_normal((32, 64)) * 0.2, "w1/bias": srng2.standard_normal(64) * 0.1,
+          "w2/kernel": srng2.standard_normal((32, 64)) * 0.2, "w2/bias": srng2.standard_normal(64) * 0.1,
+          "w3/kernel": srng2.standard_normal((64, 32)) * 0.2, "w3/bias": srng2.standard_normal(32) * 0.1}
+    jaxshim.PARAMS.clear(); jaxshim.PARAMS.update(sw)
+    sx = srng2.standard_normal((5, 32))
+    swiglu = ffn.SwiGLUFFN(hidden_features=80, out_features=32, align_to=64)      # int(80*2/3) = 53 -> 64
+    out["swiglu_x"], out["swiglu_y"] = sx, np.asarray(swiglu(J(sx)))
+    for k_, v_ in sw.items():
+        out[f"swiglu_param/{k_}"] = v_
     # inference entry point (is_training=False returns the head(cls) path = Identity -> x_norm_clstoken)
     hp = sub(P, "student_dino_head")
     jaxshim.PARAMS.clear(); jaxshim.PARAMS.update({k: v.numpy() for k, v in hp.items()})

@@ -301,3 +301,16 @@ def test_ac_compile_parallelize_axes_match_reference_function(n, monkeypatch):
             assert not isinstance(v, Partitioned), k
         else:
             assert isinstance(v, Partitioned) and v.axis == want, k
+
+
+def test_swiglu_ffn_matches_reference_class():
+    """layers/ffn_layers.py SwiGLUFFN (w3(silu(w1 x) * w2 x), hidden = 2/3 * hidden_features rounded up to align_to)
+    executed from the reference source vs the oracle's SwiGLU branch — groundwork for SURVEY §8f.1."""
+    import torch.nn.functional as F
+    x = T(G["swiglu_x"])
+    w = {k.split("/", 1)[1]: T(G[k]) for k in G.files if k.startswith("swiglu_param/")}
+    assert w["w1/kernel"].shape == (32, 64)
+    y = (F.silu(x @ w["w1/kernel"] + w["w1/bias"]) * (x @ w["w2/kernel"] + w["w2/bias"])) @ w["w3/kernel"] + w["w3/bias"]
+    assert np.abs(y.numpy() - G["swiglu_y"]).max() < 1e-13
+    from oracle.arch import ModelCfg
+    assert ModelCfg(embed_dim=20, heads=1, ffn_ratio=4.0, ffn_layer="swiglu", swiglu_align=64).swiglu_hidden == 64

@@ -66,3 +66,40 @@ def test_oracle_vit_matches_huggingface_dinov3(size, n_storage):
         assert got.shape == ref.shape
         err = (got - ref).abs().max().item() / ref.abs().max().item()
         assert err < 2e-6, err            # HF builds its sin / cos tables in float32 even for a float64 model
+
+
+def test_oracle_swiglu_block_matches_huggingface_gated_mlp():
+    """Oracle-only groundwork for SURVEY §8f.1: SwiGLU FFN  w3(silu(w1 x) * w2 x)  (layers/ffn_layers.py:52-76, hidden =
+    2/3 * 4D rounded up to `align_to`) inside the whole ViT against HF's gated-MLP DINOv3 (gate_proj / up_proj / down_proj
+    with SiLU)."""
+    from oracle.arch import ModelCfg
+    from oracle.model import backbone_forward, formula_images, formula_params, sub
+    D, depth, heads, size = 128, 2, 2, 48
+    cfg = ModelCfg(embed_dim=D, depth=depth, heads=heads, global_size=size, local_size=32, n_storage=4, ln_eps=1e-5,
+                   ffn_layer="swiglu", swiglu_align=64, n_prototypes=16, head_hidden=16, head_bottleneck=8)
+    assert cfg.swiglu_hidden == 384                                     # int(512 * 2 / 3) = 341 -> 384
+    bp = sub(formula_params(cfg, 8), "student_backbone")
+    hcfg = hf.DINOv3ViTConfig(patch_size=16, hidden_size=D, intermediate_size=cfg.swiglu_hidden, num_hidden_layers=depth,
+                              num_attention_heads=heads, hidden_act="silu", layer_norm_eps=1e-5, rope_theta=100.0, image_size=size,
+                              query_bias=True, key_bias=True, value_bias=True, num_register_tokens=4, use_gated_mlp=True)
+    model = hf.DINOv3ViTModel(hcfg).double().eval()
+    mlp_free = {k: v for k, v in bp.items() if "/mlp/" not in k}
+    for i in range(depth):                                              # placeholders so the shared mapper can run
+        mlp_free[f"blocks_{i}/mlp/Dense_0/kernel"] = torch.zeros(D, 1, dtype=torch.float64)
+        mlp_free[f"blocks_{i}/mlp/Dense_0/bias"] = torch.zeros(1, dtype=torch.float64)
+        mlp_free[f"blocks_{i}/mlp/Dense_1/kernel"] = torch.zeros(1, D, dtype=torch.float64)
+        mlp_free[f"blocks_{i}/mlp/Dense_1/bias"] = torch.zeros(D, dtype=torch.float64)
+    sd = {k: v for k, v in _to_hf_state_dict(mlp_free, depth, D).items() if ".mlp." not in k}
+    for i in range(depth):
+        b, h = f"blocks_{i}/mlp/", f"model.layer.{i}.mlp."
+        for ours, theirs in (("w1", "gate_proj"), ("w2", "up_proj"), ("w3", "down_proj")):
+            sd[h + theirs + ".weight"] = bp[b + ours + "/kernel"].t().contiguous()
+            sd[h + theirs + ".bias"] = bp[b + ours + "/bias"]
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and all("inv_freq" in k for k in missing), (missing, unexpected)
+    x = formula_images((2, size, size, 3), 78)
+    want = backbone_forward(bp, [x], [None], cfg)[0]
+    with torch.no_grad():
+        got = model(pixel_values=x.permute(0, 3, 1, 2).contiguous()).last_hidden_state
+    ref = torch.cat([want["x_norm_clstoken"][:, None], want["x_storage_tokens"], want["x_norm_patchtokens"]], dim=1)
+    assert (got - ref).abs().max().item() / ref.abs().max().item() < 2e-6
