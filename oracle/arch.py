@@ -42,6 +42,7 @@ class ModelCfg:
     ln_eps: float = 1e-6            # models/vision_transformer.py:40 (layernormbf16: 1e-5, :41)
     n_storage: int = 0              # student.n_storage_tokens (models/vision_transformer.py:106-111)
     ffn_layer: str = "mlp"          # "mlp" | "swiglu" (layers/ffn_layers.py:52-76; oracle only)
+    mask_k_bias: bool = False       # student.mask_k_bias: the k third of the qkv bias is masked to zero (upstream DINOv3)
     swiglu_align: int = 8           # swiglu / swiglu32 / swiglu64 / swiglu128 (models/vision_transformer.py:30-36)
     mlp_second_act: bool = True     # layers/ffn_layers.py:47 applies GELU after fc2 as well
 

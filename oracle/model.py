@@ -253,7 +253,11 @@ def attention(qkv, heads, sin, cos, emu: Emu):
 def block_forward(P: dict, b: str, x, sin, cos, cfg: ModelCfg, emu: Emu):
     """layers/block.py:195-201 (deterministic branch): x + ls1(attn(norm1 x)); x + ls2(mlp(norm2 x))."""
     y = emu.act(layer_norm(x, P[b + "norm1/scale"], P[b + "norm1/bias"], cfg.ln_eps))
-    qkv = emu.act(y @ emu.w(P[b + "attn/qkv/kernel"]) + P[b + "attn/qkv/bias"])
+    qkv_bias = P[b + "attn/qkv/bias"]
+    if cfg.mask_k_bias:                         # upstream LinearKMaskedBias: bias * [1 | 0 | 1] (oracle only, SURVEY 8f.1)
+        D_ = qkv_bias.shape[0] // 3
+        qkv_bias = torch.cat([qkv_bias[:D_], torch.zeros_like(qkv_bias[D_:2 * D_]), qkv_bias[2 * D_:]])
+    qkv = emu.act(y @ emu.w(P[b + "attn/qkv/kernel"]) + qkv_bias)
     o = emu.act(attention(qkv, cfg.heads, sin, cos, emu))
     p = o @ emu.w(P[b + "attn/proj/kernel"]) + P[b + "attn/proj/bias"]
     x = x + P[b + "ls1/gamma"] * emu.grad(p)

@@ -34,22 +34,25 @@ def _to_hf_state_dict(bp: dict, depth: int, D: int) -> dict:
     return sd
 
 
-@pytest.mark.parametrize("size,n_storage", [(64, 4), (48, 0)])
-def test_oracle_vit_matches_huggingface_dinov3(size, n_storage):
+@pytest.mark.parametrize("size,n_storage,mask_k_bias", [(64, 4, False), (48, 0, False), (48, 4, True)])
+def test_oracle_vit_matches_huggingface_dinov3(size, n_storage, mask_k_bias):
     from oracle.arch import ModelCfg
     from oracle.model import backbone_forward, formula_images, formula_params, sub
     D, depth, heads = 128, 2, 2
     cfg = ModelCfg(embed_dim=D, depth=depth, heads=heads, global_size=size, local_size=32, n_storage=n_storage, ln_eps=1e-5,
-                   mlp_second_act=False, n_prototypes=16, head_hidden=16, head_bottleneck=8)
+                   mlp_second_act=False, mask_k_bias=mask_k_bias, n_prototypes=16, head_hidden=16, head_bottleneck=8)
     bp = sub(formula_params(cfg, 6), "student_backbone")
     if not n_storage:
         bp["storage_tokens"] = torch.zeros(1, 0, D, dtype=torch.float64)
     hcfg = hf.DINOv3ViTConfig(patch_size=16, hidden_size=D, intermediate_size=4 * D, num_hidden_layers=depth, num_attention_heads=heads,
                               hidden_act="gelu_pytorch_tanh", layer_norm_eps=1e-5, rope_theta=100.0, image_size=size, query_bias=True,
-                              key_bias=True, value_bias=True, proj_bias=True, mlp_bias=True, layerscale_value=1.0,
+                              key_bias=not mask_k_bias, value_bias=True, proj_bias=True, mlp_bias=True, layerscale_value=1.0,
                               num_register_tokens=n_storage, use_gated_mlp=False)
     model = hf.DINOv3ViTModel(hcfg).double().eval()
-    missing, unexpected = model.load_state_dict(_to_hf_state_dict(bp, depth, D), strict=False)
+    sd = _to_hf_state_dict(bp, depth, D)
+    if mask_k_bias:                                     # HF drops the key bias altogether (upstream masks it to zero)
+        sd = {k: v for k, v in sd.items() if not k.endswith("k_proj.bias")}
+    missing, unexpected = model.load_state_dict(sd, strict=False)
     assert not unexpected and all("inv_freq" in k for k in missing), (missing, unexpected)
     n, P = 3, (size // 16) ** 2
     x = formula_images((n, size, size, 3), 77)
