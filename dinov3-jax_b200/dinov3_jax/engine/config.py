@@ -76,6 +76,8 @@ def config_for(arch: str, **kw) -> EngineConfig:
 
 def from_oracle_cfg(c) -> EngineConfig:
     """Build from any object with the same field names (tests pass oracle.arch.ModelCfg)."""
+    if getattr(c, "ffn_layer", "mlp") != "mlp" or getattr(c, "mask_k_bias", False):
+        raise NotImplementedError("SwiGLU / mask_k_bias exist in the oracle only (SURVEY 8f.1); the B200 path has mlp blocks")
     names = EngineConfig.__dataclass_fields__.keys()
     return EngineConfig(**{k: getattr(c, k) for k in names if hasattr(c, k)})
 
