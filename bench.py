@@ -105,7 +105,7 @@ def hyper(it):
     return dict(teacher_temp=0.04, lr=1e-4, wd=0.04, last_layer_lr=0.0, momentum=0.996)
 
 
-def cpu_reference_rate(arch, threads, sample_B, steps=1, warmup=0):
+def cpu_reference_rate(arch, threads, sample_B, steps=1, warmup=0, **cfg_kw):
     """Times oracle.step.train_step (CPU restatement of the reference step) on `sample_B` images per step."""
     from oracle import cfg_for
     from oracle.batch import synthetic_batch
@@ -113,17 +113,43 @@ def cpu_reference_rate(arch, threads, sample_B, steps=1, warmup=0):
     from oracle.step import init_opt_state, train_step
     threads = max(1, min(threads, 32))   # beyond ~32 threads the fp32 restatement stops scaling (many small ops)
     torch.set_num_threads(threads)
-    cfg = cfg_for(arch)
+    cfg = cfg_for(arch, **cfg_kw)
     P = init_params(cfg, 0)
     st = init_opt_state(P)
     batch = synthetic_batch(cfg, sample_B, 0)
-    times = []
+    times, first_loss = [], None
     for i in range(warmup + steps):
         t0 = time.time()
         P, st, loss, m, _ = train_step(P, st, batch, cfg, **hyper(i))
         times.append(time.time() - t0)
+        if first_loss is None:
+            first_loss = float(loss)         # loss of the un-updated parameters (what parity_check compares)
     dt = sum(times[warmup:]) / steps
-    return 2 * sample_B / dt, dt, float(loss), threads
+    return 2 * sample_B / dt, dt, float(loss), threads, first_loss
+
+
+def oracle_kw(args):
+    return dict(n_prototypes=args.prototypes, patch=args.patch, local_size=args.local_size)
+
+
+def parity_check(args, cfg, loss_cpu, local_rank):
+    """Engine vs oracle on the cpu_baseline sample: same architecture, K, parameters (oracle.init_params seed 0) and
+    batch (oracle.batch.synthetic_batch seed 0) — the loss of the un-updated parameters, relative difference."""
+    from dinov3_jax.engine import Engine
+    from oracle import cfg_for
+    from oracle.batch import synthetic_batch as oracle_batch
+    from oracle.model import init_params
+    ocfg = cfg_for(args.arch, **oracle_kw(args))
+    B = args.cpu_sample_batch
+    batch = oracle_batch(ocfg, B, 0)
+    eng = Engine(cfg, B, device=f"cuda:{local_rank}", max_masked=max(int(batch["mask_indices_list"].shape[0]), 1))
+    eng.params.load_reference_tree(init_params(ocfg, 0))
+    eng.set_batch(batch)
+    eng.forward_backward(hyper(0)["teacher_temp"])
+    loss = eng.read_metrics()["total_loss"]
+    rel = abs(loss - loss_cpu) / abs(loss_cpu)
+    return {"engine_loss": loss, "oracle_loss": loss_cpu, "rel": rel, "ok": bool(rel < 1e-3),
+            "what": f"{args.arch} full depth, K={cfg.n_prototypes}, {B} images, fp32 oracle vs bf16 engine, tolerance 1e-3"}
 
 
 def main():
@@ -139,6 +165,8 @@ def main():
     ap.add_argument("--local-size", type=int, default=96, help="98 for patch 14 (96 is not divisible, layers/patch_embed.py:48-49)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-batch", type=int, default=2, help="images per CPU-baseline step (bounded sample: ~15-25 s of CPU work)")
+    ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="wall-clock bound of the --impl reference arm")
+    ap.add_argument("--no-checks", action="store_true", help="skip parity_check / fsdp_check")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -157,17 +185,29 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        w = max(args.warmup, 0)
-        val, dt, _, used = cpu_reference_rate(args.arch, cores, args.cpu_sample_batch, steps=max(min(args.steps, 3), 1), warmup=min(w, 1))
-        cores = used
+        # The reference's JAX stack cannot be installed offline, so this arm times the CPU restatement of
+        # the same step (oracle/, kind "port") on a BOUNDED SAMPLE of the workload: `--cpu-sample-batch` images per
+        # step instead of 64.  Everything printed describes what actually ran.
+        budget = float(args.cpu_budget_s)
+        t_probe = time.time()
+        _, dt1, _, used, _ = cpu_reference_rate(args.arch, cores, args.cpu_sample_batch, steps=1, warmup=0, **oracle_kw(args))   # untimed probe = warm-up 1
+        steps = max(1, min(args.steps, int((budget - (time.time() - t_probe)) / max(dt1, 1e-3)) - max(args.warmup - 1, 0)))
+        warm = max(0, min(args.warmup - 1, int(budget / max(dt1, 1e-3)) - steps))
+        val, dt, _, used, _ = cpu_reference_rate(args.arch, cores, args.cpu_sample_batch, steps=steps, warmup=warm, **oracle_kw(args))
+        ref_cfg = dict(cfg_desc)
+        ref_cfg.update({"sample": f"{args.cpu_sample_batch} images per step (bounded sample of the {args.batch}-img/GPU step; "
+                                  f"crops/s on the CPU is taken as batch-size independent)",
+                        "global_batch": args.cpu_sample_batch, "parallelism": "single host process", "same_config": False,
+                        "extrapolated": True, "requested": {"gpus": args.gpus, "steps": args.steps, "warmup": args.warmup}})
         print(json.dumps({
             "impl": "reference", "metric": "global_crops_per_sec", "value": val, "unit": "global-crops/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+            "n_gpus": 1, "steps": steps, "warmup": warm + 1, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": cfg_desc,
-            "cpu_baseline": {"value": val, "unit": "global-crops/s", "cores": cores, "kind": "port",
+            "config": ref_cfg,
+            "cpu_baseline": {"value": val, "unit": "global-crops/s", "cores": used, "kind": "port",
                              "sample": f"torch-CPU fp32 restatement of the reference train_step (oracle/), {args.arch}, "
-                                       f"{args.cpu_sample_batch} images/step; JAX stack not installable offline"},
+                                       f"{args.cpu_sample_batch} images/step, {steps} timed steps after {warm + 1} warm-up; "
+                                       f"the reference's JAX stack is not installable offline"},
             "e2e": {"value": val, "unit": "global-crops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -282,14 +322,28 @@ def main():
         "step_roofline": {"achieved": step_tf, "peak": sustained, "unit": "TFLOP/s", "frac": step_tf / sustained,
                           "note": "attention+MLP algorithmic FLOPs (BASELINE.md §3) / step time / GPU"},
     }
+    if world > 1 and not args.no_checks:
+        from dinov3_jax.fsdp.selfcheck import fsdp_equals_single_gpu
+        try:
+            out["fsdp_check"] = fsdp_equals_single_gpu(comm, f"cuda:{local_rank}")
+        except Exception as e:                      # the timed numbers above stand; the check reports its own failure
+            out["fsdp_check"] = {"ok": False, "error": repr(e)[:300]}
+        log(f"fsdp_check: {out['fsdp_check']}")
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             log("cpu baseline (oracle port) ...")
-            v, dt, _, cores = cpu_reference_rate(args.arch, cores, args.cpu_sample_batch, steps=2, warmup=0)
+            v, dt, _, cores, loss_cpu = cpu_reference_rate(args.arch, cores, args.cpu_sample_batch, steps=2, warmup=0, **oracle_kw(args))
             log(f"cpu baseline: {dt:.1f} s/step")
             out["cpu_baseline"] = {"value": v, "unit": "global-crops/s", "cores": cores, "kind": "port",
                                    "sample": f"oracle train_step (torch-CPU fp32 restatement), {args.arch}, "
                                              f"{args.cpu_sample_batch} images per step, 2 steps of {dt:.1f} s"}
+            if not args.no_checks:
+                # the same sample through the engine (same parameters, same batch): full-size model, K prototypes
+                try:
+                    out["parity_check"] = parity_check(args, cfg, loss_cpu, local_rank)
+                except Exception as e:
+                    out["parity_check"] = {"ok": False, "error": repr(e)[:300]}
+                log(f"parity_check: {out['parity_check']}")
         print(json.dumps(out))
     if world > 1:
         torch.distributed.destroy_process_group()

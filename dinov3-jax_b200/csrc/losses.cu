@@ -45,6 +45,8 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// 1/s for a Sinkhorn column sum; a column whose terms all underflowed (s == 0) contributes nothing instead of 0/0
+__device__ __forceinline__ float rcp_pos(float s) { return s > 0.f ? __fdividef(1.f, s) : 0.f; }
 __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
   // ordered-int trick; *addr must be initialised to -inf
   if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
@@ -53,8 +55,11 @@ __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
 
 // ------------------------------------------------------------------------------------------------ Sinkhorn-Knopp
 // Q = exp(L/temp)^T; Q/=sum; 3x { Q /= rowsum*K ; Q /= colsum*B } ; Q*=B      (dino_clstoken_loss.py:35-62)
-// is a sequence of diagonal scalings:  Q[b,k] = E[b,k] * r[k] * a[b],  E = exp((L - mx)/temp)  (any global shift mx
-// cancels in the first normalisation), with   r = 1/(K * E^T a)   and   a = 1/(B * E r)   alternating.
+// is a sequence of diagonal scalings:  Q[b,k] = E[b,k] * r[k] * a[b],  E = exp((L[b,k] - cm[k])/temp), with
+//   r = 1/(K * E^T a)   and   a = 1/(B * E r)   alternating.  Any per-COLUMN shift cm[k] cancels exactly in E*r (the
+// reference has no shift at all, :39); cm[k] = max_b L[b,k] (d3_colmax, all-reduced over ranks) keeps every column's
+// largest term at 1, so a prototype far below the batch maximum keeps its Sinkhorn mass 1/K like in the reference
+// instead of underflowing to 0/0 (a single global shift loses columns more than ~3.5 below the maximum at temp 0.04).
 // The row step's E^T a (K floats) is what the reference psums over "dp" (:53 / ibot :99).
 __global__ void absmax_kernel(const float* __restrict__ L, long n, float* __restrict__ out) {
   __shared__ float sh[32];
@@ -63,6 +68,30 @@ __global__ void absmax_kernel(const float* __restrict__ L, long n, float* __rest
   m = block_max(m, sh);
   if (threadIdx.x == 0) atomic_max_float(out, m);
 }
+// cm[k] = max(cm[k], max_b L[b,k])   (cm pre-set to -inf; atomics across row slabs)
+__global__ void colmax_kernel(const float* __restrict__ L, float* __restrict__ cm, int R, int K) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int slab = (R + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * slab, r1 = min(R, r0 + slab);
+  if (k >= K || r0 >= r1) return;
+  float m = -CUDART_INF_F;
+  for (int b = r0; b < r1; ++b) m = fmaxf(m, L[(long)b * K + k]);
+  atomic_max_float(&cm[k], m);
+}
+__global__ void colmax_vec_kernel(const float* __restrict__ L, float* __restrict__ cm, int R, int K) {
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int slab = (R + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * slab, r1 = min(R, r0 + slab);
+  if (k >= K || r0 >= r1) return;
+  float4 m = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+#pragma unroll 4
+  for (int b = r0; b < r1; ++b) {
+    const float4 v = *reinterpret_cast<const float4*>(L + (long)b * K + k);
+    m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+  }
+  atomic_max_float(&cm[k], m.x); atomic_max_float(&cm[k + 1], m.y);
+  atomic_max_float(&cm[k + 2], m.z); atomic_max_float(&cm[k + 3], m.w);
+}
 // s[k] += sum_b E[b,k] * a[b]      (a == nullptr -> a = 1)
 __global__ void sk_colsum_kernel(const float* __restrict__ L, const float* __restrict__ mx, float inv_temp,
                                  const float* __restrict__ a, float* __restrict__ s, int R, int K) {
@@ -70,7 +99,7 @@ __global__ void sk_colsum_kernel(const float* __restrict__ L, const float* __res
   const int slab = (R + gridDim.y - 1) / gridDim.y;
   const int r0 = blockIdx.y * slab, r1 = min(R, r0 + slab);
   if (k >= K) return;
-  const float m = *mx;
+  const float m = mx[k];
   float acc = 0.f;
   for (int b = r0; b < r1; ++b) acc += __expf((L[(long)b * K + k] - m) * inv_temp) * (a ? a[b] : 1.f);
   atomicAdd(&s[k], acc);
@@ -81,22 +110,21 @@ __global__ void sk_rowsum_kernel(const float* __restrict__ L, const float* __res
                                  int R, int K) {
   __shared__ float sh[32];
   const int b = blockIdx.x;
-  const float m = *mx;
   float acc = 0.f;
   for (int k = threadIdx.x; k < K; k += blockDim.x)
-    acc += __expf((L[(long)b * K + k] - m) * inv_temp) / ((float)K * s[k]);
+    acc += __expf((L[(long)b * K + k] - mx[k]) * inv_temp) * rcp_pos((float)K * s[k]);
   acc = block_sum(acc, sh);
-  if (threadIdx.x == 0) a[b] = 1.f / (*btot * acc);
+  if (threadIdx.x == 0) a[b] = acc > 0.f ? 1.f / (*btot * acc) : 0.f;
 }
 // materialise teacher probabilities (tests / optional consumers): Q[b,k] = Btot * E * r[k] * a[b]
 __global__ void sk_probs_kernel(const float* __restrict__ L, const float* __restrict__ mx, float inv_temp,
                                 const float* __restrict__ s, const float* __restrict__ a,
                                 const float* __restrict__ btot, float* __restrict__ Q, int R, int K) {
   const long n = (long)R * K;
-  const float m = *mx, bt = *btot;
+  const float bt = *btot;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     const int b = (int)(i / K), k = (int)(i % K);
-    Q[i] = bt * __expf((L[i] - m) * inv_temp) / ((float)K * s[k]) * a[b];
+    Q[i] = bt * __expf((L[i] - mx[k]) * inv_temp) * rcp_pos((float)K * s[k]) * a[b];
   }
 }
 
@@ -156,7 +184,7 @@ ce_fwd_bwd_kernel(const float* __restrict__ S, float inv_ts, const float* __rest
   const float lse = gm + logf(z);
   const int p0 = t0[i], p1 = t1[i];
   const float np = (p0 >= 0 ? 1.f : 0.f) + (p1 >= 0 ? 1.f : 0.f);
-  const float mt = s_t ? *mx : 0.f, bt = s_t ? *btot : 1.f;
+  const float bt = s_t ? *btot : 1.f;
   const float c0 = (s_t && p0 >= 0) ? bt * a_t[p0] : 0.f;
   const float c1 = (s_t && p1 >= 0) ? bt * a_t[p1] : 0.f;
   const float* L0 = Lt + (long)(p0 >= 0 ? p0 : 0) * K;
@@ -167,7 +195,7 @@ ce_fwd_bwd_kernel(const float* __restrict__ S, float inv_ts, const float* __rest
     const float lsm = Si[k] * inv_ts - lse;
     float q = 0.f;
     if (s_t) {
-      const float rk = 1.f / ((float)K * s_t[k]);
+      const float rk = rcp_pos((float)K * s_t[k]), mt = mx[k];
       if (p0 >= 0) q += c0 * __expf((L0[k] - mt) * inv_tt) * rk;
       if (p1 >= 0) q += c1 * __expf((L1[k] - mt) * inv_tt) * rk;
     } else {          // teacher rows are already probabilities
@@ -199,14 +227,16 @@ __global__ void sk_colsum_vec_kernel(const float* __restrict__ L, const float* _
   const int slab = (R + gridDim.y - 1) / gridDim.y;
   const int r0 = blockIdx.y * slab, r1 = min(R, r0 + slab);
   if (k >= K) return;
-  const float c = inv_temp * 1.4426950408889634f, mc = *mx * c;
+  const float c = inv_temp * 1.4426950408889634f;
+  const float4 m4 = *reinterpret_cast<const float4*>(mx + k);
+  const float4 mc = make_float4(m4.x * c, m4.y * c, m4.z * c, m4.w * c);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
   for (int b = r0; b < r1; ++b) {
     const float4 v = *reinterpret_cast<const float4*>(L + (long)b * K + k);
     const float w = a ? a[b] : 1.f;
-    acc.x += exp2f(v.x * c - mc) * w; acc.y += exp2f(v.y * c - mc) * w;
-    acc.z += exp2f(v.z * c - mc) * w; acc.w += exp2f(v.w * c - mc) * w;
+    acc.x += exp2f(v.x * c - mc.x) * w; acc.y += exp2f(v.y * c - mc.y) * w;
+    acc.z += exp2f(v.z * c - mc.z) * w; acc.w += exp2f(v.w * c - mc.w) * w;
   }
   atomicAdd(&s[k], acc.x); atomicAdd(&s[k + 1], acc.y); atomicAdd(&s[k + 2], acc.z); atomicAdd(&s[k + 3], acc.w);
 }
@@ -215,18 +245,19 @@ __global__ void sk_rowsum_vec_kernel(const float* __restrict__ L, const float* _
                                      int R, int K) {
   __shared__ float sh[32];
   const int b = blockIdx.x;
-  const float c = inv_temp * 1.4426950408889634f, mc = *mx * c;
+  const float c = inv_temp * 1.4426950408889634f;
   const float4* Lb = reinterpret_cast<const float4*>(L + (long)b * K);
   const float4* s4 = reinterpret_cast<const float4*>(s);
+  const float4* m4 = reinterpret_cast<const float4*>(mx);
   float acc = 0.f;
 #pragma unroll 4
   for (int k = threadIdx.x; k < K / 4; k += blockDim.x) {
-    const float4 v = Lb[k], sv = s4[k];
-    acc += __fdividef(exp2f(v.x * c - mc), sv.x) + __fdividef(exp2f(v.y * c - mc), sv.y) +
-           __fdividef(exp2f(v.z * c - mc), sv.z) + __fdividef(exp2f(v.w * c - mc), sv.w);
+    const float4 v = Lb[k], sv = s4[k], mv = m4[k];
+    acc += exp2f((v.x - mv.x) * c) * rcp_pos(sv.x) + exp2f((v.y - mv.y) * c) * rcp_pos(sv.y) +
+           exp2f((v.z - mv.z) * c) * rcp_pos(sv.z) + exp2f((v.w - mv.w) * c) * rcp_pos(sv.w);
   }
   acc = block_sum(acc, sh) / (float)K;
-  if (threadIdx.x == 0) a[b] = 1.f / (*btot * acc);
+  if (threadIdx.x == 0) a[b] = acc > 0.f ? 1.f / (*btot * acc) : 0.f;
 }
 
 // vectorised cross-entropy: same contract as ce_fwd_bwd_kernel; the second pass re-reads the student row from L2
@@ -257,8 +288,9 @@ ce_fwd_bwd_vec_kernel(const float* __restrict__ S, float inv_ts, const float* __
   const int p0 = t0[i], p1 = t1[i];
   const float np = (p0 >= 0 ? 1.f : 0.f) + (p1 >= 0 ? 1.f : 0.f);
   const float ct = inv_tt * LOG2E;
-  const float mt = s_t ? *mx * ct : 0.f, bt = s_t ? *btot : 1.f;
+  const float bt = s_t ? *btot : 1.f;
   const float invK = 1.f / (float)K;
+  const float4* mx4 = reinterpret_cast<const float4*>(mx);
   const float c0 = (s_t && p0 >= 0) ? bt * a_t[p0] * invK : 0.f;
   const float c1 = (s_t && p1 >= 0) ? bt * a_t[p1] * invK : 0.f;
   const float4* L0 = reinterpret_cast<const float4*>(Lt + (long)(p0 >= 0 ? p0 : 0) * K);
@@ -274,17 +306,17 @@ ce_fwd_bwd_vec_kernel(const float* __restrict__ S, float inv_ts, const float* __
     const float l2[4] = {v.x * cs - lse2, v.y * cs - lse2, v.z * cs - lse2, v.w * cs - lse2};   // log2 softmax
     float q[4] = {0.f, 0.f, 0.f, 0.f};
     if (s_t) {
-      const float4 sv = st4[k];
-      const float r[4] = {__fdividef(1.f, sv.x), __fdividef(1.f, sv.y), __fdividef(1.f, sv.z), __fdividef(1.f, sv.w)};
+      const float4 sv = st4[k], mv = mx4[k];
+      const float r[4] = {rcp_pos(sv.x), rcp_pos(sv.y), rcp_pos(sv.z), rcp_pos(sv.w)};
       if (p0 >= 0) {
         const float4 t = L0[k];
-        q[0] += c0 * exp2f(t.x * ct - mt) * r[0]; q[1] += c0 * exp2f(t.y * ct - mt) * r[1];
-        q[2] += c0 * exp2f(t.z * ct - mt) * r[2]; q[3] += c0 * exp2f(t.w * ct - mt) * r[3];
+        q[0] += c0 * exp2f((t.x - mv.x) * ct) * r[0]; q[1] += c0 * exp2f((t.y - mv.y) * ct) * r[1];
+        q[2] += c0 * exp2f((t.z - mv.z) * ct) * r[2]; q[3] += c0 * exp2f((t.w - mv.w) * ct) * r[3];
       }
       if (p1 >= 0) {
         const float4 t = L1[k];
-        q[0] += c1 * exp2f(t.x * ct - mt) * r[0]; q[1] += c1 * exp2f(t.y * ct - mt) * r[1];
-        q[2] += c1 * exp2f(t.z * ct - mt) * r[2]; q[3] += c1 * exp2f(t.w * ct - mt) * r[3];
+        q[0] += c1 * exp2f((t.x - mv.x) * ct) * r[0]; q[1] += c1 * exp2f((t.y - mv.y) * ct) * r[1];
+        q[2] += c1 * exp2f((t.z - mv.z) * ct) * r[2]; q[3] += c1 * exp2f((t.w - mv.w) * ct) * r[3];
       }
     } else {
       if (p0 >= 0) { const float4 t = L0[k]; q[0] += t.x; q[1] += t.y; q[2] += t.z; q[3] += t.w; }
@@ -313,12 +345,20 @@ __global__ void koleo_norm_kernel(const float* __restrict__ x, float* __restrict
   const float inv = 1.f / (n + eps);
   for (int e = threadIdx.x; e < D; e += blockDim.x) xn[(long)i * D + e] = x[(long)i * D + e] * inv;
 }
+// Rows [row0, row0 + nrows) are the "local" rows whose terms enter the loss (mean over nrows); neighbours are searched
+// over all B rows.  row0 = 0, nrows = B is the plain KoLeo; a sub-range is KoLeoLossDistributed (loss/koleo_loss.py:39-70:
+// local rows against the all-gathered rows of every rank).
 __global__ void koleo_nn_kernel(const float* __restrict__ xn, int* __restrict__ nn, float* __restrict__ coef,
-                                float* __restrict__ metric, int B, int D, float eps, float w_metric, float w_grad) {
+                                float* __restrict__ metric, int B, int D, float eps, float w_metric, float w_grad,
+                                int row0, int nrows) {
   __shared__ float sh[32];
   __shared__ float best_v;
   __shared__ int best_j;
   const int i = blockIdx.x;
+  if (i < row0 || i >= row0 + nrows) {      // not a local row: no term, no gradient source
+    if (threadIdx.x == 0) { nn[i] = i; coef[i] = 0.f; }
+    return;
+  }
   if (threadIdx.x == 0) { best_v = -CUDART_INF_F; best_j = 0; }
   __syncthreads();
   for (int j = 0; j < B; ++j) {
@@ -342,9 +382,9 @@ __global__ void koleo_nn_kernel(const float* __restrict__ xn, int* __restrict__ 
     const float dn = sqrtf(dd);
     const float dist = dn + eps;                  // pairwise_distance(...) + eps
     nn[i] = j;
-    atomicAdd(metric, -w_metric * logf(dist + eps) / B);
-    // d(-w/B * log(dist+eps))/d(delta) = -w/B / (dist+eps) * delta/||delta||
-    coef[i] = dn > 0.f ? -w_grad / B / (dist + eps) / dn : 0.f;
+    atomicAdd(metric, -w_metric * logf(dist + eps) / nrows);
+    // d(-w/nrows * log(dist+eps))/d(delta) = -w/nrows / (dist+eps) * delta/||delta||
+    coef[i] = dn > 0.f ? -w_grad / nrows / (dist + eps) / dn : 0.f;
   }
 }
 // dx_i += J_norm^T ( coef_i * delta_i - sum_{j: nn(j)=i} coef_j * delta_j ),  delta_j = xn_j - xn_nn(j)
@@ -390,10 +430,23 @@ int d3_absmax(const float* L, long long n, float* out /* pre-set to -inf */, voi
   D3_CHECK_LAUNCH();
   return D3_OK;
 }
+int d3_colmax(const float* L, float* cm /* [K] pre-set to -inf */, int R, int K, void* stream) {
+  if (R <= 0) return D3_OK;
+  if (K % 4 == 0 && (uintptr_t)L % 16 == 0) {
+    const int cx = (K / 4 + 127) / 128;
+    dim3 grid(cx, max(1, min(R / 8, max(1, sm_count() * 8 / cx))));
+    colmax_vec_kernel<<<grid, 128, 0, STREAM(stream)>>>(L, cm, R, K);
+  } else {
+    dim3 grid((K + 255) / 256, max(1, min(R / 8, 64)));
+    colmax_kernel<<<grid, 256, 0, STREAM(stream)>>>(L, cm, R, K);
+  }
+  D3_CHECK_LAUNCH();
+  return D3_OK;
+}
 int d3_sinkhorn_colsum(const float* L, const float* mx, float temp, const float* a, float* s /* zeroed */, int R, int K,
                        void* stream) {
   if (R <= 0) return D3_OK;
-  if (K % 4 == 0 && (uintptr_t)L % 16 == 0) {
+  if (K % 4 == 0 && ((uintptr_t)L | (uintptr_t)mx) % 16 == 0) {
     // (K/4)/128 column CTAs x row slabs: aim at ~8 CTAs per SM
     const int cx = (K / 4 + 127) / 128;
     dim3 grid(cx, max(1, min(R / 8, max(1, sm_count() * 8 / cx))));
@@ -408,7 +461,7 @@ int d3_sinkhorn_colsum(const float* L, const float* mx, float temp, const float*
 int d3_sinkhorn_rowsum(const float* L, const float* mx, float temp, const float* s, const float* btot, float* a, int R,
                        int K, void* stream) {
   if (R <= 0) return D3_OK;
-  if (K % 4 == 0 && ((uintptr_t)L | (uintptr_t)s) % 16 == 0)
+  if (K % 4 == 0 && ((uintptr_t)L | (uintptr_t)s | (uintptr_t)mx) % 16 == 0)
     sk_rowsum_vec_kernel<<<R, 256, 0, STREAM(stream)>>>(L, mx, 1.f / temp, s, btot, a, R, K);
   else
     sk_rowsum_kernel<<<R, 256, 0, STREAM(stream)>>>(L, mx, 1.f / temp, s, btot, a, R, K);
@@ -441,7 +494,7 @@ int d3_ce_fwd_bwd(const float* S, float student_temp, const float* Lt, const flo
                   const float* s_t, const float* a_t, const float* btot, const int* t0, const int* t1, const float* wm,
                   const float* wg, const int* slot, float* metric, void* dS, int Rs, int K, void* stream) {
   if (Rs <= 0) return D3_OK;
-  if (K % 4 == 0 && ((uintptr_t)S | (uintptr_t)Lt | (uintptr_t)s_t | (uintptr_t)dS) % 16 == 0)
+  if (K % 4 == 0 && ((uintptr_t)S | (uintptr_t)Lt | (uintptr_t)s_t | (uintptr_t)dS | (uintptr_t)mx) % 16 == 0)
     ce_fwd_bwd_vec_kernel<<<Rs, 512, 0, STREAM(stream)>>>(S, 1.f / student_temp, Lt, mx, 1.f / teacher_temp, s_t, a_t, btot,
                                                          t0, t1, wm, wg, slot, metric, (__nv_bfloat16*)dS, K);
   else
@@ -450,12 +503,26 @@ int d3_ce_fwd_bwd(const float* S, float student_temp, const float* Lt, const flo
   D3_CHECK_LAUNCH();
   return D3_OK;
 }
+int d3_koleo_fwd_bwd_rows(const float* x, float* xn_scratch, float* nrm_scratch, int* nn_scratch, float* coef_scratch,
+                          float* metric, float* dx, int B, int D, int row0, int nrows, float eps, float w_metric,
+                          float w_grad, void* stream) {
+  if (B <= 1 || nrows <= 0) return D3_OK;
+  if (row0 < 0 || row0 + nrows > B) return set_error(D3_ERR_ARG, "d3_koleo_fwd_bwd_rows: local row range outside [0, B)");
+  koleo_norm_kernel<<<B, 256, 0, STREAM(stream)>>>(x, xn_scratch, nrm_scratch, D, eps);
+  koleo_nn_kernel<<<B, 256, 0, STREAM(stream)>>>(xn_scratch, nn_scratch, coef_scratch, metric, B, D, eps, w_metric,
+                                                w_grad, row0, nrows);
+  koleo_bwd_kernel<<<B, 256, D * sizeof(float), STREAM(stream)>>>(x, xn_scratch, nrm_scratch, nn_scratch, coef_scratch,
+                                                                dx, B, D, eps);
+  D3_CHECK_LAUNCH();
+  count_launch(2);
+  return D3_OK;
+}
 int d3_koleo_fwd_bwd(const float* x, float* xn_scratch, float* nrm_scratch, int* nn_scratch, float* coef_scratch,
                      float* metric, float* dx, int B, int D, float eps, float w_metric, float w_grad, void* stream) {
   if (B <= 1) return D3_OK;
   koleo_norm_kernel<<<B, 256, 0, STREAM(stream)>>>(x, xn_scratch, nrm_scratch, D, eps);
   koleo_nn_kernel<<<B, 256, 0, STREAM(stream)>>>(xn_scratch, nn_scratch, coef_scratch, metric, B, D, eps, w_metric,
-                                                w_grad);
+                                                w_grad, 0, B);
   koleo_bwd_kernel<<<B, 256, D * sizeof(float), STREAM(stream)>>>(x, xn_scratch, nrm_scratch, nn_scratch, coef_scratch,
                                                                 dx, B, D, eps);
   D3_CHECK_LAUNCH();

@@ -83,6 +83,22 @@ __global__ void adamw_ema_kernel(float* __restrict__ p, const float* __restrict_
   }
 }
 
+// teacher <- m*teacher + (1-m)*student on a flat shard, with the bf16 re-cast of the teacher's matrix region: the
+// stand-alone form of the EMA (train/ssl_meta_arch.py:644-660: `update_ema()` returns fn(ema, params, mom)) for callers
+// that keep the reference's two-call step (train_step, then update_ema); the engine's own loop uses the fused kernel.
+__global__ void ema_kernel(float* __restrict__ teacher, const float* __restrict__ student,
+                           __nv_bfloat16* __restrict__ t_bf16, long n_bf16, long n, float momentum) {
+  const long i4 = (blockIdx.x * (long)blockDim.x + threadIdx.x) * 4;
+  if (i4 >= n) return;
+  float4 t = *reinterpret_cast<const float4*>(teacher + i4);
+  const float4 p = *reinterpret_cast<const float4*>(student + i4);
+  const float w = 1.f - momentum;
+  t.x = t.x * momentum + p.x * w; t.y = t.y * momentum + p.y * w;
+  t.z = t.z * momentum + p.z * w; t.w = t.w * momentum + p.w * w;
+  *reinterpret_cast<float4*>(teacher + i4) = t;
+  if (i4 < n_bf16) *reinterpret_cast<uint2*>(t_bf16 + i4) = make_uint2(pack_bf16(t.x, t.y), pack_bf16(t.z, t.w));
+}
+
 }  // namespace d3
 
 using namespace d3;
@@ -108,6 +124,16 @@ int d3_adamw_ema(float* p, const float* g, float* m, float* v, float* teacher, v
   adamw_ema_kernel<<<(int)((th + 255) / 256), 256, 0, STREAM(stream)>>>(
       p, g, m, v, teacher, (__nv_bfloat16*)p_bf16, (__nv_bfloat16*)t_bf16, n_bf16, (const Seg*)segs, nseg, n, sumsq,
       max_norm, lr, last_layer_lr, wd, b1, b2, eps, bc1, bc2, momentum);
+  D3_CHECK_LAUNCH();
+  return D3_OK;
+}
+
+int d3_ema(float* teacher, const float* student, void* t_bf16, long long n_bf16, long long n, float momentum,
+           void* stream) {
+  if (n <= 0) return D3_OK;
+  if (n % 4 || n_bf16 % 4) return set_error(D3_ERR_ARG, "d3_ema: n, n_bf16 must be multiples of 4");
+  ema_kernel<<<(int)((n / 4 + 255) / 256), 256, 0, STREAM(stream)>>>(teacher, student, (__nv_bfloat16*)t_bf16, n_bf16, n,
+                                                                  momentum);
   D3_CHECK_LAUNCH();
   return D3_OK;
 }

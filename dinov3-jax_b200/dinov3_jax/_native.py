@@ -63,6 +63,7 @@ SIGNATURES = {
     "d3_colsum_bf16": [P, P, LL, I, I, P],
     "d3_cast_f32_bf16": [P, P, LL, P],
     "d3_absmax": [P, LL, P, P],
+    "d3_colmax": [P, P, I, I, P],
     "d3_sinkhorn_colsum": [P, P, F, P, P, I, I, P],
     "d3_sinkhorn_rowsum": [P, P, F, P, P, P, I, I, P],
     "d3_sinkhorn_probs": [P, P, F, P, P, P, P, I, I, P],
@@ -70,7 +71,9 @@ SIGNATURES = {
     "d3_center_update": [P, P, P, F, F, P, I, P],
     "d3_ce_fwd_bwd": [P, F, P, P, F, P, P, P, P, P, P, P, P, P, P, I, I, P],
     "d3_koleo_fwd_bwd": [P, P, P, P, P, P, P, I, I, F, F, F, P],
+    "d3_koleo_fwd_bwd_rows": [P, P, P, P, P, P, P, I, I, I, I, F, F, F, P],
     "d3_sumsq": [P, LL, P, P],
+    "d3_ema": [P, P, P, LL, LL, F, P],
     "d3_adamw_ema": [P, P, P, P, P, P, P, LL, P, I, LL, P, F, F, F, F, F, F, F, I, F, P],
 }
 NO_ARG_SYMBOLS = ["d3_last_error", "d3_abi_version", "d3_launch_count", "d3_reset_launch_count"]

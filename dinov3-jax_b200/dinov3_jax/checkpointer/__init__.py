@@ -76,6 +76,8 @@ def keep_last_n_checkpoints(ckpt_dir, n):
 def keep_checkpoint_copy(src):
     src = Path(src)
     dst = src.parent / f"{src.name}_keep"
+    if dst.exists():                  # re-saving the same iteration after a resume: replace the kept copy
+        shutil.rmtree(dst)
     shutil.copytree(src, dst, copy_function=lambda a, b: (Path(b).hardlink_to(a) if not Path(b).exists() else None))
     return dst
 
@@ -127,10 +129,8 @@ def _to_numpy(v):
 def save_checkpoint(ckpt_dir, *, iteration, params, optimizer_state=None, overwrite: bool = True, **others):
     """Write {iteration, model_params, optimizer_state, **others} under ckpt_dir (one .npy per leaf + manifest.json)."""
     ckpt_dir = Path(ckpt_dir).absolute()
-    if ckpt_dir.exists():
-        if not overwrite:
-            raise RuntimeError(f"Checkpoint already exists: {ckpt_dir}")
-        shutil.rmtree(ckpt_dir) if ckpt_dir.is_dir() else ckpt_dir.unlink()
+    if ckpt_dir.exists() and not overwrite:
+        raise RuntimeError(f"Checkpoint already exists: {ckpt_dir}")
     tmp = ckpt_dir.with_name(ckpt_dir.name + ".partial")
     if tmp.exists():
         shutil.rmtree(tmp)
@@ -149,7 +149,16 @@ def save_checkpoint(ckpt_dir, *, iteration, params, optimizer_state=None, overwr
         np.save(tmp / fname, arr, allow_pickle=False)
         manifest["leaves"][key] = {"file": fname, "shape": list(arr.shape), "dtype": str(arr.dtype)}
     (tmp / "manifest.json").write_text(json.dumps(manifest, indent=1))
-    tmp.rename(ckpt_dir)            # a checkpoint directory is either complete or absent
+    # swap: the new checkpoint is complete on disk before the old one goes away, so a crash at any point leaves
+    # either the old or the new checkpoint (never neither) under a name find_latest_checkpoint accepts
+    old = ckpt_dir.with_name(ckpt_dir.name + ".old")
+    if old.exists():
+        shutil.rmtree(old) if old.is_dir() else old.unlink()
+    if ckpt_dir.exists():
+        ckpt_dir.rename(old)
+    tmp.rename(ckpt_dir)
+    if old.exists():
+        shutil.rmtree(old) if old.is_dir() else old.unlink()
     return ckpt_dir
 
 
@@ -195,7 +204,11 @@ def engine_state(engine) -> dict:
     params = tree_from_flat({k: v.cpu() for k, v in engine.params.export_reference_tree("param").items()})
     mu = tree_from_flat({k: v.cpu() for k, v in engine.params.export_reference_tree("m").items()})
     nu = tree_from_flat({k: v.cpu() for k, v in engine.params.export_reference_tree("v").items()})
-    return params, {"count": int(engine.step_count), "mu": mu, "nu": nu}
+    opt = {"count": int(engine.step_count), "mu": mu, "nu": nu}
+    if getattr(engine, "centering", "sinkhorn_knopp") != "sinkhorn_knopp":
+        # "state" collection of the optional softmax-centering path (loss/dino_clstoken_loss.py:19-22)
+        opt["centers"] = {"dino": engine.center_dino.cpu(), "ibot": engine.center_ibot.cpu()}
+    return params, opt
 
 
 def load_engine_state(engine, params: dict, optimizer_state: dict | None = None):
@@ -203,6 +216,9 @@ def load_engine_state(engine, params: dict, optimizer_state: dict | None = None)
     if optimizer_state is not None:
         engine.step_count = int(optimizer_state["count"])
         engine.params.load_optimizer_tree(flat_from_tree(optimizer_state["mu"]), flat_from_tree(optimizer_state["nu"]))
+        if "centers" in optimizer_state and hasattr(engine, "center_dino"):
+            engine.center_dino.copy_(optimizer_state["centers"]["dino"])
+            engine.center_ibot.copy_(optimizer_state["centers"]["ibot"])
 
 
 # ------------------------------------------------------------------------------------------------ torch hub weights

@@ -27,13 +27,18 @@ DEFAULTS = {
              "head_bottleneck_dim": 256, "head_nlayers": 3, "head_hidden_dim": 2048},
     "gram": {"use_loss": False},
     "train": {"batch_size_per_gpu": 64, "output_dir": ".", "seed": 0, "OFFICIAL_EPOCH_LENGTH": 1250,
-              "centering": "sinkhorn_knopp", "checkpointing": False, "dataset_path": "synthetic"},
+              "centering": "sinkhorn_knopp", "checkpointing": False, "dataset_path": "synthetic", "num_workers": 0,
+              "cache_dataset": False},
     "student": {"arch": "vit_large", "patch_size": 16, "drop_path_rate": 0.3, "layerscale": 1.0e-5, "ffn_layer": "mlp",
                 "ffn_ratio": 4.0, "qkv_bias": True, "proj_bias": True, "ffn_bias": True, "norm_layer": "layernorm",
                 "n_storage_tokens": 0, "mask_k_bias": False, "pos_embed_rope_base": 100.0},
     "teacher": {"momentum_teacher": 0.992, "final_momentum_teacher": 1, "warmup_teacher_temp": 0.04,
                 "teacher_temp": 0.07, "warmup_teacher_temp_epochs": 30},
-    "crops": {"global_crops_size": 224, "local_crops_size": 96, "local_crops_number": 8},
+    "crops": {"global_crops_scale": [0.32, 1.0], "local_crops_number": 8, "local_crops_scale": [0.05, 0.32],
+              "global_crops_size": 224, "local_crops_size": 96, "global_local_crop_pairs_ratios": 1.0,
+              "gram_teacher_crops_size": None, "localcrops_subset_of_globalcrops": False, "share_color_jitter": False,
+              "horizontal_flips": True, "gram_teacher_no_distortions": False, "rgb_mean": [0.485, 0.456, 0.406],
+              "rgb_std": [0.229, 0.224, 0.225]},
     "optim": {"epochs": 100, "weight_decay": 0.04, "weight_decay_end": 0.4, "lr": 0.001, "warmup_epochs": 10,
               "min_lr": 1.0e-06, "schedule_trunc_extra": 0.0, "clip_grad": 3.0, "freeze_last_layer_epochs": 1,
               "scaling_rule": "sqrt_wrt_1024", "patch_embed_lr_mult": 0.2, "dino_head_wd_multiplier": 1.0,

@@ -97,6 +97,21 @@ def config_from_reference_cfg(cfg) -> EngineConfig:
         raise NotImplementedError("student.mask_k_bias is not on the B200 path (SURVEY 8f)")
     if cfg.gram.use_loss or cfg.dino.koleo_loss_distributed or cfg.dino.reweight_dino_local_loss:
         raise NotImplementedError("gram loss / distributed KoLeo / local-loss reweighting are not on the B200 path yet")
+    # options this engine does not implement must not be silently ignored (the run would differ from the request)
+    g = lambda node, key, default: node.get(key, default) if hasattr(node, "get") else getattr(node, key, default)
+    if "schedules" in cfg and cfg["schedules"]:
+        raise NotImplementedError("schedules (v2) block: only the v1 optim.* / teacher.* schedule keys are honoured")
+    if not g(cfg.dino, "global_ignore_diagonal", True):
+        raise NotImplementedError("dino.global_ignore_diagonal=false: the pair tables implement the default (true)")
+    if int(g(cfg.dino, "head_nlayers", 3)) != 3 or int(g(cfg.ibot, "head_nlayers", 3)) != 3:
+        raise NotImplementedError("head_nlayers != 3 (layers/dino_head.py default) is not on the B200 path")
+    if "multidistillation" in cfg and g(cfg["multidistillation"], "enabled", False):
+        raise NotImplementedError("multidistillation is outside the training hot path (SURVEY §2 out of scope)")
+    if float(g(cfg.student, "drop_path_rate", 0.0) or 0.0) > 0.0:
+        import warnings
+        warnings.warn("student.drop_path_rate > 0 is ignored: like the reference's deterministic branch "
+                      "(layers/block.py:195-201, the only one its train_step traces: deterministic=True, "
+                      "train/ssl_meta_arch.py:289), the engine applies no stochastic depth", stacklevel=2)
     arch = cfg.student.arch
     if arch not in ARCHS:
         raise ValueError(f"unknown student.arch {arch!r}")

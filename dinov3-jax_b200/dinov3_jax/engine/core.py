@@ -113,7 +113,8 @@ class HeadBufs:
 
 class SinkhornBufs:
     def __init__(self, R: int, K: int, device):
-        self.mx = torch.empty(1, dtype=f32, device=device)
+        self.mx = torch.empty(K, dtype=f32, device=device)      # per-prototype shift (column maxima / global max)
+        self.gmx = torch.empty(1, dtype=f32, device=device)
         self.s = torch.empty(K, dtype=f32, device=device)
         self.a = torch.empty(R, dtype=f32, device=device)
         self.btot = torch.empty(1, dtype=f32, device=device)
@@ -319,7 +320,7 @@ class Engine:
         L = logits[:R]
         sk.mx.fill_(float("-inf"))
         sk.btot.fill_(float(btot_local))
-        ops.absmax(L, sk.mx)
+        ops.colmax(L, sk.mx)
         if self.comm is not None:
             self.comm.all_reduce_max(sk.mx)
             self.comm.all_reduce_sum(sk.btot)
@@ -336,15 +337,16 @@ class Engine:
         """softmax((x - center)/temp) after the center EMA update (loss/dino_clstoken_loss.py:24-33,91-95), expressed
         through the same (mx, s, a, btot) scalings the cross-entropy kernel consumes."""
         L = logits[:R]
-        sk.mx.fill_(float("-inf"))
+        sk.gmx.fill_(float("-inf"))
         sk.btot.fill_(float(rows_local))
-        ops.absmax(L, sk.mx)
+        ops.absmax(L, sk.gmx)
         self._colsum.zero_()
         ops.colsum_f32(L, self._colsum)
         if self.comm is not None:
-            self.comm.all_reduce_max(sk.mx)
+            self.comm.all_reduce_max(sk.gmx)
             self.comm.all_reduce_sum(sk.btot)
             self.comm.all_reduce_sum(self._colsum)        # pmean of the local centers over "dp" (:93)
+        sk.mx.copy_(sk.gmx.expand_as(sk.mx))              # one global shift for every prototype (device-side broadcast)
         ops.center_update(center, self._colsum, sk.btot, self.center_momentum, temp, sk.s)
         ops.sinkhorn_rowsum(L, sk.mx, temp, sk.s, sk.btot, sk.a[:R])
 
@@ -592,6 +594,12 @@ class Engine:
             ops.adamw_ema(st.master, st.grad_shard, st.m, st.v, st.t_master, st.bf16_shard, st.t_bf16_shard,
                           st.layout.n_mat_shard, st.segs, st.nseg, st.sumsq, float(cfg.clip_grad or 0.0), lr,
                           last_layer_lr, wd, self.step_count, momentum, cfg.adamw_beta1, cfg.adamw_beta2)
+
+    def ema_update(self, momentum: float):
+        """Stand-alone teacher EMA (train/ssl_meta_arch.py:644-660) for callers that keep the reference's two-call
+        step: `optimizer_step(..., momentum=1.0)` leaves the teacher untouched, then this applies the EMA."""
+        for st in self.params.mods.values():
+            ops.ema(st.t_master, st.master, st.t_bf16_shard, st.layout.n_mat_shard, float(momentum))
 
     def train_step(self, batch: dict | None, *, teacher_temp: float, lr: float, wd: float, last_layer_lr: float,
                    momentum: float):

@@ -13,9 +13,9 @@ def _sinkhorn(teacher_output: torch.Tensor, teacher_temp: float, btot_local: flo
     L = teacher_output.to(f32).contiguous()
     R, K = L.shape
     dev = L.device
-    mx = torch.full((1,), float("-inf"), device=dev)
+    mx = torch.full((K,), float("-inf"), device=dev)      # per-prototype shift (cancels exactly, see csrc/losses.cu)
     btot = torch.tensor([float(btot_local)], device=dev)
-    ops.absmax(L, mx)
+    ops.colmax(L, mx)
     if comm is not None:
         comm.all_reduce_max(mx)
         comm.all_reduce_sum(btot)
@@ -29,6 +29,36 @@ def _sinkhorn(teacher_output: torch.Tensor, teacher_temp: float, btot_local: flo
         a = a_buf
     Q = torch.empty(R, K, device=dev)
     ops.sinkhorn_probs(L, mx, teacher_temp, s, a, btot, Q)
+    return Q
+
+
+def _softmax_center(obj, teacher_output, teacher_temp: float, update: bool, probs: bool = True):
+    L = teacher_output.to(f32).contiguous()
+    R, K = L.shape
+    dev = L.device
+    if obj.center is None:
+        obj.center = torch.zeros(K, device=dev)
+    gmx = torch.full((1,), float("-inf"), device=dev)
+    rows = torch.tensor([float(R)], device=dev)
+    ops.absmax(L, gmx)
+    colsum = torch.zeros(K, device=dev)
+    if update:
+        ops.colsum_f32(L, colsum)
+    if obj.comm is not None:
+        obj.comm.all_reduce_max(gmx)
+        obj.comm.all_reduce_sum(rows)
+        if update:
+            obj.comm.all_reduce_sum(colsum)
+    s = torch.empty(K, device=dev)
+    # momentum 1.0 leaves the center untouched and only produces s[k] = exp((center[k] - max center)/temp)/K
+    ops.center_update(obj.center, colsum, rows, obj.center_momentum if update else 1.0, teacher_temp, s)
+    if not probs:
+        return None
+    mx = gmx.expand(K).contiguous()
+    a = torch.empty(R, device=dev)
+    ops.sinkhorn_rowsum(L, mx, teacher_temp, s, rows, a)
+    Q = torch.empty(R, K, device=dev)
+    ops.sinkhorn_probs(L, mx, teacher_temp, s, a, rows, Q)
     return Q
 
 
@@ -48,6 +78,7 @@ class DINOLoss:
 
     def __init__(self, out_dim: int, student_temp: float = 0.1, center_momentum: float = 0.9, comm=None):
         self.out_dim, self.student_temp, self.center_momentum, self.comm = out_dim, student_temp, center_momentum, comm
+        self.center = None          # "state" collection of the reference (:19-22): [1, K] zeros, created on first use
 
     def sinkhorn_knopp_teacher(self, teacher_output, teacher_temp, n_iterations=3, init_phase=False):
         world = 1 if (self.comm is None or init_phase) else self.comm.world
@@ -55,7 +86,13 @@ class DINOLoss:
                          None if init_phase else self.comm)
 
     def softmax_center_teacher(self, teacher_output, teacher_temp, update_centers=True):
-        raise NotImplementedError("train.centering=softmax is disabled by the reference (ssl_meta_arch.py:49); only sinkhorn_knopp is on the B200 path")
+        """loss/dino_clstoken_loss.py:24-33: (optionally) apply_center_update first, then softmax((x - center)/temp).
+        Same kernels as the engine's optional centering path (engine/core.py::_softmax_center)."""
+        return _softmax_center(self, teacher_output, float(teacher_temp), update_centers)
+
+    def apply_center_update(self, teacher_output):
+        """:91-95: center <- m*center + (1-m)*pmean(mean_rows(teacher_output))."""
+        _softmax_center(self, teacher_output, 1.0, True, probs=False)
 
     def __call__(self, student_logits, teacher_probs, ignore_diagonal=False):
         S, B, K = student_logits.shape
@@ -79,6 +116,11 @@ class iBOTPatchLoss:
 
     def __init__(self, patch_out_dim: int, student_temp: float = 0.1, center_momentum: float = 0.9, comm=None):
         self.patch_out_dim, self.student_temp, self.comm = patch_out_dim, student_temp, comm
+        self.center_momentum, self.center = center_momentum, None
+
+    def softmax_center_teacher(self, teacher_patch_tokens, teacher_temp, update_centers=True):
+        """loss/ibot_patch_loss.py:28-36 (same arithmetic as DINOLoss.softmax_center_teacher, rows = masked patches)."""
+        return _softmax_center(self, teacher_patch_tokens, float(teacher_temp), update_centers)
 
     def sinkhorn_knopp_teacher(self, teacher_output, teacher_temp, n_masked_patches_tensor, n_iterations=3, init_phase=False):
         return _sinkhorn(teacher_output, float(teacher_temp), float(n_masked_patches_tensor.sum()), n_iterations,
@@ -107,5 +149,27 @@ class KoLeoLoss:
 
 
 class KoLeoLossDistributed:
-    def __init__(self, *a, **k):
-        raise NotImplementedError("dino.koleo_loss_distributed is off by default (ssl_default_config.yaml:29) and not on the B200 path yet")
+    """loss/koleo_loss.py:39-70: nearest neighbours are searched over the rows of ALL ranks (all-gather over "dp"),
+    the loss is the mean over the local rows.  The gathered matrix is tiny ([world*B, D]); the neighbour search runs in
+    the same KoLeo kernels on the concatenated rows, and the rows of this rank are picked out of the per-row terms."""
+
+    def __init__(self, topk: int = 1, loss_group_size=None, comm=None):
+        if topk != 1:
+            raise NotImplementedError("KoLeoLossDistributed: topk > 1 is not on the B200 path")
+        self.comm, self.loss_group_size = comm, loss_group_size
+
+    def __call__(self, student_output, eps=1e-8):
+        x = student_output.to(f32).contiguous()
+        B, D = x.shape
+        dev = x.device
+        if self.comm is None or self.comm.world == 1:
+            return KoLeoLoss()(x, eps)
+        world, rank = self.comm.world, self.comm.rank
+        allx = torch.empty(world * B, D, device=dev)
+        self.comm.all_gather(allx, x)
+        n = world * B
+        met, dx = torch.zeros(1, device=dev), torch.zeros(n, D, device=dev)
+        ops.koleo_fwd_bwd_rows(allx, torch.empty(n, D, device=dev), torch.empty(n, device=dev),
+                               torch.empty(n, dtype=torch.int32, device=dev), torch.empty(n, device=dev), met, dx,
+                               rank * B, B, 1.0, 0.0, eps)
+        return met[0]

@@ -231,6 +231,12 @@ def absmax(L, out):
     N.check(N.init().d3_absmax(_p(L), L.numel(), _p(out), _s()), "d3_absmax")
 
 
+def colmax(L, cm):
+    """cm[k] = max(cm[k], max_b L[b,k]); cm pre-set to -inf ([K] fp32)."""
+    R, K = L.shape
+    N.check(N.init().d3_colmax(_p(L), _p(cm), R, K, _s()), "d3_colmax")
+
+
 def sinkhorn_colsum(L, mx, temp, a, s):
     R, K = L.shape
     N.check(N.init().d3_sinkhorn_colsum(_p(L), _p(mx), temp, _p(a), _p(s), R, K, _s()), "d3_sinkhorn_colsum")
@@ -272,8 +278,21 @@ def koleo_fwd_bwd(x, xn, nrm, nn, coef, metric, dx, w_metric, w_grad, eps=1e-8):
                                       w_metric, w_grad, _s()), "d3_koleo_fwd_bwd")
 
 
+def koleo_fwd_bwd_rows(x, xn, nrm, nn, coef, metric, dx, row0, nrows, w_metric, w_grad, eps=1e-8):
+    """KoLeo with the loss terms restricted to rows [row0, row0+nrows) of the (all-gathered) matrix x."""
+    B, D = x.shape
+    assert x.dtype == f32 and nn.dtype == torch.int32
+    N.check(N.init().d3_koleo_fwd_bwd_rows(_p(x), _p(xn), _p(nrm), _p(nn), _p(coef), _p(metric), _p(dx), B, D, int(row0),
+                                           int(nrows), eps, w_metric, w_grad, _s()), "d3_koleo_fwd_bwd_rows")
+
+
 def sumsq(g, out):
     N.check(N.init().d3_sumsq(_p(g), g.numel(), _p(out), _s()), "d3_sumsq")
+
+
+def ema(teacher, student, t_bf16, n_bf16, momentum):
+    """teacher <- momentum*teacher + (1-momentum)*student (flat fp32 shards) + bf16 re-cast of the matrix region."""
+    N.check(N.init().d3_ema(_p(teacher), _p(student), _p(t_bf16), n_bf16, teacher.numel(), momentum, _s()), "d3_ema")
 
 
 def adamw_ema(p, g, m, v, teacher, p_bf16, t_bf16, n_bf16, segs, nseg, sumsq_t, max_norm, lr, last_layer_lr, wd, step,

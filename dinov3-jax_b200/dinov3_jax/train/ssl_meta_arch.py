@@ -41,11 +41,32 @@ class SSLMetaArch:
         return m["total_loss"], m
 
     def update_ema(self):
-        """The reference returns fn(ema, params, mom) (:644-660); the B200 EMA is fused into the optimizer kernel
-        (Engine.optimizer_step), so this returns a callable that documents that and is a no-op."""
-        def fn(ema_params=None, params=None, mom=None):
+        """The reference returns `fn(ema_params, params, mom)` (:644-660) that the loop applies after every step
+        (train/train.py:666).  Same contract: the returned callable applies teacher <- mom*teacher + (1-mom)*student on
+        the engine-resident shards (d3_ema) and returns the (in-place updated) ema handle.  `do_train` itself uses the
+        EMA fused into the optimizer kernel instead."""
+        def _update_ema(ema_params, params=None, mom=None):
+            engine = getattr(ema_params, "engine", None) or self.engine
+            if engine is None:
+                raise ValueError("update_ema: no engine (call build_engine / pass the EngineTree handles)")
+            if mom is None:
+                raise TypeError("update_ema(ema_params, params, mom): mom is required")
+            engine.ema_update(float(mom))
             return ema_params
-        return fn
+        return _update_ema
+
+    def build_data_augmentation_dino(self, cfg):
+        """:561-575 — the augmentation class stays in the reference's data package (torchvision host pipeline) and is
+        resolved through the package overlay."""
+        from ..data import DataAugmentationDINO
+        c = cfg.crops
+        return DataAugmentationDINO(
+            c.global_crops_scale, c.local_crops_scale, c.local_crops_number, global_crops_size=c.global_crops_size,
+            local_crops_size=c.local_crops_size, gram_teacher_crops_size=c.get("gram_teacher_crops_size", None),
+            gram_teacher_no_distortions=c.get("gram_teacher_no_distortions", False),
+            local_crops_subset_of_global_crops=c.get("localcrops_subset_of_globalcrops", False),
+            share_color_jitter=c.get("share_color_jitter", False), horizontal_flips=c.get("horizontal_flips", True),
+            mean=c.get("rgb_mean", (0.485, 0.456, 0.406)), std=c.get("rgb_std", (0.229, 0.224, 0.225)))
 
     def get_params_groups(self, params=None):
         """name -> (lr_multiplier, wd_multiplier, is_last_layer) for every student tensor (:577-598 / param_groups.py)."""
@@ -58,4 +79,10 @@ class SSLMetaArch:
         return out
 
     def prepare_for_distributed_training(self, params=None):
-        return params
+        """:600-642 shards the six sub-trees with `ac_compile_parallelize`.  Engine-resident state is sharded when the
+        engine is built with a communicator (`build_engine(comm=...)`: fsdp/layout.py), so a handle passes through;
+        a plain reference-named pytree is sharded with the mirrored policy."""
+        if params is None or hasattr(params, "engine"):
+            return params
+        from ..fsdp.ac_compile_parallelize import ac_compile_parallelize
+        return {k: ac_compile_parallelize(v, None, self.config) for k, v in params.items()}

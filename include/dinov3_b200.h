@@ -163,9 +163,13 @@ int d3_colsum_bf16(const void* x_bf16 /*[T,N], row stride ld*/, float* out /*[N]
 int d3_cast_f32_bf16(const float* src, void* dst_bf16, long long n, void* stream);
 
 /* ---- Sinkhorn-Knopp (loss/dino_clstoken_loss.py:35-62, loss/ibot_patch_loss.py:77-109) ----------------------------
- * Q[b,k] = Btot * exp((L[b,k]-mx)/temp) * r[k] * a[b],  r = 1/(K * E^T a),  a = 1/(Btot * E r); the caller alternates
- * colsum (-> all-reduce over ranks of s[K]) and rowsum three times; mx = global max (all-reduce MAX over ranks).     */
+ * Q[b,k] = Btot * exp((L[b,k]-mx[k])/temp) * r[k] * a[b],  r = 1/(K * E^T a),  a = 1/(Btot * E r); the caller alternates
+ * colsum (-> all-reduce over ranks of s[K]) and rowsum three times.  mx is a [K] vector of per-prototype shifts that
+ * cancel exactly in E*r: d3_colmax (column maxima, all-reduce MAX over ranks) for Sinkhorn, so that a prototype far
+ * below the batch maximum keeps its mass 1/K as in the reference's unshifted exp (:39); the softmax-centering path
+ * fills it with the global maximum from d3_absmax.                                                                 */
 int d3_absmax(const float* L, long long n, float* out /*pre-set to -inf*/, void* stream);
+int d3_colmax(const float* L /*[R,K]*/, float* cm /*[K] pre-set to -inf*/, int R, int K, void* stream);
 int d3_sinkhorn_colsum(const float* L /*[R,K]*/, const float* mx, float temp, const float* a /*[R] or NULL (=1)*/,
                        float* s /*[K] zeroed, +=*/, int R, int K, void* stream);
 int d3_sinkhorn_rowsum(const float* L, const float* mx, float temp, const float* s, const float* btot /*device*/,
@@ -184,7 +188,8 @@ int d3_center_update(float* center /*[K]*/, const float* colsum /*[K] (all-reduc
  * loss/ibot_patch_loss.py:13-14,55-67; weights train/ssl_meta_arch.py:480-525) ---------------------------------------
  * per student row i with teacher rows t0[i], t1[i] (-1 = none): metric[slot[i]] += wm[i] * CE_i;
  * dS[i,:] = wg[i]/student_temp * (npairs*softmax(S_i/student_temp) - sum_p Q_p)  (bf16; NULL = forward only).
- * s_t == NULL: the rows of Lt are already teacher probabilities (mx / a_t / btot ignored).                         */
+ * s_t == NULL: the rows of Lt are already teacher probabilities (mx / a_t / btot ignored); mx is the [K] shift vector
+ * of the Sinkhorn section above.                                                                                   */
 int d3_ce_fwd_bwd(const float* S /*[Rs,K]*/, float student_temp, const float* Lt /*[Rt,K] teacher logits*/,
                   const float* mx, float teacher_temp, const float* s_t /*[K]*/, const float* a_t /*[Rt]*/,
                   const float* btot, const int* t0, const int* t1, const float* wm, const float* wg, const int* slot,
@@ -194,6 +199,12 @@ int d3_ce_fwd_bwd(const float* S /*[Rs,K]*/, float student_temp, const float* Lt
 int d3_koleo_fwd_bwd(const float* x /*[B,D]*/, float* xn_scratch /*[B,D]*/, float* nrm_scratch /*[B]*/,
                      int* nn_scratch /*[B]*/, float* coef_scratch /*[B]*/, float* metric, float* dx /*[B,D] +=*/, int B,
                      int D, float eps, float w_metric, float w_grad, void* stream);
+/* KoLeoLossDistributed (loss/koleo_loss.py:39-70): x holds the all-gathered rows of every rank; only the local rows
+ * [row0, row0+nrows) contribute loss terms (mean over nrows), neighbours are searched over all B rows; dx gets the
+ * gradient for all B rows (the caller reduce-scatters the other ranks' parts).                                     */
+int d3_koleo_fwd_bwd_rows(const float* x /*[B,D]*/, float* xn_scratch, float* nrm_scratch, int* nn_scratch,
+                          float* coef_scratch, float* metric, float* dx /*[B,D] +=*/, int B, int D, int row0, int nrows,
+                          float eps, float w_metric, float w_grad, void* stream);
 
 /* ---- optimiser (train/train.py:516-541 clip, :95-106,562-563 optax.adamw; train/ssl_meta_arch.py:650-652 EMA) -------
  * flat fp32 buffers; segs = array of {int64 start; float lr_mult, wd_mult; int is_last_layer, pad} sorted by start.  */
@@ -202,6 +213,11 @@ int d3_adamw_ema(float* p, const float* g, float* m, float* v, float* teacher, v
                  long long n_bf16, const void* segs, int nseg, long long n, const float* sumsq /*device, clip*/,
                  float max_norm, float lr, float last_layer_lr, float wd, float b1, float b2, float eps, int step,
                  float momentum, void* stream);
+/* Stand-alone teacher EMA (train/ssl_meta_arch.py:644-660, the fn(ema_params, params, mom) returned by update_ema()):
+ * teacher <- momentum*teacher + (1-momentum)*student over a flat fp32 shard; the leading n_bf16 elements (matrix
+ * region) are re-cast into the teacher's bf16 compute copy.                                                        */
+int d3_ema(float* teacher, const float* student, void* t_bf16, long long n_bf16, long long n, float momentum,
+           void* stream);
 
 #ifdef __cplusplus
 }

@@ -234,3 +234,80 @@ def test_step_with_storage_tokens_and_layernormbf16():
     g = r["grads"]["student_backbone/storage_tokens"]
     e = float((r["grads_e"]["student_backbone/storage_tokens"].reshape(g.shape) - g).norm() / g.norm())
     assert e < 6e-2
+
+
+def _loader_fixture():
+    import os
+    import numpy as np
+    from conftest import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "loader_batch.npz"))
+    b = {k: torch.from_numpy(z[k]) for k in z.files}
+    for k in ("collated_global_crops", "collated_local_crops"):
+        b[k] = b[k].view(torch.bfloat16)
+    return b
+
+
+def test_loader_batch_from_reference_augmentation_through_engine_matches_oracle():
+    """Loader -> engine end to end: a batch made by the reference's own DataAugmentationDINO (fixture, see
+    tests/golden/make_loader_fixture.py) and this repo's collate goes through `Engine.train_step` unchanged, and the
+    loss equals the oracle's on the same batch."""
+    from oracle import cfg_for
+    from oracle.model import init_params
+    from oracle.step import init_opt_state, train_step
+    from dinov3_jax.engine import Engine, from_oracle_cfg
+    cfg = dataclasses.replace(cfg_for("vit_small", global_size=64, local_size=32, n_prototypes=512, head_hidden=256,
+                                      head_bottleneck=64, layerscale=0.1), depth=2)
+    batch = _loader_fixture()
+    B = batch["collated_local_crops"].shape[0] // cfg.n_local
+    P = init_params(cfg, 0, perturb=0.05)
+    eng = Engine(from_oracle_cfg(cfg), B, max_masked=int(batch["mask_indices_list"].shape[0]))
+    eng.params.load_reference_tree(P)
+    eng.train_step(batch, **HYPER)
+    met = eng.read_metrics()
+    _, _, loss, m, _ = train_step(P, init_opt_state(P), batch, cfg, **HYPER)
+    assert abs(met["total_loss"] - loss.item()) < 1e-3 * abs(loss.item()), (met["total_loss"], loss.item())
+
+
+def test_reference_call_contract_train_step_then_update_ema():
+    """`train_step(params, batch, optimizer_state, teacher_temp, iteration, root_rngs)` -> (params, optimizer_state,
+    loss, metrics) followed by `model.update_ema()(ema_params, params, mom)` (train/train.py:491-565,666;
+    ssl_meta_arch.py:644-660) gives exactly the state of the fused engine step."""
+    from dinov3_jax.configs import DinoV3SetupArgs, setup_config
+    from dinov3_jax.engine.synth import init_reference_like
+    from dinov3_jax.train.ssl_meta_arch import SSLMetaArch
+    from dinov3_jax.train.train import build_optimizer, build_schedulers, make_state, train_step
+    opts = ["train.batch_size_per_gpu=2", "student.arch=vit_small", "crops.global_crops_size=64", "crops.local_crops_size=32",
+            "dino.head_n_prototypes=512", "ibot.head_n_prototypes=512", "dino.head_hidden_dim=256", "ibot.head_hidden_dim=256",
+            "dino.head_bottleneck_dim=64", "ibot.head_bottleneck_dim=64", "optim.epochs=2", "train.OFFICIAL_EPOCH_LENGTH=10",
+            "optim.warmup_epochs=1", "teacher.warmup_teacher_temp_epochs=1", "optim.freeze_last_layer_epochs=0"]
+    batch = _loader_fixture()
+    M = int(batch["mask_indices_list"].shape[0])
+    out = []
+    for mode in ("reference_calls", "fused"):
+        config = setup_config(DinoV3SetupArgs(opts=opts))
+        model = SSLMetaArch(config)
+        eng = model.build_engine(max_masked=M)
+        init_reference_like(eng, seed=3)
+        lr_s, wd_s, mom_s, temp_s, last_s = build_schedulers(config)
+        it = 4
+        if mode == "reference_calls":
+            optimizer = build_optimizer(config, model.get_params_groups(), lr_s, wd_s, last_s)
+            params, ema_params, opt_state = make_state(eng, optimizer)
+            assert set(params.keys()) == {"student_backbone", "student_dino_head", "student_ibot_head", "teacher_backbone",
+                                          "teacher_dino_head", "teacher_ibot_head"}
+            t_before = ema_params["teacher_backbone"]["norm/scale"].clone()
+            params, opt_state, loss, metrics = train_step(params, batch, opt_state, temp_s[it], it, None)
+            assert torch.equal(ema_params["teacher_backbone"]["norm/scale"], t_before)       # teacher untouched by train_step
+            for k in ("dino_local_crops_loss", "dino_global_crops_loss", "koleo_loss", "ibot_loss",
+                      "student_backbone_grad_norm", "student_dino_head_grad_norm", "student_ibot_head_grad_norm"):
+                assert k in metrics
+            ema_params = model.update_ema()(ema_params, params, mom_s[it])
+        else:
+            eng.train_step(batch, teacher_temp=float(temp_s[it]), lr=float(lr_s[it]), wd=float(wd_s[it]),
+                           last_layer_lr=float(last_s[it]), momentum=float(mom_s[it]))
+            loss = eng.read_metrics()["total_loss"]
+        out.append((loss, eng.params.export_reference_tree("param")))
+    (la, pa), (lb, pb) = out
+    assert abs(la - lb) <= 1e-5 * abs(lb)
+    for k in pa:
+        assert torch.allclose(pa[k], pb[k], atol=2e-6, rtol=1e-5), k

@@ -341,8 +341,10 @@ def test_sinkhorn_ce_koleo_match_oracle():
     from oracle.losses import dino_loss, ibot_loss_masked, koleo_loss, sinkhorn_knopp
     R, K, temp = 24, 4096, 0.05
     L = torch.randn(R, K, device="cuda") * 0.3
-    mx = torch.full((1,), float("-inf"), device="cuda"); ops.absmax(L, mx)
-    assert mx.item() == L.max().item()
+    gmx = torch.full((1,), float("-inf"), device="cuda"); ops.absmax(L, gmx)
+    assert gmx.item() == L.max().item()
+    mx = torch.full((K,), float("-inf"), device="cuda"); ops.colmax(L, mx)
+    assert torch.equal(mx, L.max(0).values)
     btot = torch.tensor([float(R)], device="cuda")
     a, s, av = None, torch.zeros(K, device="cuda"), torch.empty(R, device="cuda")
     for _ in range(3):

@@ -51,11 +51,11 @@ timeit("colsum_bf16 [T,4D]", lambda: ops.colsum_bf16(h, cs4), TD * 4 * 2)
 if len(sys.argv) <= 2:
     M, K = 3771, 65536
     Lt = torch.randn(M, K, device=dev) * 0.3; S = torch.randn(M, K, device=dev)
-    mx = torch.full((1,), float("-inf"), device=dev); sv = torch.zeros(K, device=dev); a = torch.ones(M, device=dev)
+    mx = torch.full((K,), float("-inf"), device=dev); sv = torch.zeros(K, device=dev); a = torch.ones(M, device=dev)
     btot = torch.full((1,), float(M), device=dev)
     MK = M * K
     print(f"M={M} K={K}")
-    timeit("absmax", lambda: ops.absmax(Lt, mx), MK * 4)
+    timeit("colmax", lambda: ops.colmax(Lt, mx), MK * 4)
     timeit("sinkhorn_colsum", lambda: ops.sinkhorn_colsum(Lt, mx, 0.05, a, sv), MK * 4)
     sv.fill_(1.0)
     timeit("sinkhorn_rowsum", lambda: ops.sinkhorn_rowsum(Lt, mx, 0.05, sv, btot, a), MK * 4)

@@ -22,9 +22,9 @@ q = torch.randn(T, 3 * D, device=dev).to(bf); cs = torch.zeros(3 * D, device=dev
 ops.colsum_bf16(q, cs)
 M, K = 3771, 65536
 Lt = torch.randn(M, K, device=dev) * 0.3; S = torch.randn(M, K, device=dev)
-mx = torch.full((1,), float("-inf"), device=dev); sv = torch.zeros(K, device=dev); a = torch.ones(M, device=dev)
+mx = torch.full((K,), float("-inf"), device=dev); sv = torch.zeros(K, device=dev); a = torch.ones(M, device=dev)
 btot = torch.full((1,), float(M), device=dev)
-ops.absmax(Lt, mx)
+ops.colmax(Lt, mx)
 ops.sinkhorn_colsum(Lt, mx, 0.05, a, sv)
 ops.sinkhorn_rowsum(Lt, mx, 0.05, sv, btot, a)
 t0 = torch.arange(M, device=dev, dtype=torch.int32); t1 = torch.full((M,), -1, device=dev, dtype=torch.int32)

@@ -177,8 +177,8 @@ def g_losses():
     dev = "cuda"
     R, K, temp = 24, 4096, 0.05
     L = torch.randn(R, K, device=dev) * 0.3
-    mx = torch.full((1,), float("-inf"), device=dev); ops.absmax(L, mx)
-    print("  absmax exact:", bool(mx.item() == L.max().item()))
+    mx = torch.full((K,), float("-inf"), device=dev); ops.colmax(L, mx)
+    print("  colmax exact:", bool(torch.equal(mx, L.max(0).values)))
     btot = torch.tensor([float(R)], device=dev)
     a = None; s = torch.zeros(K, device=dev); av = torch.empty(R, device=dev)
     for it in range(3):
