@@ -8,6 +8,7 @@
 // (over the dead Q/K tiles), and a second UMMA computes O = P V with V consumed as an MN-major operand straight
 // from its TMA tile.  Operands come by TMA from the fused qkv buffer [T, 3D] (q | k | v thirds, heads contiguous).
 #include "ptx.cuh"
+#include <cstdlib>
 #include "d3_internal.h"
 
 namespace d3 {
@@ -87,7 +88,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (threadIdx.x == 0) {
+  if (warp == 0 && elect_one()) {
     mbar_expect_tx(bar_load, 16384 + 2 * kv_bytes);
     tma_load_2d(&tmQ, bar_load, sQ, h * 64, row_base + q0);
     for (int b = 0; b < sh.nbox; ++b) {
@@ -173,7 +174,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   sum = red[r] + red[128 + r];
-  if (threadIdx.x == 0) {
+  if (warp == 0 && elect_one()) {
     tc_fence_after();
     // O[128, 64] = P[128, Nkp] V[Nkp, 64]  (A = P K-major, B = V MN-major: 16 keys per UMMA_K = 2 x 1024 B)
     const uint32_t pa = smem_u32(sP), va = smem_u32(sV);
@@ -596,21 +597,27 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     }
   };
 
-  if (threadIdx.x == 0) {
-    mbar_expect_tx(bar_q, nQ * 2 * 16384);
-    for (int qt = 0; qt < nQ; ++qt) {
-      tma_load_2d(&tmQKV, bar_q, sQ + qt * 16384, h * 64, row_base + qt * 128);
-      tma_load_2d(&tmDO, bar_q, sDO + qt * 16384, h * 64, row_base + qt * 128);
+  // TMA / tcgen05 issue: one ELECTED lane of the converged warp 0 (under `threadIdx.x == 0` ptxas serialises every
+  // UTMALDG / UTCHMMA through an ELECT ... BRA.U.ANY loop, ~60-90 cycles per instruction: the accumulate MMAs of this
+  // kernel (N = 64: 32 tensor cycles each) were issue-bound)
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(bar_q, nQ * 2 * 16384);
+      for (int qt = 0; qt < nQ; ++qt) {
+        tma_load_2d(&tmQKV, bar_q, sQ + qt * 16384, h * 64, row_base + qt * 128);
+        tma_load_2d(&tmDO, bar_q, sDO + qt * 16384, h * 64, row_base + qt * 128);
+      }
+      load_kv(0);
+      if (nK > 1) load_kv(1);
+      mbar_wait(bar_q, 0);
+      mbar_wait(&bar_kv[0], 0);
+      tc_fence_after();
+      issue_sdp(0, 0);
+      umma_commit(bar_mma);
     }
-    load_kv(0);
-    if (nK > 1) load_kv(1);
-    mbar_wait(bar_q, 0);
-    mbar_wait(&bar_kv[0], 0);
-    dbg_mark(2);
-    tc_fence_after();
-    issue_sdp(0, 0);
-    umma_commit(bar_mma);
+    __syncwarp();
   }
+  dbg_mark(2);
   uint32_t mma_phase = 0;
 
 #pragma unroll 1
@@ -701,7 +708,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     tc_fence_before();
     __syncthreads();
     dbg_mark(6 + it * 4);
-    if (threadIdx.x == 0) {
+    if (warp == 0 && elect_one()) {
       tc_fence_after();
       // descriptors are built once; each UMMA_K step only adds a constant to the 14-bit start-address field
       const uint64_t dP_mn = umma_desc_sw128(smem_u32(sP), 16384, 1024);            // P  as MN-major A (keys x query rows)
@@ -797,14 +804,29 @@ using namespace d3;
 extern "C" {
 
 int d3_debug_attn_trace(long long* buf /*device [64] or NULL*/) {
+  attn_ws_set_trace(buf ? buf + 64 : nullptr);      // warp-specialised kernels: [64, 64 + 320) of the same buffer
   cudaError_t e = cudaMemcpyToSymbol(g_attn_dbg, &buf, sizeof(buf));
   return e == cudaSuccess ? D3_OK : set_error(D3_ERR_CUDA, cudaGetErrorString(e));
+}
+
+static int attn_ws_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("D3_ATTN_WS");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v;
 }
 
 int d3_attn_fwd(const void* qkv, void* o, float* lse, int n_crops, int N, int D, int H, void* stream) {
   AttnShape s;
   int rc = attn_shape(&s, n_crops, N, D, H);
   if (rc) return rc;
+  if (attn_ws_enabled()) {      // persistent warp-specialised kernel (N <= 256 tokens per crop)
+    int handled = 0;
+    if ((rc = attn_fwd_ws(qkv, o, lse, n_crops, N, D, H, reinterpret_cast<cudaStream_t>(stream), &handled))) return rc;
+    if (handled) return D3_OK;
+  }
   const long T = (long)n_crops * N;
   CUtensorMap tq, tkv;
   if ((rc = make_map(&tq, qkv, T, 3 * D, 3 * D, 128))) return rc;

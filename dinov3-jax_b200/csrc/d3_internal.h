@@ -60,6 +60,11 @@ int encode_tensor_map_2d(CUtensorMap* map, const void* ptr, int elt_bytes, cuuin
 int gemm_bf16(const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, int M, int N, int K,
               GemmEpilogue ep, int tile_n, int split_k, cudaStream_t stream);
 
+// warp-specialised persistent attention (attention_ws.cu); *handled = 0 when the shape must take the single-pass kernels
+int attn_fwd_ws(const void* qkv, void* o, float* lse, int n_crops, int N, int D, int H, cudaStream_t st, int* handled);
+
+void attn_ws_set_trace(long long* buf);
+
 #define D3_CHECK_LAUNCH()                                               \
   do {                                                                  \
     cudaError_t e__ = cudaPeekAtLastError();                            \

@@ -497,7 +497,7 @@ ln_bwd_ring_kernel(const InT* __restrict__ dy, const float* __restrict__ x, cons
   const long nrows = blockIdx.x < T ? ((long)T - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
   if (warp == LNR_CONSUMERS) {
-    if (lane == 0) {
+    if (elect_one()) {      // elected lane of the converged producer warp: plain UBLKCP, no per-instruction ELECT loop
       for (long k = 0; k < nrows; ++k) {
         const int st = (int)(k % stages);
         const long use = k / stages;

@@ -14,6 +14,9 @@
 //                    its 128 A rows and half (128) of the B columns, halving L2->SM operand traffic per FLOP
 //                    (a 1-CTA 128x256 tile needs 96 B/clk/SM of operands: above what L2 can feed 148 SMs).
 //   gemm1sm_kernel — single-CTA 128 x {64,128,256} tiles for small / ragged problems.
+// Issue discipline: TMA and tcgen05 instructions are issued by the ELECTED lane (elect.sync) of a converged warp; under a
+// `lane == 0` branch ptxas wraps every UTMALDG / UTCHMMA / UTMASTG in an ELECT ... BRA.U.ANY loop (~60-90 cycles each),
+// which is more than the 64 tensor cycles of one 256x256x16 pair MMA (tools/microbench/mma_lat.cu).
 // Roles: warp0 = TMA producer, warp1 = MMA issuer (one elected lane), warp2 = TMEM allocator, warps4-11 = epilogue
 // (TMEM -> registers -> global; two warps per TMEM lane quarter, each taking half of the tile's columns).
 // Two accumulator stages in TMEM let the epilogue of tile i overlap the main loop of tile i+1.
@@ -254,7 +257,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmEpilogue& ep, const 
     if (has_auxin) tma_load_2d_cta(tmAux, &pp.ld_bar[b], sOut + 4096, n0 + c * 32, row0);
   };
   // prologue: the first unit's buffer was last used two units ago -> its store group has drained after wait<1>
-  if (lane == 0) {
+  if (elect_one()) {
     tma_store_wait_read1();
     if (has_loads) issue_loads(c_beg, pp.unit);
   }
@@ -265,7 +268,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmEpilogue& ep, const 
     uint8_t* sOut = pp.buf + b * 6144;
     uint8_t* sAux = sOut + 4096;
     const int nc = n0 + c * 32;
-    if (lane == 0 && c + 1 < c_end) {
+    if (c + 1 < c_end && elect_one()) {
       // buffer (u+1)&1 was used by unit u-1: allow only the most recent store group (none issued since) to be pending
       tma_store_wait_read0();
       if (has_loads) issue_loads(c + 1, u + 1);
@@ -342,7 +345,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmEpilogue& ep, const 
     }
     fence_proxy_async_smem();
     __syncwarp();
-    if (lane == 0) {
+    if (elect_one()) {
       tma_store_2d(tmOut, sOut, nc, row0);
       if (store_pre) tma_store_2d(tmAux, sAux, nc, row0);
       tma_store_commit();
@@ -418,7 +421,7 @@ gemm1sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int num_work = num_m * num_n * splits;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
@@ -446,7 +449,7 @@ gemm1sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
       constexpr uint32_t a_adv = A_MN ? (2 * 1024 >> 4) : (32 >> 4);
       constexpr uint32_t b_adv = B_MN ? (2 * 1024 >> 4) : (32 >> 4);
@@ -597,7 +600,7 @@ gemm2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int num_clusters = gridDim.x >> 1;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       ClcRing ring{clc_resp, clc_full, clc_empty, 0};
@@ -630,7 +633,7 @@ gemm2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (leader && lane == 0) {
+    if (leader && elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(256, BN, A_MN, B_MN);
       constexpr uint32_t a_adv = A_MN ? (2 * 1024 >> 4) : (32 >> 4);
       constexpr uint32_t b_adv = B_MN ? (2 * 1024 >> 4) : (32 >> 4);

@@ -111,7 +111,9 @@ def attn_ref(qkv, n, N, D, H):
     return o, torch.logsumexp(s, -1)
 
 
-@pytest.mark.parametrize("n,N,H", [(3, 197, 2), (5, 37, 2), (2, 128, 1), (2, 257, 1), (4, 50, 3), (1, 1, 1), (2, 17, 6)])
+@pytest.mark.parametrize("n,N,H", [(3, 197, 2), (5, 37, 2), (2, 128, 1), (2, 257, 1), (4, 50, 3), (1, 1, 1), (2, 17, 6),
+                                   (2, 256, 1), (3, 200, 1), (7, 64, 1), (4, 65, 2), (3, 129, 1),
+                                   (40, 197, 16), (130, 37, 16), (9, 201, 8)])
 def test_attention_forward(n, N, H):
     from dinov3_jax import ops
     D = 64 * H
