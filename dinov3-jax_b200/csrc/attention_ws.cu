@@ -27,6 +27,7 @@ struct AttnWsShape {
   int slot_w;       // tensor-memory columns per slot (128 or 256)
   int n_slot;       // 512 / slot_w: query tiles in flight (2 or 4)
   int o_off;        // column of the O accumulator inside a slot
+  int mid;          // key column where the upper thread of a row takes over (multiple of 16); its packed P starts at column mid
   int stage_bytes;  // shared memory per pipeline stage
   int n_stage;      // shared-memory stages (items prefetched): 2 .. 4
   int nq_sh, ns_sh, nst_sh;   // log2 of nQ, n_slot, n_stage (all powers of two: index math by shifts, no division)
@@ -53,7 +54,7 @@ __device__ __forceinline__ float max16(const uint32_t (&v)[16]) {
 }
 
 constexpr int WS_MAX_STAGE = 4, WS_MAX_SLOT = 4;
-constexpr int WS_THREADS = 352;   // warp 0: TMA, warps 1-2: tensor-core issuers (even / odd units), warps 3-10: softmax
+constexpr int WS_THREADS = 608;   // warp 0: TMA, warps 1-2: tensor-core issuers (even / odd units), warps 3-18: softmax
 
 // Units (query tiles) are numbered u = item_local * nQ + qt in the order a CTA meets them.  Unit u lives in slot
 // u % n_slot; even units are issued by warp 1 and handled by warpgroup 0, odd units by warp 2 / warpgroup 1, so the two
@@ -85,13 +86,13 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tma_prefetch_desc(&tmKV);
     for (int i = 0; i < WS_MAX_STAGE; ++i) {
       mbar_init(&bar_full[i], 1);
-      mbar_init(&bar_empty[i], sh.nQ * 5);          // per unit: the PV commit + the four read-out warps
+      mbar_init(&bar_empty[i], sh.nQ * 9);          // per unit: the PV commit + the eight read-out warps
     }
     for (int i = 0; i < WS_MAX_SLOT; ++i) {
       mbar_init(&bar_s[i], 1);
-      mbar_init(&bar_p[i], 4);
+      mbar_init(&bar_p[i], 8);
       mbar_init(&bar_o[i], 1);
-      mbar_init(&bar_free[i], 4);
+      mbar_init(&bar_free[i], 8);
     }
     fence_mbar_init();
   }
@@ -154,8 +155,10 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const uint64_t vd = umma_desc_sw128(smem_u32(base + sh.nQ * 16384 + kv_bytes), 8192, 1024);
         const uint32_t tP = tmem + slot * sh.slot_w;
         const uint32_t tO = tP + sh.o_off;
+        // packed P: keys below sh.mid from column 0, keys from sh.mid on from column sh.mid (8 columns per 16 keys)
+        const int hi_shift = sh.mid - (sh.mid >> 1);
         for (int k = 0; k < ksteps; ++k)
-          umma_bf16_ts(tO, tP + k * 8, vd + (uint64_t)(k * 128), idesc_pv, k > 0 ? 1u : 0u);
+          umma_bf16_ts(tO, tP + k * 8 + (16 * k >= sh.mid ? hi_shift : 0), vd + (uint64_t)(k * 128), idesc_pv, k > 0 ? 1u : 0u);
         umma_commit(&bar_o[slot]);
         umma_commit(&bar_empty[st]);                  // nQ arrivals (one per unit of the item) release the stage
         ws_mark(v, 3);
@@ -170,16 +173,25 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     __syncwarp();
   } else {
     // ------------------------------------------------------------------------------------------ softmax warpgroups
-    const int wg = (warp - 3) >> 2;                      // parity of the units this warpgroup serves
-    const int r = (warp & 3) * 32 + lane;                // tile row == tensor-memory lane (a warp reaches lanes 32*(warp%4)..)
+    // 256 threads per warpgroup: two threads per query row.  Warp w of the CTA reaches tensor-memory lanes
+    // 32*(w%4)..+31, so the two warps with equal w%4 inside a warpgroup share a row quadrant and split its key columns
+    // (ch = 0 / 1).  Row maximum and row sum are exchanged through shared memory + a 256-thread named barrier.
+    const int wg = (warp - 3) >> 3;                      // parity of the units this warpgroup serves
+    const int ch = ((warp - 3) >> 2) & 1;                // column half
+    const int r = (warp & 3) * 32 + lane;                // tile row == tensor-memory lane
     const uint32_t t_lane = (uint32_t)((warp & 3) * 32) << 16;
     const float cs = sh.scale * LOG2E_WS;
     const int lag = NS > 2 ? 2 : 0;
+    float* red_mx = reinterpret_cast<float*>(tmem_slot + 4) + wg * 256;     // [2 halves][128 rows], per warpgroup
+    float* red_sum = reinterpret_cast<float*>(tmem_slot + 4) + 512;         // [slot][2 halves][128 rows]
     // state of the unit whose read-out is still pending (4-slot mode defers it behind the next unit's row math)
-    float p_mx = 0.f, p_sum = 1.f;
+    float p_mx = 0.f;
     int p_u = -1;
+    const bool tracer = ((warp - 3) & 7) == 1 && lane == 0;      // the ch = 0 warp that owns tile rows 0..31
 
-    auto readout = [&](int u, float mx, float sum) {
+    auto wg_sync = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(wg + 1) : "memory"); };
+
+    auto readout = [&](int u, float mx) {
       const int j = u >> sh.nq_sh, qt = u - (j << sh.nq_sh);
       const int item = blockIdx.x + j * gridDim.x;
       const int c = item / sh.H, h = item - c * sh.H;
@@ -192,45 +204,40 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const uint32_t tS = tmem + slot * sh.slot_w + t_lane;
       mbar_wait(&bar_o[slot], (u >> sh.ns_sh) & 1);
       tc_fence_after();
-      const bool tracer = ((warp - 3) & 3) == 1 && lane == 0;
       if (tracer) ws_mark(u, 7);
       const bool active = warp_live && !(sh.dbg & 4);
+      const float sum = red_sum[slot * 256 + r] + red_sum[slot * 256 + 128 + r];   // written before bar_p was signalled
       const float inv = 1.f / sum;
-      // two halves of 32 columns: packed to bf16 as soon as they arrive (keeps the live register set small)
-      uint4 ob[8];
+      // this thread's 32 of the row's 64 output columns, 16 at a time straight into the staging tile: the rows go out
+      // through the query tile of this unit in shared memory (dead since S = Q K^T completed); each lane parks its
+      // 64 bytes (16-byte chunks XOR-swizzled by row), then every store instruction of the warp covers eight half-rows
+      // of 64 contiguous bytes instead of 32 row-strided 16-byte pieces.
+      uint8_t* stg = smem + ((j & (NST - 1))) * sh.stage_bytes + qt * 16384 + (warp & 3) * 4096;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        uint32_t o[32];
-        if (active && !(sh.dbg & 32)) {
-          tmem_ld32(tS + sh.o_off + half * 32, o);
+        uint32_t o[16];
+        if (active) {
+          tmem_ld16(tS + sh.o_off + ch * 32 + half * 16, o);
           tmem_ld_wait();
-        }
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          ob[half * 4 + i] = make_uint4(
-              pack_bf16(__uint_as_float(o[8 * i]) * inv, __uint_as_float(o[8 * i + 1]) * inv),
-              pack_bf16(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv),
-              pack_bf16(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv),
-              pack_bf16(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv));
+          for (int i = 0; i < 2; ++i)
+            *reinterpret_cast<uint4*>(stg + lane * 128 + (((ch * 4 + half * 2 + i) ^ (lane & 7)) << 4)) = make_uint4(
+                pack_bf16(__uint_as_float(o[8 * i]) * inv, __uint_as_float(o[8 * i + 1]) * inv),
+                pack_bf16(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv),
+                pack_bf16(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv),
+                pack_bf16(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv));
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_free[slot]);     // the slot may take its next S while the rows go out to memory
       if (tracer) ws_mark(u, 8);
-      // The rows go out through the query tile of this unit in shared memory (dead since S = Q K^T completed): each lane
-      // parks its 128-byte row (16-byte chunks XOR-swizzled by row), then every store instruction of the warp covers
-      // four whole rows — 4 wavefronts instead of 32 row-strided 16-byte pieces.
-      uint8_t* stg = smem + ((j & (NST - 1))) * sh.stage_bytes + qt * 16384 + (warp & 3) * 4096;
-      if (active && !(sh.dbg & 8)) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(stg + lane * 128 + ((i ^ (lane & 7)) << 4)) = ob[i];
-      }
       __syncwarp();
-      if (active && !(sh.dbg & 16)) {
-        const int chunk = lane & 7;
+      if (active) {
+        const int chunk = ch * 4 + (lane & 3);
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int row = it * 4 + (lane >> 3);
+        for (int it = 0; it < 4; ++it) {
+          const int row = it * 8 + (lane >> 2);
           const int q = qt * 128 + (warp & 3) * 32 + row;
           const int gq = min((int)((q * sh.div_magic) >> 16), sh.G - 1);
           if (q < sh.span && c * sh.G + gq < sh.n_crops) {
@@ -238,12 +245,10 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             *reinterpret_cast<uint4*>(O + (size_t)(c * sh.span + q) * sh.D + h * 64 + chunk * 8) = v4;
           }
         }
-        if (q_valid && LSE) LSE[((size_t)(c * sh.G + g) * sh.H + h) * sh.N + (q_abs - klo)] = mx * sh.scale + logf(sum);
+        if (q_valid && LSE && ch == 0) LSE[((size_t)(c * sh.G + g) * sh.H + h) * sh.N + (q_abs - klo)] = mx * sh.scale + logf(sum);
       }
       // write-after-read on the staging rows: the shared-memory reads above have returned their data; the arrive /
-      // wait pair on bar_empty orders them before the TMA load that refills this stage.  (No proxy fence here: a
-      // fence.proxy.async per thread stalls the tensor core's in-flight operand reads — measured +1700 cycles on the
-      // concurrent S = Q K^T.)
+      // wait pair on bar_empty orders them before the TMA load that refills this stage
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_empty[(j & (NST - 1))]);
       if (tracer) ws_mark(u, 9);
@@ -256,79 +261,67 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const int g = min((int)((q_abs * sh.div_magic) >> 16), sh.G - 1);
       const int klo = g * sh.N, khi = klo + sh.N;
       const bool warp_live = q0 + (warp & 3) * 32 < sh.span;
-      // 16-column chunks any row of this warp needs (block-diagonal packing of short crops: a warp spans <= 2 crops)
+      // 16-column chunks any row of this warp needs (block-diagonal packing of short crops: a warp spans <= 2 crops);
+      // the lower thread of a row takes the chunks below sh.mid, the upper thread those from sh.mid on
       const int wlo = __reduce_min_sync(0xffffffffu, klo), whi = __reduce_max_sync(0xffffffffu, khi);
-      const int c_beg = (wlo >> 4) << 4, c_end = min(sh.Nkp, (whi + 15) & ~15);
+      const int r_beg = (wlo >> 4) << 4, r_end = min(sh.Nkp, (whi + 15) & ~15);
+      const int h_lo = ch ? sh.mid : 0, h_hi = ch ? sh.Nkp : sh.mid;       // this thread's half of the key columns
+      const int c_beg = max(r_beg, h_lo), c_end = min(r_end, h_hi);          // may be empty (c_beg >= c_end)
       // a 16-column chunk is "full" when it lies inside the key range of EVERY row of the warp: a warp-uniform test, so
       // the unmasked fast path is a real branch (a per-lane condition gets if-converted: both variants execute)
       const int f_lo = __reduce_max_sync(0xffffffffu, klo), f_hi = __reduce_min_sync(0xffffffffu, khi);
       const int slot = (u & (NS - 1));
       const uint32_t tS = tmem + slot * sh.slot_w + t_lane;
+      // packed P of key column c lives at column p_col(c): the lower half in place from column 0, the upper half in
+      // place from column sh.mid (so each thread's writes trail its own reads and never touch the other half's S)
+      const int p_base = ch ? sh.mid - (sh.mid >> 1) : 0;                    // p_col(c0) = p_base + c0 / 2
+      float* rsum = red_sum + slot * 256;
 
       mbar_wait(&bar_s[slot], (u >> sh.ns_sh) & 1);
+      // The two chains are symmetric, so left alone they run in lockstep (both in their exponentials, then both waiting
+      // on the tensor core).  Holding the second warpgroup back once, by about half an item period, keeps one chain in
+      // its MUFU-bound phase while the other is in its tensor-core / read-out phases (measured 9.3k -> 7.8k cycles per
+      // item at N = 197); nothing re-synchronises them afterwards.
+      if (u == 1 && sh.nQ == 2 && !(sh.dbg & 128)) __nanosleep(2800);
       tc_fence_after();
-      const bool tracer = ((warp - 3) & 3) == 1 && lane == 0;      // the warp that owns tile rows 0..31
       if (tracer) ws_mark(u, 4);
       float mx = -3.0e38f, sum = 0.f;
-      if (warp_live) {
-        // 32-column blocks, one block of tcgen05.ld in flight ahead of the one being computed (a trailing block may
-        // be 16 columns: c_beg / c_end are multiples of 16)
-        uint32_t va[32], vb[32];
-        auto load_blk = [&](uint32_t (&v)[32], int c0) {
-          if (c0 + 32 <= c_end) tmem_ld32(tS + c0, v);
-          else tmem_ld16(tS + c0, v);
-        };
-        auto max_half = [&](const uint32_t* v, int c0) {
+      uint32_t va[16], vb[16];
+      // ---- pass 1: maximum of this thread's half of the row
+      if (warp_live && !(sh.dbg & 1) && c_beg < c_end) {
+        auto max_chunk = [&](const uint32_t (&v)[16], int c0) {
           if (c0 >= f_lo && c0 + 16 <= f_hi) {
-            mx = fmaxf(mx, max16(*reinterpret_cast<const uint32_t (*)[16]>(v)));
+            mx = fmaxf(mx, max16(v));
           } else {
 #pragma unroll
             for (int i = 0; i < 16; ++i)
               if (c0 + i >= klo && c0 + i < khi) mx = fmaxf(mx, __uint_as_float(v[i]));
           }
         };
-        // ---- pass 1: row maximum over the row's own keys
-        if (sh.dbg & 1) mx = 0.f;
-        else if (sh.dbg & 64) {          // experiment: the micro-benchmark's fixed-bound loop (no masks), 208 columns
-          tmem_ld32(tS, va); tmem_ld_wait();
+        tmem_ld16(tS + c_beg, va);
+        tmem_ld_wait();
 #pragma unroll 1
-          for (int c0 = 0; c0 < 208; c0 += 64) {
-            const bool hasB = c0 + 32 < 208;
-            if (hasB) { if (c0 + 64 <= 208) tmem_ld32(tS + c0 + 32, vb); else tmem_ld16(tS + c0 + 32, vb); }
-            mx = fmaxf(mx, max16(*reinterpret_cast<const uint32_t (*)[16]>(va)));
-            if (c0 + 16 < 208) mx = fmaxf(mx, max16(*reinterpret_cast<const uint32_t (*)[16]>(va + 16)));
-            tmem_ld_wait();
-            if (hasB) {
-              if (c0 + 64 < 208) { if (c0 + 96 <= 208) tmem_ld32(tS + c0 + 64, va); else tmem_ld16(tS + c0 + 64, va); }
-              mx = fmaxf(mx, max16(*reinterpret_cast<const uint32_t (*)[16]>(vb)));
-              if (c0 + 48 < 208) mx = fmaxf(mx, max16(*reinterpret_cast<const uint32_t (*)[16]>(vb + 16)));
-              tmem_ld_wait();
-            }
-          }
-        } else {
-          load_blk(va, c_beg);
+        for (int c0 = c_beg; c0 < c_end; c0 += 32) {
+          const bool hasB = c0 + 16 < c_end;
+          if (hasB) tmem_ld16(tS + c0 + 16, vb);
+          max_chunk(va, c0);
           tmem_ld_wait();
-          if (tracer) ws_mark(u, 10);
-#pragma unroll 1
-          for (int c0 = c_beg; c0 < c_end; c0 += 64) {
-            if (tracer) ws_mark(u, 11 + (c0 >> 6));
-            const bool hasB = c0 + 32 < c_end;
-            if (hasB) load_blk(vb, c0 + 32);
-            max_half(va, c0);
-            if (c0 + 16 < c_end) max_half(va + 16, c0 + 16);
+          if (hasB) {
+            if (c0 + 32 < c_end) tmem_ld16(tS + c0 + 32, va);
+            max_chunk(vb, c0 + 16);
             tmem_ld_wait();
-            if (hasB) {
-              if (c0 + 64 < c_end) load_blk(va, c0 + 64);
-              max_half(vb, c0 + 32);
-              if (c0 + 48 < c_end) max_half(vb + 16, c0 + 48);
-              tmem_ld_wait();
-            }
           }
         }
-        if (tracer) ws_mark(u, 5);
-        const float mxs = mx * cs;
-        // ---- pass 2: P = 2^(s*cs - mxs) as packed bf16 over the consumed S columns (column c0/2 <= c0: in place)
-        auto emit = [&](const uint32_t* v, int c0) {
+      }
+      if (sh.dbg & 1) mx = 0.f;
+      red_mx[ch * 128 + r] = mx;
+      wg_sync();
+      mx = fmaxf(red_mx[r], red_mx[128 + r]);
+      if (tracer) ws_mark(u, 5);
+      const float mxs = mx * cs;
+      // ---- pass 2: P = 2^(s*cs - mxs) as packed bf16
+      if (warp_live) {
+        auto emit = [&](const uint32_t (&v)[16], int c0) {
           uint32_t pw[8];
           if (c0 >= f_lo && c0 + 16 <= f_hi) {
 #pragma unroll
@@ -347,36 +340,35 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
               pw[i >> 1] = pack_bf16(p0, p1);
             }
           }
-          tmem_st8(tS + (c0 >> 1), pw);
+          tmem_st8(tS + p_base + (c0 >> 1), pw);
         };
         const uint32_t zeros[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        // chunks below c_beg are zero probabilities: their packed columns [c0/2, c0/2 + 8) end at or before c_beg/2,
-        // i.e. never over S columns that are still to be read
-        for (int c0 = 0; c0 < c_beg; c0 += 16) tmem_st8(tS + (c0 >> 1), zeros);
+        // chunks of this half outside the warp's key range are zero probabilities; the ones below c_beg are written
+        // first (their packed columns lie below every column this thread still has to read)
+        for (int c0 = h_lo; c0 < min(max(c_beg, h_lo), h_hi); c0 += 16) tmem_st8(tS + p_base + (c0 >> 1), zeros);
         if (sh.dbg & 2) {
-          for (int c0 = c_beg; c0 < c_end; c0 += 16) tmem_st8(tS + (c0 >> 1), zeros);
-          sum = 1.f;
-        } else {
-          load_blk(va, c_beg);
+          for (int c0 = c_beg; c0 < c_end; c0 += 16) tmem_st8(tS + p_base + (c0 >> 1), zeros);
+          sum = 0.5f;
+        } else if (c_beg < c_end) {
+          tmem_ld16(tS + c_beg, va);
           tmem_ld_wait();
 #pragma unroll 1
-          for (int c0 = c_beg; c0 < c_end; c0 += 64) {
-            const bool hasB = c0 + 32 < c_end;
-            if (hasB) load_blk(vb, c0 + 32);
-            tmem_ld_wait();                   // vb is in registers before emit() overwrites columns [c0/2, c0/2 + 16)
+          for (int c0 = c_beg; c0 < c_end; c0 += 32) {
+            const bool hasB = c0 + 16 < c_end;
+            if (hasB) tmem_ld16(tS + c0 + 16, vb);
+            tmem_ld_wait();                   // vb is in registers before emit() overwrites packed columns under it
             emit(va, c0);
-            if (c0 + 16 < c_end) emit(va + 16, c0 + 16);
             if (hasB) {
-              if (c0 + 64 < c_end) load_blk(va, c0 + 64);
+              if (c0 + 32 < c_end) tmem_ld16(tS + c0 + 32, va);
               tmem_ld_wait();
-              emit(vb, c0 + 32);
-              if (c0 + 48 < c_end) emit(vb + 16, c0 + 48);
+              emit(vb, c0 + 16);
             }
           }
         }
-        for (int c0 = c_end; c0 < sh.Nkp; c0 += 16) tmem_st8(tS + (c0 >> 1), zeros);
+        for (int c0 = max(c_end, h_lo); c0 < h_hi; c0 += 16) tmem_st8(tS + p_base + (c0 >> 1), zeros);
         tmem_st_wait();
       }
+      rsum[ch * 128 + r] = sum;                   // read at read-out time, ordered by the bar_p -> bar_o chain
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_p[slot]);
@@ -385,13 +377,13 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       // ---- O = P V: normalise, store the row and its log-sum-exp (4-slot mode: one unit behind, so that the PV
       // product of this unit runs under the row math of the next one)
       if (lag) {
-        if (p_u >= 0) readout(p_u, p_mx, p_sum);
-        p_u = u; p_mx = mx; p_sum = sum;
+        if (p_u >= 0) readout(p_u, p_mx);
+        p_u = u; p_mx = mx;
       } else {
-        readout(u, mx, sum);
+        readout(u, mx);
       }
     }
-    if (lag && p_u >= 0) readout(p_u, p_mx, p_sum);
+    if (lag && p_u >= 0) readout(p_u, p_mx);
   }
   tc_fence_before();
   __syncthreads();
@@ -416,13 +408,19 @@ int attn_fwd_ws(const void* qkv, void* o, float* lse, int n_crops, int N, int D,
   s.n_groups = (n_crops + s.G - 1) / s.G;
   s.slot_w = s.Nkp > 128 ? 256 : 128;
   s.n_slot = 512 / s.slot_w;
-  s.o_off = s.slot_w / 2;
+  if (s.slot_w == 256) {       // two threads per row split the keys at `mid`; O sits above both packed-P ranges
+    s.mid = ((s.Nkp / 16 + 1) / 2) * 16;
+    s.o_off = 192;
+  } else {                     // narrow slots: the packed P stays contiguous (the second thread of a row only shares the read-out)
+    s.mid = s.Nkp;
+    s.o_off = 64;
+  }
   s.stage_bytes = s.nQ * 16384 + 2 * s.Nkp * 128;
   s.div_magic = (65536u + N - 1) / N;
   for (unsigned qq = 0; qq < 256; ++qq)
     if (((qq * s.div_magic) >> 16) != qq / (unsigned)N) return D3_OK;       // never for N <= 256; falls back if it did
-  s.n_stage = (220 * 1024) / s.stage_bytes;
-  if (s.n_stage < 2 || s.nQ > 2) return D3_OK;
+  s.n_stage = (216 * 1024) / s.stage_bytes;
+  if (s.n_stage < 2 || s.nQ != 2) return D3_OK;   // one-tile crop groups (96^2 local crops) stay on the single-pass kernel: 48 vs 61 us
   s.n_stage = s.n_stage >= 4 ? 4 : 2;
   s.nq_sh = s.nQ == 2 ? 1 : 0;
   s.ns_sh = s.n_slot == 4 ? 2 : 1;
@@ -441,7 +439,7 @@ int attn_fwd_ws(const void* qkv, void* o, float* lse, int n_crops, int N, int D,
   int rc;
   if ((rc = encode_tensor_map_2d_bf16(&tq, qkv, dims, strides, boxq, estr))) return rc;
   if ((rc = encode_tensor_map_2d_bf16(&tkv, qkv, dims, strides, boxkv, estr))) return rc;
-  const int smem = s.n_stage * s.stage_bytes + 512 + 1024;
+  const int smem = s.n_stage * s.stage_bytes + 256 + 6144 + 1024;     // barriers + row-reduction scratch + alignment
   static bool cfg = false;
   if (!cfg) {
     cudaFuncSetAttribute(attn_fwd_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
