@@ -164,6 +164,7 @@ def main():
     ap.add_argument("--patch", type=int, default=16)
     ap.add_argument("--local-size", type=int, default=96, help="98 for patch 14 (96 is not divisible, layers/patch_embed.py:48-49)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--remat", action="store_true", help="activation rematerialisation (train.checkpointing): BASELINE configs[4]")
     ap.add_argument("--cpu-sample-batch", type=int, default=2, help="images per CPU-baseline step (bounded sample: ~15-25 s of CPU work)")
     ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="wall-clock bound of the --impl reference arm")
     ap.add_argument("--no-checks", action="store_true", help="skip parity_check / fsdp_check")
@@ -229,7 +230,8 @@ def main():
     log(f"building synthetic batch B={B}")
     batch = synthetic_batch(cfg, B, seed=rank, pin=True)
     M = int(batch["mask_indices_list"].shape[0])
-    eng = Engine(cfg, B, device=f"cuda:{local_rank}", max_masked=M, comm=comm)
+    eng = Engine(cfg, B, device=f"cuda:{local_rank}", max_masked=M, comm=comm, remat=args.remat)
+    cfg_desc["activation_remat"] = bool(args.remat)
     if world > 1:
         cfg_desc["grad_reduce_scatter"] = ("push over NVLink peer memory (GEMM epilogue + d3_scatter_add_peers)" if eng.fsdp.push else "nccl reduce_scatter")
     cfg_desc["wgrad_stream"] = bool(eng.wgrad_overlap)

@@ -520,8 +520,8 @@ attn_bwd_alias_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
 
 __global__ void __launch_bounds__(256)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                const float* __restrict__ LSE, const float* __restrict__ Delta, __nv_bfloat16* __restrict__ dQKV,
-                const AttnShape sh) {
+                const float* __restrict__ LSE, const __nv_bfloat16* __restrict__ Og, long T_rows,
+                __nv_bfloat16* __restrict__ dQKV, const AttnShape sh) {
   // Pipelined variant for up to two query / key tiles (span <= 256): one tensor-core commit per (kt, qt) iteration —
   // the accumulate MMAs of iteration i and the S / dP MMAs of iteration i+1 are issued back to back, K / V tiles are
   // double-buffered, and every MMA / column loop is trimmed to the valid extent of the (ragged) last tile.
@@ -539,6 +539,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   uint64_t* bar_kv = bars + 1;                 // [2]
   uint64_t* bar_mma = bars + 3;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  float* red_delta = reinterpret_cast<float*>(bars + 8);     // [2 query tiles][2 column halves][128 rows]
 
   const int warp = threadIdx.x >> 5;
   const int r = threadIdx.x & 127;
@@ -619,6 +620,42 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   }
   dbg_mark(2);
   uint32_t mma_phase = 0;
+  // ---- Delta[q] = sum_d dO[q, d] * O[q, d] (softmax-backward row term) in the prologue, while the first S / dP products
+  // run: dO rows come from the TMA tile in shared memory (SWIZZLE_128B), O rows straight from global memory; the two
+  // threads of a row each take 32 of the 64 head columns.  (Replaces the separate attn_delta pass over O and dO.)
+  float dl_q0 = 0.f, dl_q1 = 0.f;
+  {
+    // the O rows do not depend on the TMA tiles: their loads are issued first and fly while the tiles land
+    uint4 ov[2][4];
+#pragma unroll
+    for (int qt = 0; qt < 2; ++qt) {
+      const int q = qt * 128 + r;
+      const bool ok = qt < nQ && q < sh.span && (long)row_base + q < T_rows;
+      const __nv_bfloat16* orow = Og + ((long)row_base + (ok ? q : 0)) * sh.D + h * 64 + ch * 32;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) ov[qt][i] = ok ? *reinterpret_cast<const uint4*>(orow + i * 8) : make_uint4(0, 0, 0, 0);
+    }
+    mbar_wait(bar_q, 0);
+#pragma unroll
+    for (int qt = 0; qt < 2; ++qt) {
+      float part = 0.f;
+      if (qt < nQ) {
+        const uint8_t* drow = sDO + qt * 16384;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint4 a = ov[qt][i];
+          const uint4 b = *reinterpret_cast<const uint4*>(drow + sw128_offset(r, ch * 32 + i * 8));
+          const float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
+          const float2 b0 = unpack_bf16(b.x), b1 = unpack_bf16(b.y), b2 = unpack_bf16(b.z), b3 = unpack_bf16(b.w);
+          part += a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y + a2.x * b2.x + a2.y * b2.y + a3.x * b3.x + a3.y * b3.y;
+        }
+        red_delta[(qt * 2 + ch) * 128 + r] = part;
+      }
+    }
+  }
+  __syncthreads();
+  dl_q0 = red_delta[r] + red_delta[128 + r];
+  if (nQ > 1) dl_q1 = red_delta[256 + r] + red_delta[384 + r];
 
 #pragma unroll 1
   for (int it = 0; it < n_it; ++it) {
@@ -643,7 +680,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const bool q_ok = (q < sh.span) && (c * sh.G + g < sh.n_crops);
     const size_t stat = ((size_t)(c * sh.G + g) * sh.H + h) * sh.N + (q_ok ? q - klo : 0);
     const float lse2 = q_ok ? LSE[stat] * LOG2E : 0.f;
-    const float dl = q_ok ? Delta[stat] : 0.f;
+    const float dl = q_ok ? (qt ? dl_q1 : dl_q0) : 0.f;
     {
       // 16-column chunks, explicit register ping-pong: the TMEM loads of the next chunk are in flight while the current
       // one is computed (tcgen05.wait::ld waits for every outstanding load of the thread)
@@ -865,7 +902,8 @@ int d3_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* ls
   s.sin_t = rope_sin; s.cos_t = rope_cos; s.prefix = rope_prefix;
   const long T = (long)n_crops * N;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  {
+  const int nq_ = (s.span + 127) / 128;
+  if (nq_ > 2) {       // three-tile (N > 256) kernel: Delta through the scratch buffer; the two-tile kernel computes it inline
     const long threads = T * (D / 8);
     attn_delta_kernel<<<(int)((threads + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)o, (const __nv_bfloat16*)d_o,
                                                                   delta_scratch, T, N, D, H);
@@ -886,8 +924,8 @@ int d3_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* ls
     const int smem = 2 * nq * 16384 + 32768 + 65536 + 64 + 1024;
     attn_bwd_alias_kernel<<<grid, 256, smem, st>>>(tqkv, tdo, lse, delta_scratch, (__nv_bfloat16*)dqkv, s);
   } else {
-    const int smem = 2 * nq * 16384 + 65536 + 65536 + 64 + 1024;
-    attn_bwd_kernel<<<grid, 256, smem, st>>>(tqkv, tdo, lse, delta_scratch, (__nv_bfloat16*)dqkv, s);
+    const int smem = 2 * nq * 16384 + 65536 + 65536 + 64 + 2048 + 1024;
+    attn_bwd_kernel<<<grid, 256, smem, st>>>(tqkv, tdo, lse, (const __nv_bfloat16*)o, T, (__nv_bfloat16*)dqkv, s);
   }
   D3_CHECK_LAUNCH();
   return D3_OK;

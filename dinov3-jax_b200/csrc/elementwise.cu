@@ -889,6 +889,54 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat1
 }
 
 
+// ------------------------------------------------------------------------------------------------ SwiGLU gate
+// SwiGLUFFN (dinov3_jax/layers/ffn_layers.py:71-76): h = silu(x1) * x2 with x1 | x2 the two halves of one [T, 2*Hs]
+// bf16 buffer (the w1 / w2 projections write the halves), and its backward
+//   dx1 = dh * x2 * silu'(x1),  dx2 = dh * silu(x1),   silu'(x) = s * (1 + x * (1 - s)),  s = sigmoid(x).
+// 8 elements (16 bytes) per thread; Hs is a multiple of 8.
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+
+__global__ void swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ x12, __nv_bfloat16* __restrict__ h, long T, int Hs) {
+  const int per_row = Hs >> 3;
+  const long g = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (g >= T * per_row) return;
+  const long row = g / per_row;
+  const int c = (int)(g - row * per_row) * 8;
+  const uint4 a = *reinterpret_cast<const uint4*>(x12 + row * 2 * Hs + c);
+  const uint4 b = *reinterpret_cast<const uint4*>(x12 + row * 2 * Hs + Hs + c);
+  const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 x1 = unpack_bf16(aw[i]), x2 = unpack_bf16(bw[i]);
+    o[i] = pack_bf16(x1.x * sigmoid_fast(x1.x) * x2.x, x1.y * sigmoid_fast(x1.y) * x2.y);
+  }
+  *reinterpret_cast<uint4*>(h + row * Hs + c) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+__global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ x12, const __nv_bfloat16* __restrict__ dh,
+                                  __nv_bfloat16* __restrict__ dx12, long T, int Hs) {
+  const int per_row = Hs >> 3;
+  const long g = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (g >= T * per_row) return;
+  const long row = g / per_row;
+  const int c = (int)(g - row * per_row) * 8;
+  const uint4 a = *reinterpret_cast<const uint4*>(x12 + row * 2 * Hs + c);
+  const uint4 b = *reinterpret_cast<const uint4*>(x12 + row * 2 * Hs + Hs + c);
+  const uint4 d = *reinterpret_cast<const uint4*>(dh + row * Hs + c);
+  const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w}, dw[4] = {d.x, d.y, d.z, d.w};
+  uint32_t o1[4], o2[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 x1 = unpack_bf16(aw[i]), x2 = unpack_bf16(bw[i]), g2 = unpack_bf16(dw[i]);
+    const float s0 = sigmoid_fast(x1.x), s1 = sigmoid_fast(x1.y);
+    o1[i] = pack_bf16(g2.x * x2.x * s0 * (1.f + x1.x * (1.f - s0)), g2.y * x2.y * s1 * (1.f + x1.y * (1.f - s1)));
+    o2[i] = pack_bf16(g2.x * x1.x * s0, g2.y * x1.y * s1);
+  }
+  *reinterpret_cast<uint4*>(dx12 + row * 2 * Hs + c) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+  *reinterpret_cast<uint4*>(dx12 + row * 2 * Hs + Hs + c) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+}
+
 // ------------------------------------------------------------------------------------------------ peer reduce-scatter
 // Push-style reduce-scatter of a flat fp32 gradient range over NVLink peer mappings (replaces psum_scatter / pmean,
 // fsdp/utils.py:61-64,108): element g of src (g = off + i) is added, scaled by alpha, into rank g / shard's slice.
@@ -1224,6 +1272,25 @@ int d3_cast_f32_bf16(const float* src, void* dst, long long n, void* stream) {
   if (((uintptr_t)src & 15) || ((uintptr_t)dst & 7)) return set_error(D3_ERR_ARG, "d3_cast_f32_bf16: alignment");
   long th = (n + 3) / 4;
   cast_f32_bf16_kernel<<<(int)((th + 255) / 256), 256, 0, STREAM(stream)>>>(src, (__nv_bfloat16*)dst, n);
+  D3_CHECK_LAUNCH();
+  return D3_OK;
+}
+
+int d3_swiglu_fwd(const void* x12, void* h, long long T, int Hs, void* stream) {
+  if (T <= 0) return D3_OK;
+  if (Hs % 8 || ((uintptr_t)x12 & 15) || ((uintptr_t)h & 15)) return set_error(D3_ERR_ARG, "d3_swiglu_fwd: Hs % 8, 16-byte alignment");
+  const long th = T * (Hs / 8);
+  swiglu_fwd_kernel<<<(int)((th + 255) / 256), 256, 0, STREAM(stream)>>>((const __nv_bfloat16*)x12, (__nv_bfloat16*)h, T, Hs);
+  D3_CHECK_LAUNCH();
+  return D3_OK;
+}
+
+int d3_swiglu_bwd(const void* x12, const void* dh, void* dx12, long long T, int Hs, void* stream) {
+  if (T <= 0) return D3_OK;
+  if (Hs % 8 || (((uintptr_t)x12 | (uintptr_t)dh | (uintptr_t)dx12) & 15)) return set_error(D3_ERR_ARG, "d3_swiglu_bwd: Hs % 8, 16-byte alignment");
+  const long th = T * (Hs / 8);
+  swiglu_bwd_kernel<<<(int)((th + 255) / 256), 256, 0, STREAM(stream)>>>((const __nv_bfloat16*)x12, (const __nv_bfloat16*)dh,
+                                                                      (__nv_bfloat16*)dx12, T, Hs);
   D3_CHECK_LAUNCH();
   return D3_OK;
 }

@@ -62,6 +62,8 @@ SIGNATURES = {
     "d3_ls_act_bwd": [P, P, P, P, P, P, I, I, I, P],
     "d3_colsum_bf16": [P, P, LL, I, I, P],
     "d3_cast_f32_bf16": [P, P, LL, P],
+    "d3_swiglu_fwd": [P, P, LL, I, P],
+    "d3_swiglu_bwd": [P, P, P, LL, I, P],
     "d3_absmax": [P, LL, P, P],
     "d3_colmax": [P, P, I, I, P],
     "d3_sinkhorn_colsum": [P, P, F, P, P, I, I, P],

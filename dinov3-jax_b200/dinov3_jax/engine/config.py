@@ -41,6 +41,9 @@ class EngineConfig:
     ln_eps: float = 1e-6             # norm_layer layernorm: 1e-6, layernormbf16: 1e-5 (models/vision_transformer.py:38-42)
     n_storage: int = 0               # student.n_storage_tokens (register tokens after cls, vision_transformer.py:106-111)
     mlp_second_act: bool = True      # reference applies GELU after fc2 too (layers/ffn_layers.py:47)
+    ffn_layer: str = "mlp"           # "mlp" | "swiglu" (layers/ffn_layers.py:52-76; SURVEY 8f.1: the 7B recipe uses swiglu64)
+    swiglu_align: int = 8            # swiglu / swiglu32 / swiglu64 / swiglu128 (models/vision_transformer.py:30-36)
+    mask_k_bias: bool = False        # student.mask_k_bias: the k third of the qkv bias is masked to zero (upstream DINOv3)
     layerwise_decay: float = 0.9
     patch_embed_lr_mult: float = 0.2
     dino_head_wd_multiplier: float = 1.0
@@ -56,6 +59,16 @@ class EngineConfig:
     @property
     def hidden(self) -> int:
         return int(self.embed_dim * self.ffn_ratio)
+
+    @property
+    def swiglu_hidden(self) -> int:
+        d = int(self.hidden * 2 / 3)                       # layers/ffn_layers.py:64-65
+        return d + (-d % self.swiglu_align)
+
+    @property
+    def ffn_width(self) -> int:
+        """Columns of the FFN's hidden activation h (what fc2 / w3 contracts over)."""
+        return self.swiglu_hidden if self.ffn_layer == "swiglu" else self.hidden
 
     def patches(self, size: int) -> int:
         return (size // self.patch) ** 2
@@ -76,8 +89,6 @@ def config_for(arch: str, **kw) -> EngineConfig:
 
 def from_oracle_cfg(c) -> EngineConfig:
     """Build from any object with the same field names (tests pass oracle.arch.ModelCfg)."""
-    if getattr(c, "ffn_layer", "mlp") != "mlp" or getattr(c, "mask_k_bias", False):
-        raise NotImplementedError("SwiGLU / mask_k_bias exist in the oracle only (SURVEY 8f.1); the B200 path has mlp blocks")
     names = EngineConfig.__dataclass_fields__.keys()
     return EngineConfig(**{k: getattr(c, k) for k in names if hasattr(c, k)})
 
@@ -91,10 +102,11 @@ def config_from_reference_cfg(cfg) -> EngineConfig:
         raise NotImplementedError("ibot.separate_head must be true (ssl_meta_arch.py:48)")
     if cfg.crops.local_crops_number <= 0:
         raise ValueError("crops.local_crops_number must be > 0 (ssl_meta_arch.py:47)")
-    if cfg.student.ffn_layer != "mlp" or cfg.student.norm_layer not in ("layernorm", "layernormbf16"):
-        raise NotImplementedError("only ffn_layer=mlp and norm_layer=layernorm|layernormbf16 are on the B200 path (SURVEY 8f)")
-    if cfg.student.get("mask_k_bias", False):
-        raise NotImplementedError("student.mask_k_bias is not on the B200 path (SURVEY 8f)")
+    ffn_table = {"mlp": ("mlp", 8), "swiglu": ("swiglu", 8), "swiglu32": ("swiglu", 32), "swiglu64": ("swiglu", 64),
+                 "swiglu128": ("swiglu", 128)}                      # models/vision_transformer.py:30-36
+    if cfg.student.ffn_layer not in ffn_table or cfg.student.norm_layer not in ("layernorm", "layernormbf16"):
+        raise NotImplementedError("ffn_layer must be mlp | swiglu[32|64|128] and norm_layer layernorm | layernormbf16 "
+                                  "(RMSNorm is not on the B200 path, SURVEY 8f)")
     if cfg.gram.use_loss or cfg.dino.koleo_loss_distributed or cfg.dino.reweight_dino_local_loss:
         raise NotImplementedError("gram loss / distributed KoLeo / local-loss reweighting are not on the B200 path yet")
     # options this engine does not implement must not be silently ignored (the run would differ from the request)
@@ -129,4 +141,7 @@ def config_from_reference_cfg(cfg) -> EngineConfig:
         patch_embed_lr_mult=cfg.optim.patch_embed_lr_mult, dino_head_wd_multiplier=cfg.optim.dino_head_wd_multiplier,
         adamw_beta1=cfg.optim.adamw_beta1, adamw_beta2=cfg.optim.adamw_beta2,
         mask_probability=cfg.ibot.mask_sample_probability, mask_ratio=tuple(cfg.ibot.mask_ratio_min_max),
-        n_storage=int(cfg.student.n_storage_tokens), ln_eps=1e-5 if cfg.student.norm_layer == "layernormbf16" else 1e-6)
+        n_storage=int(cfg.student.n_storage_tokens), ln_eps=1e-5 if cfg.student.norm_layer == "layernormbf16" else 1e-6,
+        ffn_layer=ffn_table[cfg.student.ffn_layer][0], swiglu_align=ffn_table[cfg.student.ffn_layer][1],
+        mask_k_bias=bool(cfg.student.get("mask_k_bias", False)),
+        mlp_second_act=ffn_table[cfg.student.ffn_layer][0] == "mlp")

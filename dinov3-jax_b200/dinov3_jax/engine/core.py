@@ -59,13 +59,15 @@ class CropSet:
 class Stream:
     """Activation buffers of one network pass over a list of crop sets (teacher: global only; student: global+local)."""
 
-    def __init__(self, cfg: EngineConfig, sets, device, stash: bool):
-        D, Hd, L = cfg.embed_dim, cfg.hidden, cfg.depth
+    def __init__(self, cfg: EngineConfig, sets, device, stash: bool, remat: bool = False):
+        D, Hd, L = cfg.embed_dim, cfg.ffn_width, cfg.depth
+        swiglu = cfg.ffn_layer == "swiglu"
         self.sets = sets
         self.T = sum(s.T for s in sets)
         T = self.T
-        self.stash = stash
-        nb = L if stash else 1
+        self.stash = stash                    # keep what the backward needs
+        self.per_block = stash and not remat  # ... for every block (False: one scratch set, blocks are recomputed)
+        nb = L if self.per_block else 1
         e = lambda *shape, dt=bf16: torch.empty(*shape, dtype=dt, device=device)
         self.X = [e(T, D, dt=f32) for _ in range(L + 1)] if stash else [e(T, D, dt=f32), e(T, D, dt=f32)]
         self.Xmid = [e(T, D, dt=f32) for _ in range(nb)]
@@ -75,11 +77,12 @@ class Stream:
         self.Z = [e(T, D) for _ in range(nb)]
         self.Hh = [e(T, Hd) for _ in range(nb)]
         self.Xn = e(T, D, dt=f32)
+        self.X12 = e(T, 2 * Hd) if (swiglu and not stash) else None       # teacher pass: [x1 | x2] scratch
         self.LSE = [[e(s.n, cfg.heads, s.N, dt=f32) for s in sets] for _ in range(nb)]
         if stash:
-            self.U1 = [e(T, Hd) for _ in range(L)]
-            self.U2 = [e(T, D) for _ in range(L)]
-            self.stats = [[e(T, dt=f32) for _ in range(4)] for _ in range(L)]   # mean1, rstd1, mean2, rstd2
+            self.U1 = [e(T, 2 * Hd if swiglu else Hd) for _ in range(nb)]   # mlp: u1; swiglu: [x1 | x2]
+            self.U2 = [e(T, D) for _ in range(nb)]
+            self.stats = [[e(T, dt=f32) for _ in range(4)] for _ in range(nb)]   # mean1, rstd1, mean2, rstd2
             self.fstats = [e(T, dt=f32), e(T, dt=f32)]
 
     def x_in(self, i):
@@ -89,7 +92,7 @@ class Stream:
         return self.X[i + 1] if self.stash else self.X[(i + 1) % 2]
 
     def b(self, lst, i):
-        return lst[i] if self.stash else lst[0]
+        return lst[i] if self.per_block else lst[0]
 
 
 class HeadBufs:
@@ -128,10 +131,13 @@ class Engine:
     """
 
     def __init__(self, cfg: EngineConfig, B: int, device="cuda", max_masked: int | None = None, comm=None,
-                 centering: str = "sinkhorn_knopp", center_momentum: float = 0.9):
+                 centering: str = "sinkhorn_knopp", center_momentum: float = 0.9, remat: bool = False):
         assert cfg.head_dim == 64, "kernels are specialised for head_dim 64 (every BASELINE arch)"
         assert centering in ("sinkhorn_knopp", "softmax")
         self.centering, self.center_momentum = centering, center_momentum
+        # activation rematerialisation (train.checkpointing, ssl_default_config.yaml:88): only the block inputs X[i] of
+        # the student stream are kept; each block's forward is recomputed into one scratch set right before its backward
+        self.remat = bool(remat)
         self.cfg, self.B, self.device = cfg, B, torch.device(device)
         self.comm = comm  # fsdp.runtime.Comm (None = single GPU)
         self.world = 1 if comm is None else comm.world
@@ -147,7 +153,7 @@ class Engine:
         self.s_sets = [CropSet(cfg, ng, cfg.global_size, 0, dev)]
         self.s_sets.append(CropSet(cfg, nl, cfg.local_size, self.s_sets[0].T, dev))
         self.teacher = Stream(cfg, self.t_sets, dev, stash=False)
-        self.student = Stream(cfg, self.s_sets, dev, stash=True)
+        self.student = Stream(cfg, self.s_sets, dev, stash=True, remat=self.remat)
         P = self.s_sets[0].P
         if max_masked is None:
             n_masked_crops = int(ng * cfg.mask_probability)
@@ -178,7 +184,8 @@ class Engine:
         self.koleo_coef = torch.empty(B, dtype=f32, device=dev)
         self.metrics = torch.zeros(8, dtype=f32, device=dev)   # 0 dino_local 1 dino_global 2 koleo 3 ibot
         # backward scratch over the student stream
-        T, Hd = self.student.T, cfg.hidden
+        T, Hd = self.student.T, cfg.ffn_width
+        self.swiglu = cfg.ffn_layer == "swiglu"
         e = lambda *shape, dt=bf16: torch.empty(*shape, dtype=dt, device=dev)
         self.dX = [e(T, D, dt=f32), e(T, D, dt=f32)]
         self.dXmid = e(T, D, dt=f32)
@@ -186,10 +193,15 @@ class Engine:
         # Weight-gradient GEMMs only feed the optimizer, so they run on a second stream and fill the tensor cores
         # while the main stream is in its HBM-bound kernels (LN / LayerScale backward, column sums).  The operands
         # they read (dU2, dU1, dP, dQKV) are double-buffered by block parity; events order reuse.
-        self.wgrad_overlap = os.environ.get("D3_WGRAD_STREAM", "1") != "0"
+        # (with remat the weight-gradient GEMMs read the single scratch set that the next block's recompute overwrites,
+        # so they stay on the main stream)
+        self.wgrad_overlap = os.environ.get("D3_WGRAD_STREAM", "1") != "0" and not self.remat
         nbuf = 2 if self.wgrad_overlap else 1
         self.dU2, self.dP = [e(T, D) for _ in range(nbuf)], [e(T, D) for _ in range(nbuf)]
-        self.dU1 = [e(T, Hd) for _ in range(nbuf)]
+        self.dU1 = [e(T, 2 * Hd if self.swiglu else Hd) for _ in range(nbuf)]       # swiglu: [dx1 | dx2]
+        if self.swiglu:
+            self.dH = e(T, Hd)
+            self.dZ32 = e(T, D, dt=f32)
         self.dQKV = [e(T, 3 * D) for _ in range(nbuf)]
         self.fwd_overlap = os.environ.get("D3_FWD_STREAMS", "0") == "1"   # measured: no gain (step is power-capped), off by default
         if self.fwd_overlap:
@@ -274,7 +286,7 @@ class Engine:
         w = lambda n: bb.w(p + n, teacher)
         X, Xmid, Xo = st.x_in(i), st.b(st.Xmid, i), st.x_out(i)
         Y, QKV, O, Z, Hh = st.b(st.Y, i), st.b(st.QKV, i), st.b(st.O, i), st.b(st.Z, i), st.b(st.Hh, i)
-        stats = st.stats[i] if st.stash else [None] * 4
+        stats = st.b(st.stats, i) if st.stash else [None] * 4
         ops.layernorm_fwd(X, v("norm1/scale"), v("norm1/bias"), Y, stats[0], stats[1], cfg.ln_eps)
         ops.gemm(Y, w("attn/qkv/kernel"), QKV, b_mn=True, bias=v("attn/qkv/bias"))
         lses = st.b(st.LSE, i)
@@ -284,10 +296,20 @@ class Engine:
             ops.attn_fwd(q, O[cs.row0: cs.row0 + cs.T], lse if st.stash else None, cs.n, cs.N, D, H)
         ops.gemm(O, w("attn/proj/kernel"), Xmid, b_mn=True, bias=v("attn/proj/bias"), gamma=v("ls1/gamma"), resid=X)
         ops.layernorm_fwd(Xmid, v("norm2/scale"), v("norm2/bias"), Z, stats[2], stats[3], cfg.ln_eps)
+        if cfg.ffn_layer == "swiglu":
+            # SwiGLUFFN (layers/ffn_layers.py:71-76): h = silu(z W1 + b1) * (z W2 + b2); x_out = x_mid + g2 * (h W3 + b3)
+            Hs = cfg.swiglu_hidden
+            X12 = st.b(st.U1, i) if st.stash else st.X12
+            ops.gemm(Z, w("mlp/w1/kernel"), X12[:, :Hs], b_mn=True, bias=v("mlp/w1/bias"))
+            ops.gemm(Z, w("mlp/w2/kernel"), X12[:, Hs:], b_mn=True, bias=v("mlp/w2/bias"))
+            ops.swiglu_fwd(X12, Hh)
+            ops.gemm(Hh, w("mlp/w3/kernel"), Xo, b_mn=True, bias=v("mlp/w3/bias"),
+                     store_pre=st.b(st.U2, i) if st.stash else None, gamma=v("ls2/gamma"), resid=Xmid)
+            return
         ops.gemm(Z, w("mlp/Dense_0/kernel"), Hh, b_mn=True, bias=v("mlp/Dense_0/bias"), gelu=True,
-                 store_pre=st.U1[i] if st.stash else None)
+                 store_pre=st.b(st.U1, i) if st.stash else None)
         ops.gemm(Hh, w("mlp/Dense_1/kernel"), Xo, b_mn=True, bias=v("mlp/Dense_1/bias"), gelu=cfg.mlp_second_act,
-                 store_pre=st.U2[i] if st.stash else None, gamma=v("ls2/gamma"), resid=Xmid)
+                 store_pre=st.b(st.U2, i) if st.stash else None, gamma=v("ls2/gamma"), resid=Xmid)
 
     def _backbone_fwd(self, st: Stream, images, masks_list, teacher: bool):
         cfg, bb = self.cfg, self.params.mods["backbone"]
@@ -382,8 +404,9 @@ class Engine:
         if self.wgrad_overlap and self._ev_done_live[par]:
             torch.cuda.current_stream().wait_event(self._ev_done[par])   # weight gradients of block i+2 have read dU2[par]
             self._ev_done_live[par] = False
-        return dict(ls_gamma=bb.vec(p + "ls2/gamma"), ls_u=st.U2[i], ls_gelu=cfg.mlp_second_act, ls_du=self.dU2[par],
-                    ls_dgamma=bb.gv(p + "ls2/gamma"), ls_dbias=bb.gv(p + "mlp/Dense_1/bias"))
+        out_bias = "mlp/w3/bias" if self.swiglu else "mlp/Dense_1/bias"
+        return dict(ls_gamma=bb.vec(p + "ls2/gamma"), ls_u=st.b(st.U2, i), ls_gelu=cfg.mlp_second_act and not self.swiglu,
+                    ls_du=self.dU2[par], ls_dgamma=bb.gv(p + "ls2/gamma"), ls_dbias=bb.gv(p + out_bias))
 
     def _block_bwd(self, i: int, dX, dXprev):
         """Backward of block i.  On entry dX is the gradient of the block output and self.dU2[parity(i)] already holds
@@ -392,10 +415,17 @@ class Engine:
         D, H = cfg.embed_dim, cfg.heads
         p = f"blocks_{i}/"
         v, w, gw, gv = (lambda n: bb.vec(p + n)), (lambda n: bb.w(p + n)), (lambda n: bb.gw(p + n)), (lambda n: bb.gv(p + n))
-        m1, r1, m2, r2 = st.stats[i]
+        m1, r1, m2, r2 = st.b(st.stats, i)
         par = (i & 1) if self.wgrad_overlap else 0
         dU2, dU1, dP, dQKV = self.dU2[par], self.dU1[par], self.dP[par], self.dQKV[par]
         main = torch.cuda.current_stream()
+        if self.remat:
+            # recompute this block's forward from its stashed input (writes the scratch activations, statistics, LSE and
+            # x_out again), then the LayerScale / activation backward of its MLP branch, which the stashing path gets
+            # for free from the LayerNorm backward of the block above (_ls_tail)
+            self._block_fwd(st, i, teacher=False)
+            t = self._ls_tail(i)
+            ops.ls_act_bwd(dX, t["ls_u"], t["ls_gamma"], t["ls_du"], t["ls_dgamma"], t["ls_dbias"], t["ls_gelu"])
 
         def on_wstream(slot, fn):
             """Run fn on the weight-gradient stream once the main stream has reached this point."""
@@ -410,7 +440,9 @@ class Engine:
 
         # multi-GPU: the three large weight gradients are reduce-scattered by the GEMM epilogue itself (each tile is
         # added into the owning rank's gradient shard over NVLink); the rest of the unit is pushed in grads_ready
-        fused = ("mlp/Dense_1/kernel", "mlp/Dense_0/kernel", "attn/qkv/kernel") if (self.fsdp.push and self.fsdp.push_gemm) else ()
+        big = ("mlp/w3/kernel", "mlp/w1/kernel", "mlp/w2/kernel", "attn/qkv/kernel") if self.swiglu else \
+              ("mlp/Dense_1/kernel", "mlp/Dense_0/kernel", "attn/qkv/kernel")
+        fused = big if (self.fsdp.push and self.fsdp.push_gemm) else ()
         inv_world = 1.0 / self.fsdp.world
 
         def wgrad(slot, a, b, name):
@@ -418,32 +450,53 @@ class Engine:
             on_wstream(slot, lambda: ops.gemm(a, b, gw(name), a_mn=True, b_mn=True, accum=True, scatter=spec,
                                               alpha=inv_world if spec else 1.0))
         # ---- MLP branch: x_out = x_mid + g2 * act(u2), u2 = h W2 + b2, h = gelu(u1), u1 = z W1 + b1
-        wgrad(0, st.Hh[i], dU2, "mlp/Dense_1/kernel")                                          # dW2 = h^T dU2
-        ops.gemm(dU2, w("mlp/Dense_1/kernel"), dU1, dgelu_of=st.U1[i])                         # dU1 = (dU2 W2^T) * gelu'(u1)
-        wgrad(1, st.Z[i], dU1, "mlp/Dense_0/kernel")                                           # dW1 = z^T dU1
-        ops.colsum_bf16(dU1, gv("mlp/Dense_0/bias"))
-        ops.gemm(dU1, w("mlp/Dense_0/kernel"), self.dZ)                                        # dZ = dU1 W1^T
+        if self.swiglu:
+            # x_out = x_mid + g2 * (h W3 + b3), h = silu(x1) * x2, x1 = z W1 + b1, x2 = z W2 + b2
+            Hs = cfg.swiglu_hidden
+            X12, dX12 = st.b(st.U1, i), dU1
+            wgrad(0, st.b(st.Hh, i), dU2, "mlp/w3/kernel")                                           # dW3 = h^T dU2
+            ops.gemm(dU2, w("mlp/w3/kernel"), self.dH)                                         # dh = dU2 W3^T
+            ops.swiglu_bwd(X12, self.dH, dX12)                                                 # [dx1 | dx2]
+            wgrad(1, st.b(st.Z, i), dX12[:, :Hs], "mlp/w1/kernel")                                   # dW1 = z^T dx1
+            wgrad(1, st.b(st.Z, i), dX12[:, Hs:], "mlp/w2/kernel")                                   # dW2 = z^T dx2
+            ops.colsum_bf16(dX12[:, :Hs], gv("mlp/w1/bias"))
+            ops.colsum_bf16(dX12[:, Hs:], gv("mlp/w2/bias"))
+            ops.gemm(dX12[:, :Hs], w("mlp/w1/kernel"), self.dZ32)                              # dz = dx1 W1^T + dx2 W2^T (fp32)
+            ops.gemm(dX12[:, Hs:], w("mlp/w2/kernel"), self.dZ32, accum=True)
+            dZ = self.dZ32
+        else:
+            wgrad(0, st.b(st.Hh, i), dU2, "mlp/Dense_1/kernel")                                      # dW2 = h^T dU2
+            ops.gemm(dU2, w("mlp/Dense_1/kernel"), dU1, dgelu_of=st.b(st.U1, i))                     # dU1 = (dU2 W2^T) * gelu'(u1)
+            wgrad(1, st.b(st.Z, i), dU1, "mlp/Dense_0/kernel")                                       # dW1 = z^T dU1
+            ops.colsum_bf16(dU1, gv("mlp/Dense_0/bias"))
+            ops.gemm(dU1, w("mlp/Dense_0/kernel"), self.dZ)                                    # dZ = dU1 W1^T
+            dZ = self.dZ
         # LN2 backward; its tail is the attention branch's LayerScale: x_mid = x_in + g1 * (o Wp + bp), dP = dXmid * g1
-        ops.layernorm_bwd_ls(self.dZ, st.Xmid[i], m2, r2, v("norm2/scale"), self.dXmid, dx_add=dX,
+        ops.layernorm_bwd_ls(dZ, st.b(st.Xmid, i), m2, r2, v("norm2/scale"), self.dXmid, dx_add=dX,
                              dscale=gv("norm2/scale"), dbias=gv("norm2/bias"),
                              ls_gamma=v("ls1/gamma"), ls_du=dP, ls_dbias=gv("attn/proj/bias"))
 
         def proj_wgrad():
-            ops.gemm(st.O[i], dP, gw("attn/proj/kernel"), a_mn=True, b_mn=True, accum=True)    # dWp = o^T dP
+            ops.gemm(st.b(st.O, i), dP, gw("attn/proj/kernel"), a_mn=True, b_mn=True, accum=True)    # dWp = o^T dP
             # dg1 from dWp / dbp (no stash of the projection output needed)
             ops.ls_gamma_from_wgrad(w("attn/proj/kernel"), gw("attn/proj/kernel"), v("attn/proj/bias"),
                                     gv("attn/proj/bias"), v("ls1/gamma"), gv("ls1/gamma"))
         on_wstream(2, proj_wgrad)
         ops.gemm(dP, w("attn/proj/kernel"), self.dO)                                           # dO = dP Wp^T
-        for cs, lse, delta in zip(st.sets, st.LSE[i], self.delta):
+        for cs, lse, delta in zip(st.sets, st.b(st.LSE, i), self.delta):
             sl = slice(cs.row0, cs.row0 + cs.T)
             # gradient w.r.t. the pre-RoPE projection: the inverse rotation is fused into the kernel's store stage
-            ops.attn_bwd(st.QKV[i][sl], st.O[i][sl], self.dO[sl], lse, delta, dQKV[sl], cs.n, cs.N, D, H,
+            ops.attn_bwd(st.b(st.QKV, i)[sl], st.b(st.O, i)[sl], self.dO[sl], lse, delta, dQKV[sl], cs.n, cs.N, D, H,
                          rope_sin=cs.sin, rope_cos=cs.cos, rope_prefix=cfg.prefix)
-        wgrad(3, st.Y[i], dQKV, "attn/qkv/kernel")                                             # dWqkv = y^T dQKV
-        ops.colsum_bf16(dQKV, gv("attn/qkv/bias"))
+        wgrad(3, st.b(st.Y, i), dQKV, "attn/qkv/kernel")                                             # dWqkv = y^T dQKV
+        if cfg.mask_k_bias:      # LinearKMaskedBias: no gradient reaches the k third of the bias
+            gb = gv("attn/qkv/bias")
+            ops.colsum_bf16(dQKV[:, :D], gb[:D])
+            ops.colsum_bf16(dQKV[:, 2 * D:], gb[2 * D:])
+        else:
+            ops.colsum_bf16(dQKV, gv("attn/qkv/bias"))
         ops.gemm(dQKV, w("attn/qkv/kernel"), self.dY)                                          # dY = dQKV Wqkv^T
-        tail = self._ls_tail(i - 1) if i > 0 else {}
+        tail = self._ls_tail(i - 1) if (i > 0 and not self.remat) else {}
         ops.layernorm_bwd_ls(self.dY, st.X[i], m1, r1, v("norm1/scale"), dXprev, dx_add=self.dXmid,
                              dscale=gv("norm1/scale"), dbias=gv("norm1/bias"), **tail)
         scattered = tuple(p + n for n in fused)
@@ -559,7 +612,8 @@ class Engine:
         bb = self.params.mods["backbone"]
         dXL = self.dX[1]
         ops.layernorm_bwd_ls(dXn, S_.X[cfg.depth], S_.fstats[0], S_.fstats[1], bb.vec("norm/scale"), dXL,
-                             dscale=bb.gv("norm/scale"), dbias=bb.gv("norm/bias"), **self._ls_tail(cfg.depth - 1))
+                             dscale=bb.gv("norm/scale"), dbias=bb.gv("norm/bias"),
+                             **({} if self.remat else self._ls_tail(cfg.depth - 1)))
         self.fsdp.grads_ready("backbone", "norm")
         cur, nxt = 1, 0
         for i in reversed(range(cfg.depth)):

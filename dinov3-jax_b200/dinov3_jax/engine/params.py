@@ -37,10 +37,16 @@ def backbone_spec(cfg: EngineConfig):
                  (b + "attn/qkv/kernel", (D, 3 * D), "mat"), (b + "attn/qkv/bias", (3 * D,), "vec"),
                  (b + "attn/proj/kernel", (D, D), "mat"), (b + "attn/proj/bias", (D,), "vec"),
                  (b + "ls1/gamma", (D,), "vec"),
-                 (b + "norm2/scale", (D,), "vec"), (b + "norm2/bias", (D,), "vec"),
-                 (b + "mlp/Dense_0/kernel", (D, Hd), "mat"), (b + "mlp/Dense_0/bias", (Hd,), "vec"),
-                 (b + "mlp/Dense_1/kernel", (Hd, D), "mat"), (b + "mlp/Dense_1/bias", (D,), "vec"),
-                 (b + "ls2/gamma", (D,), "vec")]
+                 (b + "norm2/scale", (D,), "vec"), (b + "norm2/bias", (D,), "vec")]
+        if cfg.ffn_layer == "swiglu":                                 # layers/ffn_layers.py:62-69
+            Hs = cfg.swiglu_hidden
+            spec += [(b + "mlp/w1/kernel", (D, Hs), "mat"), (b + "mlp/w1/bias", (Hs,), "vec"),
+                     (b + "mlp/w2/kernel", (D, Hs), "mat"), (b + "mlp/w2/bias", (Hs,), "vec"),
+                     (b + "mlp/w3/kernel", (Hs, D), "mat"), (b + "mlp/w3/bias", (D,), "vec")]
+        else:
+            spec += [(b + "mlp/Dense_0/kernel", (D, Hd), "mat"), (b + "mlp/Dense_0/bias", (Hd,), "vec"),
+                     (b + "mlp/Dense_1/kernel", (Hd, D), "mat"), (b + "mlp/Dense_1/bias", (D,), "vec")]
+        spec += [(b + "ls2/gamma", (D,), "vec")]
     spec += [("norm/scale", (D,), "vec"), ("norm/bias", (D,), "vec")]
     return spec
 
@@ -171,6 +177,11 @@ class ModuleStore:
         full = torch.zeros(self.n, dtype=torch.float32, device=dev)
         for name in self.offsets:
             self._view(full, name).copy_(tensors[name].to(device=dev, dtype=torch.float32).reshape(self.shapes[name]))
+            if self.cfg.mask_k_bias and name.endswith("attn/qkv/bias"):
+                # LinearKMaskedBias: the k third never reaches the forward; it is held at zero (and its gradient is
+                # zeroed every step, engine/core.py), which is the masked layer's arithmetic
+                third = self.shapes[name][0] // 3
+                self._view(full, name)[third:2 * third].zero_()
         master = self.t_master if teacher else self.master
         if self.world == 1:
             master.copy_(full)

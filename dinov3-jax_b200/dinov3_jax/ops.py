@@ -286,6 +286,19 @@ def koleo_fwd_bwd_rows(x, xn, nrm, nn, coef, metric, dx, row0, nrows, w_metric, 
                                            int(nrows), eps, w_metric, w_grad, _s()), "d3_koleo_fwd_bwd_rows")
 
 
+def swiglu_fwd(x12, h):
+    """h[T,Hs] = silu(x12[:, :Hs]) * x12[:, Hs:] (bf16)."""
+    T, Hs = h.shape
+    assert x12.dtype == bf16 and h.dtype == bf16 and x12.shape == (T, 2 * Hs) and x12.is_contiguous() and h.is_contiguous()
+    N.check(N.init().d3_swiglu_fwd(_p(x12), _p(h), T, Hs, _s()), "d3_swiglu_fwd")
+
+
+def swiglu_bwd(x12, dh, dx12):
+    T, Hs = dh.shape
+    assert x12.shape == (T, 2 * Hs) and dx12.shape == x12.shape and dh.is_contiguous() and dx12.is_contiguous()
+    N.check(N.init().d3_swiglu_bwd(_p(x12), _p(dh), _p(dx12), T, Hs, _s()), "d3_swiglu_bwd")
+
+
 def sumsq(g, out):
     N.check(N.init().d3_sumsq(_p(g), g.numel(), _p(out), _s()), "d3_sumsq")
 

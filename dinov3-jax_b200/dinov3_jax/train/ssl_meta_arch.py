@@ -26,8 +26,10 @@ class SSLMetaArch:
 
     # -- B200 engine -------------------------------------------------------------------------------------------------
     def build_engine(self, device="cuda", comm=None, max_masked=None) -> Engine:
+        # train.checkpointing (ssl_default_config.yaml:88-89): activation rematerialisation of the student blocks
+        remat = bool(self.config.train.get("checkpointing", False) or self.config.train.get("checkpointing_full", False))
         self.engine = Engine(self.engine_config, self.config.train.batch_size_per_gpu, device=device,
-                             max_masked=max_masked, comm=comm)
+                             max_masked=max_masked, comm=comm, remat=remat)
         return self.engine
 
     def __call__(self, data, *, teacher_temp=0, iteration=0, deterministic=True, init_phase=False):

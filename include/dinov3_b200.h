@@ -162,6 +162,12 @@ int d3_colsum_bf16(const void* x_bf16 /*[T,N], row stride ld*/, float* out /*[N]
                    void* stream);
 int d3_cast_f32_bf16(const float* src, void* dst_bf16, long long n, void* stream);
 
+/* ---- SwiGLU FFN gate (layers/ffn_layers.py:52-76, the 7B recipe's ffn_layer: swiglu64): x12 = [x1 | x2] is the [T, 2*Hs]
+ * bf16 output of the w1 / w2 projections; h = silu(x1) * x2; backward dx1 = dh*x2*silu'(x1), dx2 = dh*silu(x1).     */
+int d3_swiglu_fwd(const void* x12_bf16 /*[T,2Hs]*/, void* h_bf16 /*[T,Hs]*/, long long T, int Hs, void* stream);
+int d3_swiglu_bwd(const void* x12_bf16, const void* dh_bf16 /*[T,Hs]*/, void* dx12_bf16 /*[T,2Hs]*/, long long T, int Hs,
+                  void* stream);
+
 /* ---- Sinkhorn-Knopp (loss/dino_clstoken_loss.py:35-62, loss/ibot_patch_loss.py:77-109) ----------------------------
  * Q[b,k] = Btot * exp((L[b,k]-mx[k])/temp) * r[k] * a[b],  r = 1/(K * E^T a),  a = 1/(Btot * E r); the caller alternates
  * colsum (-> all-reduce over ranks of s[K]) and rowsum three times.  mx is a [K] vector of per-prototype shifts that

@@ -41,15 +41,18 @@ def test_cli_surface():
 
 def test_storage_tokens_and_norm_layer_map_onto_the_engine_config():
     """student.n_storage_tokens / student.norm_layer (models/vision_transformer.py:38-42,106-111) are on the B200 path;
-    SwiGLU / RMSNorm / mask_k_bias are not and are rejected loudly."""
+    so are SwiGLU (all four alignments) and mask_k_bias; RMSNorm is not and is rejected loudly."""
     cfg = setup_config(DinoV3SetupArgs(opts=["student.n_storage_tokens=4", "student.norm_layer=layernormbf16"]))
     e = config_from_reference_cfg(cfg)
     assert e.n_storage == 4 and e.prefix == 5 and e.ln_eps == 1e-5
     assert e.tokens(224) == 196 + 5 and e.tokens(96) == 36 + 5
     assert config_from_reference_cfg(setup_config(DinoV3SetupArgs())).ln_eps == 1e-6
-    for bad in ("student.ffn_layer=swiglu64", "student.norm_layer=rmsnorm", "student.mask_k_bias=true"):
-        with pytest.raises(NotImplementedError):
-            config_from_reference_cfg(setup_config(DinoV3SetupArgs(opts=[bad])))
+    with pytest.raises(NotImplementedError):
+        config_from_reference_cfg(setup_config(DinoV3SetupArgs(opts=["student.norm_layer=rmsnorm"])))
+    s = config_from_reference_cfg(setup_config(DinoV3SetupArgs(opts=["student.ffn_layer=swiglu64", "student.mask_k_bias=true"])))
+    assert s.ffn_layer == "swiglu" and s.swiglu_align == 64 and s.mask_k_bias and not s.mlp_second_act
+    assert s.swiglu_hidden == 2752 and s.ffn_width == 2752                  # int(4096 * 2 / 3) = 2730 -> next multiple of 64
+    assert config_from_reference_cfg(setup_config(DinoV3SetupArgs(opts=["student.ffn_layer=swiglu"]))).swiglu_hidden == 2736
 
 
 def test_parameter_spec_contains_storage_tokens_with_the_reference_multipliers():

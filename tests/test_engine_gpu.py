@@ -311,3 +311,61 @@ def test_reference_call_contract_train_step_then_update_ema():
     assert abs(la - lb) <= 1e-5 * abs(lb)
     for k in pa:
         assert torch.allclose(pa[k], pb[k], atol=2e-6, rtol=1e-5), k
+
+
+def test_step_with_swiglu_ffn():
+    """SwiGLU FFN (layers/ffn_layers.py:52-76, hidden 2/3 * 4D rounded up to swiglu_align) on the GPU path:
+    w1 | w2 projections, fused silu-gate kernel, w3 + LayerScale, and the hand-written backward."""
+    from oracle import tiny_cfg
+    r = run_pair(tiny_cfg(ffn_layer="swiglu", swiglu_align=64, layerscale=0.5), 3, seed=4)
+    check(r)
+    for name in ("mlp/w1/kernel", "mlp/w2/kernel", "mlp/w3/kernel", "mlp/w1/bias", "mlp/w2/bias", "mlp/w3/bias"):
+        k = f"student_backbone/blocks_0/{name}"
+        g = r["grads"][k]
+        e = float((r["grads_e"][k].reshape(g.shape) - g).norm() / g.norm())
+        assert e < 6e-2, (name, e)
+
+
+def test_step_with_mask_k_bias():
+    """student.mask_k_bias (upstream LinearKMaskedBias): the k third of the qkv bias does not reach the
+    forward and gets no gradient; the parameter stays where it was (zero)."""
+    from oracle import tiny_cfg
+    r = run_pair(tiny_cfg(mask_k_bias=True, layerscale=0.5), 3, seed=5)
+    check(r)
+    D = 128
+    for i in range(2):
+        k = f"student_backbone/blocks_{i}/attn/qkv/bias"
+        assert float(r["grads_e"][k].reshape(-1)[D:2 * D].abs().max()) == 0.0
+        assert float(r["newp_e"][k].reshape(-1)[D:2 * D].abs().max()) == 0.0
+        gq = r["grads"][k].reshape(-1)
+        assert float(gq[D:2 * D].abs().max()) == 0.0                      # the oracle agrees: masked bias, zero gradient
+
+
+def test_activation_remat_equals_stashing():
+    """train.checkpointing (ssl_default_config.yaml:88): recomputing each student block in the backward gives the same
+    loss and, to the bf16 level, the same gradients as keeping its activations: the recomputing path takes the
+    LayerScale / GELU backward of the MLP branch from the stand-alone kernel (exact tanh) instead of the tail fused into
+    the LayerNorm backward (hardware tanh.approx, 2^-11), everything else is identical."""
+    from dinov3_jax.engine import Engine, from_oracle_cfg
+    from oracle import tiny_cfg
+    from oracle.batch import synthetic_batch
+    from oracle.model import init_params
+    cfg = tiny_cfg(layerscale=0.5, depth=3)
+    B = 3
+    P = init_params(cfg, 0, perturb=0.05)
+    batch = synthetic_batch(cfg, B, 1)
+    out = []
+    for remat in (False, True):
+        eng = Engine(from_oracle_cfg(cfg), B, max_masked=int(batch["mask_indices_list"].shape[0]), remat=remat)
+        assert eng.student.per_block == (not remat)
+        eng.params.load_reference_tree(P)
+        eng.set_batch(batch)
+        eng.forward_backward(HYPER["teacher_temp"])
+        g = {k: v.cpu() for k, v in eng.params.export_reference_tree("grad").items()}
+        eng.optimizer_step(HYPER["lr"], HYPER["wd"], HYPER["last_layer_lr"], HYPER["momentum"])
+        out.append((eng.read_metrics()["total_loss"], g))
+    (la, ga), (lb, gb) = out
+    assert abs(la - lb) <= 1e-6 * abs(la)
+    num = sum(float(((ga[k] - gb[k]) ** 2).sum()) for k in ga)
+    den = sum(float((ga[k] ** 2).sum()) for k in ga)
+    assert (num / den) ** 0.5 < 5e-3

@@ -460,3 +460,18 @@ def test_token_assembly_with_storage_tokens_bit_exact():
     rows = torch.empty(idx.numel(), dtype=torch.int32, device="cuda")
     ops.token_rows(idx, rows, idx.numel(), P, 0, prefix=1 + R)
     assert torch.equal(X.view(-1, D)[rows.long()], mt.expand(idx.numel(), D))        # masked rows hold the mask token
+
+
+def test_swiglu_gate_forward_backward():
+    from dinov3_jax import ops
+    T, Hs = 1000, 344
+    x12 = (torch.randn(T, 2 * Hs, device="cuda") * 1.5).to(torch.bfloat16)
+    dh = torch.randn(T, Hs, device="cuda").to(torch.bfloat16)
+    h = torch.empty(T, Hs, device="cuda", dtype=torch.bfloat16)
+    dx12 = torch.empty(T, 2 * Hs, device="cuda", dtype=torch.bfloat16)
+    ops.swiglu_fwd(x12, h)
+    ops.swiglu_bwd(x12, dh, dx12)
+    x = x12.float().requires_grad_(True)
+    ref = torch.nn.functional.silu(x[:, :Hs]) * x[:, Hs:]
+    ref.backward(dh.float())
+    assert rel(h, ref) < BF16_TOL and rel(dx12, x.grad) < BF16_TOL

@@ -107,7 +107,7 @@ def test_unsupported_options_raise():
     with pytest.raises(NotImplementedError):
         SSLMetaArch(setup_config(DinoV3SetupArgs(opts=["train.centering=centering"])))
     with pytest.raises(NotImplementedError):
-        SSLMetaArch(setup_config(DinoV3SetupArgs(opts=["student.ffn_layer=swiglu"])))
+        SSLMetaArch(setup_config(DinoV3SetupArgs(opts=["student.norm_layer=rmsnorm"])))
 
 
 def test_do_train_runs_three_iterations():
