@@ -240,6 +240,39 @@ __global__ void sk_colsum_vec_kernel(const float* __restrict__ L, const float* _
   }
   atomicAdd(&s[k], acc.x); atomicAdd(&s[k + 1], acc.y); atomicAdd(&s[k + 2], acc.z); atomicAdd(&s[k + 3], acc.w);
 }
+// Deterministic column sums: every row slab writes its partial sums to part[slab][K] (no atomics), a second kernel adds
+// the slabs in a fixed order.  The atomic version perturbs s[k] in the last bit from run to run, which flips a few bf16
+// roundings of the iBOT d(logits) and grows to ~3e-3 in the embedding gradients through the bf16 backward chain
+// (tools/check_determinism.py); with this the whole dX chain of a step is bit-reproducible.
+__global__ void sk_colsum_part_kernel(const float* __restrict__ L, const float* __restrict__ mx, float inv_temp,
+                                      const float* __restrict__ a, float* __restrict__ part, int R, int K) {
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int slab = (R + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * slab, r1 = min(R, r0 + slab);
+  if (k >= K) return;
+  const float c = inv_temp * 1.4426950408889634f;
+  const float4 m4 = *reinterpret_cast<const float4*>(mx + k);
+  const float4 mc = make_float4(m4.x * c, m4.y * c, m4.z * c, m4.w * c);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int b = r0; b < r1; ++b) {
+    const float4 v = *reinterpret_cast<const float4*>(L + (long)b * K + k);
+    const float w = a ? a[b] : 1.f;
+    acc.x += exp2f(v.x * c - mc.x) * w; acc.y += exp2f(v.y * c - mc.y) * w;
+    acc.z += exp2f(v.z * c - mc.z) * w; acc.w += exp2f(v.w * c - mc.w) * w;
+  }
+  *reinterpret_cast<float4*>(part + (long)blockIdx.y * K + k) = acc;
+}
+__global__ void sk_colsum_combine_kernel(const float* __restrict__ part, float* __restrict__ s, int slabs, int K) {
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (k >= K) return;
+  float4 acc = *reinterpret_cast<const float4*>(s + k);
+  for (int i = 0; i < slabs; ++i) {
+    const float4 v = *reinterpret_cast<const float4*>(part + (long)i * K + k);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  *reinterpret_cast<float4*>(s + k) = acc;
+}
 __global__ void sk_rowsum_vec_kernel(const float* __restrict__ L, const float* __restrict__ mx, float inv_temp,
                                      const float* __restrict__ s, const float* __restrict__ btot, float* __restrict__ a,
                                      int R, int K) {
@@ -456,6 +489,21 @@ int d3_sinkhorn_colsum(const float* L, const float* mx, float temp, const float*
     sk_colsum_kernel<<<grid, 256, 0, STREAM(stream)>>>(L, mx, 1.f / temp, a, s, R, K);
   }
   D3_CHECK_LAUNCH();
+  return D3_OK;
+}
+int d3_sinkhorn_colsum_det(const float* L, const float* mx, float temp, const float* a, float* s /* zeroed, += */,
+                           float* scratch /* [D3_SK_SLABS, K] */, int R, int K, void* stream) {
+  if (R <= 0) return D3_OK;
+  if (K % 4 || (((uintptr_t)L | (uintptr_t)mx | (uintptr_t)s | (uintptr_t)scratch) % 16))
+    return set_error(D3_ERR_ARG, "d3_sinkhorn_colsum_det: K % 4 == 0 and 16-byte aligned buffers");
+  const int cx = (K / 4 + 127) / 128;
+  int slabs = max(1, min(R / 8, max(1, sm_count() * 8 / cx)));
+  if (slabs > D3_SK_SLABS) slabs = D3_SK_SLABS;
+  dim3 grid(cx, slabs);
+  sk_colsum_part_kernel<<<grid, 128, 0, STREAM(stream)>>>(L, mx, 1.f / temp, a, scratch, R, K);
+  sk_colsum_combine_kernel<<<cx, 128, 0, STREAM(stream)>>>(scratch, s, slabs, K);
+  D3_CHECK_LAUNCH();
+  count_launch(1);
   return D3_OK;
 }
 int d3_sinkhorn_rowsum(const float* L, const float* mx, float temp, const float* s, const float* btot, float* a, int R,

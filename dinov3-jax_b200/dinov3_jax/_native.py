@@ -67,6 +67,7 @@ SIGNATURES = {
     "d3_absmax": [P, LL, P, P],
     "d3_colmax": [P, P, I, I, P],
     "d3_sinkhorn_colsum": [P, P, F, P, P, I, I, P],
+    "d3_sinkhorn_colsum_det": [P, P, F, P, P, P, I, I, P],
     "d3_sinkhorn_rowsum": [P, P, F, P, P, P, I, I, P],
     "d3_sinkhorn_probs": [P, P, F, P, P, P, P, I, I, P],
     "d3_colsum_f32": [P, P, I, I, P],

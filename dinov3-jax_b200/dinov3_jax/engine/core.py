@@ -168,6 +168,7 @@ class Engine:
         self.h_t_ibot = HeadBufs(cfg, self.max_masked, dev, stash=False)
         self.sk_dino = SinkhornBufs(ng, K, dev)
         self.sk_ibot = SinkhornBufs(self.max_masked, K, dev)
+        self.sk_scratch = torch.empty(ops.SK_SLABS * K, dtype=f32, device=dev) if K % 4 == 0 else None
         # centers of the optional softmax-centering path ("state" collection of the reference: dino_clstoken_loss.py:19-22)
         self.center_dino = torch.zeros(K, dtype=f32, device=dev)
         self.center_ibot = torch.zeros(K, dtype=f32, device=dev)
@@ -349,7 +350,10 @@ class Engine:
         a = None
         for _ in range(n_iter):
             sk.s.zero_()
-            ops.sinkhorn_colsum(L, sk.mx, temp, a, sk.s)
+            if self.sk_scratch is not None:      # atomics-free column sums: the step's dX chain is bit-reproducible
+                ops.sinkhorn_colsum_det(L, sk.mx, temp, a, sk.s, self.sk_scratch)
+            else:
+                ops.sinkhorn_colsum(L, sk.mx, temp, a, sk.s)
             if self.comm is not None:
                 self.comm.all_reduce_sum(sk.s)          # psum of the row sums (:53 / ibot :99)
             ops.sinkhorn_rowsum(L, sk.mx, temp, sk.s, sk.btot, sk.a[:R])

@@ -65,11 +65,13 @@ class FsdpRuntime:
         self.push = False
         self.push_gemm = os.environ.get("D3_FSDP_PUSH_GEMM", "1") != "0"     # 0: only the stand-alone push kernel
         self._peer_ptrs = {}
-        # Default: on for 2 ranks (validated: tools/check_fsdp.py + bench, profiles/r01_fsdp_push_*.log).  At 8 ranks the
-        # stand-alone push kernel works but the GEMM-epilogue scatter raised an asynchronous launch failure on ViT-L
-        # (open issue), so larger worlds keep the NCCL reduce-scatter unless D3_FSDP_PUSH=1 is set.
+        # Default: on at every world size.  Round 1 saw an asynchronous launch failure with the GEMM-epilogue scatter at 8
+        # ranks on ViT-L; in round 2 it no longer occurs (tools/check_fsdp_push.py: pushed shards == NCCL reduce-scatter
+        # to 8e-8 at 8 ranks with ViT-L block shapes; bench.py --gpus 8 with the push path: profiles/r02_*8gpu*), after the
+        # issue path of every TMA / tcgen05 / bulk-copy instruction moved to elect.sync.  D3_FSDP_PUSH=0 selects the
+        # NCCL reduce-scatter.
         want = os.environ.get("D3_FSDP_PUSH", "auto")
-        if self.cuda and self.world > 1 and comm.backend == "nccl" and (want == "1" or (want == "auto" and self.world == 2)):
+        if self.cuda and self.world > 1 and comm.backend == "nccl" and want in ("1", "auto"):
             self._setup_push()
 
     def _setup_push(self):

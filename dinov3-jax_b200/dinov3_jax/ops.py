@@ -242,6 +242,16 @@ def sinkhorn_colsum(L, mx, temp, a, s):
     N.check(N.init().d3_sinkhorn_colsum(_p(L), _p(mx), temp, _p(a), _p(s), R, K, _s()), "d3_sinkhorn_colsum")
 
 
+SK_SLABS = 16     # D3_SK_SLABS (include/dinov3_b200.h)
+
+
+def sinkhorn_colsum_det(L, mx, temp, a, s, scratch):
+    """sinkhorn_colsum without atomics (bit-reproducible); scratch: fp32 [SK_SLABS, K]."""
+    R, K = L.shape
+    assert scratch.dtype == f32 and scratch.numel() >= SK_SLABS * K
+    N.check(N.init().d3_sinkhorn_colsum_det(_p(L), _p(mx), temp, _p(a), _p(s), _p(scratch), R, K, _s()), "d3_sinkhorn_colsum_det")
+
+
 def sinkhorn_rowsum(L, mx, temp, s, btot, a):
     R, K = L.shape
     N.check(N.init().d3_sinkhorn_rowsum(_p(L), _p(mx), temp, _p(s), _p(btot), _p(a), R, K, _s()), "d3_sinkhorn_rowsum")

@@ -178,6 +178,11 @@ int d3_absmax(const float* L, long long n, float* out /*pre-set to -inf*/, void*
 int d3_colmax(const float* L /*[R,K]*/, float* cm /*[K] pre-set to -inf*/, int R, int K, void* stream);
 int d3_sinkhorn_colsum(const float* L /*[R,K]*/, const float* mx, float temp, const float* a /*[R] or NULL (=1)*/,
                        float* s /*[K] zeroed, +=*/, int R, int K, void* stream);
+/* Same sums without atomics (bit-reproducible): row slabs write partial sums to scratch[D3_SK_SLABS][K], which a second
+ * launch adds to s in a fixed order.                                                                                */
+#define D3_SK_SLABS 16
+int d3_sinkhorn_colsum_det(const float* L, const float* mx, float temp, const float* a, float* s /*[K] zeroed, +=*/,
+                           float* scratch /*[D3_SK_SLABS, K]*/, int R, int K, void* stream);
 int d3_sinkhorn_rowsum(const float* L, const float* mx, float temp, const float* s, const float* btot /*device*/,
                        float* a /*[R]*/, int R, int K, void* stream);
 int d3_sinkhorn_probs(const float* L, const float* mx, float temp, const float* s, const float* a, const float* btot,
