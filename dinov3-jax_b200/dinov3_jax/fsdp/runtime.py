@@ -46,6 +46,16 @@ class Comm:
         return None
 
 
+class _EventWork:
+    """`wait()` like a c10d Work: makes the current stream wait for an event recorded on the gather stream."""
+
+    def __init__(self, ev):
+        self.ev = ev
+
+    def wait(self):
+        torch.cuda.current_stream().wait_event(self.ev)
+
+
 class FsdpRuntime:
     """Schedules the collectives of one rank.  `stores`: dict module -> ModuleStore (engine/params.py)."""
 
@@ -64,6 +74,10 @@ class FsdpRuntime:
         # GEMM's epilogue for the big matrices (ops.gemm(scatter=...)), from d3_scatter_add_peers for the rest.
         self.push = False
         self.push_gemm = os.environ.get("D3_FSDP_PUSH_GEMM", "1") != "0"     # 0: only the stand-alone push kernel
+        # parameter all-gather of the bf16 matrices through the copy engines (peer-mapped shards) instead of NCCL kernels
+        # that take SMs from the persistent GEMM grids; D3_FSDP_DMA_GATHER=0 keeps NCCL
+        self.dma_gather = os.environ.get("D3_FSDP_DMA_GATHER", "1") != "0"
+        self._peer_views = {}
         self._peer_ptrs = {}
         # Default: on at every world size.  Round 1 saw an asynchronous launch failure with the GEMM-epilogue scatter at 8
         # ranks on ViT-L; in round 2 it no longer occurs (tools/check_fsdp_push.py: pushed shards == NCCL reduce-scatter
@@ -84,6 +98,18 @@ class FsdpRuntime:
                 st.grad_shard = shard
                 self._peer_ptrs[name] = [int(p) for p in hdl.buffer_ptrs]
                 st._symm_handle = hdl
+                if self.dma_gather and st.bf16_shard.numel():
+                    # bf16 matrix shards (student + teacher) in peer-mapped memory: the parameter all-gather becomes
+                    # plain device-to-device copies out of the peers' shards (copy engines, no SM, no NCCL kernel)
+                    hs = {}
+                    for attr in ("bf16_shard", "t_bf16_shard"):
+                        old = getattr(st, attr)
+                        buf = symm_mem.empty(old.numel(), dtype=torch.bfloat16, device=old.device)
+                        h = symm_mem.rendezvous(buf, self.comm.group)
+                        buf.copy_(old)
+                        setattr(st, attr, buf)
+                        hs[attr] = h
+                    st._symm_param_handles = hs
             torch.cuda.synchronize()
             torch.distributed.barrier(group=self.comm.group)
             self.push = True
@@ -144,7 +170,17 @@ class FsdpRuntime:
             sa, sb = L.shard_range(unit, "mat")
             src = (st.t_bf16_shard if teacher else st.bf16_shard)[sa:sb]
             dst = (st.t_bf16 if teacher else st.bf16)[ma:mb]
-            works.append(self.comm.all_gather(dst, src, async_op=True))
+            if self.push and self.dma_gather and hasattr(st, "_symm_param_handles"):
+                # tiled all-gather (fsdp/utils.py:66) as world copies: slice r of the unit comes from rank r's shard
+                n = sb - sa
+                views = self._shard_views(module, st, teacher)
+                for r in range(self.world):
+                    dst[r * n:(r + 1) * n].copy_(views[r][sa:sb], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream())
+                works.append(_EventWork(ev))
+            else:
+                works.append(self.comm.all_gather(dst, src, async_op=True))
         va, vb = unit.vec
         if vb > va:
             sa, sb = L.shard_range(unit, "vec")
@@ -152,6 +188,16 @@ class FsdpRuntime:
             dst = (st.t_vecs if teacher else st.vecs)[va - L.n_mat: vb - L.n_mat]
             works.append(self.comm.all_gather(dst, src, async_op=True))
         self._pending[(module, unit.name, teacher)] = works
+
+    def _shard_views(self, module: str, st, teacher: bool):
+        key = (module, teacher)
+        if key not in self._peer_views:
+            attr = "t_bf16_shard" if teacher else "bf16_shard"
+            h = st._symm_param_handles[attr]
+            n = getattr(st, attr).numel()
+            self._peer_views[key] = [getattr(st, attr) if r == self.comm.rank else h.get_buffer(r, (n,), torch.bfloat16, 0)
+                                     for r in range(self.world)]
+        return self._peer_views[key]
 
     def prefetch(self, items):
         """items: iterable of (module, unit, teacher) in use order.  All gathers are queued on the side stream at once:
@@ -161,6 +207,14 @@ class FsdpRuntime:
         if self.side is not None:
             self.side.wait_stream(torch.cuda.current_stream())   # parameters come from the previous optimizer step
             with torch.cuda.stream(self.side):
+                if self.push and self.dma_gather:
+                    # the copies below read the PEERS' shards: every rank's optimizer step must have finished.  (The
+                    # opposite hazard - a peer's next optimizer step overwriting a shard still being copied - is closed
+                    # by the fence all-reduce of finish_grads: a rank reaches it only after its backward, i.e. after all
+                    # of its gathers of this step were consumed.)
+                    st0 = next(iter(self.stores.values()))
+                    if hasattr(st0, "_symm_handle"):
+                        st0._symm_handle.barrier(0)
                 for module, unit, teacher in items:
                     self._issue_gather(module, unit, teacher)
         else:
