@@ -463,8 +463,7 @@ class Engine:
             ops.swiglu_bwd(X12, self.dH, dX12)                                                 # [dx1 | dx2]
             wgrad(1, st.b(st.Z, i), dX12[:, :Hs], "mlp/w1/kernel")                                   # dW1 = z^T dx1
             wgrad(1, st.b(st.Z, i), dX12[:, Hs:], "mlp/w2/kernel")                                   # dW2 = z^T dx2
-            ops.colsum_bf16(dX12[:, :Hs], gv("mlp/w1/bias"))
-            ops.colsum_bf16(dX12[:, Hs:], gv("mlp/w2/bias"))
+            on_wstream(1, lambda: (ops.colsum_bf16(dX12[:, :Hs], gv("mlp/w1/bias")), ops.colsum_bf16(dX12[:, Hs:], gv("mlp/w2/bias"))))
             ops.gemm(dX12[:, :Hs], w("mlp/w1/kernel"), self.dZ32)                              # dz = dx1 W1^T + dx2 W2^T (fp32)
             ops.gemm(dX12[:, Hs:], w("mlp/w2/kernel"), self.dZ32, accum=True)
             dZ = self.dZ32
@@ -472,7 +471,8 @@ class Engine:
             wgrad(0, st.b(st.Hh, i), dU2, "mlp/Dense_1/kernel")                                      # dW2 = h^T dU2
             ops.gemm(dU2, w("mlp/Dense_1/kernel"), dU1, dgelu_of=st.b(st.U1, i))                     # dU1 = (dU2 W2^T) * gelu'(u1)
             wgrad(1, st.b(st.Z, i), dU1, "mlp/Dense_0/kernel")                                       # dW1 = z^T dU1
-            ops.colsum_bf16(dU1, gv("mlp/Dense_0/bias"))
+            # bias gradients are column sums that only feed the optimizer: they ride on the weight-gradient stream
+            on_wstream(1, lambda: ops.colsum_bf16(dU1, gv("mlp/Dense_0/bias")))
             ops.gemm(dU1, w("mlp/Dense_0/kernel"), self.dZ)                                    # dZ = dU1 W1^T
             dZ = self.dZ
         # LN2 backward; its tail is the attention branch's LayerScale: x_mid = x_in + g1 * (o Wp + bp), dP = dXmid * g1
@@ -493,12 +493,15 @@ class Engine:
             ops.attn_bwd(st.b(st.QKV, i)[sl], st.b(st.O, i)[sl], self.dO[sl], lse, delta, dQKV[sl], cs.n, cs.N, D, H,
                          rope_sin=cs.sin, rope_cos=cs.cos, rope_prefix=cfg.prefix)
         wgrad(3, st.b(st.Y, i), dQKV, "attn/qkv/kernel")                                             # dWqkv = y^T dQKV
-        if cfg.mask_k_bias:      # LinearKMaskedBias: no gradient reaches the k third of the bias
-            gb = gv("attn/qkv/bias")
-            ops.colsum_bf16(dQKV[:, :D], gb[:D])
-            ops.colsum_bf16(dQKV[:, 2 * D:], gb[2 * D:])
-        else:
-            ops.colsum_bf16(dQKV, gv("attn/qkv/bias"))
+
+        def qkv_bias_grad():
+            if cfg.mask_k_bias:      # LinearKMaskedBias: no gradient reaches the k third of the bias
+                gb = gv("attn/qkv/bias")
+                ops.colsum_bf16(dQKV[:, :D], gb[:D])
+                ops.colsum_bf16(dQKV[:, 2 * D:], gb[2 * D:])
+            else:
+                ops.colsum_bf16(dQKV, gv("attn/qkv/bias"))
+        on_wstream(3, qkv_bias_grad)
         ops.gemm(dQKV, w("attn/qkv/kernel"), self.dY)                                          # dY = dQKV Wqkv^T
         tail = self._ls_tail(i - 1) if (i > 0 and not self.remat) else {}
         ops.layernorm_bwd_ls(self.dY, st.X[i], m1, r1, v("norm1/scale"), dXprev, dx_add=self.dXmid,

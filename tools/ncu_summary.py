@@ -1,34 +1,35 @@
-"""Summarise an .ncu-rep (read here with `ncu -i`, no GPU needed) into the few numbers the roofline uses."""
+"""Print the roofline-relevant metrics of every launch in an .ncu-rep, optionally labelled.
+usage: python tools/ncu_summary.py rep.ncu-rep [label-file]   (label file: one line per launch: name | algorithmic bytes | flops)"""
 import csv, subprocess, sys
-
-WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
-        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
-        "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
-        "lts__t_sector_hit_rate.pct", "l1tex__t_bytes.sum", "lts__t_bytes.sum"]
-
-
-def main(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(out.splitlines()))
-    hdr, units = rows[0], rows[1]
-    idx = {h: i for i, h in enumerate(hdr)}
-    print(f"# {path}: {len(rows) - 2} kernel launches (ncu --set full --clock-control none --import-source on)")
-    for r in rows[2:]:
-        print("kernel:", r[idx["Kernel Name"]][:90], " grid", r[idx.get("launch__grid_size", 0)])
-        for w in WANT:
-            if w in idx:
-                print(f"    {w:68s} {r[idx[w]]:>16s} {units[idx[w]]}")
-        try:
-            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
-            rd = float(r[idx["dram__bytes_read.sum"]]) * scale[units[idx["dram__bytes_read.sum"]]]
-            wr = float(r[idx["dram__bytes_write.sum"]]) * scale[units[idx["dram__bytes_write.sum"]]]
-            print(f"    {'traffic = dram read + write':68s} {(rd + wr) / 1e6:16.1f} Mbyte")
-            t = float(r[idx["gpu__time_duration.sum"]]) * {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}.get(units[idx["gpu__time_duration.sum"]], 1e-6)
-            print(f"    {'dram traffic / duration':68s} {(rd + wr) / t / 1e9:16.1f} GB/s")
-        except Exception:
-            pass
-
-
-if __name__ == "__main__":
-    main(sys.argv[1])
+rep = sys.argv[1]
+labels = [l.rstrip("\n").split("|") for l in open(sys.argv[2])] if len(sys.argv) > 2 else []
+out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(out.splitlines()))
+h = rows[0]; idx = {k: i for i, k in enumerate(h)}
+want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "lts__t_sector_hit_rate.pct",
+        "launch__grid_size", "launch__block_size", "smsp__cycles_active.avg"]
+units = rows[1]
+def val(r, k):
+    if k not in idx: return None
+    v = r[idx[k]].replace(",", "")
+    try: return float(v)
+    except ValueError: return v
+def to_bytes(x, unit):
+    return x * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+def to_us(x, unit):
+    return x * {"ns": 1e-3, "us": 1, "ms": 1e3, "s": 1e6}.get(unit, 1)
+for n, r in enumerate(rows[2:]):
+    name = r[idx["Kernel Name"]].split("(")[0]
+    us = to_us(val(r, "gpu__time_duration.sum"), units[idx["gpu__time_duration.sum"]])
+    rd = to_bytes(val(r, "dram__bytes_read.sum"), units[idx["dram__bytes_read.sum"]]); wr = to_bytes(val(r, "dram__bytes_write.sum"), units[idx["dram__bytes_write.sum"]])
+    line = (f"launch {n}: {name[:48]:48s} {us:9.1f} us  dram {rd / 1e6:8.1f} MB rd + {wr / 1e6:8.1f} MB wr = {(rd + wr) / 1e6:8.1f} MB "
+            f"({(rd + wr) / us / 1e3:7.1f} GB/s)  tensor {val(r, 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active')}%  "
+            f"xu {val(r, 'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active')}%  warps {val(r, 'sm__warps_active.avg.pct_of_peak_sustained_active')}%  "
+            f"regs {val(r, 'launch__registers_per_thread')}  L2 hit {val(r, 'lts__t_sector_hit_rate.pct')}%")
+    if n < len(labels):
+        lab, alg, fl = labels[n][0].strip(), float(labels[n][1]), float(labels[n][2])
+        line = f"[{lab}] " + line + f"  | algorithmic {alg / 1e6:.1f} MB -> traffic ratio {(rd + wr) / alg:.2f}"
+        if fl: line += f", {fl / us / 1e6:.0f} TFLOP/s"
+    print(line)
