@@ -39,22 +39,23 @@ def peaks():
 
 
 def ncu_traffic():
-    """dram read+write bytes per launch of the GEMM kernel from the committed `ncu --set full` capture (mean over the
-    captured launches), or None when no capture summary is present."""
-    p = os.path.join(ROOT, "profiles", "r01_ncu_full_gemm2sm.txt")
+    """DRAM traffic of the roofline kernel from the committed `ncu --set full` capture of GEMM launches with KNOWN shapes
+    (profiles/r02_ncu_gemm_labeled.txt, tools/ncu_gemm_labeled.py): per labelled launch the measured dram read+write
+    bytes, the algorithmic bytes and their ratio; `traffic` in the JSON line is the first one (the qkv projection)."""
+    import re
+    p = os.path.join(ROOT, "profiles", "r02_ncu_gemm_labeled.txt")
     if not os.path.exists(p):
         return None
-    vals = []
+    launches = []
     for line in open(p):
-        if "traffic = dram read + write" in line:
-            f = line.split()
-            try:
-                v = float(f[-2]); unit = f[-1]
-                vals.append(v * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}.get(unit, 1.0))
-            except Exception:
-                pass
-    return {"bytes_per_launch_mean": sum(vals) / len(vals), "launches": len(vals),
-            "source": "profiles/r01_ncu_full_gemm2sm.txt (ncu --set full, 4 consecutive block GEMMs of a step)"} if vals else None
+        m = re.match(r"\[(.*?)\] launch \d+: .*? = +([\d.]+) MB .*algorithmic ([\d.]+) MB -> traffic ratio ([\d.]+)", line)
+        if m:
+            launches.append({"launch": m.group(1), "dram_bytes": float(m.group(2)) * 1e6, "algorithmic_bytes": float(m.group(3)) * 1e6,
+                             "traffic_ratio": float(m.group(4))})
+    if not launches:
+        return None
+    return {"bytes_per_launch": launches[0]["dram_bytes"], "labelled_launches": launches,
+            "source": "profiles/r02_ncu_gemm_labeled.txt (ncu --set full --clock-control none, tools/ncu_gemm_labeled.py)"}
 
 
 class ClockSampler:
@@ -317,8 +318,10 @@ def main():
                 "ms_per_step": ms_e2e, "loss": loss},
         "roofline": {"bound": "tensor", "kernel": "gemm2sm_kernel + gemm1sm_kernel (every tcgen05 GEMM launch of one step)",
                      "achieved": gemm_tf, "peak": sustained, "unit": "TFLOP/s", "frac": gemm_tf / sustained,
-                     "traffic": traffic["bytes_per_launch_mean"] if traffic else None,
-                     "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)",
+                     "traffic": traffic["bytes_per_launch"] if traffic else None,
+                     "traffic_unit": "bytes of ONE labelled launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full): "
+                                     "labelled_launches[0], the qkv projection",
+                     "traffic_labelled_launches": traffic["labelled_launches"] if traffic else None,
                      "traffic_source": traffic["source"] if traffic else None, "peak_source": f"bf16_tflops_sustained ({how})", "launches": len(prof),
                      "share_of_step": g_ms / ms if ms else None},
         "step_roofline": {"achieved": step_tf, "peak": sustained, "unit": "TFLOP/s", "frac": step_tf / sustained,

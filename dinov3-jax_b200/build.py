@@ -10,7 +10,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 CSRC = ROOT / "csrc"
 OUT = ROOT / "libdinov3_b200.so"
-SOURCES = ["api.cu", "gemm_tc.cu", "attention.cu", "attention_ws.cu", "elementwise.cu", "losses.cu", "optim.cu"]
+SOURCES = ["api.cu", "gemm_tc.cu", "attention.cu", "attention_ws.cu", "elementwise.cu", "losses.cu", "optim.cu", "augment.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 

@@ -75,6 +75,10 @@ SIGNATURES = {
     "d3_ce_fwd_bwd": [P, F, P, P, F, P, P, P, P, P, P, P, P, P, P, I, I, P],
     "d3_koleo_fwd_bwd": [P, P, P, P, P, P, P, I, I, F, F, F, P],
     "d3_koleo_fwd_bwd_rows": [P, P, P, P, P, P, P, I, I, I, I, F, F, F, P],
+    "d3_aug_resized_crop": [P, I, I, I, P, I, P, I, P],
+    "d3_aug_color": [P, P, I, I, P, P],
+    "d3_aug_blur": [P, P, P, P, I, I, P],
+    "d3_aug_finish": [P, P, P, I, I, C.POINTER(C.c_float), C.POINTER(C.c_float), P],
     "d3_sumsq": [P, LL, P, P],
     "d3_ema": [P, P, P, LL, LL, F, P],
     "d3_adamw_ema": [P, P, P, P, P, P, P, LL, P, I, LL, P, F, F, F, F, F, F, F, I, F, P],

@@ -145,6 +145,8 @@ def build_data_loader_from_cfg(config, model, start_iter: int = 0):
       synthetic            one fixed random batch per rank (benchmarks / smoke runs) — announced loudly;
       synthetic:noise      the reference decoder's own image distribution (noise images) through the DINO augmentation
                            and `collate_data_and_cast` (the full host pipeline, no files needed);
+      synthetic:gpu        the same image distribution generated in HBM (uint8 [B,224,224,3]) through the ON-GPU
+                           augmentation + mask pipeline (data/gpu_augment.py, SURVEY §8f.3): no host pixel work at all;
       anything else        the reference's `make_dataset` / `make_data_loader` (data/loaders.py), which stay in the
                            reference checkout and resolve through the package overlay (needs that checkout + its deps).
     """
@@ -164,6 +166,18 @@ def build_data_loader_from_cfg(config, model, start_iter: int = 0):
             while True:
                 yield fixed
         return forever()
+    if path.startswith("synthetic:gpu"):
+        from ..data.gpu_augment import GpuBatchPipeline
+        pipe = GpuBatchPipeline(config, seed=config.train.seed + 1000 * rank + start_iter)
+        dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+        gen = torch.Generator(device=dev).manual_seed(config.train.seed + 7919 * rank + start_iter)
+
+        def gpu_batches():
+            while True:
+                noise = torch.randn((B, 224, 224, 3), device=dev, generator=gen)        # decoders.py:31-34 on the device
+                lo, hi = noise.amin((1, 2, 3), keepdim=True), noise.amax((1, 2, 3), keepdim=True)
+                yield pipe(((noise - lo) / (hi - lo) * 255).to(torch.uint8))
+        return gpu_batches()
     img_size, patch = config.crops.global_crops_size, config.student.patch_size
     grid = img_size // patch
     mask_generator = MaskingGenerator(input_size=(grid, grid), max_num_patches=0.5 * img_size // patch * img_size // patch)

@@ -230,6 +230,21 @@ int d3_adamw_ema(float* p, const float* g, float* m, float* v, float* teacher, v
 int d3_ema(float* teacher, const float* student, void* t_bf16, long long n_bf16, long long n, float momentum,
            void* stream);
 
+/* ---- On-GPU DINO multi-crop augmentation (replaces the per-sample torchvision host pipeline of
+ * dinov3_jax/data/augmentations.py:23-230 for a batch of decoded uint8 images resident in HBM).  Random parameters are
+ * drawn on the host and passed as one 64-byte record per output crop:
+ *   struct { int img, x0, y0, w, h, flip; int order[4]; float fb, fc, fs, fh; int gray, solarize; }
+ * (order[] = ColorJitter op order: 0 brightness 1 contrast 2 saturation 3 hue; order[0] = -1: jitter not applied).
+ * Images are fp32 in [0,1] between the stages, like torchvision.transforms.v2.functional on float tensors.           */
+int d3_aug_resized_crop(const void* src_u8 /*[n_img,H,W,3]*/, int n_img, int H, int W, const void* crops /*device*/,
+                        int n_crops, float* out /*[n_crops,S,S,3]*/, int S, void* stream);   /* RandomResizedCrop(bicubic, antialias) + flip */
+int d3_aug_color(float* x /*[n_crops,S,S,3] in place*/, const void* crops, int n_crops, int S,
+                 float* gray_sum /*[n_crops] zeroed*/, void* stream);                      /* ColorJitter + RandomGrayscale */
+int d3_aug_blur(const float* x, float* tmp, float* y, const void* blur /*device float sigma[n_crops], <= 0: none*/,
+                int n_crops, int S, void* stream);                                          /* GaussianBlur(9, sigma) */
+int d3_aug_finish(const float* x, void* out_bf16 /*[n_crops,S,S,3]*/, const void* crops, int n_crops, int S,
+                  const float* mean3 /*host*/, const float* std3 /*host*/, void* stream);     /* Solarize(128) + Normalize + bf16 */
+
 #ifdef __cplusplus
 }
 #endif

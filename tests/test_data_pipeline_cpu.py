@@ -80,3 +80,28 @@ def test_args_parser_keeps_the_reference_flags():
                                       "--opts", "a.b=1", "c=2"])
     assert a.seed == 7 and a.config_file == "x.yaml" and a.no_resume and a.opts == ["a.b=1", "c=2"]
     assert get_args_parser().parse_args([]).seed == 12                      # train/train.py:66 default
+
+
+def test_gpu_augment_parameter_sampling_follows_torchvision_rules():
+    """Host side of the on-GPU augmentation: crop boxes inside the image with area / aspect ratio in the configured
+    ranges, crop-major record order, the reference's blur probabilities as coded (0.0 / 0.9 / 0.5), solarize only on the
+    second global crop, and the 64-byte record layout the kernels read."""
+    from dinov3_jax.data.gpu_augment import CROP_DTYPE, GpuDataAugmentationDINO
+    assert CROP_DTYPE.itemsize == 64 and CROP_DTYPE.fields["order"][1] == 24 and CROP_DTYPE.fields["fb"][1] == 40
+    aug = GpuDataAugmentationDINO((0.32, 1.0), (0.05, 0.32), 8, seed=1)
+    B, H, W = 64, 300, 400
+    (g, gb), (l, lb) = aug.sample(B, H, W)
+    assert g.shape == (2 * B,) and l.shape == (8 * B,)
+    assert (g["img"] == np.tile(np.arange(B), 2)).all() and (l["img"] == np.tile(np.arange(B), 8)).all()
+    for rec, scale in ((g, (0.32, 1.0)), (l, (0.05, 0.32))):
+        assert (rec["x0"] >= 0).all() and (rec["y0"] >= 0).all() and (rec["x0"] + rec["w"] <= W).all() and (rec["y0"] + rec["h"] <= H).all()
+        area = rec["w"] * rec["h"] / (H * W)
+        assert area.min() > scale[0] * 0.9 and area.max() < scale[1] * 1.1
+        ratio = rec["w"] / rec["h"]
+        assert ratio.min() > 0.74 and ratio.max() < 1.35
+    assert (gb[:B] == 0).all()                               # GaussianBlur(p=1.0) -> RandomApply(p=0.0): never applied
+    assert 0.75 < (gb[B:] > 0).mean() <= 1.0                 # GaussianBlur(p=0.1) -> applied with probability 0.9
+    assert 0.35 < (lb > 0).mean() < 0.65
+    assert g["solarize"][:B].sum() == 0 and 0 < g["solarize"][B:].sum() < B and l["solarize"].sum() == 0
+    jit = g["order"][:, 0] >= 0
+    assert 0.6 < jit.mean() < 0.95 and all(sorted(o) == [0, 1, 2, 3] for o in g["order"][jit])

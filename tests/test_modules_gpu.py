@@ -157,3 +157,18 @@ def test_vit_and_head_against_reference_golden(native):
     x = torch.from_numpy(G["head_x"]).cuda()
     assert rel(head(x), torch.from_numpy(G["head_logits"])) < 2e-2
     assert rel(head(x, no_last_layer=True), torch.from_numpy(G["head_bottleneck"])) < 2e-2
+
+
+def test_do_train_with_the_gpu_data_pipeline(tmp_path):
+    """train.dataset_path=synthetic:gpu: images in HBM -> on-GPU augmentation + masks -> engine, through do_train."""
+    from dinov3_jax.configs import DinoV3SetupArgs, setup_config
+    from dinov3_jax.train import SSLMetaArch
+    from dinov3_jax.train.train import do_train
+    opts = ["train.dataset_path=synthetic:gpu", "train.batch_size_per_gpu=2", "student.arch=vit_small", "crops.global_crops_size=64",
+            "crops.local_crops_size=32", "dino.head_n_prototypes=512", "ibot.head_n_prototypes=512", "dino.head_hidden_dim=256",
+            "ibot.head_hidden_dim=256", "dino.head_bottleneck_dim=64", "ibot.head_bottleneck_dim=64", "optim.epochs=1",
+            "train.OFFICIAL_EPOCH_LENGTH=4", "optim.warmup_epochs=0", "teacher.warmup_teacher_temp_epochs=0",
+            "optim.freeze_last_layer_epochs=0", f"train.output_dir={tmp_path}", "checkpointing.period=100"]
+    config = setup_config(DinoV3SetupArgs(opts=opts))
+    m = do_train(config, SSLMetaArch(config), resume=False, max_iters=3, print_freq=1)
+    assert m["total_loss"] == m["total_loss"] and m["total_loss"] > 0
