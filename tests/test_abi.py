@@ -31,7 +31,7 @@ def test_python_signature_table_matches_header():
 def test_abi_version_and_error_string():
     from dinov3_jax import _native
     lib = _native.lib()
-    assert lib.d3_abi_version() == 2
+    assert lib.d3_abi_version() == 3
     assert isinstance(lib.d3_last_error(), bytes)
 
 
