@@ -957,6 +957,34 @@ __global__ void scatter_add_peers_kernel(const float* __restrict__ src, long n4,
   }
 }
 
+// Small all-reduce over NVLink peer mappings (jax.lax.psum / pmax of the loss heads' K-vectors and scalars:
+// loss/dino_clstoken_loss.py:53, loss/ibot_patch_loss.py:99, train/train.py:516-541): every rank reads all ranks'
+// staged inputs and reduces them in rank order, so all ranks obtain bit-identical results.  One pull of world x n
+// floats (n = 2K + 4 = 512 KB at K = 65536) replaces an NCCL ring whose cost at this size is pure latency.  The loads
+// bypass the (non-coherent) L1: the same staging addresses are re-read every other call.
+struct PeerCPtrs { const float* p[8]; };
+template <int OP>
+__global__ void allreduce_peers_kernel(PeerCPtrs peers, int world, float* __restrict__ out, long n4, long n) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    float4 acc = __ldcv(reinterpret_cast<const float4*>(peers.p[0]) + i);
+    for (int r = 1; r < world; ++r) {
+      const float4 v = __ldcv(reinterpret_cast<const float4*>(peers.p[r]) + i);
+      if (OP == 0) { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+      else { acc.x = fmaxf(acc.x, v.x); acc.y = fmaxf(acc.y, v.y); acc.z = fmaxf(acc.z, v.z); acc.w = fmaxf(acc.w, v.w); }
+    }
+    reinterpret_cast<float4*>(out)[i] = acc;
+  }
+  if (blockIdx.x == 0)
+    for (long i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) {
+      float acc = __ldcv(peers.p[0] + i);
+      for (int r = 1; r < world; ++r) {
+        const float v = __ldcv(peers.p[r] + i);
+        acc = OP == 0 ? acc + v : fmaxf(acc, v);
+      }
+      out[i] = acc;
+    }
+}
+
 }  // namespace d3
 
 using namespace d3;
@@ -1184,6 +1212,24 @@ int d3_scatter_add_peers(const float* src, long long n, float* const* peers /*ho
   const int blocks = (int)min((n4 + 255) / 256, (long)sm_count() * 4);
   scatter_add_peers_kernel<<<blocks, 256, 0, STREAM(stream)>>>(src, n4, pp, (unsigned long long)off, (unsigned)shard, alpha,
                                                               scatter_mode());
+  D3_CHECK_LAUNCH();
+  return D3_OK;
+}
+
+int d3_allreduce_peers(const float* const* peers /*host array [world]*/, int world, float* out, long long n, int op,
+                       void* stream) {
+  if (n <= 0) return D3_OK;
+  if (world < 1 || world > 8 || (op != 0 && op != 1)) return set_error(D3_ERR_ARG, "d3_allreduce_peers: 1..8 ranks, op 0 (sum) | 1 (max)");
+  PeerCPtrs pp;
+  long al = (long)(uintptr_t)out;
+  for (int i = 0; i < 8; ++i) {
+    pp.p[i] = i < world ? peers[i] : nullptr;
+    if (i < world) al |= (long)(uintptr_t)peers[i];
+  }
+  const long n4 = (al % 16 == 0) ? n / 4 : 0;      // unaligned buffers: scalar path for everything
+  const int blocks = (int)max(1L, min((n4 + 255) / 256, (long)sm_count() * 2));
+  if (op == 0) allreduce_peers_kernel<0><<<blocks, 256, 0, STREAM(stream)>>>(pp, world, out, n4, n);
+  else allreduce_peers_kernel<1><<<blocks, 256, 0, STREAM(stream)>>>(pp, world, out, n4, n);
   D3_CHECK_LAUNCH();
   return D3_OK;
 }

@@ -79,6 +79,14 @@ class FsdpRuntime:
         self.dma_gather = os.environ.get("D3_FSDP_DMA_GATHER", "1") != "0"
         self._peer_views = {}
         self._peer_ptrs = {}
+        # vector regions (LN / bias / LayerScale: ~1 MB per module): ONE all-gather per (module, teacher|student) and one
+        # permutation kernel at step start instead of one NCCL kernel per unit — ~50 fewer NCCL launches co-running
+        # with (and taking SMs from) the teacher pass's persistent GEMMs.  D3_FSDP_VEC_BULK=0: per-unit gathers.
+        self.vec_bulk = os.environ.get("D3_FSDP_VEC_BULK", "1") != "0"
+        self._fence_barrier = os.environ.get("D3_FSDP_FENCE_BARRIER", "1") != "0"   # 0: NCCL all-reduce as the push fence
+        self._push_side = os.environ.get("D3_FSDP_PUSH_SIDE", "1") != "0"          # 0: stand-alone pushes on the compute stream
+        self._vec_perm = {}
+        self._vec_tmp = {}
         # Default: on at every world size.  Round 1 saw an asynchronous launch failure with the GEMM-epilogue scatter at 8
         # ranks on ViT-L; in round 2 it no longer occurs (tools/check_fsdp_push.py: pushed shards == NCCL reduce-scatter
         # to 8e-8 at 8 ranks with ViT-L block shapes; bench.py --gpus 8 with the push path: profiles/r02_*8gpu*), after the
@@ -117,6 +125,31 @@ class FsdpRuntime:
             import warnings
             warnings.warn(f"symmetric-memory gradient push disabled ({type(e).__name__}: {e}); using NCCL reduce-scatter")
             self.push = False
+
+    def setup_small_allreduce(self, n_floats: int):
+        """Symmetric-memory staging buffer for small all-reduces over peer mappings (d3_allreduce_peers); None when the
+        peer-memory path is not active (the caller then uses NCCL).  D3_FSDP_SMALL_AR=0 keeps NCCL."""
+        import os
+        if not self.push or os.environ.get("D3_FSDP_SMALL_AR", "1") == "0":
+            return None
+        import torch.distributed._symmetric_memory as symm_mem
+        dev = next(iter(self.stores.values())).grad_shard.device
+        buf = symm_mem.empty(n_floats, dtype=torch.float32, device=dev)
+        hdl = symm_mem.rendezvous(buf, self.comm.group)
+        buf.zero_()
+        torch.cuda.synchronize()
+        torch.distributed.barrier(group=self.comm.group)
+        self._ar = (buf, hdl, [int(p) for p in hdl.buffer_ptrs])
+        return buf
+
+    def small_allreduce(self, off: int, n: int, out: torch.Tensor, op: str):
+        """out[:n] = reduce over ranks of stage[off:off+n] (every rank gets identical bits).  One symmetric-memory barrier
+        (all ranks have written their inputs; also: all ranks have finished the reads of every EARLIER reduction, which
+        is what allows a staging range to be rewritten two calls later) + one pull kernel."""
+        from .. import ops
+        buf, hdl, ptrs = self._ar
+        hdl.barrier(2)
+        ops.allreduce_peers([p + 4 * off for p in ptrs], out, n, op)
 
     def scatter_spec(self, module: str, unit_name: str, tensor: str):
         """(peer pointers at this unit's shard slice, offset of the tensor inside the unit's matrix range, shard length)
@@ -182,12 +215,46 @@ class FsdpRuntime:
             else:
                 works.append(self.comm.all_gather(dst, src, async_op=True))
         va, vb = unit.vec
-        if vb > va:
+        if vb > va and self.vec_bulk:
+            works.append(self._vec_done[(module, teacher)])
+        elif vb > va:
             sa, sb = L.shard_range(unit, "vec")
             src = (st.t_master if teacher else st.master)[sa:sb]
             dst = (st.t_vecs if teacher else st.vecs)[va - L.n_mat: vb - L.n_mat]
             works.append(self.comm.all_gather(dst, src, async_op=True))
         self._pending[(module, unit.name, teacher)] = works
+
+    def _gather_vecs(self, module: str, teacher: bool):
+        """All vector regions of a module in one collective: rank r's vector shard is contiguous
+        ([n_mat_shard, n_shard) of its shard buffer, fsdp/layout.py), so one all-gather gives [world][n_vec_shard];
+        an index_select with a precomputed permutation lays it out unit-major like the single-GPU buffer."""
+        st = self.stores[module]
+        L = st.layout
+        nv = L.n_shard - L.n_mat_shard
+        dst = st.t_vecs if teacher else st.vecs
+        if nv == 0:
+            return None
+        if module not in self._vec_perm:
+            import numpy as np
+            perm = np.empty(L.n - L.n_mat, dtype=np.int64)
+            for u in L.units:
+                va, vb = u.vec
+                if vb <= va:
+                    continue
+                s_u = (vb - va) // self.world
+                so = L.shard_vec_off[u.name] - L.n_mat_shard
+                for r in range(self.world):
+                    perm[va - L.n_mat + r * s_u: va - L.n_mat + (r + 1) * s_u] = r * nv + so + np.arange(s_u)
+            self._vec_perm[module] = torch.from_numpy(perm).to(dst.device)
+            self._vec_tmp[module] = torch.empty(self.world * nv, dtype=dst.dtype, device=dst.device)
+        tmp = self._vec_tmp[module]
+        self.comm.all_gather(tmp, (st.t_master if teacher else st.master)[L.n_mat_shard:L.n_shard])
+        torch.index_select(tmp, 0, self._vec_perm[module], out=dst)
+        if self.cuda:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            return _EventWork(ev)
+        return None
 
     def _shard_views(self, module: str, st, teacher: bool):
         key = (module, teacher)
@@ -204,6 +271,13 @@ class FsdpRuntime:
         NCCL executes them back to back while the compute stream works through earlier units."""
         if self.world == 1 or (self._debug & 1):
             return
+        items = list(items)
+        self._vec_done = {}
+
+        def vecs_first():
+            if self.vec_bulk:
+                for module, teacher in dict.fromkeys((m, t) for m, _, t in items):
+                    self._vec_done[(module, teacher)] = self._gather_vecs(module, teacher)
         if self.side is not None:
             self.side.wait_stream(torch.cuda.current_stream())   # parameters come from the previous optimizer step
             with torch.cuda.stream(self.side):
@@ -215,9 +289,11 @@ class FsdpRuntime:
                     st0 = next(iter(self.stores.values()))
                     if hasattr(st0, "_symm_handle"):
                         st0._symm_handle.barrier(0)
+                vecs_first()
                 for module, unit, teacher in items:
                     self._issue_gather(module, unit, teacher)
         else:
+            vecs_first()
             for module, unit, teacher in items:
                 self._issue_gather(module, unit, teacher)
 
@@ -239,10 +315,18 @@ class FsdpRuntime:
         L = st.layout
         unit = next(u for u in L.units if u.name == unit_name)
         if self.push:
+            # the stand-alone pushes (proj matrices, vectors, heads, embed: 0.84 ms per ViT-L step at 2 ranks in the
+            # kernel timeline) only feed the optimizer: they run on the side stream, off the backward's critical path;
+            # finish_grads() joins it before the fence
             cur = torch.cuda.current_stream()
+            ps = self.side if (self.side is not None and self._push_side) else cur
+            if ps is not cur:
+                ps.wait_stream(cur)
             if also_after is not None:
-                cur.wait_event(also_after)
-            self._push_ranges(module, unit, tuple(scattered))
+                ps.wait_event(also_after)
+            with torch.cuda.stream(ps):
+                self._push_ranges(module, unit, tuple(scattered))
+            self._pushed_on_side = ps is not cur
             return
 
         def issue():
@@ -269,11 +353,19 @@ class FsdpRuntime:
             w.wait()
         self._grad_works = []
         if self.push:
+            if getattr(self, "_pushed_on_side", False):
+                torch.cuda.current_stream().wait_stream(self.side)
+                self._pushed_on_side = False
             # every rank's pushes are complete once its stream reaches this collective; the all-reduce completes on a
             # rank only after all ranks have joined, so afterwards every contribution has landed in the local shard
+            # (a symmetric-memory barrier on this stream has the same property at a fraction of an all-reduce's latency)
+            st0 = next(iter(self.stores.values()))
+            if self._fence_barrier and hasattr(st0, "_symm_handle"):
+                st0._symm_handle.barrier(1)
+                return
             self._fence = getattr(self, "_fence", None)
             if self._fence is None:
-                self._fence = torch.zeros(1, device=next(iter(self.stores.values())).grad_shard.device)
+                self._fence = torch.zeros(1, device=st0.grad_shard.device)
             self.comm.all_reduce_sum(self._fence)
 
     # ------------------------------------------------------------------------------------------ utilities

@@ -150,6 +150,13 @@ def scatter_add_peers(src, peers, off, shard, alpha):
             "d3_scatter_add_peers")
 
 
+def allreduce_peers(peers, out, n, op="sum"):
+    """out[:n] = reduce over ranks (rank order) of the float buffers at the peer-mapped addresses `peers` (d3_allreduce_peers)."""
+    assert out.dtype == f32 and out.is_contiguous() and out.numel() >= n
+    arr = (C.c_void_p * len(peers))(*peers)
+    N.check(N.init().d3_allreduce_peers(arr, len(peers), _p(out), int(n), {"sum": 0, "max": 1}[op], _s()), "d3_allreduce_peers")
+
+
 def ls_gamma_from_wgrad(W, dW, bias, dbias, gamma, dgamma):
     K, Nn = W.shape
     assert W.dtype == bf16 and dW.dtype == f32 and W.is_contiguous() and dW.is_contiguous()

@@ -122,6 +122,14 @@ int d3_set_scatter_mode(int mode);
 int d3_scatter_add_peers(const float* src, long long n, float* const* peers /*host array [world]*/, int world,
                          long long off, int shard, float alpha, void* stream);
 
+/* Small all-reduce over NVLink peer mappings: out[i] = reduce over r (in rank order: identical bits on every rank) of
+ * peers[r][i]; op 0 = sum (jax.lax.psum: loss/dino_clstoken_loss.py:53, loss/ibot_patch_loss.py:99, the gradient norms of
+ * train/train.py:516-541), 1 = max.  peers[r] = rank r's staged input (pointer valid in THIS process); the caller
+ * brackets the call with a cross-rank barrier after the inputs were written (and re-uses an input buffer no earlier than
+ * two barriers later).                                                                                                 */
+int d3_allreduce_peers(const float* const* peers /*host array [world]*/, int world, float* out, long long n, int op,
+                       void* stream);
+
 /* ---- RoPE (layers/attention.py:14-20,69-90; tables from layers/rope_position_encoding.py:117-123) -----------------
  * in place on the q and k thirds of qkv bf16 [T,3D]; tokens t < prefix of every crop are left untouched.             */
 int d3_rope(void* qkv_bf16, const float* sin_t /*[P,hd]*/, const float* cos_t, long long T, int tokens_per_crop,

@@ -116,6 +116,44 @@ def _worker(rank, world, port, ret):
         dist.destroy_process_group()
 
 
+def _runtime_worker(rank, world, port, ret, bulk):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), D3_FSDP_VEC_BULK="1" if bulk else "0")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from dinov3_jax.engine.params import ModuleStore, backbone_spec
+        from dinov3_jax.fsdp.runtime import Comm, FsdpRuntime
+        st = ModuleStore("backbone", backbone_spec(CFG), CFG, "cpu", world=world, rank=rank)
+        L = st.layout
+        torch.manual_seed(0)
+        full = torch.randn(L.n)
+        idx = torch.from_numpy(L.full_to_shard_index(rank))
+        for teacher, scale in ((False, 1.0), (True, -2.0)):
+            (st.t_master if teacher else st.master).copy_(full[idx] * scale)
+            (st.t_bf16_shard if teacher else st.bf16_shard).copy_((full[idx] * scale)[:L.n_mat_shard].to(torch.bfloat16))
+        rt = FsdpRuntime(Comm(), {"backbone": st}, "cpu")
+        rt.prefetch([("backbone", u, t) for t in (True, False) for u in L.units])
+        for t in (True, False):
+            for u in L.units:
+                rt.acquire("backbone", u.name, t)
+        ok = True
+        for teacher, scale in ((False, 1.0), (True, -2.0)):
+            ok &= torch.equal(st.t_vecs if teacher else st.vecs, full[L.n_mat:] * scale)
+            ok &= torch.equal(st.t_bf16 if teacher else st.bf16, (full[:L.n_mat] * scale).to(torch.bfloat16))
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("bulk", [True, False])
+def test_gloo_world2_runtime_prefetch_fills_the_compute_buffers(bulk):
+    """FsdpRuntime.prefetch / acquire: per-unit matrix gathers + (bulk: one all-gather and a permutation per module |
+    per-unit) vector gathers reproduce the single-GPU buffers for student and teacher."""
+    world = 2
+    ret = mp.Manager().dict()
+    mp.spawn(_runtime_worker, args=(world, _free_port(), ret, bulk), nprocs=world, join=True)
+    assert all(ret[r] for r in range(world))
+
+
 def test_gloo_world2_gather_and_reduce_scatter():
     world = 2
     mgr = mp.Manager()

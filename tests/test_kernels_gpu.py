@@ -475,3 +475,20 @@ def test_swiglu_gate_forward_backward():
     ref = torch.nn.functional.silu(x[:, :Hs]) * x[:, Hs:]
     ref.backward(dh.float())
     assert rel(h, ref) < BF16_TOL and rel(dx12, x.grad) < BF16_TOL
+
+
+@pytest.mark.parametrize("n,world,op", [(2 * 65536 + 4, 8, "sum"), (2 * 65536, 2, "max"), (3, 4, "sum"), (1031, 3, "max")])
+def test_allreduce_peers_matches_rank_ordered_reduction(n, world, op):
+    """d3_allreduce_peers: `world` local buffers stand in for the ranks' symmetric staging buffers; the result is the
+    reduction in rank order (bit-exact against the same order in torch), also for unaligned views and n % 4 != 0."""
+    from dinov3_jax import ops
+    g = torch.Generator(device="cuda").manual_seed(n + world)
+    base = [torch.randn(n + 4, device="cuda", generator=g) for _ in range(world)]
+    for shift in (0, 1):                                  # shift 1: 4-byte aligned only -> scalar path
+        ins = [b[shift:shift + n] for b in base]
+        out = torch.full((n,), float("nan"), device="cuda")
+        ops.allreduce_peers([t.data_ptr() for t in ins], out, n, op)
+        ref = ins[0].clone()
+        for t in ins[1:]:
+            ref = ref + t if op == "sum" else torch.maximum(ref, t)
+        assert torch.equal(out, ref)
