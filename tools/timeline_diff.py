@@ -3,6 +3,13 @@ time per step in each and the difference; per stream busy time; compute-stream i
 import json, sys
 a, b = (json.load(open(p)) for p in sys.argv[1:3])
 def summarise(t):
+    # drop the first profiled step (the ranks' profilers start at different times: one long wait at the first barrier)
+    rows = t["rows"]
+    ends = [i for i, r in enumerate(rows) if "adamw_ema" in r["name"]]
+    per = len(ends) // t["nstep"]
+    if t["nstep"] > 1 and per:
+        rows = rows[ends[per - 1] + 1:]
+        t = dict(t, rows=rows, nstep=t["nstep"] - 1)
     n = t["nstep"]; by = {}; streams = {}
     for r in t["rows"]:
         k = r["name"].split("(")[0][:60]
