@@ -165,6 +165,9 @@ def main():
     ap.add_argument("--patch", type=int, default=16)
     ap.add_argument("--local-size", type=int, default=96, help="98 for patch 14 (96 is not divisible, layers/patch_embed.py:48-49)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gram", choices=["off", "ema", "frozen"], default="off",
+                    help="add the Gram-anchoring term (gram.use_loss; SURVEY 8f.2): ema = EMA teacher's patches as targets, "
+                         "frozen = a third backbone pass with a snapshot of the teacher; off = the BASELINE headline workload")
     ap.add_argument("--remat", action="store_true", help="activation rematerialisation (train.checkpointing): BASELINE configs[4]")
     ap.add_argument("--cpu-sample-batch", type=int, default=2, help="images per CPU-baseline step (bounded sample: ~15-25 s of CPU work)")
     ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="wall-clock bound of the --impl reference arm")
@@ -227,6 +230,12 @@ def main():
     from dinov3_jax.engine.synth import synthetic_batch, init_reference_like
     _native.init(local_rank)
     cfg = config_for(args.arch, n_prototypes=args.prototypes, patch=args.patch, local_size=args.local_size)
+    if args.gram != "off":
+        import dataclasses
+        cfg = dataclasses.replace(cfg, gram_use_loss=True, gram_ema_teacher=args.gram == "ema", gram_it_load_ema_teacher=0,
+                                  gram_remove_only_teacher_neg=True)
+        cfg_desc["workload"] += f" + Gram anchoring ({args.gram} teacher)"
+        cfg_desc["gram"] = args.gram
     B = args.batch
     log(f"building synthetic batch B={B}")
     batch = synthetic_batch(cfg, B, seed=rank, pin=True)

@@ -446,6 +446,44 @@ __global__ void koleo_bwd_kernel(const float* __restrict__ x, const float* __res
   for (int e = threadIdx.x; e < D; e += blockDim.x) dx[(long)i * D + e] += gsm[e] * inv - x[(long)i * D + e] * c2;
 }
 
+// ---- Gram-anchoring loss (loss/gram_loss.py:13-50): elementwise stage between the similarity GEMMs and the backward
+// GEMM.  Ss = Xs Xs^T and St = Xt Xt^T are fp32 [n, n] (tcgen05 GEMMs); per element
+//   mode 1 (remove_neg):              s' = max(s, 0), t' = max(t, 0),            ds'/ds = [s > 0]
+//   mode 2 (remove_only_teacher_neg): s' = (s < 0 && t < 0) ? 0 : s, t' = max(t, 0), ds'/ds = !(s < 0 && t < 0)
+//   mode 0:                           s' = s, t' = t
+// loss += inv_count * sum (s' - t')^2 ;  G = (s' - t') * ds'/ds  (bf16: the A operand of dX = (4 w / n^2) G Xs).
+__global__ void gram_diff_kernel(const float* __restrict__ Ss, const float* __restrict__ St, __nv_bfloat16* __restrict__ G,
+                                 long n4, int mode, float inv_count, float* __restrict__ loss) {
+  __shared__ float sh[32];
+  float acc = 0.f;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    const float4 s4 = reinterpret_cast<const float4*>(Ss)[i];
+    const float4 t4 = reinterpret_cast<const float4*>(St)[i];
+    const float sv[4] = {s4.x, s4.y, s4.z, s4.w}, tv[4] = {t4.x, t4.y, t4.z, t4.w};
+    float g[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float s = sv[j], t = tv[j], d = 1.f;
+      if (mode == 1) { d = s > 0.f ? 1.f : 0.f; s = fmaxf(s, 0.f); t = fmaxf(t, 0.f); }
+      else if (mode == 2) { if (s < 0.f && t < 0.f) { s = 0.f; d = 0.f; } t = fmaxf(t, 0.f); }
+      const float e = s - t;
+      acc = fmaf(e, e, acc);
+      g[j] = e * d;
+    }
+    if (G) reinterpret_cast<uint2*>(G)[i] = make_uint2(pack_bf16(g[0], g[1]), pack_bf16(g[2], g[3]));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0 && loss) atomicAdd(loss, t * inv_count);
+  }
+}
+
 }  // namespace d3
 
 using namespace d3;
@@ -565,6 +603,19 @@ int d3_koleo_fwd_bwd_rows(const float* x, float* xn_scratch, float* nrm_scratch,
   count_launch(2);
   return D3_OK;
 }
+int d3_gram_diff(const float* Ss, const float* St, void* G_bf16, long long n_elems, int mode, float inv_count, float* loss,
+                 void* stream) {
+  if (n_elems <= 0) return D3_OK;
+  if (mode < 0 || mode > 2) return set_error(D3_ERR_ARG, "d3_gram_diff: mode 0 | 1 (remove_neg) | 2 (remove_only_teacher_neg)");
+  if ((n_elems % 4) || (((uintptr_t)Ss | (uintptr_t)St) % 16) || ((uintptr_t)G_bf16 % 8))
+    return set_error(D3_ERR_ARG, "d3_gram_diff: n_elems % 4 == 0 and 16-byte aligned similarity buffers");
+  const long n4 = n_elems / 4;
+  const int blocks = (int)std::min<long>((n4 + 255) / 256, (long)sm_count() * 8);
+  gram_diff_kernel<<<blocks, 256, 0, STREAM(stream)>>>(Ss, St, (__nv_bfloat16*)G_bf16, n4, mode, inv_count, loss);
+  D3_CHECK_LAUNCH();
+  return D3_OK;
+}
+
 int d3_koleo_fwd_bwd(const float* x, float* xn_scratch, float* nrm_scratch, int* nn_scratch, float* coef_scratch,
                      float* metric, float* dx, int B, int D, float eps, float w_metric, float w_grad, void* stream) {
   if (B <= 1) return D3_OK;

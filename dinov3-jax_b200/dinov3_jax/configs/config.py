@@ -25,7 +25,11 @@ DEFAULTS = {
     "ibot": {"loss_weight": 1.0, "mask_sample_probability": 0.5, "mask_ratio_min_max": [0.1, 0.5],
              "mask_random_circular_shift": False, "separate_head": True, "head_n_prototypes": 65536,
              "head_bottleneck_dim": 256, "head_nlayers": 3, "head_hidden_dim": 2048},
-    "gram": {"use_loss": False},
+    "gram": {"use_loss": False, "compute_stats": False, "loss_weight": 1.0, "ema_teacher": False, "ckpt": None,
+             "it_load_ema_teacher": -1, "rep_update": True, "update_frequency": 50000, "it_first_update": 0,
+             "max_updates": None, "normalized": True, "img_level": False, "remove_neg": False,
+             "remove_only_teacher_neg": False, "tokens_used": "all", "global_teacher_resize_method": "bicubic",
+             "global_teacher_resize_antialias": False, "loss_weight_schedule": None},   # ssl_default_config.yaml:55-73
     "train": {"batch_size_per_gpu": 64, "output_dir": ".", "seed": 0, "OFFICIAL_EPOCH_LENGTH": 1250,
               "centering": "sinkhorn_knopp", "checkpointing": False, "dataset_path": "synthetic", "num_workers": 0,
               "cache_dataset": False},

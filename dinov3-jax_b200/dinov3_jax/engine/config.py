@@ -51,6 +51,20 @@ class EngineConfig:
     adamw_beta2: float = 0.999
     mask_probability: float = 0.5
     mask_ratio: tuple = (0.1, 0.5)
+    # Gram anchoring (configs/ssl_default_config.yaml:55-73, loss/gram_loss.py, train/ssl_meta_arch.py:165-254)
+    gram_use_loss: bool = False
+    gram_loss_weight: float = 1.0
+    gram_ema_teacher: bool = False    # true: the EMA teacher's patch tokens are the targets (no third backbone pass)
+    gram_normalized: bool = True
+    gram_img_level: bool = False
+    gram_remove_neg: bool = False
+    gram_remove_only_teacher_neg: bool = False
+    gram_tokens_used: str = "all"     # all | masked | unmasked
+    gram_it_load_ema_teacher: int = -1
+    gram_rep_update: bool = True
+    gram_update_frequency: int = 50000
+    gram_it_first_update: int = 0
+    gram_max_updates: int | None = None
 
     @property
     def head_dim(self) -> int:
@@ -107,8 +121,38 @@ def config_from_reference_cfg(cfg) -> EngineConfig:
     if cfg.student.ffn_layer not in ffn_table or cfg.student.norm_layer not in ("layernorm", "layernormbf16"):
         raise NotImplementedError("ffn_layer must be mlp | swiglu[32|64|128] and norm_layer layernorm | layernormbf16 "
                                   "(RMSNorm is not on the B200 path, SURVEY 8f)")
-    if cfg.gram.use_loss or cfg.dino.koleo_loss_distributed or cfg.dino.reweight_dino_local_loss:
-        raise NotImplementedError("gram loss / distributed KoLeo / local-loss reweighting are not on the B200 path yet")
+    if cfg.dino.koleo_loss_distributed or cfg.dino.reweight_dino_local_loss:
+        raise NotImplementedError("distributed KoLeo inside the step / local-loss reweighting are not on the B200 path yet")
+    gram_kw = {}
+    if cfg.gram.use_loss:
+        gg = cfg.gram
+        if gg.get("img_level", False):
+            raise NotImplementedError("gram.img_level=true (per-image Gram matrices) is not on the B200 path; the batch-level "
+                                      "form (the default, img_level: false) is")
+        if str(gg.get("tokens_used", "all")) != "all":
+            raise NotImplementedError("gram.tokens_used masked | unmasked is not on the B200 path (all patch tokens are)")
+        if gg.get("compute_stats", False):
+            import warnings
+            warnings.warn("gram.compute_stats: the stats_only/* metrics are not produced by the B200 engine", stacklevel=2)
+        if gg.get("ckpt", None) is not None:
+            raise NotImplementedError("gram.ckpt: load the gram teacher with dinov3_jax.checkpointer and Engine.gram_teacher_load "
+                                      "instead of a path in the config")
+        gsz = cfg.crops.get("gram_teacher_crops_size", None)
+        if gsz is not None and int(gsz) != int(cfg.crops.global_crops_size):
+            raise NotImplementedError("crops.gram_teacher_crops_size != global_crops_size (hi-res gram teacher + feature "
+                                      "resize) is not on the B200 path")
+        if gg.get("loss_weight_schedule", None):
+            raise NotImplementedError("gram.loss_weight_schedule: pass gram_loss_weight per step to Engine.train_step instead")
+        if bool(gg.get("remove_neg", False)) and bool(gg.get("remove_only_teacher_neg", False)):
+            raise ValueError("gram.remove_neg and gram.remove_only_teacher_neg are exclusive (loss/gram_loss.py:20)")
+        if not gg.get("ema_teacher", False) and int(gg.get("it_load_ema_teacher", -1)) < 0:
+            raise ValueError("if no gram checkpoint is provided, gram.it_load_ema_teacher must be >= 0 (ssl_meta_arch.py:215-218)")
+        gram_kw = dict(gram_use_loss=True, gram_loss_weight=float(gg.loss_weight), gram_ema_teacher=bool(gg.ema_teacher),
+                       gram_normalized=bool(gg.normalized), gram_img_level=False, gram_remove_neg=bool(gg.remove_neg),
+                       gram_remove_only_teacher_neg=bool(gg.remove_only_teacher_neg), gram_tokens_used=str(gg.tokens_used),
+                       gram_it_load_ema_teacher=int(gg.it_load_ema_teacher), gram_rep_update=bool(gg.rep_update),
+                       gram_update_frequency=int(gg.update_frequency), gram_it_first_update=int(gg.it_first_update),
+                       gram_max_updates=gg.get("max_updates", None))
     # options this engine does not implement must not be silently ignored (the run would differ from the request)
     g = lambda node, key, default: node.get(key, default) if hasattr(node, "get") else getattr(node, key, default)
     if "schedules" in cfg and cfg["schedules"]:
@@ -144,4 +188,4 @@ def config_from_reference_cfg(cfg) -> EngineConfig:
         n_storage=int(cfg.student.n_storage_tokens), ln_eps=1e-5 if cfg.student.norm_layer == "layernormbf16" else 1e-6,
         ffn_layer=ffn_table[cfg.student.ffn_layer][0], swiglu_align=ffn_table[cfg.student.ffn_layer][1],
         mask_k_bias=bool(cfg.student.get("mask_k_bias", False)),
-        mlp_second_act=ffn_table[cfg.student.ffn_layer][0] == "mlp")
+        mlp_second_act=ffn_table[cfg.student.ffn_layer][0] == "mlp", **gram_kw)

@@ -236,9 +236,131 @@ class Engine:
         self._build_ce_tables()
         self._build_rows()
         self.step_count = 0
+        self._init_gram()
         self.masks_u8 = torch.zeros(ng, P, dtype=torch.uint8, device=dev)
         self.mask_idx = torch.zeros(self.max_masked, dtype=torch.int64, device=dev)
         self.M = 0
+
+    # ------------------------------------------------------------------------------------------------ Gram anchoring
+    def _init_gram(self):
+        """Buffers of the Gram-anchoring term (loss/gram_loss.py:13-50, train/ssl_meta_arch.py:165-254,527-541):
+        MSE between the patch-similarity matrices of the student's and a gram teacher's global-crop patch tokens, over
+        the rank's whole local batch (gram.img_level: false).  The gram teacher is the EMA teacher itself
+        (gram.ema_teacher: true) or a frozen snapshot of it (`gram_teacher_load_from_ema`, scheduled by `gram_schedule`)
+        run through the teacher path at the global-crop resolution."""
+        cfg, dev = self.cfg, self.device
+        self.gram_active = False
+        self._gram_w = float(cfg.gram_loss_weight)
+        self._gram_snapshot_pending = False
+        self.gram_updates = 0
+        if not cfg.gram_use_loss:
+            return
+        if cfg.gram_img_level or cfg.gram_tokens_used != "all":
+            raise NotImplementedError("gram.img_level=true / gram.tokens_used != all are not on the B200 path")
+        sg = self.s_sets[0]
+        D = cfg.embed_dim
+        n = sg.n * sg.P
+        rows = (torch.arange(sg.n, dtype=torch.int32)[:, None] * sg.N + cfg.prefix
+                + torch.arange(sg.P, dtype=torch.int32)[None, :]).reshape(-1)
+        self.gram_rows = rows.to(dev)
+        self.gram_n = n
+        e = lambda *shape, dt: torch.empty(*shape, dtype=dt, device=dev)
+        self.gram_fs, self.gram_ft = e(n, D, dt=f32), e(n, D, dt=f32)        # gathered final-norm patch tokens
+        self.gram_xs, self.gram_xt = e(n, D, dt=bf16), e(n, D, dt=bf16)      # (normalised) GEMM operands
+        self.gram_nrm_s, self.gram_nrm_t = e(n, dt=f32), e(n, dt=f32)
+        self.gram_Ss, self.gram_St = e(n, n, dt=f32), e(n, n, dt=f32)
+        self.gram_G = e(n, n, dt=bf16)
+        self.gram_dX, self.gram_dF = e(n, D, dt=bf16), e(n, D, dt=bf16)
+        self.gram_mode = ops.GRAM_MODES[(bool(cfg.gram_remove_neg), bool(cfg.gram_remove_only_teacher_neg))]
+        if cfg.gram_ema_teacher:
+            self.gram_active = True
+        else:
+            bb = self.params.mods["backbone"]
+            bb.g_bf16 = torch.zeros_like(bb.t_bf16)                          # frozen full copies on every rank
+            bb.g_vecs = torch.zeros(bb.n - bb.n_mat, dtype=f32, device=dev)
+
+    def gram_teacher_load_from_ema(self):
+        """The gram teacher becomes a frozen copy of the current EMA teacher.  The copy is taken inside the next step,
+        right after the EMA teacher's forward, when its gathered full-size buffers are valid on every rank."""
+        assert self.cfg.gram_use_loss and not self.cfg.gram_ema_teacher
+        self._gram_snapshot_pending = True
+
+    def gram_teacher_load(self, tensors: dict):
+        """Gram teacher weights from a checkpoint: `tensors` maps the backbone's tensor names (reference layout, e.g.
+        'blocks_0/attn/qkv/kernel', as in export_reference_tree without the 'teacher_backbone/' prefix) to arrays."""
+        assert self.cfg.gram_use_loss and not self.cfg.gram_ema_teacher
+        bb = self.params.mods["backbone"]
+        full = torch.zeros(bb.n, dtype=f32, device=self.device)
+        for name in bb.offsets:
+            bb._view(full, name).copy_(torch.as_tensor(tensors[name]).to(device=self.device, dtype=f32).reshape(bb.shapes[name]))
+            if self.cfg.mask_k_bias and name.endswith("attn/qkv/bias"):
+                third = bb.shapes[name][0] // 3
+                bb._view(full, name)[third:2 * third].zero_()
+        ops.cast_f32_bf16(full[:bb.n_mat].contiguous(), bb.g_bf16)
+        bb.g_vecs.copy_(full[bb.n_mat:])
+        self.gram_active = True
+
+    def gram_schedule(self, iteration: int):
+        """When the gram teacher is refreshed (upstream DINOv3 train loop; the reference's loop has no such code):
+        loaded from the EMA teacher at gram.it_load_ema_teacher, then, with gram.rep_update, every
+        gram.update_frequency iterations from gram.it_first_update on, at most gram.max_updates times."""
+        cfg = self.cfg
+        if not cfg.gram_use_loss or cfg.gram_ema_teacher:
+            return
+        if iteration == cfg.gram_it_load_ema_teacher:
+            self.gram_teacher_load_from_ema()
+        elif (cfg.gram_rep_update and self.gram_active and iteration >= cfg.gram_it_first_update
+              and (iteration + 1) % cfg.gram_update_frequency == 0
+              and (cfg.gram_max_updates is None or self.gram_updates < cfg.gram_max_updates)):
+            self.gram_teacher_load_from_ema()
+            self.gram_updates += 1
+
+    def _gram_features(self, Xn, feats, x_bf16, nrm):
+        """Patch tokens of the global crops out of a final-norm output -> the Gram operands (L2-normalised rows)."""
+        n, D = self.gram_n, self.cfg.embed_dim
+        if self.cfg.gram_normalized:
+            ops.gather_rows(Xn, self.gram_rows, n, D, dst_f32=feats)
+            ops.l2norm_fwd(feats, x_bf16, nrm, 1e-12)
+        else:
+            ops.gather_rows(Xn, self.gram_rows, n, D, dst_bf16=x_bf16)
+
+    def _gram_teacher_targets(self):
+        """Called at the end of the teacher pass (the EMA teacher's outputs have been gathered into the head buffers)."""
+        cfg, T_ = self.cfg, self.teacher
+        if not cfg.gram_ema_teacher:
+            bb = self.params.mods["backbone"]
+            if self._gram_snapshot_pending:
+                bb.g_bf16.copy_(bb.t_bf16)
+                bb.g_vecs.copy_(bb.t_vecs)
+                self._gram_snapshot_pending = False
+                self.gram_active = True
+            if not self.gram_active:
+                return
+            # the same kernels and buffers as the EMA teacher's pass, reading the frozen weights
+            keep = (bb.t_bf16, bb.t_vecs)
+            bb.t_bf16, bb.t_vecs = bb.g_bf16, bb.g_vecs
+            try:
+                self._backbone_fwd(T_, [self.g_img], [None], teacher=True)
+            finally:
+                bb.t_bf16, bb.t_vecs = keep
+        self._gram_features(T_.Xn, self.gram_ft, self.gram_xt, self.gram_nrm_t)
+
+    def _gram_loss_bwd(self, dXn):
+        """loss/gram_loss.py:38-50 on the tensor cores: St = Xt Xt^T, Ss = Xs Xs^T, elementwise negative removal + squared
+        difference (d3_gram_diff), dXs = (4 w / n^2) G Xs (G symmetric), back through the row normalisation, added to the
+        gradient of the student's final-norm output."""
+        n, D = self.gram_n, self.cfg.embed_dim
+        inv = 1.0 / (float(n) * float(n))
+        ops.gemm(self.gram_xt, self.gram_xt, self.gram_St)
+        ops.gemm(self.gram_xs, self.gram_xs, self.gram_Ss)
+        ops.gram_diff(self.gram_Ss, self.gram_St, self.gram_G, self.gram_mode, inv, self.metrics[4:5])
+        ops.gemm(self.gram_G, self.gram_xs, self.gram_dX, b_mn=True, alpha=4.0 * self._gram_w * inv)
+        if self.cfg.gram_normalized:
+            ops.l2norm_bwd(self.gram_dX, self.gram_fs, self.gram_nrm_s, self.gram_dF)
+            src = self.gram_dF
+        else:
+            src = self.gram_dX
+        ops.scatter_add_rows(src, self.gram_rows, dXn, n, D)
 
     # ------------------------------------------------------------------------------------------------ static tables
     def _build_rows(self):
@@ -355,27 +477,6 @@ class Engine:
         ops.gemm(r(hb.H2), w("mlp/layers_4/kernel"), r(hb.U3), b_mn=True, bias=v("mlp/layers_4/bias"))
         ops.l2norm_fwd(r(hb.U3), r(hb.Yn), r(hb.nrm), 1e-12)
         ops.gemm(r(hb.Yn), w("last_layer/kernel"), r(hb.logits), b_mn=True)
-
-    def _sinkhorn(self, sk: SinkhornBufs, logits, R: int, temp: float, btot_local: float, n_iter: int = 3):
-        """loss/dino_clstoken_loss.py:35-62 as alternating diagonal scalings (see csrc/losses.cu)."""
-        L = logits[:R]
-        sk.mx.fill_(float("-inf"))
-        sk.btot.fill_(float(btot_local))
-        ops.colmax(L, sk.mx)
-        if self.comm is not None:
-            self.comm.all_reduce_max(sk.mx)
-            self.comm.all_reduce_sum(sk.btot)
-        a = None
-        for _ in range(n_iter):
-            sk.s.zero_()
-            if self.sk_scratch is not None:      # atomics-free column sums: the step's dX chain is bit-reproducible
-                ops.sinkhorn_colsum_det(L, sk.mx, temp, a, sk.s, self.sk_scratch)
-            else:
-                ops.sinkhorn_colsum(L, sk.mx, temp, a, sk.s)
-            if self.comm is not None:
-                self.comm.all_reduce_sum(sk.s)          # psum of the row sums (:53 / ibot :99)
-            ops.sinkhorn_rowsum(L, sk.mx, temp, sk.s, sk.btot, sk.a[:R])
-            a = sk.a[:R]
 
     def _sinkhorn_pair(self, R_d: int, R_i: int, temp: float, n_iter: int = 3):
         """Both heads' Sinkhorn-Knopp normalisations (DINO cls logits, iBOT masked-patch logits) in lock step: the
@@ -634,6 +735,8 @@ class Engine:
             else:
                 self._softmax_center(self.sk_dino, self.center_dino, self.h_t_dino.logits, ng, teacher_temp, ng)
                 self._softmax_center(self.sk_ibot, self.center_ibot, self.h_t_ibot.logits, M, teacher_temp, M)
+            if cfg.gram_use_loss:
+                self._gram_teacher_targets()
 
         if self.fwd_overlap:
             main = torch.cuda.current_stream()
@@ -649,6 +752,8 @@ class Engine:
         self._backbone_fwd(S_, [self.g_img, self.l_img], [self.masks_u8, None], teacher=False)
         ops.gather_rows(S_.Xn, self.rows_cls_s, self.Rc, D, dst_bf16=self.h_s_dino.A0, dst_f32=self.cls_f32)
         ops.gather_rows(S_.Xn, self.rows_masked_t, M, D, dst_bf16=self.h_s_ibot.A0)
+        if self.gram_active:
+            self._gram_features(S_.Xn, self.gram_fs, self.gram_xs, self.gram_nrm_s)
         self._head_fwd(self.h_s_dino, "dino_head", self.Rc, teacher=False, stash=True)
         self._head_fwd(self.h_s_ibot, "ibot_head", M, teacher=False, stash=True)
         # ---- losses + d(logits) (train/ssl_meta_arch.py:463-525)
@@ -677,6 +782,8 @@ class Engine:
         dXn.zero_()
         ops.scatter_add_rows(self.h_s_dino.dA0, self.rows_cls_s, dXn, self.Rc, D)
         ops.scatter_add_rows(self.h_s_ibot.dA0, self.rows_masked_t, dXn, M, D)
+        if self.gram_active:
+            self._gram_loss_bwd(dXn)
         bb = self.params.mods["backbone"]
         dXL = self.dX[1]
         ops.layernorm_bwd_ls(dXn, S_.X[cfg.depth], S_.fstats[0], S_.fstats[1], bb.vec("norm/scale"), dXL,
@@ -734,9 +841,13 @@ class Engine:
             ops.ema(st.t_master, st.master, st.t_bf16_shard, st.layout.n_mat_shard, float(momentum))
 
     def train_step(self, batch: dict | None, *, teacher_temp: float, lr: float, wd: float, last_layer_lr: float,
-                   momentum: float):
+                   momentum: float, gram_loss_weight: float | None = None, iteration: int | None = None):
         if batch is not None:
             self.set_batch(batch)
+        if self.cfg.gram_use_loss:
+            if gram_loss_weight is not None:       # gram.loss_weight_schedule[iteration] (train/ssl_meta_arch.py:534-537)
+                self._gram_w = float(gram_loss_weight)
+            self.gram_schedule(self.step_count if iteration is None else int(iteration))
         self.forward_backward(teacher_temp)
         self.optimizer_step(lr, wd, last_layer_lr, momentum)
 
@@ -756,7 +867,11 @@ class Engine:
         loss = (cfg.dino_loss_weight * l_scale * m[0] + cfg.dino_loss_weight * g_scale * m[1]
                 + cfg.koleo_loss_weight * ng * m[2] + cfg.ibot_loss_weight * m[3])
         out = {"dino_local_crops_loss": m[0], "dino_local_loss_weight": 1.0, "dino_global_crops_loss": m[1],
-               "koleo_loss": m[2], "ibot_loss": m[3], "local_batch_size": float(self.B), "total_loss": loss}
+               "koleo_loss": m[2], "ibot_loss": m[3], "local_batch_size": float(self.B)}
+        if self.gram_active:                       # train/ssl_meta_arch.py:538-541
+            loss += self._gram_w * m[4]
+            out["gram_loss"], out["gram_loss_weight"] = m[4], self._gram_w
+        out["total_loss"] = loss
         for name, st in self.params.mods.items():
             out[f"student_{name}_grad_norm"] = math.sqrt(max(st.sumsq.item(), 0.0))
         return out

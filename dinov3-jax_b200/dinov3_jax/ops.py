@@ -150,6 +150,16 @@ def scatter_add_peers(src, peers, off, shard, alpha):
             "d3_scatter_add_peers")
 
 
+GRAM_MODES = {(False, False): 0, (True, False): 1, (False, True): 2}      # (remove_neg, remove_only_teacher_neg)
+
+
+def gram_diff(Ss, St, G, mode: int, inv_count: float, loss):
+    """Elementwise stage of the Gram loss (d3_gram_diff): loss += inv_count * sum (s' - t')^2, G = (s' - t') ds'/ds (bf16)."""
+    assert Ss.dtype == f32 and St.dtype == f32 and Ss.is_contiguous() and St.is_contiguous() and Ss.numel() == St.numel()
+    assert G is None or (G.dtype == bf16 and G.is_contiguous() and G.numel() == Ss.numel())
+    N.check(N.init().d3_gram_diff(_p(Ss), _p(St), _p(G), Ss.numel(), int(mode), float(inv_count), _p(loss), _s()), "d3_gram_diff")
+
+
 def allreduce_peers(peers, out, n, op="sum"):
     """out[:n] = reduce over ranks (rank order) of the float buffers at the peer-mapped addresses `peers` (d3_allreduce_peers)."""
     assert out.dtype == f32 and out.is_contiguous() and out.numel() >= n

@@ -125,6 +125,7 @@ def train_step(params, batch, optimizer_state, teacher_temp, iteration, root_rng
         raise ValueError("optimizer_state must come from make_state(engine, build_optimizer(...))")
     it = int(iteration)
     engine.set_batch(batch)
+    engine.gram_schedule(it)                 # gram teacher refresh points (no-op unless gram.use_loss with a frozen teacher)
     engine.forward_backward(float(teacher_temp))
     if clip_grads is not None and float(clip_grads or 0.0) != float(engine.cfg.clip_grad or 0.0):
         raise ValueError("clip_grads differs from the engine configuration (optim.clip_grad)")
@@ -248,7 +249,7 @@ def do_train(config, model: SSLMetaArch, resume: bool = False, data_loader=None,
         except StopIteration:
             break
         engine.train_step(data, teacher_temp=float(temp_s[it]), lr=float(lr_s[it]), wd=float(wd_s[it]),
-                          last_layer_lr=float(last_s[it]), momentum=float(mom_s[it]))
+                          last_layer_lr=float(last_s[it]), momentum=float(mom_s[it]), iteration=it)
         if ck_cfg is not None and (it + 1) % int(ck_cfg.period) == 0:
             params_tree, opt_tree = engine_state(engine)                 # collective under FSDP (all-gathers the shards)
             if distributed.is_main_process():

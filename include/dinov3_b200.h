@@ -214,6 +214,14 @@ int d3_ce_fwd_bwd(const float* S /*[Rs,K]*/, float student_temp, const float* Lt
                   const float* btot, const int* t0, const int* t1, const float* wm, const float* wg, const int* slot,
                   float* metric, void* dS_bf16, int Rs, int K, void* stream);
 
+/* ---- Gram-anchoring loss (loss/gram_loss.py:13-50), elementwise stage: given the similarity matrices
+ * Ss = Xs Xs^T, St = Xt Xt^T (fp32 [n*n], produced by d3_gemm_bf16 on the L2-normalised patch features) applies the
+ * negative-removal mode (0 none | 1 remove_neg | 2 remove_only_teacher_neg, lines 40-48), accumulates
+ * *loss += inv_count * sum (s' - t')^2 (line 50: mean) and writes G = (s' - t') * ds'/ds as bf16 (or skips it when
+ * G_bf16 is NULL), the left operand of the backward GEMM dXs = (4 w / n^2) G Xs.                                    */
+int d3_gram_diff(const float* Ss, const float* St, void* G_bf16, long long n_elems, int mode, float inv_count, float* loss,
+                 void* stream);
+
 /* ---- KoLeo (loss/koleo_loss.py:16-35), forward + backward: metric += w_metric * loss; dx += w_grad * dloss/dx ------ */
 int d3_koleo_fwd_bwd(const float* x /*[B,D]*/, float* xn_scratch /*[B,D]*/, float* nrm_scratch /*[B]*/,
                      int* nn_scratch /*[B]*/, float* coef_scratch /*[B]*/, float* metric, float* dx /*[B,D] +=*/, int B,

@@ -73,8 +73,8 @@ def gram_loss(output_feats, target_feats, apply_norm: bool = True, img_level: bo
               remove_only_teacher_neg: bool = False):
     """loss/gram_loss.py:13-50 (not on the round-1 GPU path): MSE between the patch-similarity (Gram)
     matrices of student and gram-teacher features, per image ([B, N, D]) or over the whole batch ([B*N, D])."""
-    assert remove_neg != remove_only_teacher_neg
-    t, s = target_feats, output_feats
+    assert not (remove_neg and remove_only_teacher_neg)   # the reference asserts exactly one (gram_loss.py:20); its YAML
+    t, s = target_feats, output_feats                      # default (both false, ssl_default_config.yaml:68-69) = no removal
     if apply_norm:
         t = t / torch.linalg.norm(t, dim=-1, keepdim=True)
         s = s / torch.linalg.norm(s, dim=-1, keepdim=True)
@@ -83,7 +83,7 @@ def gram_loss(output_feats, target_feats, apply_norm: bool = True, img_level: bo
     t_sim, s_sim = t @ t.transpose(-1, -2), s @ s.transpose(-1, -2)
     if remove_neg:
         t_sim, s_sim = t_sim.clamp_min(0.0), s_sim.clamp_min(0.0)
-    else:
+    elif remove_only_teacher_neg:
         s_sim = torch.where((s_sim < 0) & (t_sim < 0), torch.zeros_like(s_sim), s_sim)
         t_sim = t_sim.clamp_min(0.0)
     return ((s_sim - t_sim) ** 2).mean()

@@ -5,18 +5,25 @@ import numpy as np
 import torch
 
 from .arch import ModelCfg
-from .losses import dino_loss, ibot_loss_masked, koleo_loss, sinkhorn_knopp
+from .losses import dino_loss, gram_loss, ibot_loss_masked, koleo_loss, sinkhorn_knopp
 from .model import Emu, backbone_forward, head_forward, sub
 
 STUDENT_MODULES = ("student_backbone", "student_dino_head", "student_ibot_head")
 
 
 def ssl_forward(params: dict, batch: dict, teacher_temp: float, cfg: ModelCfg, emu: Emu = Emu(False),
-                world: int = 1, allreduce=None, dtype=torch.float32, return_aux: bool = False, centers=None):
+                world: int = 1, allreduce=None, dtype=torch.float32, return_aux: bool = False, centers=None,
+                gram: dict | None = None):
     """train/ssl_meta_arch.py:289-363 (__call__), :366-402 (teacher), :406-460 (student), :463-557 (losses).
 
     Single-device semantics: `batch` holds this rank's B images, crop-major.
-    """
+
+    `gram`: {"weight", "ema_teacher", "normalized", "img_level", "remove_neg", "remove_only_teacher_neg"} adds
+    the Gram-anchoring term of train/ssl_meta_arch.py:527-541 with loss/gram_loss.py:13-50 (pinned against the
+    reference's GramLoss, tests/golden).  PARITY UNPINNED for the call path: the reference's own
+    (ssl_meta_arch.py:337-347: `get_gram_teacher_output` is called but not defined, `.reshpae`) does not execute, so
+    the features follow upstream DINOv3: student = the global crops' final-norm patch tokens, teacher = the same
+    tokens of the gram teacher (`gram_backbone/...` parameters) or, with ema_teacher, of the EMA teacher."""
     n_g, n_l = cfg.n_global, cfg.n_local
     g = batch["collated_global_crops"].to(dtype)      # bf16 crops promoted at the first conv (SURVEY fact 4)
     l = batch["collated_local_crops"].to(dtype)
@@ -72,6 +79,18 @@ def ssl_forward(params: dict, batch: dict, teacher_temp: float, cfg: ModelCfg, e
     metrics = {"dino_local_crops_loss": L_local.detach(), "dino_local_loss_weight": torch.tensor(1.0),
                "dino_global_crops_loss": L_global.detach(), "koleo_loss": L_koleo.detach(),
                "ibot_loss": L_ibot.detach(), "local_batch_size": torch.tensor(float(B))}
+    if gram is not None:
+        with torch.no_grad():
+            if gram.get("ema_teacher", False):
+                gt_patch = t_patch
+            else:
+                gt_patch = backbone_forward(sub(params, "gram_backbone"), [g], [None], cfg, emu)[0]["x_norm_patchtokens"]
+        L_gram = gram_loss(g_patch, gt_patch, apply_norm=gram.get("normalized", True), img_level=gram.get("img_level", False),
+                           remove_neg=gram.get("remove_neg", False),
+                           remove_only_teacher_neg=gram.get("remove_only_teacher_neg", False))
+        loss = loss + gram["weight"] * L_gram
+        metrics["gram_loss"] = L_gram.detach()
+        metrics["gram_loss_weight"] = torch.tensor(float(gram["weight"]))
     if return_aux:
         aux = {"t_cls": t_cls, "t_patch_logits": t_patch_logits, "t_cls_logits": t_cls_logits,
                "cls_centered": cls_centered, "patch_centered": patch_centered, "g_cls": g_cls, "l_cls": l_cls,

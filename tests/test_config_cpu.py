@@ -65,3 +65,21 @@ def test_parameter_spec_contains_storage_tokens_with_the_reference_multipliers()
     lr_cls, wd_cls, _ = lr_wd_multipliers("backbone", "cls_token", cfg)
     assert (lr, wd, last) == (lr_cls, wd_cls, False)            # same layer-0 group as cls / mask tokens (param_groups.py:117-129)
     assert abs(lr - cfg.layerwise_decay ** (cfg.depth + 1)) < 1e-12
+
+
+def test_gram_keys_map_onto_the_engine_config():
+    """gram.* (configs/ssl_default_config.yaml:55-73; train/ssl_meta_arch.py:165-254): the batch-level Gram term with the
+    EMA teacher or a frozen snapshot is on the B200 path; the variants that are not raise."""
+    e = config_from_reference_cfg(setup_config(DinoV3SetupArgs(opts=["gram.use_loss=true", "gram.ema_teacher=true",
+                                                                      "gram.loss_weight=2.0", "gram.remove_only_teacher_neg=true"])))
+    assert e.gram_use_loss and e.gram_ema_teacher and e.gram_loss_weight == 2.0 and e.gram_remove_only_teacher_neg
+    assert not e.gram_img_level and e.gram_tokens_used == "all" and e.gram_normalized
+    e = config_from_reference_cfg(setup_config(DinoV3SetupArgs(opts=["gram.use_loss=true", "gram.it_load_ema_teacher=0",
+                                                                      "gram.update_frequency=100", "crops.gram_teacher_crops_size=224"])))
+    assert e.gram_use_loss and not e.gram_ema_teacher and e.gram_it_load_ema_teacher == 0 and e.gram_update_frequency == 100
+    assert not config_from_reference_cfg(setup_config(DinoV3SetupArgs())).gram_use_loss
+    with pytest.raises(ValueError):              # no checkpoint and no load iteration (ssl_meta_arch.py:215-218)
+        config_from_reference_cfg(setup_config(DinoV3SetupArgs(opts=["gram.use_loss=true"])))
+    for bad in (["gram.img_level=true"], ["crops.gram_teacher_crops_size=448"], ["gram.ckpt=/x"]):
+        with pytest.raises(NotImplementedError):
+            config_from_reference_cfg(setup_config(DinoV3SetupArgs(opts=["gram.use_loss=true", "gram.ema_teacher=true"] + bad)))

@@ -369,3 +369,76 @@ def test_activation_remat_equals_stashing():
     num = sum(float(((ga[k] - gb[k]) ** 2).sum()) for k in ga)
     den = sum(float((ga[k] ** 2).sum()) for k in ga)
     assert (num / den) ** 0.5 < 5e-3
+
+
+# --------------------------------------------------------------------------------------------------- Gram anchoring (8f.2)
+def _gram_pair(mode, only_gram):
+    """Engine step with the Gram term vs oracle.step.ssl_forward(gram=...) under autograd."""
+    from dinov3_jax.engine import Engine, from_oracle_cfg
+    from oracle import tiny_cfg
+    from oracle.batch import synthetic_batch
+    from oracle.model import init_params
+    from oracle.step import ssl_forward
+    kw = dict(dino_loss_weight=0.0, ibot_loss_weight=0.0, koleo_loss_weight=0.0) if only_gram else {}
+    cfg = tiny_cfg(layerscale=0.5, **kw)
+    B, W = 3, 25.0
+    P = init_params(cfg, 6, perturb=0.05)
+    batch = synthetic_batch(cfg, B, 6)
+    remove_neg = mode == "frozen_remove_neg"
+    gram = dict(weight=W, ema_teacher=mode in ("ema",), normalized=True, img_level=False, remove_neg=remove_neg,
+                remove_only_teacher_neg=False)
+    ecfg = dataclasses.replace(from_oracle_cfg(cfg), gram_use_loss=True, gram_loss_weight=W, gram_ema_teacher=mode == "ema",
+                               gram_remove_neg=remove_neg, gram_it_load_ema_teacher=0)
+    eng = Engine(ecfg, B, max_masked=max(int(batch["mask_indices_list"].shape[0]), 1))
+    eng.params.load_reference_tree(P)
+    full = dict(P)
+    if mode == "snapshot":               # gram teacher := EMA teacher, taken inside the step by the schedule
+        for k, v in P.items():
+            if k.startswith("teacher_backbone/"):
+                full["gram_backbone/" + k[len("teacher_backbone/"):]] = v
+    elif mode != "ema":                  # a different frozen network, loaded from a checkpoint tree
+        P2 = init_params(cfg, 7, perturb=0.05)
+        tree = {k[len("teacher_backbone/"):]: v for k, v in P2.items() if k.startswith("teacher_backbone/")}
+        eng.gram_teacher_load(tree)
+        full.update({"gram_backbone/" + k: v for k, v in tree.items()})
+    student = {k: v.detach().clone().requires_grad_(True) for k, v in P.items() if k.startswith("student_")}
+    full.update(student)
+    loss, m = ssl_forward(full, batch, HYPER["teacher_temp"], cfg, gram=gram)
+    keys = list(student)
+    gl = torch.autograd.grad(loss, [student[k] for k in keys], allow_unused=True)
+    grads = {k: (g if g is not None else torch.zeros_like(student[k])) for k, g in zip(keys, gl)}
+    eng.train_step(batch, iteration=0, **HYPER) if mode == "snapshot" else (eng.set_batch(batch), eng.forward_backward(HYPER["teacher_temp"]))
+    met = eng.read_metrics()
+    grads_e = None
+    if mode != "snapshot":
+        grads_e = {k: v.cpu() for k, v in eng.params.export_reference_tree("grad").items()}
+    return met, float(loss), m, grads, grads_e
+
+
+@pytest.mark.parametrize("mode", ["ema", "frozen", "frozen_remove_neg", "snapshot"])
+def test_step_with_gram_anchoring(mode):
+    """SURVEY 8f.2 on the GPU path: Gram-anchoring term (loss/gram_loss.py:13-50 at batch level; train/ssl_meta_arch.py:
+    527-541) with the EMA teacher, a frozen gram teacher loaded from a tree, negative removal, and the scheduled
+    snapshot of the EMA teacher (gram.it_load_ema_teacher)."""
+    met, loss, m, grads, grads_e = _gram_pair(mode, only_gram=False)
+    assert abs(met["gram_loss"] - float(m["gram_loss"])) < 2e-2 * float(m["gram_loss"]), (met["gram_loss"], float(m["gram_loss"]))
+    assert met["gram_loss_weight"] == 25.0
+    assert abs(met["total_loss"] - loss) < 2e-3 * abs(loss)
+    if grads_e is not None:
+        num = sum(((grads_e[k].reshape(g.shape) - g) ** 2).sum() for k, g in grads.items())
+        den = sum((g ** 2).sum() for g in grads.values())
+        assert float(torch.sqrt(num / den)) < 3e-2
+
+
+def test_gram_term_gradient_alone():
+    """Only the Gram term carries weight: every backbone gradient is the Gram backward (similarity GEMMs, d3_gram_diff,
+    G Xs GEMM, row-normalisation backward, scatter into the final-norm gradient) and nothing else."""
+    met, loss, m, grads, grads_e = _gram_pair("frozen", only_gram=True)
+    assert abs(met["total_loss"] - loss) < 2e-2 * abs(loss)
+    bb = {k: g for k, g in grads.items() if k.startswith("student_backbone/") and float(g.norm()) > 0}
+    num = sum(((grads_e[k].reshape(g.shape) - g) ** 2).sum() for k, g in bb.items())
+    den = sum((g ** 2).sum() for g in bb.values())
+    assert float(den) > 0 and float(torch.sqrt(num / den)) < 4e-2
+    for k, g in grads.items():
+        if not k.startswith("student_backbone/"):
+            assert float(grads_e[k].abs().max()) == 0.0, k        # no gradient reaches the heads

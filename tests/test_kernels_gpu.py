@@ -492,3 +492,62 @@ def test_allreduce_peers_matches_rank_ordered_reduction(n, world, op):
         for t in ins[1:]:
             ref = ref + t if op == "sum" else torch.maximum(ref, t)
         assert torch.equal(out, ref)
+
+
+# --------------------------------------------------------------------------------------------------- Gram loss (8f.2)
+def _gram_gpu(fs, ft, mode, weight=1.0, n_valid=None):
+    """Loss and d(weight * loss)/d(fs) of loss/gram_loss.py through the library: l2norm -> two similarity GEMMs ->
+    d3_gram_diff -> backward GEMM -> l2norm backward.  fs, ft: fp32 [n, D] on the GPU (n % 8 == 0, D % 8 == 0)."""
+    from dinov3_jax import ops
+    n, D = fs.shape
+    nv = n if n_valid is None else n_valid
+    bf, f32 = torch.bfloat16, torch.float32
+    xs, xt = torch.empty(n, D, dtype=bf, device="cuda"), torch.empty(n, D, dtype=bf, device="cuda")
+    ns, nt = torch.empty(n, device="cuda"), torch.empty(n, device="cuda")
+    ops.l2norm_fwd(fs, xs, ns, 1e-12)
+    ops.l2norm_fwd(ft, xt, nt, 1e-12)
+    Ss, St = torch.empty(n, n, device="cuda"), torch.empty(n, n, device="cuda")
+    ops.gemm(xt, xt, St)
+    ops.gemm(xs, xs, Ss)
+    G = torch.empty(n, n, dtype=bf, device="cuda")
+    loss = torch.zeros(1, device="cuda")
+    inv = 1.0 / (nv * nv)
+    ops.gram_diff(Ss, St, G, mode, inv, loss)
+    dX = torch.empty(n, D, dtype=bf, device="cuda")
+    ops.gemm(G, xs, dX, b_mn=True, alpha=4.0 * weight * inv)
+    dF = torch.empty(n, D, dtype=bf, device="cuda")
+    ops.l2norm_bwd(dX, fs, ns, dF)
+    return float(loss.item()), dF.float()
+
+
+@pytest.mark.parametrize("remove_neg,only_teacher", [(True, False), (False, True), (False, False)])
+def test_gram_loss_forward_backward_match_oracle(remove_neg, only_teacher):
+    """the Gram-anchoring loss over a batch of patch tokens (img_level false) and its gradient w.r.t. the
+    student features, against oracle.losses.gram_loss (pinned to the reference's GramLoss) under autograd."""
+    from dinov3_jax import ops
+    from oracle.losses import gram_loss
+    n, D = 384, 128
+    g = torch.Generator().manual_seed(5)
+    base = torch.randn(n, D, generator=g)
+    fs = (base + 0.5 * torch.randn(n, D, generator=g)).requires_grad_(True)
+    ft = base + 0.5 * torch.randn(n, D, generator=g)
+    ref = gram_loss(fs[None].double(), ft[None].double(), img_level=False, remove_neg=remove_neg, remove_only_teacher_neg=only_teacher)
+    (gref,) = torch.autograd.grad(ref, fs)
+    loss, dF = _gram_gpu(fs.detach().cuda(), ft.cuda(), ops.GRAM_MODES[(remove_neg, only_teacher)])
+    ref_v = float(ref.detach())
+    assert abs(loss - ref_v) < 2e-2 * ref_v                      # bf16 operands of the similarity GEMMs
+    err = float((dF.cpu() - gref.float()).norm() / gref.float().norm())
+    assert err < 3e-2, err
+
+
+def test_gram_loss_reference_golden_value():
+    """The batch-level value the reference's own GramLoss produced for the committed fixture (tests/golden/make_golden.py:
+    27 tokens x 16 channels, zero-padded here to the kernels' 8-element granularity; zero rows add nothing to the sum)."""
+    import numpy as np
+    import os
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.npz"))
+    s, t = torch.from_numpy(G["gram_s"]).float().reshape(-1, 16), torch.from_numpy(G["gram_t"]).float().reshape(-1, 16)
+    n = s.shape[0]
+    pad = lambda x: torch.nn.functional.pad(x, (0, 64 - 16, 0, 32 - n)).contiguous().cuda()
+    loss, _ = _gram_gpu(pad(s), pad(t), 1, n_valid=n)
+    assert abs(loss - float(G["gram_batch"])) < 2e-2 * float(G["gram_batch"])

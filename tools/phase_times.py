@@ -19,7 +19,7 @@ for _ in range(3): eng.train_step(None, **hyper)
 marks = []
 def mark(name):
     e = torch.cuda.Event(enable_timing=True); e.record(); marks.append((name, e))
-orig = {k: getattr(eng, k) for k in ("_backbone_fwd", "_head_fwd", "_sinkhorn", "_head_bwd", "_block_bwd", "optimizer_step")}
+orig = {k: getattr(eng, k) for k in ("_backbone_fwd", "_head_fwd", "_sinkhorn_pair", "_head_bwd", "_block_bwd", "optimizer_step")}
 def wrap(name, label_fn):
     f = orig[name]
     def g(*a, **k):
@@ -27,7 +27,7 @@ def wrap(name, label_fn):
     setattr(eng, name, g)
 wrap("_backbone_fwd", lambda st, imgs, masks, teacher: "backbone fwd teacher" if teacher else "backbone fwd student")
 wrap("_head_fwd", lambda hb, module, R, teacher, stash: f"heads fwd {'teacher' if teacher else 'student'}")
-wrap("_sinkhorn", lambda *a, **k: "sinkhorn")
+wrap("_sinkhorn_pair", lambda *a, **k: "sinkhorn")
 wrap("_head_bwd", lambda *a, **k: "heads bwd (+CE, before)")
 wrap("_block_bwd", lambda i, *a: "blocks bwd")
 wrap("optimizer_step", lambda *a, **k: "optimizer (sumsq+adamw+ema)")

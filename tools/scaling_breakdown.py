@@ -57,7 +57,7 @@ step_ms = e0.elapsed_time(e1) / 6
 marks = []
 def mark(name):
     e = torch.cuda.Event(enable_timing=True); e.record(); marks.append((name, e))
-names = ("_backbone_fwd", "_head_fwd", "_sinkhorn", "_head_bwd", "_block_bwd", "optimizer_step")
+names = ("_backbone_fwd", "_head_fwd", "_sinkhorn_pair", "_head_bwd", "_block_bwd", "optimizer_step")
 orig = {k: getattr(eng, k) for k in names}
 def wrap(name, label_fn):
     f = orig[name]
@@ -66,7 +66,7 @@ def wrap(name, label_fn):
     setattr(eng, name, g)
 wrap("_backbone_fwd", lambda st, imgs, masks, teacher: "backbone fwd teacher" if teacher else "backbone fwd student")
 wrap("_head_fwd", lambda hb, module, R, teacher, stash: f"heads fwd {'teacher' if teacher else 'student'}")
-wrap("_sinkhorn", lambda *a, **k: "sinkhorn")
+wrap("_sinkhorn_pair", lambda *a, **k: "sinkhorn")
 wrap("_head_bwd", lambda *a, **k: "heads bwd (+CE, KoLeo before)")
 wrap("_block_bwd", lambda i, *a: "blocks bwd")
 wrap("optimizer_step", lambda *a, **k: "grad fence + sumsq + adamw/ema")
