@@ -957,6 +957,68 @@ __global__ void scatter_add_peers_kernel(const float* __restrict__ src, long n4,
   }
 }
 
+// Bicubic resize of token feature maps [n, Hs, Ws, D] -> [n, Hd, Wd, D] (fp32): the gram teacher's patch tokens, computed
+// at crops.gram_teacher_crops_size, brought to the student's patch grid (gram.global_teacher_resize_method: bicubic,
+// gram.global_teacher_resize_antialias; upstream DINOv3 get_gram_teacher_output -> F.interpolate).  Definitions follow
+// torch: antialias = 0 is upsample_bicubic2d (align_corners false: 4 taps, Keys a = -0.75, indices clamped to the edge),
+// antialias = 1 is _upsample_bicubic2d_aa (a = -0.5, support 2 * max(scale, 1), normalised taps clipped to the map).
+__device__ __forceinline__ float cubic_keys(float x, float a) {
+  x = fabsf(x);
+  if (x <= 1.f) return ((a + 2.f) * x - (a + 3.f)) * x * x + 1.f;
+  if (x < 2.f) return ((a * x - 5.f * a) * x + 8.f * a) * x - 4.f * a;
+  return 0.f;
+}
+constexpr int RS_TAPS = 16;
+__device__ __forceinline__ int resize_taps(int o, int in, int out, int aa, int* idx, float* w) {
+  const float scale = (float)in / (float)out;
+  if (!aa) {
+    const float real = scale * (o + 0.5f) - 0.5f;
+    const float fl = floorf(real);
+    const float t = real - fl;
+    const int i0 = (int)fl;
+    for (int k = 0; k < 4; ++k) {
+      idx[k] = min(max(i0 - 1 + k, 0), in - 1);
+      w[k] = cubic_keys(t + 1.f - k, -0.75f);
+    }
+    return 4;
+  }
+  const float sup = 2.f * fmaxf(scale, 1.f), inv = 1.f / fmaxf(scale, 1.f);
+  const float c = scale * (o + 0.5f);
+  const int lo = max((int)(c - sup + 0.5f), 0), hi = min((int)(c + sup + 0.5f), in);
+  int n = 0;
+  float tot = 0.f;
+  for (int x = lo; x < hi && n < RS_TAPS; ++x, ++n) {
+    idx[n] = x;
+    w[n] = cubic_keys((x - c + 0.5f) * inv, -0.5f);
+    tot += w[n];
+  }
+  for (int k = 0; k < n; ++k) w[k] /= tot;
+  return n;
+}
+__global__ void resize_tokens_kernel(const float* __restrict__ src, float* __restrict__ dst, int Hs, int Ws, int Hd, int Wd,
+                                     int D, int aa) {
+  const int ox = blockIdx.x % Wd, oy = (blockIdx.x / Wd) % Hd, n = blockIdx.x / (Wd * Hd);
+  int ix[RS_TAPS], iy[RS_TAPS];
+  float wx[RS_TAPS], wy[RS_TAPS];
+  const int nx = resize_taps(ox, Ws, Wd, aa, ix, wx), ny = resize_taps(oy, Hs, Hd, aa, iy, wy);
+  const float* base = src + (size_t)n * Hs * Ws * D;
+  float* out = dst + (((size_t)n * Hd + oy) * Wd + ox) * D;
+  for (int d = threadIdx.x * 4; d < D; d += blockDim.x * 4) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int a = 0; a < ny; ++a) {
+      float4 row = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int b = 0; b < nx; ++b) {
+        const float4 v = *reinterpret_cast<const float4*>(base + ((size_t)iy[a] * Ws + ix[b]) * D + d);
+        row.x = fmaf(wx[b], v.x, row.x); row.y = fmaf(wx[b], v.y, row.y);
+        row.z = fmaf(wx[b], v.z, row.z); row.w = fmaf(wx[b], v.w, row.w);
+      }
+      acc.x = fmaf(wy[a], row.x, acc.x); acc.y = fmaf(wy[a], row.y, acc.y);
+      acc.z = fmaf(wy[a], row.z, acc.z); acc.w = fmaf(wy[a], row.w, acc.w);
+    }
+    *reinterpret_cast<float4*>(out + d) = acc;
+  }
+}
+
 // Small all-reduce over NVLink peer mappings (jax.lax.psum / pmax of the loss heads' K-vectors and scalars:
 // loss/dino_clstoken_loss.py:53, loss/ibot_patch_loss.py:99, train/train.py:516-541): every rank reads all ranks'
 // staged inputs and reduces them in rank order, so all ranks obtain bit-identical results.  One pull of world x n
@@ -1212,6 +1274,19 @@ int d3_scatter_add_peers(const float* src, long long n, float* const* peers /*ho
   const int blocks = (int)min((n4 + 255) / 256, (long)sm_count() * 4);
   scatter_add_peers_kernel<<<blocks, 256, 0, STREAM(stream)>>>(src, n4, pp, (unsigned long long)off, (unsigned)shard, alpha,
                                                               scatter_mode());
+  D3_CHECK_LAUNCH();
+  return D3_OK;
+}
+
+int d3_resize_tokens_bicubic(const float* src, float* dst, int n, int Hs, int Ws, int Hd, int Wd, int D, int antialias,
+                             void* stream) {
+  if (n <= 0) return D3_OK;
+  if (Hs <= 0 || Ws <= 0 || Hd <= 0 || Wd <= 0 || D <= 0 || (D % 4) || (((uintptr_t)src | (uintptr_t)dst) % 16))
+    return set_error(D3_ERR_ARG, "d3_resize_tokens_bicubic: D % 4 == 0, 16-byte aligned maps");
+  if (antialias && (2.f * 2.f * fmaxf((float)Hs / Hd, (float)Ws / Wd) + 1.f > (float)RS_TAPS))
+    return set_error(D3_ERR_ARG, "d3_resize_tokens_bicubic: antialiased down-scaling factor too large (<= 3.75)");
+  const int threads = min(256, max(32, ((D / 4 + 31) / 32) * 32));
+  resize_tokens_kernel<<<n * Hd * Wd, threads, 0, STREAM(stream)>>>(src, dst, Hs, Ws, Hd, Wd, D, antialias ? 1 : 0);
   D3_CHECK_LAUNCH();
   return D3_OK;
 }

@@ -65,6 +65,8 @@ class EngineConfig:
     gram_update_frequency: int = 50000
     gram_it_first_update: int = 0
     gram_max_updates: int | None = None
+    gram_teacher_size: int | None = None      # crops.gram_teacher_crops_size: the gram teacher's crop resolution (None: global_size)
+    gram_resize_antialias: bool = False       # gram.global_teacher_resize_antialias (method: bicubic)
 
     @property
     def head_dim(self) -> int:
@@ -138,9 +140,17 @@ def config_from_reference_cfg(cfg) -> EngineConfig:
             raise NotImplementedError("gram.ckpt: load the gram teacher with dinov3_jax.checkpointer and Engine.gram_teacher_load "
                                       "instead of a path in the config")
         gsz = cfg.crops.get("gram_teacher_crops_size", None)
-        if gsz is not None and int(gsz) != int(cfg.crops.global_crops_size):
-            raise NotImplementedError("crops.gram_teacher_crops_size != global_crops_size (hi-res gram teacher + feature "
-                                      "resize) is not on the B200 path")
+        if gsz is not None and not isinstance(gsz, int):
+            raise NotImplementedError("multi-resolution crops.gram_teacher_crops_size lists (train/train.py:718-769): the engine "
+                                      "is built for one resolution triple")
+        if gsz is not None and gg.get("ema_teacher", False):
+            raise ValueError("crops.gram_teacher_crops_size should be None when gram.ema_teacher=True (ssl_meta_arch.py:243-244)")
+        if gsz is not None and (int(gsz) // cfg.student.patch_size) ** 2 + 1 + int(cfg.student.n_storage_tokens) > 448:
+            raise NotImplementedError("crops.gram_teacher_crops_size: the single-pass attention kernel holds at most 448 tokens "
+                                      "per crop (gram teacher crops up to 320^2 at patch 16)")
+        if gsz is not None and int(gsz) != int(cfg.crops.global_crops_size) and \
+                str(gg.get("global_teacher_resize_method", "bicubic")) != "bicubic":
+            raise NotImplementedError("gram.global_teacher_resize_method must be bicubic")
         if gg.get("loss_weight_schedule", None):
             raise NotImplementedError("gram.loss_weight_schedule: pass gram_loss_weight per step to Engine.train_step instead")
         if bool(gg.get("remove_neg", False)) and bool(gg.get("remove_only_teacher_neg", False)):
@@ -152,7 +162,9 @@ def config_from_reference_cfg(cfg) -> EngineConfig:
                        gram_remove_only_teacher_neg=bool(gg.remove_only_teacher_neg), gram_tokens_used=str(gg.tokens_used),
                        gram_it_load_ema_teacher=int(gg.it_load_ema_teacher), gram_rep_update=bool(gg.rep_update),
                        gram_update_frequency=int(gg.update_frequency), gram_it_first_update=int(gg.it_first_update),
-                       gram_max_updates=gg.get("max_updates", None))
+                       gram_max_updates=gg.get("max_updates", None),
+                       gram_teacher_size=None if gsz is None else int(gsz),
+                       gram_resize_antialias=bool(gg.get("global_teacher_resize_antialias", False)))
     # options this engine does not implement must not be silently ignored (the run would differ from the request)
     g = lambda node, key, default: node.get(key, default) if hasattr(node, "get") else getattr(node, key, default)
     if "schedules" in cfg and cfg["schedules"]:

@@ -272,12 +272,24 @@ class Engine:
         self.gram_G = e(n, n, dt=bf16)
         self.gram_dX, self.gram_dF = e(n, D, dt=bf16), e(n, D, dt=bf16)
         self.gram_mode = ops.GRAM_MODES[(bool(cfg.gram_remove_neg), bool(cfg.gram_remove_only_teacher_neg))]
+        self.gram_stream, self.gram_img = None, None
         if cfg.gram_ema_teacher:
             self.gram_active = True
         else:
             bb = self.params.mods["backbone"]
             bb.g_bf16 = torch.zeros_like(bb.t_bf16)                          # frozen full copies on every rank
             bb.g_vecs = torch.zeros(bb.n - bb.n_mat, dtype=f32, device=dev)
+            gs = cfg.gram_teacher_size
+            if gs is not None and gs != cfg.global_size:
+                # the gram teacher sees its own (larger) crops: a third token stream at that resolution; its patch tokens are
+                # resized to the student's grid before the similarity matrices (upstream get_gram_teacher_output)
+                self.g_sets = [CropSet(cfg, sg.n, gs, 0, dev)]
+                assert self.g_sets[0].N <= 448, "gram teacher crops: at most 448 tokens per crop (attention forward kernel)"
+                self.gram_stream = Stream(cfg, self.g_sets, dev, stash=False)
+                gp = self.g_sets[0]
+                self.gram_rows_hi = (torch.arange(gp.n, dtype=torch.int32)[:, None] * gp.N + cfg.prefix
+                                     + torch.arange(gp.P, dtype=torch.int32)[None, :]).reshape(-1).to(dev)
+                self.gram_hi = e(gp.n * gp.P, D, dt=f32)
 
     def gram_teacher_load_from_ema(self):
         """The gram teacher becomes a frozen copy of the current EMA teacher.  The copy is taken inside the next step,
@@ -336,13 +348,28 @@ class Engine:
                 self.gram_active = True
             if not self.gram_active:
                 return
-            # the same kernels and buffers as the EMA teacher's pass, reading the frozen weights
+            # the same kernels (and, at the global-crop resolution, the same buffers) as the EMA teacher's pass, reading
+            # the frozen weights
+            hi = self.gram_stream is not None
+            if hi and self.gram_img is None:
+                raise ValueError("no gram teacher crops in the data, have you set cfg.crops.gram_teacher_crops_size? "
+                                 "(train/ssl_meta_arch.py:310-313)")
             keep = (bb.t_bf16, bb.t_vecs)
             bb.t_bf16, bb.t_vecs = bb.g_bf16, bb.g_vecs
             try:
-                self._backbone_fwd(T_, [self.g_img], [None], teacher=True)
+                self._backbone_fwd(self.gram_stream if hi else T_, [self.gram_img if hi else self.g_img], [None], teacher=True)
             finally:
                 bb.t_bf16, bb.t_vecs = keep
+            if hi:
+                gp, sg, D = self.g_sets[0], self.s_sets[0], cfg.embed_dim
+                ops.gather_rows(self.gram_stream.Xn, self.gram_rows_hi, gp.n * gp.P, D, dst_f32=self.gram_hi)
+                ops.resize_tokens_bicubic(self.gram_hi, self.gram_ft, gp.n, gp.Hp, gp.Hp, sg.Hp, sg.Hp, D,
+                                          cfg.gram_resize_antialias)
+                if cfg.gram_normalized:
+                    ops.l2norm_fwd(self.gram_ft, self.gram_xt, self.gram_nrm_t, 1e-12)
+                else:
+                    ops.cast_f32_bf16(self.gram_ft.reshape(-1), self.gram_xt.reshape(-1))
+                return
         self._gram_features(T_.Xn, self.gram_ft, self.gram_xt, self.gram_nrm_t)
 
     def _gram_loss_bwd(self, dXn):
@@ -703,6 +730,8 @@ class Engine:
         to = lambda t, dt=None: t.to(device=dev, dtype=dt, non_blocking=True)
         self.g_img = to(batch["collated_global_crops"], bf16).contiguous()
         self.l_img = to(batch["collated_local_crops"], bf16).contiguous()
+        if self.gram_stream is not None and batch.get("collated_gram_teacher_crops", None) is not None:
+            self.gram_img = to(batch["collated_gram_teacher_crops"], bf16).contiguous()
         masks = batch["collated_masks"]
         self.masks_u8.copy_(masks.to(torch.uint8) if masks.dtype != torch.uint8 else masks, non_blocking=True)
         idx = batch["mask_indices_list"]

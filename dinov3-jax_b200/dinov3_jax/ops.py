@@ -160,6 +160,14 @@ def gram_diff(Ss, St, G, mode: int, inv_count: float, loss):
     N.check(N.init().d3_gram_diff(_p(Ss), _p(St), _p(G), Ss.numel(), int(mode), float(inv_count), _p(loss), _s()), "d3_gram_diff")
 
 
+def resize_tokens_bicubic(src, dst, n, Hs, Ws, Hd, Wd, D, antialias: bool):
+    """fp32 token maps [n,Hs,Ws,D] -> [n,Hd,Wd,D] (d3_resize_tokens_bicubic; torch bicubic / antialiased-bicubic arithmetic)."""
+    assert src.dtype == f32 and dst.dtype == f32 and src.is_contiguous() and dst.is_contiguous()
+    assert src.numel() == n * Hs * Ws * D and dst.numel() == n * Hd * Wd * D
+    N.check(N.init().d3_resize_tokens_bicubic(_p(src), _p(dst), n, Hs, Ws, Hd, Wd, D, int(bool(antialias)), _s()),
+            "d3_resize_tokens_bicubic")
+
+
 def allreduce_peers(peers, out, n, op="sum"):
     """out[:n] = reduce over ranks (rank order) of the float buffers at the peer-mapped addresses `peers` (d3_allreduce_peers)."""
     assert out.dtype == f32 and out.is_contiguous() and out.numel() >= n

@@ -222,6 +222,12 @@ int d3_ce_fwd_bwd(const float* S /*[Rs,K]*/, float student_temp, const float* Lt
 int d3_gram_diff(const float* Ss, const float* St, void* G_bf16, long long n_elems, int mode, float inv_count, float* loss,
                  void* stream);
 
+/* Gram teacher features at crops.gram_teacher_crops_size -> the student's patch grid (gram.global_teacher_resize_method:
+ * bicubic, gram.global_teacher_resize_antialias; configs/ssl_default_config.yaml:71-72): fp32 token maps
+ * [n, Hs, Ws, D] -> [n, Hd, Wd, D], torch's upsample_bicubic2d (antialias 0) / _upsample_bicubic2d_aa (1) arithmetic. */
+int d3_resize_tokens_bicubic(const float* src, float* dst, int n, int Hs, int Ws, int Hd, int Wd, int D, int antialias,
+                             void* stream);
+
 /* ---- KoLeo (loss/koleo_loss.py:16-35), forward + backward: metric += w_metric * loss; dx += w_grad * dloss/dx ------ */
 int d3_koleo_fwd_bwd(const float* x /*[B,D]*/, float* xn_scratch /*[B,D]*/, float* nrm_scratch /*[B]*/,
                      int* nn_scratch /*[B]*/, float* coef_scratch /*[B]*/, float* metric, float* dx /*[B,D] +=*/, int B,

@@ -84,7 +84,18 @@ def ssl_forward(params: dict, batch: dict, teacher_temp: float, cfg: ModelCfg, e
             if gram.get("ema_teacher", False):
                 gt_patch = t_patch
             else:
-                gt_patch = backbone_forward(sub(params, "gram_backbone"), [g], [None], cfg, emu)[0]["x_norm_patchtokens"]
+                # the gram teacher sees its own crops when the loader provides them (crops.gram_teacher_crops_size,
+                # data/augmentations.py:197-205); features at another resolution are resized to the student's patch grid
+                # (upstream get_gram_teacher_output: F.interpolate, gram.global_teacher_resize_method / _antialias)
+                gc = batch.get("collated_gram_teacher_crops", None)
+                gin = g if gc is None else gc.to(dtype)
+                gt_patch = backbone_forward(sub(params, "gram_backbone"), [gin], [None], cfg, emu)[0]["x_norm_patchtokens"]
+                if gt_patch.shape[1] != g_patch.shape[1]:
+                    n_, Pg, Dm = gt_patch.shape
+                    Hg, Hs = int(round(Pg ** 0.5)), int(round(g_patch.shape[1] ** 0.5))
+                    gt_patch = torch.nn.functional.interpolate(
+                        gt_patch.reshape(n_, Hg, Hg, Dm).permute(0, 3, 1, 2), size=(Hs, Hs), mode="bicubic", align_corners=False,
+                        antialias=bool(gram.get("resize_antialias", False))).permute(0, 2, 3, 1).reshape(n_, Hs * Hs, Dm)
         L_gram = gram_loss(g_patch, gt_patch, apply_norm=gram.get("normalized", True), img_level=gram.get("img_level", False),
                            remove_neg=gram.get("remove_neg", False),
                            remove_only_teacher_neg=gram.get("remove_only_teacher_neg", False))

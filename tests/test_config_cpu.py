@@ -80,6 +80,16 @@ def test_gram_keys_map_onto_the_engine_config():
     assert not config_from_reference_cfg(setup_config(DinoV3SetupArgs())).gram_use_loss
     with pytest.raises(ValueError):              # no checkpoint and no load iteration (ssl_meta_arch.py:215-218)
         config_from_reference_cfg(setup_config(DinoV3SetupArgs(opts=["gram.use_loss=true"])))
-    for bad in (["gram.img_level=true"], ["crops.gram_teacher_crops_size=448"], ["gram.ckpt=/x"]):
+    for bad in (["gram.img_level=true"], ["gram.tokens_used=masked"], ["gram.ckpt=/x"]):
         with pytest.raises(NotImplementedError):
             config_from_reference_cfg(setup_config(DinoV3SetupArgs(opts=["gram.use_loss=true", "gram.ema_teacher=true"] + bad)))
+    # a gram teacher at its own resolution: up to 448 tokens per crop (320^2 at patch 16), bicubic resize of its features
+    frozen = ["gram.use_loss=true", "gram.it_load_ema_teacher=0"]
+    e = config_from_reference_cfg(setup_config(DinoV3SetupArgs(opts=frozen + ["crops.gram_teacher_crops_size=320",
+                                                                             "gram.global_teacher_resize_antialias=true"])))
+    assert e.gram_teacher_size == 320 and e.gram_resize_antialias
+    with pytest.raises(NotImplementedError):
+        config_from_reference_cfg(setup_config(DinoV3SetupArgs(opts=frozen + ["crops.gram_teacher_crops_size=448"])))
+    with pytest.raises(ValueError):              # ssl_meta_arch.py:243-244
+        config_from_reference_cfg(setup_config(DinoV3SetupArgs(opts=["gram.use_loss=true", "gram.ema_teacher=true",
+                                                                      "crops.gram_teacher_crops_size=224"])))

@@ -415,6 +415,49 @@ def _gram_pair(mode, only_gram):
     return met, float(loss), m, grads, grads_e
 
 
+def test_gram_teacher_at_its_own_resolution():
+    """crops.gram_teacher_crops_size != global_crops_size: the frozen gram teacher runs on `collated_gram_teacher_crops`
+    (data/collate.py:33-38,81-82) through a third token stream and its patch tokens are resized (bicubic) to the student's
+    grid before the Gram matrices; loss and gradients against the oracle (F.interpolate)."""
+    from dinov3_jax.engine import Engine, from_oracle_cfg
+    from oracle import tiny_cfg
+    from oracle.batch import synthetic_batch
+    from oracle.model import init_params
+    from oracle.step import ssl_forward
+    cfg = tiny_cfg(layerscale=0.5)
+    B, W, GS = 2, 25.0, 96                       # student global crops 64^2 (4x4 patches), gram teacher 96^2 (6x6)
+    P = init_params(cfg, 8, perturb=0.05)
+    batch = synthetic_batch(cfg, B, 8)
+    g = torch.Generator().manual_seed(3)
+    batch["collated_gram_teacher_crops"] = torch.randn(cfg.n_global * B, GS, GS, 3, generator=g).to(torch.bfloat16)
+    for aa in (False, True):
+        ecfg = dataclasses.replace(from_oracle_cfg(cfg), gram_use_loss=True, gram_loss_weight=W, gram_it_load_ema_teacher=0,
+                                   gram_teacher_size=GS, gram_resize_antialias=aa)
+        eng = Engine(ecfg, B, max_masked=max(int(batch["mask_indices_list"].shape[0]), 1))
+        eng.params.load_reference_tree(P)
+        P2 = init_params(cfg, 9, perturb=0.05)
+        tree = {k[len("teacher_backbone/"):]: v for k, v in P2.items() if k.startswith("teacher_backbone/")}
+        eng.gram_teacher_load(tree)
+        full = dict(P)
+        full.update({"gram_backbone/" + k: v for k, v in tree.items()})
+        student = {k: v.detach().clone().requires_grad_(True) for k, v in P.items() if k.startswith("student_")}
+        full.update(student)
+        loss, m = ssl_forward(full, batch, HYPER["teacher_temp"], cfg,
+                              gram=dict(weight=W, ema_teacher=False, remove_neg=False, remove_only_teacher_neg=False,
+                                        resize_antialias=aa))
+        keys = list(student)
+        gl = torch.autograd.grad(loss, [student[k] for k in keys], allow_unused=True)
+        eng.set_batch(batch)
+        eng.forward_backward(HYPER["teacher_temp"])
+        met = eng.read_metrics()
+        assert abs(met["gram_loss"] - float(m["gram_loss"])) < 2e-2 * float(m["gram_loss"]), (aa, met["gram_loss"], float(m["gram_loss"]))
+        assert abs(met["total_loss"] - float(loss)) < 2e-3 * abs(float(loss))
+        ge = {k: v.cpu() for k, v in eng.params.export_reference_tree("grad").items()}
+        num = sum(((ge[k].reshape(g_.shape) - g_) ** 2).sum() for k, g_ in zip(keys, gl) if g_ is not None)
+        den = sum((g_ ** 2).sum() for g_ in gl if g_ is not None)
+        assert float(torch.sqrt(num / den)) < 3e-2
+
+
 @pytest.mark.parametrize("mode", ["ema", "frozen", "frozen_remove_neg", "snapshot"])
 def test_step_with_gram_anchoring(mode):
     """SURVEY 8f.2 on the GPU path: Gram-anchoring term (loss/gram_loss.py:13-50 at batch level; train/ssl_meta_arch.py:

@@ -551,3 +551,18 @@ def test_gram_loss_reference_golden_value():
     pad = lambda x: torch.nn.functional.pad(x, (0, 64 - 16, 0, 32 - n)).contiguous().cuda()
     loss, _ = _gram_gpu(pad(s), pad(t), 1, n_valid=n)
     assert abs(loss - float(G["gram_batch"])) < 2e-2 * float(G["gram_batch"])
+
+
+@pytest.mark.parametrize("Hs,Hd,aa", [(20, 14, False), (20, 14, True), (6, 4, False), (4, 7, False), (32, 14, True), (5, 5, False)])
+def test_resize_tokens_bicubic_matches_torch_interpolate(Hs, Hd, aa):
+    """d3_resize_tokens_bicubic (gram teacher features -> student patch grid) against torch.nn.functional.interpolate,
+    mode bicubic, align_corners False, with and without antialias."""
+    from dinov3_jax import ops
+    n, D = 3, 72
+    g = torch.Generator().manual_seed(Hs * 100 + Hd)
+    x = torch.randn(n, Hs, Hs + 1, D, generator=g)                       # non-square source: Ws = Hs + 1
+    ref = torch.nn.functional.interpolate(x.permute(0, 3, 1, 2), size=(Hd, Hd + 2), mode="bicubic", align_corners=False,
+                                          antialias=aa).permute(0, 2, 3, 1).contiguous()
+    out = torch.empty(n, Hd, Hd + 2, D, device="cuda")
+    ops.resize_tokens_bicubic(x.cuda().contiguous(), out, n, Hs, Hs + 1, Hd, Hd + 2, D, aa)
+    assert float((out.cpu() - ref).abs().max()) < 2e-5 * max(1.0, float(ref.abs().max()))
