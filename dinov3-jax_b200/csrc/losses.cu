@@ -452,8 +452,11 @@ __global__ void koleo_bwd_kernel(const float* __restrict__ x, const float* __res
 //   mode 2 (remove_only_teacher_neg): s' = (s < 0 && t < 0) ? 0 : s, t' = max(t, 0), ds'/ds = !(s < 0 && t < 0)
 //   mode 0:                           s' = s, t' = t
 // loss += inv_count * sum (s' - t')^2 ;  G = (s' - t') * ds'/ds  (bf16: the A operand of dX = (4 w / n^2) G Xs).
+// block > 0 (gram.img_level: true, gram_loss.py:24-26): only the diagonal blocks of `block` x `block` tokens (one image each)
+// count; everything else contributes nothing and gets G = 0 (the full similarity GEMM is kept: one launch, 128x the
+// needed FLOPs at 196 tokens per image, still ~1 ms on the tensor cores).
 __global__ void gram_diff_kernel(const float* __restrict__ Ss, const float* __restrict__ St, __nv_bfloat16* __restrict__ G,
-                                 long n4, int mode, float inv_count, float* __restrict__ loss) {
+                                 long n4, int mode, float inv_count, float* __restrict__ loss, int n, int block) {
   __shared__ float sh[32];
   float acc = 0.f;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
@@ -461,9 +464,13 @@ __global__ void gram_diff_kernel(const float* __restrict__ Ss, const float* __re
     const float4 t4 = reinterpret_cast<const float4*>(St)[i];
     const float sv[4] = {s4.x, s4.y, s4.z, s4.w}, tv[4] = {t4.x, t4.y, t4.z, t4.w};
     float g[4];
+    const long e0 = i * 4;
+    const int row_blk = block > 0 ? (int)(e0 / n) / block : 0;
+    const int col0 = block > 0 ? (int)(e0 % n) : 0;               // n % 4 == 0: the four elements share a row
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float s = sv[j], t = tv[j], d = 1.f;
+      if (block > 0 && (col0 + j) / block != row_blk) { g[j] = 0.f; continue; }
       if (mode == 1) { d = s > 0.f ? 1.f : 0.f; s = fmaxf(s, 0.f); t = fmaxf(t, 0.f); }
       else if (mode == 2) { if (s < 0.f && t < 0.f) { s = 0.f; d = 0.f; } t = fmaxf(t, 0.f); }
       const float e = s - t;
@@ -604,14 +611,16 @@ int d3_koleo_fwd_bwd_rows(const float* x, float* xn_scratch, float* nrm_scratch,
   return D3_OK;
 }
 int d3_gram_diff(const float* Ss, const float* St, void* G_bf16, long long n_elems, int mode, float inv_count, float* loss,
-                 void* stream) {
+                 int n, int block, void* stream) {
   if (n_elems <= 0) return D3_OK;
   if (mode < 0 || mode > 2) return set_error(D3_ERR_ARG, "d3_gram_diff: mode 0 | 1 (remove_neg) | 2 (remove_only_teacher_neg)");
   if ((n_elems % 4) || (((uintptr_t)Ss | (uintptr_t)St) % 16) || ((uintptr_t)G_bf16 % 8))
     return set_error(D3_ERR_ARG, "d3_gram_diff: n_elems % 4 == 0 and 16-byte aligned similarity buffers");
   const long n4 = n_elems / 4;
   const int blocks = (int)std::min<long>((n4 + 255) / 256, (long)sm_count() * 8);
-  gram_diff_kernel<<<blocks, 256, 0, STREAM(stream)>>>(Ss, St, (__nv_bfloat16*)G_bf16, n4, mode, inv_count, loss);
+  if (block > 0 && (n <= 0 || (n % 4) || (long long)n * n != n_elems || (n % block)))
+    return set_error(D3_ERR_ARG, "d3_gram_diff: block-diagonal form needs n % 4 == 0, n % block == 0 and n_elems == n * n");
+  gram_diff_kernel<<<blocks, 256, 0, STREAM(stream)>>>(Ss, St, (__nv_bfloat16*)G_bf16, n4, mode, inv_count, loss, n, block);
   D3_CHECK_LAUNCH();
   return D3_OK;
 }

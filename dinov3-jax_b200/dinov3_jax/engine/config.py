@@ -128,11 +128,10 @@ def config_from_reference_cfg(cfg) -> EngineConfig:
     gram_kw = {}
     if cfg.gram.use_loss:
         gg = cfg.gram
-        if gg.get("img_level", False):
-            raise NotImplementedError("gram.img_level=true (per-image Gram matrices) is not on the B200 path; the batch-level "
-                                      "form (the default, img_level: false) is")
-        if str(gg.get("tokens_used", "all")) != "all":
-            raise NotImplementedError("gram.tokens_used masked | unmasked is not on the B200 path (all patch tokens are)")
+        if str(gg.get("tokens_used", "all")) not in ("all", "masked", "unmasked"):
+            raise ValueError("gram.tokens_used must be all | masked | unmasked (ssl_meta_arch.py:221)")
+        if str(gg.get("tokens_used", "all")) != "all" and gg.get("img_level", False):
+            raise ValueError("gram.tokens_used masked | unmasked needs gram.img_level: false (ssl_meta_arch.py:222-223)")
         if gg.get("compute_stats", False):
             import warnings
             warnings.warn("gram.compute_stats: the stats_only/* metrics are not produced by the B200 engine", stacklevel=2)
@@ -158,7 +157,7 @@ def config_from_reference_cfg(cfg) -> EngineConfig:
         if not gg.get("ema_teacher", False) and int(gg.get("it_load_ema_teacher", -1)) < 0:
             raise ValueError("if no gram checkpoint is provided, gram.it_load_ema_teacher must be >= 0 (ssl_meta_arch.py:215-218)")
         gram_kw = dict(gram_use_loss=True, gram_loss_weight=float(gg.loss_weight), gram_ema_teacher=bool(gg.ema_teacher),
-                       gram_normalized=bool(gg.normalized), gram_img_level=False, gram_remove_neg=bool(gg.remove_neg),
+                       gram_normalized=bool(gg.normalized), gram_img_level=bool(gg.get("img_level", False)), gram_remove_neg=bool(gg.remove_neg),
                        gram_remove_only_teacher_neg=bool(gg.remove_only_teacher_neg), gram_tokens_used=str(gg.tokens_used),
                        gram_it_load_ema_teacher=int(gg.it_load_ema_teacher), gram_rep_update=bool(gg.rep_update),
                        gram_update_frequency=int(gg.update_frequency), gram_it_first_update=int(gg.it_first_update),

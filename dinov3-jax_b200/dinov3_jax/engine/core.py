@@ -255,22 +255,26 @@ class Engine:
         self.gram_updates = 0
         if not cfg.gram_use_loss:
             return
-        if cfg.gram_img_level or cfg.gram_tokens_used != "all":
-            raise NotImplementedError("gram.img_level=true / gram.tokens_used != all are not on the B200 path")
+        assert cfg.gram_tokens_used in ("all", "masked", "unmasked")         # train/ssl_meta_arch.py:221
+        if cfg.gram_tokens_used != "all" and cfg.gram_img_level:
+            raise ValueError("gram.tokens_used masked | unmasked needs gram.img_level: false (train/ssl_meta_arch.py:222-223)")
         sg = self.s_sets[0]
         D = cfg.embed_dim
         n = sg.n * sg.P
         rows = (torch.arange(sg.n, dtype=torch.int32)[:, None] * sg.N + cfg.prefix
                 + torch.arange(sg.P, dtype=torch.int32)[None, :]).reshape(-1)
-        self.gram_rows = rows.to(dev)
-        self.gram_n = n
+        self.gram_rows_all = rows.to(dev)                                    # token row of every global-crop patch
+        self.gram_rows = self.gram_rows_all                                  # rows in use: all | masked | unmasked (set_batch)
+        self.gram_n = n                                                      # live row count; buffers hold the maximum
+        self.gram_block = sg.P if cfg.gram_img_level else 0                  # per-image Gram matrices: diagonal blocks
         e = lambda *shape, dt: torch.empty(*shape, dtype=dt, device=dev)
-        self.gram_fs, self.gram_ft = e(n, D, dt=f32), e(n, D, dt=f32)        # gathered final-norm patch tokens
-        self.gram_xs, self.gram_xt = e(n, D, dt=bf16), e(n, D, dt=bf16)      # (normalised) GEMM operands
-        self.gram_nrm_s, self.gram_nrm_t = e(n, dt=f32), e(n, dt=f32)
-        self.gram_Ss, self.gram_St = e(n, n, dt=f32), e(n, n, dt=f32)
-        self.gram_G = e(n, n, dt=bf16)
-        self.gram_dX, self.gram_dF = e(n, D, dt=bf16), e(n, D, dt=bf16)
+        npad = (n + 7) // 8 * 8
+        self.gram_fs, self.gram_ft = e(npad, D, dt=f32), e(npad, D, dt=f32)  # gathered final-norm patch tokens
+        self.gram_xs, self.gram_xt = e(npad, D, dt=bf16), e(npad, D, dt=bf16)  # (normalised) GEMM operands
+        self.gram_nrm_s, self.gram_nrm_t = e(npad, dt=f32), e(npad, dt=f32)
+        self.gram_Ss, self.gram_St = e(npad * npad, dt=f32), e(npad * npad, dt=f32)
+        self.gram_G = e(npad * npad, dt=bf16)
+        self.gram_dX, self.gram_dF = e(npad, D, dt=bf16), e(npad, D, dt=bf16)
         self.gram_mode = ops.GRAM_MODES[(bool(cfg.gram_remove_neg), bool(cfg.gram_remove_only_teacher_neg))]
         self.gram_stream, self.gram_img = None, None
         if cfg.gram_ema_teacher:
@@ -280,6 +284,8 @@ class Engine:
             bb.g_bf16 = torch.zeros_like(bb.t_bf16)                          # frozen full copies on every rank
             bb.g_vecs = torch.zeros(bb.n - bb.n_mat, dtype=f32, device=dev)
             gs = cfg.gram_teacher_size
+            if gs is not None and gs != cfg.global_size and cfg.gram_tokens_used != "all":
+                raise NotImplementedError("gram.tokens_used masked | unmasked with a gram teacher at its own resolution")
             if gs is not None and gs != cfg.global_size:
                 # the gram teacher sees its own (larger) crops: a third token stream at that resolution; its patch tokens are
                 # resized to the student's grid before the similarity matrices (upstream get_gram_teacher_output)
@@ -328,13 +334,21 @@ class Engine:
             self.gram_updates += 1
 
     def _gram_features(self, Xn, feats, x_bf16, nrm):
-        """Patch tokens of the global crops out of a final-norm output -> the Gram operands (L2-normalised rows)."""
+        """The selected global-crop patch tokens of a final-norm output -> the Gram operands (L2-normalised rows).  The row
+        count is padded to the kernels' 8-row granule with zero rows (zero similarity on both sides: no contribution)."""
         n, D = self.gram_n, self.cfg.embed_dim
+        if n == 0:
+            return
+        npad = (n + 7) // 8 * 8
         if self.cfg.gram_normalized:
             ops.gather_rows(Xn, self.gram_rows, n, D, dst_f32=feats)
-            ops.l2norm_fwd(feats, x_bf16, nrm, 1e-12)
+            if npad > n:
+                feats[n:npad].zero_()
+            ops.l2norm_fwd(feats[:npad], x_bf16[:npad], nrm[:npad], 1e-12)
         else:
             ops.gather_rows(Xn, self.gram_rows, n, D, dst_bf16=x_bf16)
+            if npad > n:
+                x_bf16[n:npad].zero_()
 
     def _gram_teacher_targets(self):
         """Called at the end of the teacher pass (the EMA teacher's outputs have been gathered into the head buffers)."""
@@ -363,27 +377,38 @@ class Engine:
             if hi:
                 gp, sg, D = self.g_sets[0], self.s_sets[0], cfg.embed_dim
                 ops.gather_rows(self.gram_stream.Xn, self.gram_rows_hi, gp.n * gp.P, D, dst_f32=self.gram_hi)
-                ops.resize_tokens_bicubic(self.gram_hi, self.gram_ft, gp.n, gp.Hp, gp.Hp, sg.Hp, sg.Hp, D,
+                ops.resize_tokens_bicubic(self.gram_hi, self.gram_ft[:sg.n * sg.P], gp.n, gp.Hp, gp.Hp, sg.Hp, sg.Hp, D,
                                           cfg.gram_resize_antialias)
+                n = self.gram_n                       # all patch tokens (a multiple of 8 is not guaranteed: pad with zero rows)
+                npad = (n + 7) // 8 * 8
+                if npad > n:
+                    self.gram_ft[n:npad].zero_()
                 if cfg.gram_normalized:
-                    ops.l2norm_fwd(self.gram_ft, self.gram_xt, self.gram_nrm_t, 1e-12)
+                    ops.l2norm_fwd(self.gram_ft[:npad], self.gram_xt[:npad], self.gram_nrm_t[:npad], 1e-12)
                 else:
-                    ops.cast_f32_bf16(self.gram_ft.reshape(-1), self.gram_xt.reshape(-1))
+                    ops.cast_f32_bf16(self.gram_ft[:npad].reshape(-1), self.gram_xt[:npad].reshape(-1))
                 return
         self._gram_features(T_.Xn, self.gram_ft, self.gram_xt, self.gram_nrm_t)
 
     def _gram_loss_bwd(self, dXn):
         """loss/gram_loss.py:38-50 on the tensor cores: St = Xt Xt^T, Ss = Xs Xs^T, elementwise negative removal + squared
-        difference (d3_gram_diff), dXs = (4 w / n^2) G Xs (G symmetric), back through the row normalisation, added to the
-        gradient of the student's final-norm output."""
+        difference (d3_gram_diff; per-image blocks only with gram.img_level), dXs = (4 w / count) G Xs (G symmetric), back
+        through the row normalisation, added to the gradient of the student's final-norm output."""
         n, D = self.gram_n, self.cfg.embed_dim
-        inv = 1.0 / (float(n) * float(n))
-        ops.gemm(self.gram_xt, self.gram_xt, self.gram_St)
-        ops.gemm(self.gram_xs, self.gram_xs, self.gram_Ss)
-        ops.gram_diff(self.gram_Ss, self.gram_St, self.gram_G, self.gram_mode, inv, self.metrics[4:5])
-        ops.gemm(self.gram_G, self.gram_xs, self.gram_dX, b_mn=True, alpha=4.0 * self._gram_w * inv)
+        if n == 0:
+            return
+        npad = (n + 7) // 8 * 8
+        count = float(n) * float(self.gram_block) if self.gram_block else float(n) * float(n)   # entries under the mean
+        inv = 1.0 / count
+        xs, xt = self.gram_xs[:npad], self.gram_xt[:npad]
+        Ss, St = self.gram_Ss[:npad * npad].view(npad, npad), self.gram_St[:npad * npad].view(npad, npad)
+        G = self.gram_G[:npad * npad].view(npad, npad)
+        ops.gemm(xt, xt, St)
+        ops.gemm(xs, xs, Ss)
+        ops.gram_diff(Ss, St, G, self.gram_mode, inv, self.metrics[4:5], block=self.gram_block)
+        ops.gemm(G, xs, self.gram_dX[:npad], b_mn=True, alpha=4.0 * self._gram_w * inv)
         if self.cfg.gram_normalized:
-            ops.l2norm_bwd(self.gram_dX, self.gram_fs, self.gram_nrm_s, self.gram_dF)
+            ops.l2norm_bwd(self.gram_dX[:npad], self.gram_fs[:npad], self.gram_nrm_s[:npad], self.gram_dF[:npad])
             src = self.gram_dF
         else:
             src = self.gram_dX
@@ -739,6 +764,15 @@ class Engine:
         assert self.M <= self.max_masked, f"M={self.M} exceeds max_masked={self.max_masked}"
         self.mask_idx[: self.M].copy_(idx, non_blocking=True)
         ops.token_rows(self.mask_idx, self.rows_masked_t, self.M, self.s_sets[0].P, 0, prefix=self.cfg.prefix)
+        if self.cfg.gram_use_loss and self.cfg.gram_tokens_used != "all":
+            # gram.tokens_used (train/ssl_meta_arch.py:221-223; upstream: student_patches[masks] / [~masks])
+            n_all = self.gram_rows_all.numel()
+            if self.cfg.gram_tokens_used == "masked":
+                self.gram_rows, self.gram_n = self.rows_masked_t, self.M
+            else:
+                # stable sort of the mask bits: unmasked patch positions first, in order (no host sync, count known)
+                order = torch.argsort(self.masks_u8.reshape(-1).to(torch.int16), stable=True)[: n_all - self.M]
+                self.gram_rows, self.gram_n = self.gram_rows_all[order].contiguous(), n_all - self.M
 
     def forward_backward(self, teacher_temp: float):
         cfg, B, M = self.cfg, self.B, self.M

@@ -179,7 +179,7 @@ class GramLoss:
     """loss/gram_loss.py:13-50: MSE between the patch-similarity (Gram) matrices of student and gram-teacher
     features.  The value is computed with the library: row normalisation (d3_l2norm_fwd), similarity matrices on the
     tensor cores (d3_gemm_bf16, bf16 operands / fp32 accumulate), negative removal + squared difference (d3_gram_diff).
-    `img_level=True` runs the per-image matrices one image at a time.  The training engine uses the same kernels with the
+    `img_level=True` takes the diagonal (per-image) blocks of the batch's similarity matrix.  The training engine uses the same kernels with the
     backward fused in (engine/core.py:_gram_loss_bwd)."""
 
     def __init__(self, apply_norm: bool = True, img_level: bool = True, remove_neg: bool = True,
@@ -188,9 +188,9 @@ class GramLoss:
         self.apply_norm, self.img_level = apply_norm, img_level
         self.remove_neg, self.remove_only_teacher_neg = remove_neg, remove_only_teacher_neg
 
-    def _one(self, s: torch.Tensor, t: torch.Tensor, acc: torch.Tensor, inv: float):
+    def _one(self, s: torch.Tensor, t: torch.Tensor, acc: torch.Tensor, inv: float, block: int = 0):
         n, D = s.shape
-        pn, pd = -n % 8, -D % 8                               # kernels work in 8-element granules; zero padding adds nothing
+        pn, pd = (0 if block else -n % 8), -D % 8             # kernels work in 8-element granules; zero padding adds nothing
         if pn or pd:
             s, t = torch.nn.functional.pad(s, (0, pd, 0, pn)), torch.nn.functional.pad(t, (0, pd, 0, pn))
         s, t = s.to(f32).contiguous(), t.to(f32).contiguous()
@@ -205,17 +205,20 @@ class GramLoss:
         Ss, St = torch.empty(m, m, dtype=f32, device=s.device), torch.empty(m, m, dtype=f32, device=s.device)
         ops.gemm(xs, xs, Ss)
         ops.gemm(xt, xt, St)
-        ops.gram_diff(Ss, St, None, ops.GRAM_MODES[(self.remove_neg, self.remove_only_teacher_neg)], inv, acc)
+        ops.gram_diff(Ss, St, None, ops.GRAM_MODES[(self.remove_neg, self.remove_only_teacher_neg)], inv, acc, block=block)
 
     def __call__(self, output_feats: torch.Tensor, target_feats: torch.Tensor, img_level: bool = True) -> torch.Tensor:
         acc = torch.zeros(1, dtype=f32, device=output_feats.device)
+        s = output_feats.reshape(-1, output_feats.shape[-1])
+        t = target_feats.reshape(-1, target_feats.shape[-1])
         if img_level:
             assert output_feats.dim() == 3 and target_feats.dim() == 3          # gram_loss.py:25-26
             Bn, n, _ = output_feats.shape
-            for b in range(Bn):
-                self._one(output_feats[b], target_feats[b], acc, 1.0 / (Bn * n * n))
+            if (Bn * n) % 8 == 0 and n % 4 == 0:
+                self._one(s, t, acc, 1.0 / (Bn * n * n), block=n)
+            else:                                             # odd sizes: one image at a time
+                for b in range(Bn):
+                    self._one(output_feats[b], target_feats[b], acc, 1.0 / (Bn * n * n))
         else:
-            s = output_feats.reshape(-1, output_feats.shape[-1])
-            t = target_feats.reshape(-1, target_feats.shape[-1])
             self._one(s, t, acc, 1.0 / (s.shape[0] * s.shape[0]))
         return acc[0]

@@ -153,11 +153,13 @@ def scatter_add_peers(src, peers, off, shard, alpha):
 GRAM_MODES = {(False, False): 0, (True, False): 1, (False, True): 2}      # (remove_neg, remove_only_teacher_neg)
 
 
-def gram_diff(Ss, St, G, mode: int, inv_count: float, loss):
-    """Elementwise stage of the Gram loss (d3_gram_diff): loss += inv_count * sum (s' - t')^2, G = (s' - t') ds'/ds (bf16)."""
+def gram_diff(Ss, St, G, mode: int, inv_count: float, loss, block: int = 0):
+    """Elementwise stage of the Gram loss (d3_gram_diff): loss += inv_count * sum (s' - t')^2, G = (s' - t') ds'/ds (bf16);
+    block > 0 restricts both to the diagonal blocks of block x block tokens (per-image Gram matrices)."""
     assert Ss.dtype == f32 and St.dtype == f32 and Ss.is_contiguous() and St.is_contiguous() and Ss.numel() == St.numel()
     assert G is None or (G.dtype == bf16 and G.is_contiguous() and G.numel() == Ss.numel())
-    N.check(N.init().d3_gram_diff(_p(Ss), _p(St), _p(G), Ss.numel(), int(mode), float(inv_count), _p(loss), _s()), "d3_gram_diff")
+    N.check(N.init().d3_gram_diff(_p(Ss), _p(St), _p(G), Ss.numel(), int(mode), float(inv_count), _p(loss), int(Ss.shape[0]),
+                                  int(block), _s()), "d3_gram_diff")
 
 
 def resize_tokens_bicubic(src, dst, n, Hs, Ws, Hd, Wd, D, antialias: bool):

@@ -218,9 +218,11 @@ int d3_ce_fwd_bwd(const float* S /*[Rs,K]*/, float student_temp, const float* Lt
  * Ss = Xs Xs^T, St = Xt Xt^T (fp32 [n*n], produced by d3_gemm_bf16 on the L2-normalised patch features) applies the
  * negative-removal mode (0 none | 1 remove_neg | 2 remove_only_teacher_neg, lines 40-48), accumulates
  * *loss += inv_count * sum (s' - t')^2 (line 50: mean) and writes G = (s' - t') * ds'/ds as bf16 (or skips it when
- * G_bf16 is NULL), the left operand of the backward GEMM dXs = (4 w / n^2) G Xs.                                    */
+ * G_bf16 is NULL), the left operand of the backward GEMM dXs = (4 w / n^2) G Xs.
+ * block > 0 (gram.img_level: true): Ss / St are [n, n] and only the diagonal blocks of block x block tokens (one image
+ * each) count; the rest contributes nothing and gets G = 0.                                                           */
 int d3_gram_diff(const float* Ss, const float* St, void* G_bf16, long long n_elems, int mode, float inv_count, float* loss,
-                 void* stream);
+                 int n, int block, void* stream);
 
 /* Gram teacher features at crops.gram_teacher_crops_size -> the student's patch grid (gram.global_teacher_resize_method:
  * bicubic, gram.global_teacher_resize_antialias; configs/ssl_default_config.yaml:71-72): fp32 token maps

@@ -96,7 +96,13 @@ def ssl_forward(params: dict, batch: dict, teacher_temp: float, cfg: ModelCfg, e
                     gt_patch = torch.nn.functional.interpolate(
                         gt_patch.reshape(n_, Hg, Hg, Dm).permute(0, 3, 1, 2), size=(Hs, Hs), mode="bicubic", align_corners=False,
                         antialias=bool(gram.get("resize_antialias", False))).permute(0, 2, 3, 1).reshape(n_, Hs * Hs, Dm)
-        L_gram = gram_loss(g_patch, gt_patch, apply_norm=gram.get("normalized", True), img_level=gram.get("img_level", False),
+        gs_patch = g_patch
+        used = gram.get("tokens_used", "all")                    # train/ssl_meta_arch.py:221-223 (upstream: patches[masks] / [~masks])
+        if used != "all":
+            assert not gram.get("img_level", False)
+            sel = masks if used == "masked" else ~masks
+            gs_patch, gt_patch = g_patch[sel], gt_patch[sel]
+        L_gram = gram_loss(gs_patch, gt_patch, apply_norm=gram.get("normalized", True), img_level=gram.get("img_level", False),
                            remove_neg=gram.get("remove_neg", False),
                            remove_only_teacher_neg=gram.get("remove_only_teacher_neg", False))
         loss = loss + gram["weight"] * L_gram

@@ -80,9 +80,16 @@ def test_gram_keys_map_onto_the_engine_config():
     assert not config_from_reference_cfg(setup_config(DinoV3SetupArgs())).gram_use_loss
     with pytest.raises(ValueError):              # no checkpoint and no load iteration (ssl_meta_arch.py:215-218)
         config_from_reference_cfg(setup_config(DinoV3SetupArgs(opts=["gram.use_loss=true"])))
-    for bad in (["gram.img_level=true"], ["gram.tokens_used=masked"], ["gram.ckpt=/x"]):
-        with pytest.raises(NotImplementedError):
-            config_from_reference_cfg(setup_config(DinoV3SetupArgs(opts=["gram.use_loss=true", "gram.ema_teacher=true"] + bad)))
+    with pytest.raises(NotImplementedError):
+        config_from_reference_cfg(setup_config(DinoV3SetupArgs(opts=["gram.use_loss=true", "gram.ema_teacher=true", "gram.ckpt=/x"])))
+    e = config_from_reference_cfg(setup_config(DinoV3SetupArgs(opts=["gram.use_loss=true", "gram.ema_teacher=true",
+                                                                      "gram.tokens_used=masked"])))
+    assert e.gram_tokens_used == "masked"
+    assert config_from_reference_cfg(setup_config(DinoV3SetupArgs(opts=["gram.use_loss=true", "gram.ema_teacher=true",
+                                                                         "gram.img_level=true"]))).gram_img_level
+    with pytest.raises(ValueError):              # ssl_meta_arch.py:222-223
+        config_from_reference_cfg(setup_config(DinoV3SetupArgs(opts=["gram.use_loss=true", "gram.ema_teacher=true",
+                                                                      "gram.tokens_used=unmasked", "gram.img_level=true"])))
     # a gram teacher at its own resolution: up to 448 tokens per crop (320^2 at patch 16), bicubic resize of its features
     frozen = ["gram.use_loss=true", "gram.it_load_ema_teacher=0"]
     e = config_from_reference_cfg(setup_config(DinoV3SetupArgs(opts=frozen + ["crops.gram_teacher_crops_size=320",

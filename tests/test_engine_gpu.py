@@ -385,10 +385,15 @@ def _gram_pair(mode, only_gram):
     P = init_params(cfg, 6, perturb=0.05)
     batch = synthetic_batch(cfg, B, 6)
     remove_neg = mode == "frozen_remove_neg"
-    gram = dict(weight=W, ema_teacher=mode in ("ema",), normalized=True, img_level=False, remove_neg=remove_neg,
-                remove_only_teacher_neg=False)
-    ecfg = dataclasses.replace(from_oracle_cfg(cfg), gram_use_loss=True, gram_loss_weight=W, gram_ema_teacher=mode == "ema",
-                               gram_remove_neg=remove_neg, gram_it_load_ema_teacher=0)
+    used = mode[len("ema_"):] if mode in ("ema_masked", "ema_unmasked") else "all"
+    img_level = mode == "ema_img_level"
+    ema = mode.startswith("ema")
+    gram = dict(weight=W, ema_teacher=ema, normalized=mode != "ema_img_level", img_level=img_level, remove_neg=remove_neg,
+                remove_only_teacher_neg=img_level, tokens_used=used)
+    ecfg = dataclasses.replace(from_oracle_cfg(cfg), gram_use_loss=True, gram_loss_weight=W, gram_ema_teacher=ema,
+                               gram_remove_neg=remove_neg, gram_it_load_ema_teacher=0, gram_tokens_used=used,
+                               gram_img_level=img_level, gram_remove_only_teacher_neg=img_level,
+                               gram_normalized=mode != "ema_img_level")
     eng = Engine(ecfg, B, max_masked=max(int(batch["mask_indices_list"].shape[0]), 1))
     eng.params.load_reference_tree(P)
     full = dict(P)
@@ -396,7 +401,7 @@ def _gram_pair(mode, only_gram):
         for k, v in P.items():
             if k.startswith("teacher_backbone/"):
                 full["gram_backbone/" + k[len("teacher_backbone/"):]] = v
-    elif mode != "ema":                  # a different frozen network, loaded from a checkpoint tree
+    elif not ema:                        # a different frozen network, loaded from a checkpoint tree
         P2 = init_params(cfg, 7, perturb=0.05)
         tree = {k[len("teacher_backbone/"):]: v for k, v in P2.items() if k.startswith("teacher_backbone/")}
         eng.gram_teacher_load(tree)
@@ -451,18 +456,19 @@ def test_gram_teacher_at_its_own_resolution():
         eng.forward_backward(HYPER["teacher_temp"])
         met = eng.read_metrics()
         assert abs(met["gram_loss"] - float(m["gram_loss"])) < 2e-2 * float(m["gram_loss"]), (aa, met["gram_loss"], float(m["gram_loss"]))
-        assert abs(met["total_loss"] - float(loss)) < 2e-3 * abs(float(loss))
+        assert abs(met["total_loss"] - float(loss.detach())) < 2e-3 * abs(float(loss.detach()))
         ge = {k: v.cpu() for k, v in eng.params.export_reference_tree("grad").items()}
         num = sum(((ge[k].reshape(g_.shape) - g_) ** 2).sum() for k, g_ in zip(keys, gl) if g_ is not None)
         den = sum((g_ ** 2).sum() for g_ in gl if g_ is not None)
         assert float(torch.sqrt(num / den)) < 3e-2
 
 
-@pytest.mark.parametrize("mode", ["ema", "frozen", "frozen_remove_neg", "snapshot"])
+@pytest.mark.parametrize("mode", ["ema", "frozen", "frozen_remove_neg", "snapshot", "ema_masked", "ema_unmasked", "ema_img_level"])
 def test_step_with_gram_anchoring(mode):
     """SURVEY 8f.2 on the GPU path: Gram-anchoring term (loss/gram_loss.py:13-50 at batch level; train/ssl_meta_arch.py:
-    527-541) with the EMA teacher, a frozen gram teacher loaded from a tree, negative removal, and the scheduled
-    snapshot of the EMA teacher (gram.it_load_ema_teacher)."""
+    527-541) with the EMA teacher, a frozen gram teacher loaded from a tree, negative removal, the scheduled snapshot of
+    the EMA teacher (gram.it_load_ema_teacher), gram.tokens_used masked / unmasked (ragged row counts), and per-image Gram
+    matrices (gram.img_level, un-normalised features, teacher-only negative removal)."""
     met, loss, m, grads, grads_e = _gram_pair(mode, only_gram=False)
     assert abs(met["gram_loss"] - float(m["gram_loss"])) < 2e-2 * float(m["gram_loss"]), (met["gram_loss"], float(m["gram_loss"]))
     assert met["gram_loss_weight"] == 25.0

@@ -566,3 +566,24 @@ def test_resize_tokens_bicubic_matches_torch_interpolate(Hs, Hd, aa):
     out = torch.empty(n, Hd, Hd + 2, D, device="cuda")
     ops.resize_tokens_bicubic(x.cuda().contiguous(), out, n, Hs, Hs + 1, Hd, Hd + 2, D, aa)
     assert float((out.cpu() - ref).abs().max()) < 2e-5 * max(1.0, float(ref.abs().max()))
+
+
+def test_gram_loss_class_against_the_reference_fixture():
+    """dinov3_jax.loss.GramLoss (the reference's class name and call signature, loss/gram_loss.py:13-50) on the values the
+    reference's own class produced for the committed fixture: per image and over the batch; and the block-diagonal
+    (single-GEMM) form of the per-image loss against the oracle on aligned sizes."""
+    import numpy as np
+    import os
+    from dinov3_jax.loss import GramLoss
+    from oracle.losses import gram_loss
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.npz"))
+    s, t = torch.from_numpy(G["gram_s"]).float().cuda(), torch.from_numpy(G["gram_t"]).float().cuda()
+    gl = GramLoss()
+    assert abs(float(gl(s, t, img_level=True)) - float(G["gram_img"])) < 2e-2 * float(G["gram_img"])
+    assert abs(float(gl(s, t, img_level=False)) - float(G["gram_batch"])) < 2e-2 * float(G["gram_batch"])
+    g = torch.Generator().manual_seed(1)
+    s2, t2 = torch.randn(4, 16, 64, generator=g), torch.randn(4, 16, 64, generator=g)
+    for kw in (dict(remove_neg=True, remove_only_teacher_neg=False), dict(remove_neg=False, remove_only_teacher_neg=True)):
+        ref = float(gram_loss(s2.double(), t2.double(), img_level=True, **kw))
+        got = float(GramLoss(**kw)(s2.cuda(), t2.cuda(), img_level=True))
+        assert abs(got - ref) < 2e-2 * ref, (kw, got, ref)
