@@ -253,6 +253,7 @@ class Engine:
         self._gram_w = float(cfg.gram_loss_weight)
         self._gram_snapshot_pending = False
         self.gram_updates = 0
+        self.gram_stream, self.gram_img = None, None
         if not cfg.gram_use_loss:
             return
         assert cfg.gram_tokens_used in ("all", "masked", "unmasked")         # train/ssl_meta_arch.py:221
@@ -276,7 +277,6 @@ class Engine:
         self.gram_G = e(npad * npad, dt=bf16)
         self.gram_dX, self.gram_dF = e(npad, D, dt=bf16), e(npad, D, dt=bf16)
         self.gram_mode = ops.GRAM_MODES[(bool(cfg.gram_remove_neg), bool(cfg.gram_remove_only_teacher_neg))]
-        self.gram_stream, self.gram_img = None, None
         if cfg.gram_ema_teacher:
             self.gram_active = True
         else:
