@@ -1,5 +1,6 @@
 """Training driver with the reference's entry points (dinov3_jax/train/train.py): `get_args_parser`, `main`,
-`do_train`, `build_schedulers`, `build_optimizer`, `train_step`, `build_data_loader_from_cfg`.
+`do_train`, `build_schedulers`, `build_optimizer`, `train_step`, `build_data_loader_from_cfg`,
+`build_multi_resolution_data_loader_from_cfg`.
 
 Launch one process per GPU:  torchrun --nproc-per-node N -m dinov3_jax.train.train --config-file cfg.yaml --opts k=v
 The loop keeps the reference's shape (:622-706) minus its per-step host syncs: metrics are read every `print_freq`.
@@ -139,6 +140,27 @@ def make_state(engine, optimizer):
     """(params, ema_params, optimizer_state) handles for the reference-style step functions."""
     params = EngineTree(engine, "param")
     return params, params, EngineTree(engine, "m", optimizer=optimizer)
+
+
+def build_multi_resolution_data_loader_from_cfg(config, model, start_iter: int = 0, seed: int = 65537):
+    """train/train.py:718-769: one loader per (global, local, gram-teacher) crop-size triple.  The engine's buffers, RoPE
+    tables and kernels are laid out for ONE triple, so a single-entry configuration (ints, or lists of length one) is
+    built exactly like the reference does (config copy with `train.seed + 1`) and anything longer raises: train each
+    resolution stage with its own engine (what the reference's 7B recipe does stage by stage in its YAMLs)."""
+    import copy
+    as_list = lambda v: [v] if (v is None or isinstance(v, (int, float))) else list(v)
+    gs, ls = as_list(config.crops.global_crops_size), as_list(config.crops.local_crops_size)
+    gram = as_list(config.crops.get("gram_teacher_crops_size", None))
+    ratios = as_list(config.crops.get("global_local_crop_pairs_ratios", 1.0))
+    assert len(gs) == len(ls) == len(gram) == len(ratios)
+    if len(gs) != 1:
+        raise NotImplementedError("multi-resolution crop lists: the B200 engine is built for one (global, local, gram) size "
+                                  "triple; run one engine per resolution stage")
+    config_i = copy.deepcopy(config)
+    config_i.crops.global_crops_size, config_i.crops.local_crops_size = gs[0], ls[0]
+    config_i.crops.gram_teacher_crops_size = gram[0]
+    config_i.train.seed = config.train.seed + 1
+    return build_data_loader_from_cfg(config=config_i, model=model, start_iter=start_iter)
 
 
 def build_data_loader_from_cfg(config, model, start_iter: int = 0):

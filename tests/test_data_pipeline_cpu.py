@@ -105,3 +105,23 @@ def test_gpu_augment_parameter_sampling_follows_torchvision_rules():
     assert g["solarize"][:B].sum() == 0 and 0 < g["solarize"][B:].sum() < B and l["solarize"].sum() == 0
     jit = g["order"][:, 0] >= 0
     assert 0.6 < jit.mean() < 0.95 and all(sorted(o) == [0, 1, 2, 3] for o in g["order"][jit])
+
+
+def test_multi_resolution_builder_accepts_one_triple_and_rejects_lists():
+    """train/train.py:718-769: one (global, local, gram) size triple builds the ordinary loader with seed + 1; resolution
+    lists raise (the engine is laid out for one triple)."""
+    from dinov3_jax.configs import DinoV3SetupArgs, setup_config
+    from dinov3_jax.train.train import build_multi_resolution_data_loader_from_cfg
+
+    class Model:
+        pass
+    cfg = setup_config(DinoV3SetupArgs(opts=["train.dataset_path=synthetic", "student.arch=vit_small", "train.batch_size_per_gpu=1"]))
+    from dinov3_jax.engine import config_from_reference_cfg
+    m = Model(); m.engine_config = config_from_reference_cfg(cfg)
+    loader = build_multi_resolution_data_loader_from_cfg(cfg, m, 0)
+    b = next(iter(loader))
+    assert tuple(b["collated_global_crops"].shape) == (2, 224, 224, 3) and tuple(b["collated_local_crops"].shape) == (8, 96, 96, 3)
+    cfg.crops.global_crops_size, cfg.crops.local_crops_size = [224, 448], [96, 112]
+    cfg.crops.gram_teacher_crops_size, cfg.crops.global_local_crop_pairs_ratios = [None, None], [1.0, 1.0]
+    with pytest.raises(NotImplementedError):
+        build_multi_resolution_data_loader_from_cfg(cfg, m, 0)
