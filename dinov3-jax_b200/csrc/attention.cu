@@ -520,11 +520,15 @@ attn_bwd_alias_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
 
 __global__ void __launch_bounds__(256)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                const float* __restrict__ LSE, const __nv_bfloat16* __restrict__ Og, long T_rows,
-                __nv_bfloat16* __restrict__ dQKV, const AttnShape sh) {
+                const __grid_constant__ CUtensorMap tmO, const float* __restrict__ LSE,
+                __nv_bfloat16* __restrict__ dQKV, const AttnShape sh, const int n_items) {
   // Pipelined variant for up to two query / key tiles (span <= 256): one tensor-core commit per (kt, qt) iteration —
   // the accumulate MMAs of iteration i and the S / dP MMAs of iteration i+1 are issued back to back, K / V tiles are
   // double-buffered, and every MMA / column loop is trimmed to the valid extent of the (ragged) last tile.
+  // PERSISTENT over (crop group, head) items (item = blockIdx.x + k * gridDim.x, head fastest): tensor memory and the
+  // barriers are set up once per CTA, and the TMA loads of the NEXT item's Q / dO / O / K / V tiles are issued as soon as
+  // the last MMA of the current item has retired — they land while the dK / dV / dQ accumulators are read out, rotated
+  // back and stored (6 k of the 39 k cycles of an item were spent waiting for its tiles).
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nQ = (sh.span + 127) / 128, nK = nQ;
@@ -534,6 +538,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   uint8_t* sV = sK + 32768;                    // [2][128 x 64]
   uint8_t* sP = sV + 32768;                    // [2 chunks of 64 keys][128 q x 128 B] 32 KB
   uint8_t* sDS = sP + 32768;                   // 32 KB
+  uint8_t* sO = sP;                            // [nQ][128 x 64] forward outputs: only live in the item's prologue (Delta)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + 32768);
   uint64_t* bar_q = bars;
   uint64_t* bar_kv = bars + 1;                 // [2]
@@ -544,13 +549,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int r = threadIdx.x & 127;
   const int ch = threadIdx.x >> 7;
-  const int h = blockIdx.x, c = blockIdx.y;
-  const int row_base = c * sh.span;
+  int h = 0, c = 0, row_base = 0;              // the current item (lambdas below read them by reference)
   const int n_it = nK * nQ;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmO);
     mbar_init(bar_q, 1);
     mbar_init(&bar_kv[0], 1);
     mbar_init(&bar_kv[1], 1);
@@ -569,11 +574,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const float cs = sh.scale * LOG2E;
 
   auto tile_extent = [&](int t) { return min(128, ((sh.span - t * 128) + 15) & ~15); };   // valid rows/cols, multiple of 16
-  auto load_kv = [&](int kt) {     // thread 0
-    const int bsel = kt & 1;
-    mbar_expect_tx(&bar_kv[bsel], 2 * 16384);
-    tma_load_2d(&tmQKV, &bar_kv[bsel], sK + bsel * 16384, sh.D + h * 64, row_base + kt * 128);
-    tma_load_2d(&tmQKV, &bar_kv[bsel], sV + bsel * 16384, 2 * sh.D + h * 64, row_base + kt * 128);
+  auto load_item = [&](int item) {     // elected lane of warp 0: every tile of one (crop group, head) item
+    const int hh = item % sh.H, rb = (item / sh.H) * sh.span;
+    mbar_expect_tx(bar_q, nQ * 3 * 16384);
+    for (int qt = 0; qt < nQ; ++qt) {
+      tma_load_2d(&tmQKV, bar_q, sQ + qt * 16384, hh * 64, rb + qt * 128);
+      tma_load_2d(&tmDO, bar_q, sDO + qt * 16384, hh * 64, rb + qt * 128);
+      tma_load_2d(&tmO, bar_q, sO + qt * 16384, hh * 64, rb + qt * 128);
+    }
+    for (int kt = 0; kt < nK; ++kt) {
+      mbar_expect_tx(&bar_kv[kt], 2 * 16384);
+      tma_load_2d(&tmQKV, &bar_kv[kt], sK + kt * 16384, sh.D + hh * 64, rb + kt * 128);
+      tma_load_2d(&tmQKV, &bar_kv[kt], sV + kt * 16384, 2 * sh.D + hh * 64, rb + kt * 128);
+    }
   };
   auto issue_sdp = [&](int kt, int qt) {   // thread 0: S = Q K^T and dP = dO V^T for this tile pair, N trimmed
     const uint64_t qd = umma_desc_sw128(smem_u32(sQ + qt * 16384), 16, 1024), dod = umma_desc_sw128(smem_u32(sDO + qt * 16384), 16, 1024);
@@ -602,16 +615,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   // UTMALDG / UTCHMMA through an ELECT ... BRA.U.ANY loop, ~60-90 cycles per instruction: the accumulate MMAs of this
   // kernel (N = 64: 32 tensor cycles each) were issue-bound)
   if (warp == 0) {
+    if (elect_one() && (int)blockIdx.x < n_items) load_item(blockIdx.x);
+    __syncwarp();
+  }
+  uint32_t mma_phase = 0;
+  uint32_t par = 0;                            // parity of the per-item barriers (bar_q, bar_kv): one completion per item
+#pragma unroll 1
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x, par ^= 1) {
+  h = item % sh.H;
+  c = item / sh.H;
+  row_base = c * sh.span;
+  if (warp == 0) {
     if (elect_one()) {
-      mbar_expect_tx(bar_q, nQ * 2 * 16384);
-      for (int qt = 0; qt < nQ; ++qt) {
-        tma_load_2d(&tmQKV, bar_q, sQ + qt * 16384, h * 64, row_base + qt * 128);
-        tma_load_2d(&tmDO, bar_q, sDO + qt * 16384, h * 64, row_base + qt * 128);
-      }
-      load_kv(0);
-      if (nK > 1) load_kv(1);
-      mbar_wait(bar_q, 0);
-      mbar_wait(&bar_kv[0], 0);
+      mbar_wait(bar_q, par);
+      mbar_wait(&bar_kv[0], par);
       tc_fence_after();
       issue_sdp(0, 0);
       umma_commit(bar_mma);
@@ -619,31 +636,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     __syncwarp();
   }
   dbg_mark(2);
-  uint32_t mma_phase = 0;
   // ---- Delta[q] = sum_d dO[q, d] * O[q, d] (softmax-backward row term) in the prologue, while the first S / dP products
-  // run: dO rows come from the TMA tile in shared memory (SWIZZLE_128B), O rows straight from global memory; the two
-  // threads of a row each take 32 of the 64 head columns.  (Replaces the separate attn_delta pass over O and dO.)
+  // run: dO and O rows come from their TMA tiles in shared memory (SWIZZLE_128B; the O tile borrows the P staging area,
+  // which is first written after the barrier below); the two threads of a row each take 32 of the 64 head columns.
+  // (Replaces the separate attn_delta pass over O and dO.)
   float dl_q0 = 0.f, dl_q1 = 0.f;
   {
-    // the O rows do not depend on the TMA tiles: their loads are issued first and fly while the tiles land
-    uint4 ov[2][4];
-#pragma unroll
-    for (int qt = 0; qt < 2; ++qt) {
-      const int q = qt * 128 + r;
-      const bool ok = qt < nQ && q < sh.span && (long)row_base + q < T_rows;
-      const __nv_bfloat16* orow = Og + ((long)row_base + (ok ? q : 0)) * sh.D + h * 64 + ch * 32;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) ov[qt][i] = ok ? *reinterpret_cast<const uint4*>(orow + i * 8) : make_uint4(0, 0, 0, 0);
-    }
-    mbar_wait(bar_q, 0);
+    mbar_wait(bar_q, par);
 #pragma unroll
     for (int qt = 0; qt < 2; ++qt) {
       float part = 0.f;
       if (qt < nQ) {
         const uint8_t* drow = sDO + qt * 16384;
+        const uint8_t* orow = sO + qt * 16384;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const uint4 a = ov[qt][i];
+          const uint4 a = *reinterpret_cast<const uint4*>(orow + sw128_offset(r, ch * 32 + i * 8));
           const uint4 b = *reinterpret_cast<const uint4*>(drow + sw128_offset(r, ch * 32 + i * 8));
           const float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
           const float2 b0 = unpack_bf16(b.x), b1 = unpack_bf16(b.y), b2 = unpack_bf16(b.z), b3 = unpack_bf16(b.w);
@@ -775,7 +783,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       if (it + 1 < n_it) {             // S / dP of the next iteration ride on the same commit
         const int kt2 = (it + 1) / nQ, qt2 = (it + 1) - kt2 * nQ;
         if (kt2 != kt) {
-          mbar_wait(&bar_kv[kt2 & 1], (kt2 >> 1) & 1);
+          mbar_wait(&bar_kv[kt2 & 1], par);
           tc_fence_after();
         }
         issue_sdp(kt2, qt2);
@@ -786,8 +794,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   dbg_mark(20);
   __syncwarp();
   mbar_wait(bar_mma, mma_phase);
+  mma_phase ^= 1;
   tc_fence_after();
   dbg_mark(21);
+  // every MMA of this item has retired: its shared-memory tiles are dead -> start the next item's loads now, under the
+  // accumulator read-out below
+  if (warp == 0) {
+    if (elect_one() && item + (int)gridDim.x < n_items) load_item(item + gridDim.x);
+    __syncwarp();
+  }
   store_dkdv(nK - 1);
   dbg_mark(22);
   // ---- dQ: query tile qt is written by the threads with ch == (qt & 1)
@@ -804,6 +819,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     }
   }
   dbg_mark(23);
+  }   // items
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_free<512>(tmem);
@@ -909,9 +925,10 @@ int d3_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* ls
                                                                   delta_scratch, T, N, D, H);
     D3_CHECK_LAUNCH();
   }
-  CUtensorMap tqkv, tdo;
+  CUtensorMap tqkv, tdo, to;
   if ((rc = make_map(&tqkv, qkv, T, 3 * D, 3 * D, 128))) return rc;
   if ((rc = make_map(&tdo, d_o, T, D, D, 128))) return rc;
+  if ((rc = make_map(&to, o, T, D, D, 128))) return rc;
   static bool cfg = false;
   if (!cfg) {
     cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
@@ -925,7 +942,12 @@ int d3_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* ls
     attn_bwd_alias_kernel<<<grid, 256, smem, st>>>(tqkv, tdo, lse, delta_scratch, (__nv_bfloat16*)dqkv, s);
   } else {
     const int smem = 2 * nq * 16384 + 65536 + 65536 + 64 + 2048 + 1024;
-    attn_bwd_kernel<<<grid, 256, smem, st>>>(tqkv, tdo, lse, (const __nv_bfloat16*)o, T, (__nv_bfloat16*)dqkv, s);
+    // persistent: one CTA per SM walks the (crop group, head) items; D3_ATTN_BWD_PERSIST=0 launches one CTA per item
+    static int persist = -1;
+    if (persist < 0) { const char* e = getenv("D3_ATTN_BWD_PERSIST"); persist = (e && e[0] == '0') ? 0 : 1; }
+    const int n_items = (int)grid.x * (int)grid.y;
+    const int ctas = persist ? min(n_items, sm_count()) : n_items;
+    attn_bwd_kernel<<<ctas, 256, smem, st>>>(tqkv, tdo, to, lse, (__nv_bfloat16*)dqkv, s, n_items);
   }
   D3_CHECK_LAUNCH();
   return D3_OK;
