@@ -201,10 +201,19 @@ def engine_state(engine) -> dict:
     top-level modules (train/ssl_meta_arch.py:62-64,86-87,130-131); the optimizer state mirrors optax.adamw's
     (count, mu, nu) over the student modules (train/train.py:95-106).  Under FSDP every rank calls this (collective
     all-gathers of the shards); rank 0 writes."""
-    params = tree_from_flat({k: v.cpu() for k, v in engine.params.export_reference_tree("param").items()})
+    flat = {k: v.cpu() for k, v in engine.params.export_reference_tree("param").items()}
+    bb = engine.params.mods["backbone"]
+    if getattr(engine, "gram_active", False) and hasattr(bb, "g_bf16"):
+        # frozen gram teacher (gram.use_loss with its own backbone, SURVEY 8f.2; full copies on every rank): without it a
+        # resumed run would train without the Gram term until the next scheduled refresh
+        full = torch.cat([bb.g_bf16.float(), bb.g_vecs])
+        flat.update({f"gram_backbone/{k}": v.cpu() for k, v in bb.export_full(full).items()})
+    params = tree_from_flat(flat)
     mu = tree_from_flat({k: v.cpu() for k, v in engine.params.export_reference_tree("m").items()})
     nu = tree_from_flat({k: v.cpu() for k, v in engine.params.export_reference_tree("v").items()})
     opt = {"count": int(engine.step_count), "mu": mu, "nu": nu}
+    if getattr(engine, "gram_active", False) and hasattr(bb, "g_bf16"):
+        opt["gram_updates"] = int(engine.gram_updates)
     if getattr(engine, "centering", "sinkhorn_knopp") != "sinkhorn_knopp":
         # "state" collection of the optional softmax-centering path (loss/dino_clstoken_loss.py:19-22)
         opt["centers"] = {"dino": engine.center_dino.cpu(), "ibot": engine.center_ibot.cpu()}
@@ -212,7 +221,13 @@ def engine_state(engine) -> dict:
 
 
 def load_engine_state(engine, params: dict, optimizer_state: dict | None = None):
-    engine.params.load_reference_tree(flat_from_tree(params))
+    flat = flat_from_tree(params)
+    engine.params.load_reference_tree(flat)
+    gram = {k[len("gram_backbone/"):]: v for k, v in flat.items() if k.startswith("gram_backbone/")}
+    if gram and getattr(engine.cfg, "gram_use_loss", False) and not engine.cfg.gram_ema_teacher:
+        engine.gram_teacher_load(gram)
+        if optimizer_state is not None and "gram_updates" in optimizer_state:
+            engine.gram_updates = int(optimizer_state["gram_updates"])
     if optimizer_state is not None:
         engine.step_count = int(optimizer_state["count"])
         engine.params.load_optimizer_tree(flat_from_tree(optimizer_state["mu"]), flat_from_tree(optimizer_state["nu"]))

@@ -420,6 +420,40 @@ def _gram_pair(mode, only_gram):
     return met, float(loss), m, grads, grads_e
 
 
+def test_checkpoint_keeps_the_frozen_gram_teacher(tmp_path):
+    """The frozen gram teacher (taken from the EMA teacher at gram.it_load_ema_teacher) is part of the saved state: a
+    restored engine has the Gram term active with the same frozen weights, and its next step matches the original's."""
+    from dinov3_jax.checkpointer import engine_state, load_checkpoint, load_engine_state, save_checkpoint
+    from dinov3_jax.engine import Engine, from_oracle_cfg
+    from oracle import tiny_cfg
+    from oracle.batch import synthetic_batch
+    from oracle.model import init_params
+    cfg = tiny_cfg(layerscale=0.5)
+    B = 2
+    batch = synthetic_batch(cfg, B, 0)
+    mm = max(int(batch["mask_indices_list"].shape[0]), 1)
+    ecfg = dataclasses.replace(from_oracle_cfg(cfg), gram_use_loss=True, gram_loss_weight=10.0, gram_it_load_ema_teacher=0,
+                               gram_update_frequency=1000)
+    a = Engine(ecfg, B, max_masked=mm)
+    a.params.load_reference_tree(init_params(cfg, 0, perturb=0.05))
+    a.train_step(batch, iteration=0, **HYPER)             # snapshot of the EMA teacher taken inside this step
+    assert a.gram_active and "gram_loss" in a.read_metrics()
+    params, opt = engine_state(a)
+    assert "gram_backbone" in params
+    save_checkpoint(tmp_path / "0", iteration=0, params=params, optimizer_state=opt)
+    b = Engine(ecfg, B, max_masked=mm)
+    ck = load_checkpoint(tmp_path / "0", abstract_model_params=engine_state(b)[0], strict_loading=False)
+    load_engine_state(b, ck["model_params"], ck["optimizer_state"])
+    assert b.gram_active
+    bba, bbb = a.params.mods["backbone"], b.params.mods["backbone"]
+    assert torch.equal(bba.g_bf16, bbb.g_bf16) and torch.equal(bba.g_vecs, bbb.g_vecs)
+    for e in (a, b):
+        e.train_step(batch, iteration=1, **HYPER)
+    ma, mb = a.read_metrics(), b.read_metrics()
+    assert abs(ma["gram_loss"] - mb["gram_loss"]) <= 1e-5 * abs(ma["gram_loss"])
+    assert abs(ma["total_loss"] - mb["total_loss"]) <= 1e-5 * abs(ma["total_loss"])
+
+
 def test_gram_teacher_at_its_own_resolution():
     """crops.gram_teacher_crops_size != global_crops_size: the frozen gram teacher runs on `collated_gram_teacher_crops`
     (data/collate.py:33-38,81-82) through a third token stream and its patch tokens are resized (bicubic) to the student's
