@@ -31,7 +31,8 @@ reference cannot be executed end to end here.  The oracle is pinned as far as th
   * analytic micro-cases (uniform Sinkhorn, LN of constant rows, orthogonal KoLeo pairs ...) in `tests/`, and the AdamW
     rule against torch.optim.AdamW.
 What is therefore *not* pinned: the third-party op semantics themselves (flax gelu/LayerNorm/attention defaults,
-optax adamw) and the optax.multi_transform wiring / update application of train/train.py (imports optax) — "parity
-unpinned" for those, stated here and in DESIGN.md.
+optax adamw), the optax.multi_transform wiring / update application of train/train.py (imports optax), and the call path
+of the Gram-anchoring term (train/ssl_meta_arch.py:337-347 does not execute in the reference; loss/gram_loss.py itself is
+pinned through tests/golden) — "parity unpinned" for those, stated here and in DESIGN.md.
 """
 from .arch import ARCHS, ModelCfg, tiny_cfg, cfg_for  # noqa: F401
