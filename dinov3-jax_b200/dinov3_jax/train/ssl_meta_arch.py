@@ -22,7 +22,25 @@ class SSLMetaArch:
         self.dino_loss_weight = config.dino.loss_weight
         self.dino_koleo_loss_weight = config.dino.koleo_loss_weight
         self.ibot_loss_weight = config.ibot.loss_weight
+        # gram anchoring (:165-254): same attribute names and the same configuration errors
+        g = config.gram
+        self.gram_use_loss = bool(g.use_loss)
+        self.gram_ema_teacher = bool(g.get("ema_teacher", False)) if self.gram_use_loss else False
+        self.has_gram_teacher = self.gram_use_loss and not self.gram_ema_teacher
+        self.gram_loss_weight = g.get("loss_weight", None) if self.gram_use_loss else None
+        self.gram_img_level = g.get("img_level", None) if self.gram_use_loss else None
+        self.gram_tokens_used = g.get("tokens_used", None) if self.gram_use_loss else None
+        self.gram_compute_stats = g.get("compute_stats", None) if self.gram_use_loss else None
+        if self.gram_use_loss:
+            if self.gram_ema_teacher and g.get("ckpt", None) is not None:
+                raise ValueError("Cannot use both `gram.ema_teacher` and `gram.ckpt` at the same time. Please set one of them to False.")
+            if config.crops.get("gram_teacher_crops_size", None) is None and self.has_gram_teacher:
+                raise ValueError("config.crops.gram_teacher_crops_size must be set to use gram loss")          # :241-242
         self.engine = None
+
+    @property
+    def gram_teacher_initialized(self) -> bool:
+        return bool(self.engine is not None and self.engine.gram_active and self.has_gram_teacher)
 
     # -- B200 engine -------------------------------------------------------------------------------------------------
     def build_engine(self, device="cuda", comm=None, max_masked=None) -> Engine:

@@ -100,3 +100,17 @@ def test_gram_keys_map_onto_the_engine_config():
     with pytest.raises(ValueError):              # ssl_meta_arch.py:243-244
         config_from_reference_cfg(setup_config(DinoV3SetupArgs(opts=["gram.use_loss=true", "gram.ema_teacher=true",
                                                                       "crops.gram_teacher_crops_size=224"])))
+
+
+def test_meta_arch_gram_attributes_and_errors():
+    """SSLMetaArch mirrors the gram attributes and configuration errors of train/ssl_meta_arch.py:165-254."""
+    from dinov3_jax.train import SSLMetaArch
+    m = SSLMetaArch(setup_config(DinoV3SetupArgs(opts=["gram.use_loss=true", "gram.ema_teacher=true"])))
+    assert m.gram_use_loss and m.gram_ema_teacher and not m.has_gram_teacher and m.gram_loss_weight == 1.0
+    assert not m.gram_teacher_initialized and m.engine_config.gram_use_loss
+    m = SSLMetaArch(setup_config(DinoV3SetupArgs(opts=["gram.use_loss=true", "gram.it_load_ema_teacher=0",
+                                                        "crops.gram_teacher_crops_size=224"])))
+    assert m.has_gram_teacher and m.engine_config.gram_teacher_size == 224
+    with pytest.raises(ValueError, match="gram_teacher_crops_size must be set"):
+        SSLMetaArch(setup_config(DinoV3SetupArgs(opts=["gram.use_loss=true", "gram.it_load_ema_teacher=0"])))
+    assert not SSLMetaArch(setup_config(DinoV3SetupArgs())).gram_use_loss
